@@ -1,0 +1,362 @@
+/*
+ * snk_oracle.c — TEST INFRASTRUCTURE ONLY. CPU restatement (plain C) of the reference's per-read
+ * filter / trim / statistics path, used as the checker for the CUDA engine. Nothing in the product
+ * path (soapnuke_b200/) may include, link or call this file; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs do.
+ *
+ * Parity pinning: the reference ships no tests or golden vectors, so this
+ * restatement is pinned against the UNMODIFIED reference binary compiled into oracle/_ref/SOAPnuke
+ * (oracle/Makefile): tests/test_oracle_vs_reference.py runs both on the same FASTQ and compares the
+ * clean FASTQ and all report files byte for byte, and tests/golden/ holds outputs of that binary.
+ *
+ * Each function cites the reference file:line (relative to the reference tree) it follows.
+ * It works on the same fixed-stride SoA batches and fills the same result/statistics layouts as the
+ * engine (include/snk_engine.h supplies only those POD definitions).
+ */
+#include <math.h>
+#include <limits.h>
+#include <string.h>
+#include <stdio.h>
+#include "../include/snk_engine.h"
+
+#define ORC_EXPORT __attribute__((visibility("default")))
+
+static int float_to_int_x86(float f)
+{
+    /* the reference assigns float quotients to int (read_filter.cpp:724,769); on x86-64 cvttss2si
+       yields INT_MIN for NaN / out-of-range, which is what the compiled reference does. */
+    if (!(f == f) || f >= 2147483648.0f || f < -2147483648.0f) return INT_MIN;
+    return (int)f;
+}
+
+/* read_filter.cpp:707-790 adapter_pos(). Out-of-range read positions (reads shorter than the
+ * adapter window; UB in the reference) compare as mismatches here. */
+ORC_EXPORT int orc_adapter_pos(const uint8_t* read, int readLen, const uint8_t* adapter, int adptLen,
+                               int adaMis, float adaMR, int adaEdge)
+{
+    if (adptLen == 0) return -1;
+    const int minEdge5 = 5;
+    float misGrad5 = (float)((adptLen - minEdge5) / (adaMis + 1));   /* :714 integer division first */
+    float misGrad = (float)((adptLen - adaEdge) / (adaMis + 1));     /* :715 */
+    int segMatchThr = (int)ceilf((float)adptLen * adaMR);            /* :717 */
+    int r1, mis, seg, budget;
+    for (r1 = 1; r1 <= minEdge5; ++r1) {                             /* :720-742 phase 1 */
+        mis = 0; seg = 0;
+        budget = float_to_int_x86((float)(adptLen - r1) / misGrad5);
+        for (int c = 0; c < adptLen - r1; ++c) {
+            int same = (c < readLen) && adapter[r1 + c] == read[c];
+            if (same) { if (++seg >= segMatchThr) return 0; }
+            else { mis++; seg = 0; if (mis > budget) break; }
+        }
+        if (mis <= budget) return 0;
+    }
+    for (r1 = 0; r1 <= readLen - adptLen; ++r1) {                    /* :743-764 phase 2 */
+        seg = 0; mis = 0;
+        for (int c = 0; c < adptLen; ++c) {
+            if (adapter[c] == read[r1 + c]) { if (++seg >= segMatchThr) return r1; }
+            else { mis++; seg = 0; if (mis > adaMis) break; }
+        }
+        if (mis <= adaMis) return r1;
+    }
+    for (r1 = 0; r1 < adptLen - adaEdge; ++r1) {                     /* :765-788 phase 3 */
+        mis = 0; seg = 0;
+        budget = float_to_int_x86((float)r1 / misGrad);
+        int base = readLen - r1 - adaEdge;
+        for (int c = 0; c < r1 + adaEdge; ++c) {
+            int idx = base + c;
+            int same = (idx >= 0 && idx < readLen) && adapter[c] == read[idx];
+            if (same) { if (++seg >= segMatchThr) return base; }
+            else { mis++; seg = 0; if (mis > budget) break; }
+        }
+        if (mis <= budget) return base;
+    }
+    return -1;
+}
+
+/* everything stat_read / fastq_trim leave behind for one mate */
+typedef struct {
+    int len;
+    int a, c, g, t, n;
+    int contig;
+    float n_ratio, a_ratio, lowq_ratio, mean_q;
+    int has_adapter;
+    /* C_fastq cut bookkeeping (sequence.h:69), -1 as set by C_fastq_init (peprocess.cpp:1674-1689) */
+    int head_hdcut, head_lqcut, tail_hdcut, tail_lqcut, adacut_pos;
+    int head_cut, clean_len;    /* result of fastq_trim */
+    int bad_base;               /* unrecognized base seen */
+} orc_read;
+
+static int trimming_enabled(const snk_params* p)
+{
+    /* read_filter.cpp:343-355 */
+    return p->has_hard_trim || p->has_trim_bad_head || p->has_trim_bad_tail || p->index_remove ||
+           p->ada_trim || p->contam_trim || p->polyG_tail != -1;
+}
+static int cutback_enabled(const snk_params* p)
+{
+    /* peprocess.cpp:1441, seprocess.cpp:881 */
+    return p->ada_trim || p->contam_trim || p->has_hard_trim || p->has_trim_bad_head || p->has_trim_bad_tail;
+}
+
+/* read_filter.cpp:80-313 stat_read (adapter + counters) followed by :338-471 fastq_trim */
+static void orc_stat_and_trim(const snk_params* p, int mate, const uint8_t* seq, const uint8_t* qual,
+                              int len, orc_read* r)
+{
+    memset(r, 0, sizeof(*r));
+    r->len = len;
+    r->head_hdcut = r->head_lqcut = r->tail_hdcut = r->tail_lqcut = r->adacut_pos = -1;
+    /* :175-188 first adapter in the list that hits wins */
+    int ada_pos = -1;
+    for (int i = 0; i < p->n_adapters[mate]; i++) {
+        ada_pos = orc_adapter_pos(seq, len, (const uint8_t*)p->adapter[mate][i], p->adapter_len[mate][i],
+                                  p->ada_mis[mate], p->ada_mr[mate], p->ada_edge[mate]);
+        if (ada_pos >= 0) break;
+    }
+    if (ada_pos >= 0) { r->has_adapter = 1; r->adacut_pos = len - ada_pos; }
+    /* :255-287 base loop */
+    int last_char = 'Q', contig = 0, max_contig = 1;
+    for (int i = 0; i < len; i++) {
+        int ch = seq[i];
+        if (p->polyX_num != -1) {
+            if (ch == last_char) { contig++; if (max_contig < contig) max_contig = contig; }
+            else contig = 1;
+        }
+        last_char = ch;
+        switch (ch) {
+            case 'a': case 'A': r->a++; break;
+            case 'c': case 'C': r->c++; break;
+            case 'g': case 'G': r->g++; break;
+            case 't': case 'T': r->t++; break;
+            case 'n': case 'N': r->n++; break;
+            default: r->bad_base = 1; break;       /* :282-285 exit(1) */
+        }
+    }
+    r->contig = max_contig;
+    r->a_ratio = (float)r->a / (float)len;          /* :290 */
+    r->n_ratio = (float)r->n / (float)len;          /* :294 */
+    /* :296-311 quality loop */
+    int total = 0, low = 0;
+    for (int i = 0; i < len; i++) {
+        int q = (int)qual[i] - p->quality_phred;
+        total += q;
+        if (q <= p->low_qual) low++;
+    }
+    r->lowq_ratio = (float)low / (float)len;
+    r->mean_q = (float)total / (float)len;
+
+    /* ---- fastq_trim, read_filter.cpp:338-471 ---- */
+    r->head_cut = 0; r->clean_len = len;
+    if (!trimming_enabled(p)) return;               /* :354-355 */
+    int head_cut = 0, tail_cut = 0;
+    if (p->has_hard_trim) {                         /* :384-389 */
+        r->head_hdcut = p->hard_head[mate];
+        r->tail_hdcut = p->hard_tail[mate];
+        head_cut = r->head_hdcut; tail_cut = r->tail_hdcut;
+    }
+    if (p->has_trim_bad_head || p->has_trim_bad_tail) {   /* :390-429 */
+        int hthr = p->has_trim_bad_head ? p->bad_head_thr : 0, hmax = p->has_trim_bad_head ? p->bad_head_max : 0;
+        int tthr = p->has_trim_bad_tail ? p->bad_tail_thr : 0, tmax = p->has_trim_bad_tail ? p->bad_tail_max : 0;
+        int hix = 0, tix = 0;
+        for (int ix = 0; ix < hmax && ix < len; ix++) {   /* bounded by len: reference reads past the end (UB) */
+            if ((int)qual[ix] - p->quality_phred < hthr) hix++; else break;
+        }
+        for (int ix = 0; ix < tmax && ix < len; ix++) {
+            if ((int)qual[len - ix - 1] - p->quality_phred < tthr) tix++; else break;
+        }
+        r->head_lqcut = hix; r->tail_lqcut = tix;
+        if (hix > head_cut) head_cut = hix;
+        if (tix > tail_cut) tail_cut = tix;
+    }
+    if (p->ada_trim) {                              /* :430-442 */
+        if (r->adacut_pos > 0 && r->adacut_pos > tail_cut) tail_cut = r->adacut_pos;
+    }
+    if (p->polyG_tail != -1) {                      /* :454-461, polyG_number :472-482 */
+        int ng = 0;
+        for (int i = len - 1; i >= 0; i--) { if (seq[i] == 'G' || seq[i] == 'g') ng++; else break; }
+        if ((float)ng >= p->polyG_tail) { if (ng > tail_cut) tail_cut = ng; }
+    }
+    if (head_cut + tail_cut > len) { r->head_cut = 0; r->clean_len = 0; }   /* :462-464 */
+    else { r->head_cut = head_cut; r->clean_len = len - head_cut - tail_cut; }
+}
+
+static void ts_bump(uint64_t* ts, int arr, long idx)
+{
+    long flat = (long)arr * SNK_MAX_READ_LEN + idx;     /* negative idx spills into the previous array */
+    if (flat >= 0 && flat < SNK_TS_WORDS) ts[flat]++;
+}
+
+/* peprocess.cpp:1105-1204 (fq1), :1323-1421 (fq2), seprocess.cpp:645-740: one record into one table.
+ * which: 0 = PE fq1 (index base raw_length), 1 = PE fq2 (index base sequence.size()), 2 = SE */
+static void orc_stat_record(const snk_params* p, uint64_t* file, int which, const uint8_t* seq,
+                            const uint8_t* qual, int slen, int raw_length,
+                            int head_hdcut, int head_lqcut, int tail_hdcut, int tail_lqcut, int adacut_pos,
+                            uint64_t key_index, uint32_t* err)
+{
+    uint64_t* gs = file + SNK_FILE_GS_OFF;
+    uint64_t* bs = file + SNK_FILE_BS_OFF;
+    uint64_t* qs = file + SNK_FILE_QS_OFF;
+    uint64_t* ts = file + SNK_FILE_TS_OFF;
+    if (head_hdcut > 0 || head_lqcut > 0) {
+        if (head_hdcut >= head_lqcut) ts_bump(ts, SNK_TS_HT, head_hdcut);
+        else ts_bump(ts, SNK_TS_HLQ, head_lqcut);
+    }
+    int ada_cond = (which == 2) ? (adacut_pos >= 0) : (adacut_pos > 0);   /* seprocess.cpp:658 vs peprocess.cpp:1118 */
+    if (tail_hdcut > 0 || tail_lqcut > 0 || ada_cond) {
+        long base = (which == 1) ? slen : raw_length;
+        if (tail_hdcut >= tail_lqcut) {
+            if (tail_hdcut >= adacut_pos) ts_bump(ts, SNK_TS_TT, base - tail_hdcut + 1);
+            else ts_bump(ts, SNK_TS_TA, base - adacut_pos + 1);
+        } else {
+            if (tail_lqcut >= adacut_pos) ts_bump(ts, SNK_TS_TLQ, base - tail_lqcut + 1);
+            else ts_bump(ts, SNK_TS_TA, base - adacut_pos + 1);
+        }
+    }
+    for (int i = 0; i < slen; i++) {
+        switch (seq[i]) {
+            case 'a': case 'A': bs[i * 5 + 0]++; gs[SNK_GS_A]++; break;
+            case 'c': case 'C': bs[i * 5 + 1]++; gs[SNK_GS_C]++; break;
+            case 'g': case 'G': bs[i * 5 + 2]++; gs[SNK_GS_G]++; break;
+            case 't': case 'T': bs[i * 5 + 3]++; gs[SNK_GS_T]++; break;
+            case 'n': case 'N': bs[i * 5 + 4]++; gs[SNK_GS_N]++; break;
+            default: *err |= 1u; break;
+        }
+        int q = (int)qual[i] - p->quality_phred;    /* clean uses rebased char - outputQualityPhred == same q */
+        if (q < 0 || q >= SNK_QBINS) *err |= 2u;
+        else qs[(size_t)i * SNK_QBINS + q]++;
+        if (q >= 20) gs[SNK_GS_Q20]++;
+        if (q >= 30) gs[SNK_GS_Q30]++;
+    }
+    gs[SNK_GS_BASES] += (uint64_t)slen;
+    gs[SNK_GS_READS] += 1;
+    uint64_t key = ((key_index + 1) << 16) | (uint64_t)slen;
+    if (key > gs[SNK_GS_LAST_KEY]) gs[SNK_GS_LAST_KEY] = key;
+}
+
+static void fs_dis(uint64_t* fs, int base, int a, int b)
+{
+    /* pe_dis + switch, sequence.cpp:392-399 and e.g. :292-302 */
+    if (a) fs[base + 1]++;
+    if (b) fs[base + 2]++;
+    if (a && b) fs[base + 3]++;
+    fs[base]++;
+}
+
+/* sequence.cpp:198-387 pe_discard (contam/tile/fov/dup/overlap branches are out of scope) */
+static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_read* r2, uint64_t* fs,
+                          int* mask, uint32_t* err)
+{
+    int a, b;
+#define DIS(cat, base) do { if (a || b) { fs_dis(fs, base, a, b); *mask = (a ? 1 : 0) | (b ? 2 : 0); return cat; } } while (0)
+    if (p->min_read_length != -1) {
+        /* size_t < int comparison: negative thresholds other than -1 convert to huge unsigned */
+        a = (uint64_t)r1->clean_len < (uint64_t)(int64_t)p->min_read_length;
+        b = (uint64_t)r2->clean_len < (uint64_t)(int64_t)p->min_read_length;
+        DIS(SNK_DROP_SHORT, SNK_FS_SHORT);
+    } else if (r1->clean_len == 0 || r2->clean_len == 0) { *mask = 0; return SNK_DROP_EMPTY; }
+    if (p->max_read_length != -1) {
+        a = (uint64_t)r1->clean_len > (uint64_t)(int64_t)p->max_read_length;
+        b = (uint64_t)r2->clean_len > (uint64_t)(int64_t)p->max_read_length;
+        DIS(SNK_DROP_LONG, SNK_FS_LONG);
+    }
+    if (p->n_ratio != -1) { a = r1->n_ratio >= p->n_ratio; b = r2->n_ratio >= p->n_ratio; DIS(SNK_DROP_N, SNK_FS_N); }
+    if (p->highA_ratio != -1) { a = r1->a_ratio >= p->highA_ratio; b = r2->a_ratio >= p->highA_ratio; DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA); }
+    if (p->polyX_num != -1) { a = r1->contig >= p->polyX_num; b = r2->contig >= p->polyX_num; DIS(SNK_DROP_POLYX, SNK_FS_POLYX); }
+    if (p->low_qual_ratio != -1) {
+        a = r1->lowq_ratio >= p->low_qual_ratio; b = r2->lowq_ratio >= p->low_qual_ratio;
+        if ((a || b) && (r1->lowq_ratio > 1 || r2->lowq_ratio > 1)) *err |= 4u;   /* :335-338 */
+        DIS(SNK_DROP_LOWQ, SNK_FS_LOWQ);
+    }
+    if (p->mean_quality != -1) { a = r1->mean_q < (float)p->mean_quality; b = r2->mean_q < (float)p->mean_quality; DIS(SNK_DROP_MEANQ, SNK_FS_MEANQ); }
+    if (!p->ada_trim) { a = r1->has_adapter; b = r2->has_adapter; DIS(SNK_DROP_ADAPTER, SNK_FS_ADAPTER); }
+#undef DIS
+    *mask = 0;
+    return SNK_KEEP;
+}
+
+/* sequence.cpp:76-178 se_discard */
+static int orc_se_discard(const snk_params* p, const orc_read* r, uint64_t* fs)
+{
+    if (p->min_read_length != -1 && (uint64_t)r->clean_len < (uint64_t)(int64_t)p->min_read_length) { fs[SNK_FS_SHORT]++; return SNK_DROP_SHORT; }
+    if (p->max_read_length != -1 && (uint64_t)r->clean_len > (uint64_t)(int64_t)p->max_read_length) { fs[SNK_FS_LONG]++; return SNK_DROP_LONG; }
+    if (p->n_ratio != -1 && r->n_ratio >= p->n_ratio) { fs[SNK_FS_N]++; return SNK_DROP_N; }
+    if (p->highA_ratio != -1 && r->a_ratio >= p->highA_ratio) { fs[SNK_FS_HIGHA]++; return SNK_DROP_HIGHA; }
+    if (p->polyX_num != -1 && r->contig >= p->polyX_num) { fs[SNK_FS_POLYX]++; return SNK_DROP_POLYX; }
+    if (p->low_qual_ratio != -1 && r->lowq_ratio >= p->low_qual_ratio) { fs[SNK_FS_LOWQ]++; return SNK_DROP_LOWQ; }
+    if (p->mean_quality != -1 && r->mean_q < (float)p->mean_quality) { fs[SNK_FS_MEANQ]++; return SNK_DROP_MEANQ; }
+    if (r->has_adapter && !p->ada_trim) { fs[SNK_FS_ADAPTER]++; return SNK_DROP_ADAPTER; }
+    return SNK_KEEP;
+}
+
+static void fill_result(snk_read_result* o, const orc_read* r, int cat, int mask)
+{
+    o->head_cut = (uint16_t)r->head_cut;
+    o->clean_len = (uint16_t)r->clean_len;
+    o->category = (uint8_t)cat;
+    o->mate_mask = (uint8_t)mask;
+    o->adacut_pos = (int16_t)r->adacut_pos;
+}
+
+/* filter_pe_fqs (peprocess.cpp:1424-1484) + stat_pe_fqs raw (:1923) + stat_pe_fqs clean (:1961).
+ * stats: n_slots blocks of SNK_SLOT_WORDS uint64, accumulated into. err: sticky error bits. */
+ORC_EXPORT int orc_filter_pe(const snk_params* p, const snk_batch* b1, const snk_batch* b2,
+                             snk_read_result* out1, snk_read_result* out2, uint64_t* stats,
+                             uint64_t first_index, uint32_t* err)
+{
+    if (b1->n != b2->n) return 1;
+    int cutback = cutback_enabled(p);
+    for (uint32_t i = 0; i < b1->n; i++) {
+        uint64_t gi = first_index + i;
+        int slot = (int)((gi / (uint64_t)p->slot_block) % (uint64_t)p->n_slots);
+        uint64_t* S = stats + (size_t)slot * SNK_SLOT_WORDS;
+        const uint8_t* s1 = b1->seq + (size_t)i * b1->stride; const uint8_t* q1 = b1->qual + (size_t)i * b1->stride;
+        const uint8_t* s2 = b2->seq + (size_t)i * b2->stride; const uint8_t* q2 = b2->qual + (size_t)i * b2->stride;
+        orc_read r1, r2;
+        orc_stat_and_trim(p, 0, s1, q1, b1->len[i], &r1);
+        orc_stat_and_trim(p, 1, s2, q2, b2->len[i], &r2);
+        if (r1.bad_base || r2.bad_base) *err |= 1u;
+        int mask = 0;
+        int cat = orc_pe_discard(p, &r1, &r2, S, &mask, err);
+        fill_result(&out1[i], &r1, cat, mask);
+        fill_result(&out2[i], &r2, cat, mask);
+        /* raw tables: raw records keep raw_length==0 and -1 cuts unless copied back (peprocess.cpp:1441-1459) */
+        orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_RAW1), 0, s1, q1, r1.len, 0,
+                        cutback ? r1.head_hdcut : -1, cutback ? r1.head_lqcut : -1, cutback ? r1.tail_hdcut : -1,
+                        cutback ? r1.tail_lqcut : -1, cutback ? r1.adacut_pos : -1, gi, err);
+        orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_RAW2), 1, s2, q2, r2.len, 0,
+                        cutback ? r2.head_hdcut : -1, cutback ? r2.head_lqcut : -1, cutback ? r2.tail_hdcut : -1,
+                        cutback ? r2.tail_lqcut : -1, cutback ? r2.adacut_pos : -1, gi, err);
+        if (cat == SNK_KEEP) {
+            /* clean records are the filter's trimmed copies: real raw_length, all bookkeeping ints */
+            orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_CLEAN1), 0, s1 + r1.head_cut, q1 + r1.head_cut, r1.clean_len, r1.len,
+                            r1.head_hdcut, r1.head_lqcut, r1.tail_hdcut, r1.tail_lqcut, r1.adacut_pos, gi, err);
+            orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_CLEAN2), 1, s2 + r2.head_cut, q2 + r2.head_cut, r2.clean_len, r2.len,
+                            r2.head_hdcut, r2.head_lqcut, r2.tail_hdcut, r2.tail_lqcut, r2.adacut_pos, gi, err);
+        }
+    }
+    return 0;
+}
+
+/* filter_se_fqs (seprocess.cpp:871-917) + stat_se_fqs raw (:1967) + clean (:2007) */
+ORC_EXPORT int orc_filter_se(const snk_params* p, const snk_batch* b1, snk_read_result* out1,
+                             uint64_t* stats, uint64_t first_index, uint32_t* err)
+{
+    int cutback = cutback_enabled(p);
+    for (uint32_t i = 0; i < b1->n; i++) {
+        uint64_t gi = first_index + i;
+        int slot = (int)((gi / (uint64_t)p->slot_block) % (uint64_t)p->n_slots);
+        uint64_t* S = stats + (size_t)slot * SNK_SLOT_WORDS;
+        const uint8_t* s1 = b1->seq + (size_t)i * b1->stride; const uint8_t* q1 = b1->qual + (size_t)i * b1->stride;
+        orc_read r1;
+        orc_stat_and_trim(p, 0, s1, q1, b1->len[i], &r1);
+        if (r1.bad_base) *err |= 1u;
+        int cat = orc_se_discard(p, &r1, S);
+        fill_result(&out1[i], &r1, cat, cat ? 1 : 0);
+        orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_RAW1), 2, s1, q1, r1.len, 0,
+                        cutback ? r1.head_hdcut : -1, cutback ? r1.head_lqcut : -1, cutback ? r1.tail_hdcut : -1,
+                        cutback ? r1.tail_lqcut : -1, cutback ? r1.adacut_pos : -1, gi, err);
+        if (cat == SNK_KEEP)
+            orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_CLEAN1), 2, s1 + r1.head_cut, q1 + r1.head_cut, r1.clean_len, r1.len,
+                            r1.head_hdcut, r1.head_lqcut, r1.tail_hdcut, r1.tail_lqcut, r1.adacut_pos, gi, err);
+    }
+    return 0;
+}

@@ -1,0 +1,250 @@
+"""ctypes mirror of include/snk_engine.h (the C ABI of the engine).
+
+Only PODs and prototypes live here; the product code is the shared library built from
+soapnuke_b200/csrc (CUDA) and soapnuke_b200/host (C++). There is deliberately NO CPU fallback:
+if the library is missing, `load_engine()` raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+ENGINE_LIB = os.path.join(HERE, "lib", "libsnk_engine.so")
+
+ABI_VERSION = 1
+MAX_READ_LEN = 1000
+QBINS = 64
+MAX_ADAPTERS = 8
+MAX_ADAPTER_LEN = 128
+MAX_SLOTS = 256
+
+FS_COUNT = 32
+GS_COUNT = 16
+FILE_COUNT = 4
+TS_COUNT = 5
+BS_WORDS = MAX_READ_LEN * 5
+QS_WORDS = MAX_READ_LEN * QBINS
+TS_WORDS = TS_COUNT * MAX_READ_LEN
+FILE_WORDS = GS_COUNT + BS_WORDS + QS_WORDS + TS_WORDS
+FILE_GS_OFF = 0
+FILE_BS_OFF = GS_COUNT
+FILE_QS_OFF = GS_COUNT + BS_WORDS
+FILE_TS_OFF = GS_COUNT + BS_WORDS + QS_WORDS
+SLOT_WORDS = FS_COUNT + FILE_COUNT * FILE_WORDS
+
+RAW1, RAW2, CLEAN1, CLEAN2 = 0, 1, 2, 3
+GS_READS, GS_BASES, GS_A, GS_C, GS_G, GS_T, GS_N, GS_Q20, GS_Q30, GS_LAST_KEY = range(10)
+
+CATEGORY_NAMES = ["keep", "short", "long", "n", "highA", "polyX", "lowq", "meanq", "adapter", "empty"]
+FS_BASE = {"adapter": 0, "n": 4, "highA": 8, "polyX": 12, "lowq": 16, "meanq": 20, "short": 24, "long": 28}
+
+
+def slot_file_off(f):
+    return FS_COUNT + f * FILE_WORDS
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32),
+        ("is_pe", C.c_int32),
+        ("quality_phred", C.c_int32),
+        ("out_quality_phred", C.c_int32),
+        ("low_qual", C.c_int32),
+        ("low_qual_ratio", C.c_float),
+        ("mean_quality", C.c_int32),
+        ("n_ratio", C.c_float),
+        ("highA_ratio", C.c_float),
+        ("polyG_tail", C.c_float),
+        ("polyX_num", C.c_int32),
+        ("min_read_length", C.c_int32),
+        ("max_read_length", C.c_int32),
+        ("ada_trim", C.c_int32),
+        ("contam_trim", C.c_int32),
+        ("ada_mis", C.c_int32 * 2),
+        ("ada_mr", C.c_float * 2),
+        ("ada_edge", C.c_int32 * 2),
+        ("n_adapters", C.c_int32 * 2),
+        ("adapter_len", (C.c_int32 * MAX_ADAPTERS) * 2),
+        ("adapter", ((C.c_char * MAX_ADAPTER_LEN) * MAX_ADAPTERS) * 2),
+        ("has_hard_trim", C.c_int32),
+        ("hard_head", C.c_int32 * 2),
+        ("hard_tail", C.c_int32 * 2),
+        ("has_trim_bad_head", C.c_int32),
+        ("bad_head_thr", C.c_int32),
+        ("bad_head_max", C.c_int32),
+        ("has_trim_bad_tail", C.c_int32),
+        ("bad_tail_thr", C.c_int32),
+        ("bad_tail_max", C.c_int32),
+        ("index_remove", C.c_int32),
+        ("max_base_quality", C.c_int32),
+        ("n_slots", C.c_int32),
+        ("slot_block", C.c_int64),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("seq", C.c_void_p),
+        ("qual", C.c_void_p),
+        ("len", C.c_void_p),
+        ("n", C.c_uint32),
+        ("stride", C.c_uint32),
+    ]
+
+
+class ReadResult(C.Structure):
+    _fields_ = [
+        ("head_cut", C.c_uint16),
+        ("clean_len", C.c_uint16),
+        ("category", C.c_uint8),
+        ("mate_mask", C.c_uint8),
+        ("adacut_pos", C.c_int16),
+    ]
+
+
+import numpy as _np
+
+RESULT_DTYPE = _np.dtype([("head_cut", "<u2"), ("clean_len", "<u2"), ("category", "u1"),
+                          ("mate_mask", "u1"), ("adacut_pos", "<i2")])
+assert RESULT_DTYPE.itemsize == C.sizeof(ReadResult) == 8
+
+
+def ref_threads_partition(threads_requested, nprocs=None):
+    """(n_slots, slot_block) exactly as the reference derives them:
+    patchSize = T_requested*20000/8 (process_argv.cpp:541-544), T clamped to nprocs afterwards
+    (process_argv.cpp:905-910), patch = 160/T (peprocess.cpp:81), block = patchSize*patch pairs
+    (peprocess.cpp:2063: thread_read_block = 4*patchSize*patch lines)."""
+    if nprocs is None:
+        nprocs = os.cpu_count() or 1
+    patch_size = threads_requested * 20000 // 8
+    t = min(threads_requested, nprocs)
+    patch = 160 // t
+    return t, patch_size * patch, patch_size
+
+
+def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qual=5, low_qual_ratio=0.5,
+                mean_quality=-1, n_ratio=0.05, highA_ratio=-1.0, polyG_tail=-1.0, polyX_num=-1,
+                min_read_length=30, max_read_length=-1, quality_phred=33, out_quality_phred=33,
+                ada_mis=(2, 2), ada_mr=(0.5, 0.5), ada_edge=(6, 6), hard_trim=None,
+                trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
+                contam_trim=False, index_remove=False):
+    """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
+    Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
+    p = Params()
+    p.abi_version = ABI_VERSION
+    p.is_pe = 1 if is_pe else 0
+    p.quality_phred = quality_phred
+    p.out_quality_phred = out_quality_phred
+    p.low_qual = low_qual
+    p.low_qual_ratio = low_qual_ratio
+    p.mean_quality = mean_quality
+    p.n_ratio = n_ratio
+    p.highA_ratio = highA_ratio
+    p.polyG_tail = polyG_tail
+    p.polyX_num = polyX_num
+    p.min_read_length = min_read_length
+    p.max_read_length = max_read_length
+    p.ada_trim = 1 if ada_trim else 0
+    p.contam_trim = 1 if contam_trim else 0
+    p.index_remove = 1 if index_remove else 0
+    for m in range(2):
+        p.ada_mis[m] = ada_mis[m]
+        p.ada_mr[m] = ada_mr[m]
+        p.ada_edge[m] = ada_edge[m]
+    for m, ada in enumerate((adapter1, adapter2)):
+        if ada is None:
+            lst = []
+        elif isinstance(ada, (str, bytes)):
+            lst = [ada]
+        else:
+            lst = list(ada)
+        assert len(lst) <= MAX_ADAPTERS
+        p.n_adapters[m] = len(lst)
+        for i, a in enumerate(lst):
+            if isinstance(a, str):
+                a = a.encode()
+            assert len(a) < MAX_ADAPTER_LEN
+            p.adapter_len[m][i] = len(a)
+            p.adapter[m][i].value = a
+    if hard_trim is not None:
+        p.has_hard_trim = 1
+        ht = list(hard_trim)
+        if len(ht) == 2:
+            ht = ht + [0, 0]
+        p.hard_head[0], p.hard_tail[0], p.hard_head[1], p.hard_tail[1] = ht
+    if trim_bad_head is not None:
+        p.has_trim_bad_head = 1
+        p.bad_head_thr, p.bad_head_max = trim_bad_head
+    if trim_bad_tail is not None:
+        p.has_trim_bad_tail = 1
+        p.bad_tail_thr, p.bad_tail_max = trim_bad_tail
+    p.max_base_quality = max_base_quality
+    n_slots, block, _ = ref_threads_partition(threads, nprocs)
+    p.n_slots = n_slots
+    p.slot_block = block
+    return p
+
+
+def make_batch(seq, qual, length):
+    """snk_batch over numpy arrays (kept alive by the caller)."""
+    assert seq.dtype == _np.uint8 and qual.dtype == _np.uint8 and length.dtype == _np.uint16
+    assert seq.flags.c_contiguous and qual.flags.c_contiguous and length.flags.c_contiguous
+    n, stride = seq.shape
+    assert qual.shape == (n, stride) and length.shape == (n,) and stride % 16 == 0
+    b = Batch()
+    b.seq = seq.ctypes.data
+    b.qual = qual.ctypes.data
+    b.len = length.ctypes.data
+    b.n = n
+    b.stride = stride
+    return b
+
+
+_PROTOS = {
+    "snk_last_error": (C.c_char_p, []),
+    "snk_abi_version": (C.c_int, []),
+    "snk_stats_slot_words": (C.c_size_t, []),
+    "snk_params_check": (C.c_int, [C.POINTER(Params)]),
+    "snk_engine_create": (C.c_int, [C.POINTER(Params), C.c_int, C.POINTER(C.c_void_p)]),
+    "snk_engine_destroy": (C.c_int, [C.c_void_p]),
+    "snk_filter_pe_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint64]),
+    "snk_filter_se_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_uint64]),
+    "snk_engine_lanes": (C.c_int, [C.c_void_p]),
+    "snk_filter_pe_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint64]),
+    "snk_filter_se_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), C.c_void_p, C.c_uint64]),
+    "snk_engine_lane_sync": (C.c_int, [C.c_void_p, C.c_int]),
+    "snk_filter_pe_device": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "snk_filter_se_device": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_uint64, C.c_void_p]),
+    "snk_engine_stats_reset": (C.c_int, [C.c_void_p]),
+    "snk_engine_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "snk_engine_stats_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "snk_engine_error_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "snk_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+    "snk_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "snk_host_free": (C.c_int, [C.c_void_p]),
+    "snk_report_write_pe": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_char_p]),
+    "snk_report_write_se": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_char_p]),
+}
+EXPORTED_SYMBOLS = sorted(_PROTOS)
+
+_engine_lib = None
+
+
+def load_engine():
+    """dlopen the in-tree engine library. Fails loudly when it is missing: no fallback exists."""
+    global _engine_lib
+    if _engine_lib is None:
+        if not os.path.exists(ENGINE_LIB):
+            raise RuntimeError(
+                f"{ENGINE_LIB} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the engine has no CPU fallback)")
+        lib = C.CDLL(ENGINE_LIB)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        if lib.snk_abi_version() != ABI_VERSION:
+            raise RuntimeError("ABI version mismatch between abi.py and libsnk_engine.so")
+        _engine_lib = lib
+    return _engine_lib

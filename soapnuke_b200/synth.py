@@ -1,0 +1,145 @@
+"""Deterministic synthetic FASTQ generator and small FASTQ <-> SoA helpers.
+
+Bases iid uniform ACGT; quality per position clip(round(N(mu_p, 6)), 2, 40) + 33 with mu_p linear
+37 -> 28 over the read; per-pair class by u ~ U(0,1): 10 % adapter read-through at insert
+k ~ U[20, L-10) (adapter written from k on both mates), 3 % N-rich (each base -> N w.p. 0.08),
+5 % low-quality (all Q ~ U[2,8)), 4 % (polyg_frac) mate-2 polyG tail of length 5 + k/3, rest clean.
+"""
+import numpy as np
+
+ADAPTER1 = b"AAGTCGGAGGCCAAGCGGTCTTAGGAAGACAA"            # -f, process_argv.cpp:1042
+ADAPTER2 = b"AAGTCGGATCGTAGCCATGTCGTTCTGTGAGCCAAGGAGTTG"  # -r
+SRNA_ADAPTER3 = b"TCGTATGCCGTCTTCTGCTTG"
+
+_ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+
+def stride_for(max_len):
+    return (max_len + 15) // 16 * 16
+
+
+def _quals(rng, n, L):
+    mu = np.linspace(37.0, 28.0, L, dtype=np.float32)
+    q = rng.standard_normal((n, L), dtype=np.float32) * 6.0 + mu
+    q = np.clip(np.rint(q), 2, 40).astype(np.uint8)
+    return q
+
+
+def gen_mate_arrays(rng, n, L):
+    seq = _ACGT[rng.integers(0, 4, size=(n, L), dtype=np.uint8)]
+    qual = _quals(rng, n, L)
+    return seq, qual
+
+
+def gen_pairs(n, L=150, seed=1002, polyg_frac=0.04, adapter1=ADAPTER1, adapter2=ADAPTER2,
+              var_len=False, se=False, insert_range=None):
+    """Return dict with seq1, qual1, len1 (and seq2, qual2, len2 unless se) as fixed-stride SoA
+    (uint8 [n][stride], zero padded; uint16 [n])."""
+    rng = np.random.default_rng(seed)
+    stride = stride_for(L)
+    out = {}
+    u = rng.random(n)
+    if insert_range is None:
+        insert_range = (20, max(21, L - 10))
+    k = rng.integers(insert_range[0], insert_range[1], size=n)
+    cls_ada = u < 0.10
+    cls_n = (u >= 0.10) & (u < 0.13)
+    cls_lq = (u >= 0.13) & (u < 0.18)
+    cls_pg = (u >= 0.18) & (u < 0.18 + polyg_frac)
+    mates = (1,) if se else (1, 2)
+    for m in mates:
+        seq, qual = gen_mate_arrays(rng, n, L)
+        ada = np.frombuffer(adapter1 if m == 1 else adapter2, dtype=np.uint8)
+        if ada.size:
+            idx = np.nonzero(cls_ada)[0]
+            for i in idx:                      # 10 % of reads; small python loop is fine for tests
+                s = int(k[i]); e = min(L, s + ada.size)
+                seq[i, s:e] = ada[: e - s]
+        nmask = cls_n[:, None] & (rng.random((n, L)) < 0.08)
+        seq[nmask] = ord("N")
+        lq = np.nonzero(cls_lq)[0]
+        qual[lq] = rng.integers(2, 8, size=(lq.size, L), dtype=np.uint8)
+        if m == 2 or se:
+            pg = np.nonzero(cls_pg)[0]
+            for i in pg:
+                t = 5 + int(k[i]) // 3
+                seq[i, L - t:] = ord("G")
+        length = np.full(n, L, dtype=np.uint16)
+        if var_len:
+            length = rng.integers(max(35, L // 2), L + 1, size=n).astype(np.uint16)
+        S = np.zeros((n, stride), dtype=np.uint8)
+        Q = np.zeros((n, stride), dtype=np.uint8)
+        S[:, :L] = seq
+        Q[:, :L] = qual + 33
+        if var_len:
+            col = np.arange(stride)[None, :]
+            pad = col >= length[:, None]
+            S[pad] = 0
+            Q[pad] = 0
+        out[f"seq{m}"] = S
+        out[f"qual{m}"] = Q
+        out[f"len{m}"] = length
+    out["n"] = n
+    out["L"] = L
+    out["stride"] = stride
+    return out
+
+
+def read_ids(n, mate, first=0):
+    return [b"@SYN:1:1101:%d:%d/%d" % ((first + i) // 1000, (first + i) % 1000, mate) for i in range(n)]
+
+
+def write_fastq(path, seq, qual, length, mate, first=0, gz=False):
+    import gzip
+    n = seq.shape[0]
+    ids = read_ids(n, mate, first)
+    parts = []
+    for i in range(n):
+        l = int(length[i])
+        parts.append(ids[i] + b"\n" + seq[i, :l].tobytes() + b"\n+\n" + qual[i, :l].tobytes() + b"\n")
+    data = b"".join(parts)
+    if gz:
+        with gzip.open(path, "wb", compresslevel=2) as f:
+            f.write(data)
+    else:
+        with open(path, "wb") as f:
+            f.write(data)
+
+
+def clean_fastq_bytes(seq, qual, length, results, mate, first=0, phred_shift=0):
+    """Rebuild the clean FASTQ text the reference writes (peprocess.cpp:3414) from per-read results."""
+    n = seq.shape[0]
+    ids = read_ids(n, mate, first)
+    parts = []
+    for i in range(n):
+        if results["category"][i] != 0:
+            continue
+        h = int(results["head_cut"][i]); l = int(results["clean_len"][i])
+        q = qual[i, h:h + l]
+        if phred_shift:
+            q = (q.astype(np.int16) + phred_shift).astype(np.uint8)
+        parts.append(ids[i] + b"\n" + seq[i, h:h + l].tobytes() + b"\n+\n" + q.tobytes() + b"\n")
+    return b"".join(parts)
+
+
+def parse_fastq(data, stride=None):
+    """FASTQ text -> (ids, seq[n][stride], qual[n][stride], len[n])."""
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    n = len(lines) // 4
+    ids = lines[0::4][:n]
+    seqs = lines[1::4][:n]
+    quals = lines[3::4][:n]
+    mx = max((len(s) for s in seqs), default=0)
+    if stride is None:
+        stride = stride_for(max(mx, 1))
+    S = np.zeros((n, stride), dtype=np.uint8)
+    Q = np.zeros((n, stride), dtype=np.uint8)
+    Ln = np.zeros(n, dtype=np.uint16)
+    for i in range(n):
+        l = len(seqs[i])
+        S[i, :l] = np.frombuffer(seqs[i], dtype=np.uint8)
+        Q[i, :l] = np.frombuffer(quals[i], dtype=np.uint8)
+        Ln[i] = l
+    return ids, S, Q, Ln
