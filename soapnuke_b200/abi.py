@@ -110,14 +110,15 @@ RESULT_DTYPE = _np.dtype([("head_cut", "<u2"), ("clean_len", "<u2"), ("category"
 assert RESULT_DTYPE.itemsize == C.sizeof(ReadResult) == 8
 
 
-def ref_threads_partition(threads_requested, nprocs=None):
+def ref_threads_partition(threads_requested, nprocs=None, patch_size=None):
     """(n_slots, slot_block) exactly as the reference derives them:
     patchSize = T_requested*20000/8 (process_argv.cpp:541-544), T clamped to nprocs afterwards
     (process_argv.cpp:905-910), patch = 160/T (peprocess.cpp:81), block = patchSize*patch pairs
     (peprocess.cpp:2063: thread_read_block = 4*patchSize*patch lines)."""
     if nprocs is None:
         nprocs = os.cpu_count() or 1
-    patch_size = threads_requested * 20000 // 8
+    if not patch_size:                      # config key `patch=` overrides (process_argv.cpp:1370-1372)
+        patch_size = threads_requested * 20000 // 8
     t = min(threads_requested, nprocs)
     patch = 160 // t
     return t, patch_size * patch, patch_size
@@ -128,7 +129,7 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
                 min_read_length=30, max_read_length=-1, quality_phred=33, out_quality_phred=33,
                 ada_mis=(2, 2), ada_mr=(0.5, 0.5), ada_edge=(6, 6), hard_trim=None,
                 trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
-                contam_trim=False, index_remove=False):
+                contam_trim=False, index_remove=False, patch_size=None):
     """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
     Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
     p = Params()
@@ -180,7 +181,7 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
         p.has_trim_bad_tail = 1
         p.bad_tail_thr, p.bad_tail_max = trim_bad_tail
     p.max_base_quality = max_base_quality
-    n_slots, block, _ = ref_threads_partition(threads, nprocs)
+    n_slots, block, _ = ref_threads_partition(threads, nprocs, patch_size)
     p.n_slots = n_slots
     p.slot_block = block
     return p

@@ -1,0 +1,40 @@
+// host_common.cpp — error slot and parameter validation shared by the engine and the CLI.
+#include "host_common.h"
+#include <cstring>
+
+namespace snk {
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error() { return g_err.c_str(); }
+
+// What the hot path needs from the parameters. The reference would divide by zero / index out of
+// range on these (read_filter.cpp:714-715); reject them up front instead.
+int params_check(const snk_params& p)
+{
+    if (p.abi_version != SNK_ABI_VERSION) { set_error("snk_params.abi_version mismatch"); return 1; }
+    if (p.n_slots < 1 || p.n_slots > SNK_MAX_SLOTS) { set_error("n_slots out of range"); return 1; }
+    if (p.slot_block < 1) { set_error("slot_block must be >= 1"); return 1; }
+    if (p.quality_phred != 33 && p.quality_phred != 64) { set_error("qualityPhred value error"); return 1; }
+    if (p.out_quality_phred != 33 && p.out_quality_phred != 64) { set_error("outputQualityPhred value error"); return 1; }
+    for (int m = 0; m < 2; m++) {
+        if (p.n_adapters[m] < 0 || p.n_adapters[m] > SNK_MAX_ADAPTERS) { set_error("too many adapters"); return 1; }
+        if (p.n_adapters[m] > 0 && p.ada_mis[m] + 1 == 0) { set_error("adaMis must not be -1"); return 1; }
+        if (p.n_adapters[m] > 0 && p.ada_edge[m] < 0) { set_error("adaEdge must be >= 0"); return 1; }
+        for (int i = 0; i < p.n_adapters[m]; i++) {
+            int L = p.adapter_len[m][i];
+            if (L < 0 || L >= SNK_MAX_ADAPTER_LEN) { set_error("adapter too long"); return 1; }
+            if ((int)strnlen(p.adapter[m][i], SNK_MAX_ADAPTER_LEN) < L) { set_error("adapter_len exceeds adapter string"); return 1; }
+        }
+    }
+    if (p.has_hard_trim) for (int m = 0; m < 2; m++)
+        if (p.hard_head[m] < 0 || p.hard_tail[m] < 0) { set_error("trim value format error"); return 1; }
+    return 0;
+}
+}
+
+extern "C" {
+const char* snk_last_error(void) { return snk::last_error(); }
+int snk_abi_version(void) { return SNK_ABI_VERSION; }
+size_t snk_stats_slot_words(void) { return SNK_SLOT_WORDS; }
+int snk_params_check(const snk_params* p) { if (!p) { snk::set_error("null params"); return 1; } return snk::params_check(*p); }
+}
