@@ -201,6 +201,10 @@ int snk_engine_stats_reset(snk_engine* e);
 int snk_engine_stats(snk_engine* e, uint64_t* dst);
 /* device pointer of the live table (for NCCL all-reduce by the caller) and its size in words */
 int snk_engine_stats_device(snk_engine* e, uint64_t** d_ptr, size_t* words);
+/* device-to-device copies of the whole table out of / into the engine (e.g. to a torch tensor that
+ * is then all-reduced with NCCL by the caller). Asynchronous on `stream`. */
+int snk_engine_stats_to_device(snk_engine* e, void* d_dst, void* stream);
+int snk_engine_stats_from_device(snk_engine* e, const void* d_src, void* stream);
 /* sticky error flags raised by kernels: bit0 = unrecognized base (read_filter.cpp:282),
  * bit1 = quality outside [0,SNK_QBINS), bit2 = low quality ratio > 1 (sequence.cpp:335) */
 int snk_engine_error_flags(snk_engine* e, uint32_t* flags, uint64_t* first_bad_index);

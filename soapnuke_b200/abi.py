@@ -124,6 +124,42 @@ def ref_threads_partition(threads_requested, nprocs=None, patch_size=None):
     return t, patch_size * patch, patch_size
 
 
+def ref_output_order(n, threads_requested, nprocs=None, patch_size=None, gz_input=False, pe=True):
+    """Order in which the reference emits the surviving records of an n-read input.
+
+    Worker i owns blocks b with b % T == i (peprocess.cpp:2092) and writes each batch of patchSize
+    reads to the temp file thread.<i>.<cycle>; the concat thread then appends the files cycle-major,
+    thread-minor (peprocess.cpp:2957-2990). The cycle label of a full batch is computed from a line
+    counter that, for plain-text input, has already advanced past the batch's last line
+    (peprocess.cpp:2248 file1_line_num vs :2141 file2_line_num for .gz input). So with plain input
+    the last batch before every cycle boundary is labelled with the NEXT cycle and is emitted after
+    the other workers' next-cycle data. Inputs shorter than one cycle (block*T reads) come out in
+    input order, and so does every SE run (seprocess.cpp:1080,1153 label before incrementing).
+    Returns a list of read indices."""
+    t, block, patch_size = ref_threads_partition(threads_requested, nprocs, patch_size)
+    cyc = block * t
+    keyed = []
+    per_thread_fill = {}
+    start = 0
+    # walk the input block by block; inside a block batches are patch_size long
+    for b0 in range(0, n, block):
+        i = (b0 // block) % t
+        b1 = min(n, b0 + block)
+        for s0 in range(b0, b1, patch_size):
+            s1 = min(b1, s0 + patch_size)
+            full = (s1 - s0) == patch_size
+            if full:
+                label = (s1 // cyc) if (pe and not gz_input) else ((s1 - 1) // cyc)
+            else:
+                label = n // cyc            # flushed at EOF (peprocess.cpp:2166,2277)
+            keyed.append((label, i, s0, s1))
+    keyed.sort(key=lambda k: (k[0], k[1], k[2]))
+    order = []
+    for _, _, s0, s1 in keyed:
+        order.extend(range(s0, s1))
+    return order
+
+
 def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qual=5, low_qual_ratio=0.5,
                 mean_quality=-1, n_ratio=0.05, highA_ratio=-1.0, polyG_tail=-1.0, polyX_num=-1,
                 min_read_length=30, max_read_length=-1, quality_phred=33, out_quality_phred=33,
@@ -220,6 +256,8 @@ _PROTOS = {
     "snk_engine_stats_reset": (C.c_int, [C.c_void_p]),
     "snk_engine_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
     "snk_engine_stats_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "snk_engine_stats_to_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "snk_engine_stats_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_engine_error_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "snk_engine_launch_count": (C.c_uint64, [C.c_void_p]),
     "snk_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),

@@ -1,0 +1,86 @@
+// dev_params.h — host-side preparation of the device parameter block (shared by engine.cu and the
+// CPU replay harness in tests/coretest).
+#pragma once
+#include <cmath>
+#include <climits>
+#include <cstring>
+#include "filter_core.cuh"
+
+namespace snkcore {
+
+inline int float_to_int_x86(float f)
+{
+    // the reference assigns float quotients to int; cvttss2si gives INT_MIN for NaN / overflow
+    if (!(f == f) || f >= 2147483648.0f || f < -2147483648.0f) return INT_MIN;
+    return (int)f;
+}
+
+inline void prepare_adapter(const snk_params& p, int mate, int idx, AdapterDev& a)
+{
+    memset(&a, 0, sizeof(a));
+    const int A = p.adapter_len[mate][idx];
+    const int adaMis = p.ada_mis[mate], adaEdge = p.ada_edge[mate];
+    const float adaMR = p.ada_mr[mate];
+    a.len = A;
+    memcpy(a.seq, p.adapter[mate][idx], (size_t)A);
+    if (A == 0) return;
+    const float misGrad5 = (float)((A - 5) / (adaMis + 1));          // read_filter.cpp:714
+    const float misGrad = (float)((A - adaEdge) / (adaMis + 1));     // :715
+    a.seg_thr = (int)ceilf((float)A * adaMR);                         // :717
+    a.budget2 = adaMis;
+    a.edge = adaEdge;
+    a.n3 = A - adaEdge > 0 ? A - adaEdge : 0;
+    for (int r1 = 1; r1 <= 5; r1++) a.budget1[r1 - 1] = float_to_int_x86((float)(A - r1) / misGrad5);   // :724
+    for (int r1 = 0; r1 < a.n3 && r1 < SNK_MAX_ADAPTER_LEN; r1++) a.budget3[r1] = float_to_int_x86((float)r1 / misGrad);   // :769
+    bool fast = true;
+    for (int i = 0; i < A; i++) {
+        const char ch = (char)a.seq[i];
+        if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') fast = false;
+    }
+    a.fast = fast ? 1 : 0;
+    int k = A < 16 ? A : 16;
+    if (a.seg_thr < k) k = a.seg_thr;
+    if (k < 0) k = 0;
+    a.pre_k = k;
+    a.pre_mask = k >= 16 ? 0x55555555u : (((1u << (2 * k)) - 1u) & 0x55555555u);
+    uint32_t code = 0;
+    for (int i = 0; i < 16 && i < A; i++) {
+        const uint32_t ch = a.seq[i];
+        code |= ((ch >> 1) & 3u) << (2 * i);
+    }
+    a.code0 = code;
+}
+
+inline void prepare_params(const snk_params& p, DevParams& d)
+{
+    memset(&d, 0, sizeof(d));
+    d.is_pe = p.is_pe;
+    d.phred = p.quality_phred;
+    d.low_qual = p.low_qual;
+    d.low_qual_ratio = p.low_qual_ratio;
+    d.mean_quality = p.mean_quality;
+    d.n_ratio = p.n_ratio; d.highA_ratio = p.highA_ratio; d.polyG_tail = p.polyG_tail;
+    d.polyX_num = p.polyX_num;
+    d.min_len = p.min_read_length; d.max_len = p.max_read_length;
+    d.ada_trim = p.ada_trim;
+    d.has_hard = p.has_hard_trim;
+    d.has_lq = p.has_trim_bad_head || p.has_trim_bad_tail;
+    d.trimming = p.has_hard_trim || d.has_lq || p.index_remove || p.ada_trim || p.contam_trim || p.polyG_tail != -1;
+    d.cutback = p.ada_trim || p.contam_trim || p.has_hard_trim || p.has_trim_bad_head || p.has_trim_bad_tail;
+    for (int m = 0; m < 2; m++) { d.hard_head[m] = p.hard_head[m]; d.hard_tail[m] = p.hard_tail[m]; }
+    d.bad_head_thr = p.has_trim_bad_head ? p.bad_head_thr : 0; d.bad_head_max = p.has_trim_bad_head ? p.bad_head_max : 0;
+    d.bad_tail_thr = p.has_trim_bad_tail ? p.bad_tail_thr : 0; d.bad_tail_max = p.has_trim_bad_tail ? p.bad_tail_max : 0;
+    d.n_slots = p.n_slots;
+    d.slot_block = p.slot_block;
+    int qb = p.max_base_quality + 1;
+    if (qb < 1) qb = 1;
+    if (qb > SNK_QBINS) qb = SNK_QBINS;
+    d.qb = qb;
+    for (int m = 0; m < 2; m++) {
+        d.n_adapters[m] = p.n_adapters[m];
+        for (int i = 0; i < p.n_adapters[m]; i++) prepare_adapter(p, m, i, d.ada[m][i]);
+    }
+}
+
+
+} // namespace snkcore

@@ -1,0 +1,369 @@
+// engine.cu — host side of the CUDA engine and its extern "C" ABI (include/snk_engine.h).
+//
+// Owns the device statistics tables, the per-lane device staging buffers and streams, prepares the
+// device parameter block (adapter budgets evaluated once with the reference's expression types,
+// read_filter.cpp:714-724,769) and launches filter_kernel. There is no CPU implementation of the
+// hot path in this library: without a CUDA device every compute entry point fails.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <mutex>
+#include "filter_kernel.cuh"
+#include "dev_params.h"
+#include "../host/host_common.h"
+
+using namespace snkcore;
+
+namespace {
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            snk::set_error(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " #expr);   \
+            return 1;                                                                               \
+        }                                                                                           \
+    } while (0)
+
+constexpr int kLanes = 3;
+constexpr size_t kSmemLimit = 227 * 1024;
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    uint8_t* d_buf = nullptr;      // one allocation: seq1, qual1, seq2, qual2, len1, len2, out1, out2
+    size_t cap = 0;
+    // results are copied back after the kernel; remember where
+    bool pending = false;
+};
+
+struct LaunchPlan {
+    int maxc;          // template instantiation
+    uint32_t R, X, W;
+    int qb;
+    size_t smem;
+    int grid;
+};
+
+} // namespace
+
+struct snk_engine {
+    int device = 0;
+    int num_sms = 0;
+    snk_params params;
+    DevParams dev;
+    unsigned long long* d_stats = nullptr;
+    size_t stats_words = 0;
+    unsigned int* d_err = nullptr;           // [0] flags
+    unsigned long long* d_err_index = nullptr;
+    Lane lanes[kLanes];
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+namespace {
+
+template <int MAXC, int MATES>
+int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
+{
+    auto kern = filter_kernel<MAXC, MATES>;
+    static size_t smem_set = 0;               // per instantiation: raise the opt-in limit only when needed
+    if (lp.smem > smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        smem_set = kSmemLimit;
+    }
+    kern<<<lp.grid, kThreads, lp.smem, stream>>>(dp, ka);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+
+template <int MATES>
+int launch_mates(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
+{
+    switch (lp.maxc) {
+        case 4: return launch_one<4, MATES>(e, dp, ka, lp, stream);
+        case 7: return launch_one<7, MATES>(e, dp, ka, lp, stream);
+        case 10: return launch_one<10, MATES>(e, dp, ka, lp, stream);
+        case 16: return launch_one<16, MATES>(e, dp, ka, lp, stream);
+        default: return launch_one<63, MATES>(e, dp, ka, lp, stream);
+    }
+}
+
+int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t first, LaunchPlan& lp, TileMap& tm)
+{
+    if (stride == 0 || stride % 16 != 0 || stride > 1008) { snk::set_error("batch stride must be a multiple of 16 in [16,1008]"); return 1; }
+    const uint32_t chunks = stride / 16;
+    lp.maxc = chunks <= 4 ? 4 : chunks <= 7 ? 7 : chunks <= 10 ? 10 : chunks <= 16 ? 16 : 63;
+    lp.W = stride / 4;
+    lp.X = align_up(2u * mates * lp.W, 32);
+    int qb = e->dev.qb;
+    const uint32_t maxR = kThreads / mates;
+    uint32_t R = 0;
+    for (;;) {
+        // largest multiple of 32 (<= maxR) whose plan fits
+        for (uint32_t r = maxR; r >= 32; r -= 32) {
+            if (plan_smem(mates, r, stride, lp.X, qb).total <= kSmemLimit) { R = r; break; }
+        }
+        if (R) break;
+        if (qb <= 0) { snk::set_error("read stride too large for the shared-memory tile"); return 1; }
+        qb = qb > 4 ? qb - 4 : 0;   // bins >= qb fall back to global atomics (hist_item gq_over)
+    }
+    lp.R = R; lp.qb = qb;
+    lp.smem = plan_smem(mates, R, stride, lp.X, qb).total;
+    tm = make_tile_map(first, n, R, (uint64_t)e->params.slot_block);
+    lp.grid = (int)(tm.ntiles < (uint32_t)e->num_sms ? tm.ntiles : (uint32_t)e->num_sms);
+    if (lp.grid < 1) lp.grid = 1;
+    return 0;
+}
+
+int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch* d2, snk_read_result* o1,
+                  snk_read_result* o2, uint64_t first, cudaStream_t stream)
+{
+    if (!d1 || (mates == 2 && !d2)) { snk::set_error("null batch"); return 1; }
+    if (mates == 2 && (d1->n != d2->n || d1->stride != d2->stride)) { snk::set_error("reads number in fq1 and fq2 are different"); return 1; }
+    if (d1->n == 0) return 0;
+    if ((mates == 2) != (e->params.is_pe != 0)) { snk::set_error("engine was created for the other read layout (PE/SE)"); return 1; }
+    LaunchPlan lp; TileMap tm;
+    if (make_plan(e, mates, d1->stride, d1->n, first, lp, tm)) return 1;
+    KernelArgs ka;
+    memset(&ka, 0, sizeof(ka));
+    ka.seq[0] = d1->seq; ka.qual[0] = d1->qual; ka.len[0] = d1->len; ka.out[0] = o1;
+    if (mates == 2) { ka.seq[1] = d2->seq; ka.qual[1] = d2->qual; ka.len[1] = d2->len; ka.out[1] = o2; }
+    for (int m = 0; m < mates; m++)
+        if (((uintptr_t)ka.seq[m] | (uintptr_t)ka.qual[m]) & 15 || ((uintptr_t)ka.out[m] & 7) || ((uintptr_t)ka.len[m] & 1)) {
+            snk::set_error("device buffers must be 16-byte aligned (seq/qual) and 8-byte aligned (results)");
+            return 1;
+        }
+    ka.stats = e->d_stats; ka.err_flags = e->d_err; ka.err_index = e->d_err_index;
+    ka.stride = d1->stride; ka.R = lp.R; ka.items_w = lp.W; ka.X = lp.X; ka.tm = tm;
+    DevParams dp = e->dev;
+    dp.qb = lp.qb;               // may have been lowered so that this stride's histograms fit
+    return (mates == 2) ? launch_mates<2>(e, dp, ka, lp, stream) : launch_mates<1>(e, dp, ka, lp, stream);
+}
+
+size_t batch_bytes(int mates, uint32_t n, uint32_t stride)
+{
+    const size_t rows = (size_t)n * stride;
+    const size_t lens = ((size_t)n * 2 + 255) / 256 * 256;
+    const size_t outs = ((size_t)n * sizeof(snk_read_result) + 255) / 256 * 256;
+    return (size_t)mates * (2 * (rows + 256) + lens + outs);
+}
+
+int lane_reserve(Lane& L, size_t bytes)
+{
+    if (L.cap >= bytes) return 0;
+    if (L.d_buf) CUDA_TRY(cudaFree(L.d_buf));
+    L.d_buf = nullptr; L.cap = 0;
+    const size_t want = bytes + bytes / 8;
+    CUDA_TRY(cudaMalloc(&L.d_buf, want));
+    L.cap = want;
+    return 0;
+}
+
+int filter_host_async(snk_engine* e, int lane, int mates, const snk_batch* r1, const snk_batch* r2,
+                      snk_read_result* out1, snk_read_result* out2, uint64_t first)
+{
+    if (!e) { snk::set_error("null engine"); return 1; }
+    if (lane < 0 || lane >= kLanes) { snk::set_error("lane out of range"); return 1; }
+    if (!r1 || !out1 || (mates == 2 && (!r2 || !out2))) { snk::set_error("null batch or result buffer"); return 1; }
+    if (mates == 2 && (r1->n != r2->n || r1->stride != r2->stride)) { snk::set_error("reads number in fq1 and fq2 are different"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    Lane& L = e->lanes[lane];
+    const uint32_t n = r1->n, stride = r1->stride;
+    if (n == 0) return 0;
+    CUDA_TRY(cudaStreamSynchronize(L.stream));        // the lane's buffers are free again
+    if (lane_reserve(L, batch_bytes(mates, n, stride))) return 1;
+    const size_t rows = (size_t)n * stride;
+    const size_t rows_al = (rows + 255) / 256 * 256 + 256;
+    const size_t lens = ((size_t)n * 2 + 255) / 256 * 256;
+    const size_t outs = ((size_t)n * sizeof(snk_read_result) + 255) / 256 * 256;
+    uint8_t* p = L.d_buf;
+    snk_batch d[2];
+    snk_read_result* dout[2] = {nullptr, nullptr};
+    const snk_batch* h[2] = {r1, r2};
+    for (int m = 0; m < mates; m++) {
+        uint8_t* dseq = p; p += rows_al;
+        uint8_t* dqual = p; p += rows_al;
+        uint16_t* dlen = reinterpret_cast<uint16_t*>(p); p += lens;
+        dout[m] = reinterpret_cast<snk_read_result*>(p); p += outs;
+        CUDA_TRY(cudaMemcpyAsync(dseq, h[m]->seq, rows, cudaMemcpyHostToDevice, L.stream));
+        CUDA_TRY(cudaMemcpyAsync(dqual, h[m]->qual, rows, cudaMemcpyHostToDevice, L.stream));
+        CUDA_TRY(cudaMemcpyAsync(dlen, h[m]->len, (size_t)n * 2, cudaMemcpyHostToDevice, L.stream));
+        d[m].seq = dseq; d[m].qual = dqual; d[m].len = dlen; d[m].n = n; d[m].stride = stride;
+    }
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        if (launch_filter(e, mates, &d[0], mates == 2 ? &d[1] : nullptr, dout[0], dout[1], first, L.stream)) return 1;
+    }
+    snk_read_result* hout[2] = {out1, out2};
+    for (int m = 0; m < mates; m++)
+        CUDA_TRY(cudaMemcpyAsync(hout[m], dout[m], (size_t)n * sizeof(snk_read_result), cudaMemcpyDeviceToHost, L.stream));
+    L.pending = true;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int snk_engine_create(const snk_params* p, int device, snk_engine** out)
+{
+    if (!p || !out) { snk::set_error("null argument"); return 1; }
+    if (snk::params_check(*p)) return 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        snk::set_error("no CUDA device available: the filter engine has no CPU fallback");
+        return 1;
+    }
+    if (device < 0 || device >= ndev) { snk::set_error("CUDA device index out of range"); return 1; }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { snk::set_error("this engine is built for sm_100a (Blackwell) only"); return 1; }
+    snk_engine* e = new snk_engine();
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    e->params = *p;
+    prepare_params(*p, e->dev);
+    e->stats_words = (size_t)p->n_slots * SNK_SLOT_WORDS;
+    if (cudaMalloc(&e->d_stats, e->stats_words * 8) != cudaSuccess ||
+        cudaMalloc(&e->d_err, 16) != cudaSuccess || cudaMalloc(&e->d_err_index, 8) != cudaSuccess) {
+        snk::set_error("cudaMalloc failed for the statistics tables");
+        delete e;
+        return 1;
+    }
+    for (int i = 0; i < kLanes; i++) CUDA_TRY(cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking));
+    *out = e;
+    return snk_engine_stats_reset(e);
+}
+
+int snk_engine_destroy(snk_engine* e)
+{
+    if (!e) return 0;
+    cudaSetDevice(e->device);
+    for (int i = 0; i < kLanes; i++) {
+        if (e->lanes[i].stream) { cudaStreamSynchronize(e->lanes[i].stream); cudaStreamDestroy(e->lanes[i].stream); }
+        if (e->lanes[i].d_buf) cudaFree(e->lanes[i].d_buf);
+    }
+    cudaFree(e->d_stats); cudaFree(e->d_err); cudaFree(e->d_err_index);
+    delete e;
+    return 0;
+}
+
+int snk_engine_lanes(snk_engine* e) { (void)e; return kLanes; }
+
+int snk_filter_pe_async(snk_engine* e, int lane, const snk_batch* r1, const snk_batch* r2,
+                        snk_read_result* out1, snk_read_result* out2, uint64_t first_index)
+{
+    return filter_host_async(e, lane, 2, r1, r2, out1, out2, first_index);
+}
+int snk_filter_se_async(snk_engine* e, int lane, const snk_batch* r1, snk_read_result* out1, uint64_t first_index)
+{
+    return filter_host_async(e, lane, 1, r1, nullptr, out1, nullptr, first_index);
+}
+int snk_engine_lane_sync(snk_engine* e, int lane)
+{
+    if (!e || lane < 0 || lane >= kLanes) { snk::set_error("bad lane"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(e->lanes[lane].stream));
+    e->lanes[lane].pending = false;
+    return 0;
+}
+int snk_filter_pe_host(snk_engine* e, const snk_batch* r1, const snk_batch* r2, snk_read_result* out1,
+                       snk_read_result* out2, uint64_t first_index)
+{
+    if (filter_host_async(e, 0, 2, r1, r2, out1, out2, first_index)) return 1;
+    return snk_engine_lane_sync(e, 0);
+}
+int snk_filter_se_host(snk_engine* e, const snk_batch* r1, snk_read_result* out1, uint64_t first_index)
+{
+    if (filter_host_async(e, 0, 1, r1, nullptr, out1, nullptr, first_index)) return 1;
+    return snk_engine_lane_sync(e, 0);
+}
+
+int snk_filter_pe_device(snk_engine* e, const snk_batch* d_r1, const snk_batch* d_r2, snk_read_result* d_out1,
+                         snk_read_result* d_out2, uint64_t first_index, void* stream)
+{
+    if (!e) { snk::set_error("null engine"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->mu);
+    return launch_filter(e, 2, d_r1, d_r2, d_out1, d_out2, first_index, (cudaStream_t)stream);
+}
+int snk_filter_se_device(snk_engine* e, const snk_batch* d_r1, snk_read_result* d_out1, uint64_t first_index, void* stream)
+{
+    if (!e) { snk::set_error("null engine"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    std::lock_guard<std::mutex> g(e->mu);
+    return launch_filter(e, 1, d_r1, nullptr, d_out1, nullptr, first_index, (cudaStream_t)stream);
+}
+
+int snk_engine_stats_reset(snk_engine* e)
+{
+    if (!e) { snk::set_error("null engine"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemset(e->d_stats, 0, e->stats_words * 8));
+    CUDA_TRY(cudaMemset(e->d_err, 0, 16));
+    CUDA_TRY(cudaMemset(e->d_err_index, 0xFF, 8));
+    return 0;
+}
+int snk_engine_stats(snk_engine* e, uint64_t* dst)
+{
+    if (!e || !dst) { snk::set_error("null argument"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(dst, e->d_stats, e->stats_words * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int snk_engine_stats_device(snk_engine* e, uint64_t** d_ptr, size_t* words)
+{
+    if (!e || !d_ptr || !words) { snk::set_error("null argument"); return 1; }
+    *d_ptr = reinterpret_cast<uint64_t*>(e->d_stats);
+    *words = e->stats_words;
+    return 0;
+}
+int snk_engine_stats_to_device(snk_engine* e, void* d_dst, void* stream)
+{
+    if (!e || !d_dst) { snk::set_error("null argument"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpyAsync(d_dst, e->d_stats, e->stats_words * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int snk_engine_stats_from_device(snk_engine* e, const void* d_src, void* stream)
+{
+    if (!e || !d_src) { snk::set_error("null argument"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaMemcpyAsync(e->d_stats, d_src, e->stats_words * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+int snk_engine_error_flags(snk_engine* e, uint32_t* flags, uint64_t* first_bad_index)
+{
+    if (!e || !flags) { snk::set_error("null argument"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned int f = 0; unsigned long long idx = 0;
+    CUDA_TRY(cudaMemcpy(&f, e->d_err, 4, cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(&idx, e->d_err_index, 8, cudaMemcpyDeviceToHost));
+    *flags = f;
+    if (first_bad_index) *first_bad_index = idx;
+    return 0;
+}
+uint64_t snk_engine_launch_count(snk_engine* e) { return e ? e->launches : 0; }
+
+int snk_host_alloc(void** p, size_t bytes)
+{
+    if (!p) { snk::set_error("null argument"); return 1; }
+    CUDA_TRY(cudaHostAlloc(p, bytes, cudaHostAllocDefault));
+    return 0;
+}
+int snk_host_free(void* p)
+{
+    CUDA_TRY(cudaFreeHost(p));
+    return 0;
+}
+
+} // extern "C"

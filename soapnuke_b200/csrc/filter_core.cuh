@@ -1,0 +1,541 @@
+// filter_core.cuh — per-read / per-position device functions of the filter kernel.
+//
+// Everything here is `__host__ __device__`: the CUDA kernel (filter_kernel.cu) is the only product
+// user, but the same functions also compile as plain C++ so that tests can replay the kernel's
+// thread/tile structure on a CPU without a GPU (tests/coretest, TEST-ONLY harness).
+//
+// What the functions restate (reference file:line):
+//   scan_read        stat_read counters + adapter search   read_filter.cpp:80-313, 707-790
+//                    followed by fastq_trim                 read_filter.cpp:338-482
+//   decide_pair/se   pe_discard / se_discard                sequence.cpp:198-387, 76-178
+//   hist_item        stat_pe_fqs / stat_se_fqs tables       peprocess.cpp:1144-1203, seprocess.cpp:683-739
+//   trim_stat_*      trimming-position tables               peprocess.cpp:1107-1143, 1325-1360; seprocess.cpp:647-682
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include "../../include/snk_engine.h"
+
+#if defined(__CUDACC__)
+#define SNK_HD __host__ __device__ __forceinline__
+#define SNK_ALIGN16 __align__(16)
+#else
+#define SNK_HD static inline
+#define SNK_ALIGN16 alignas(16)
+#endif
+
+namespace snkcore {
+
+// ------------------------------------------------------------------ portable intrinsics
+SNK_HD uint32_t popc32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t)__popc(x);
+#else
+    return (uint32_t)__builtin_popcount(x);
+#endif
+}
+// low 32 bits of (hi:lo) >> sh, sh in [0,31]
+SNK_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t sh)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+// sum of the four bytes of w
+SNK_HD uint32_t bytesum(uint32_t w)
+{
+#ifdef __CUDA_ARCH__
+    return __dp4a(w, 0x01010101u, 0u);
+#else
+    return (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
+#endif
+}
+SNK_HD int ctz32(uint32_t x)   // x != 0
+{
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+SNK_HD int clz32(uint32_t x)   // x != 0
+{
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return __builtin_clz(x);
+#endif
+}
+
+struct SNK_ALIGN16 U4 { uint32_t x, y, z, w; };
+SNK_HD U4 load16(const uint8_t* p)
+{
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const U4*>(p);
+#else
+    U4 v; memcpy(&v, p, 16); return v;
+#endif
+}
+SNK_HD uint32_t load4(const uint8_t* p)   // p 4-byte aligned
+{
+#ifdef __CUDA_ARCH__
+    return *reinterpret_cast<const uint32_t*>(p);
+#else
+    uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+
+// ------------------------------------------------------------------ device parameters
+// One adapter, preprocessed on the host (engine.cu: prepare_adapter) so that no float arithmetic
+// of adapter_pos (read_filter.cpp:714-724,769) runs on the device: the per-offset mismatch budgets
+// are evaluated once with the reference's own expression types.
+struct AdapterDev {
+    int32_t  len;        // adptLen (0 => no match possible)
+    int32_t  fast;       // 1: only uppercase A/C/G/T, so the 2-bit prefilter is exact
+    int32_t  seg_thr;    // segMatchThr = (int)ceil(adptLen * adaMR)
+    int32_t  budget2;    // phase 2 budget = adaMis
+    int32_t  edge;       // adaEdge
+    int32_t  n3;         // number of phase-3 offsets = max(0, adptLen - adaEdge)
+    int32_t  pre_k;      // prefilter window: min(16, adptLen, seg_thr); 0 disables the prefilter
+    uint32_t pre_mask;   // 0x55555555 restricted to the low 2*pre_k bits
+    uint32_t code0;      // 2-bit codes (A=0,C=1,T=2,G=3) of adapter[0..15]
+    int32_t  budget1[5]; // phase 1 budgets for r1 = 1..5
+    int32_t  pad_[2];
+    int32_t  budget3[SNK_MAX_ADAPTER_LEN];   // phase 3 budget per r1
+    uint8_t  seq[SNK_MAX_ADAPTER_LEN];
+};
+
+struct DevParams {
+    int32_t is_pe;
+    int32_t phred;
+    int32_t low_qual;
+    float   low_qual_ratio;
+    int32_t mean_quality;
+    float   n_ratio, highA_ratio, polyG_tail;
+    int32_t polyX_num;
+    int32_t min_len, max_len;
+    int32_t ada_trim;
+    int32_t trimming;      // read_filter.cpp:354: any trim option or polyG
+    int32_t cutback;       // peprocess.cpp:1441: cut ints copied back to the raw records
+    int32_t has_hard, hard_head[2], hard_tail[2];
+    int32_t has_lq;        // trimBadHead or trimBadTail given
+    int32_t bad_head_thr, bad_head_max, bad_tail_thr, bad_tail_max;
+    int32_t n_adapters[2];
+    int32_t n_slots;
+    int32_t qb;            // quality bins kept in shared memory (max_base_quality+1, <= SNK_QBINS)
+    int64_t slot_block;
+    AdapterDev ada[2][SNK_MAX_ADAPTERS];
+};
+
+// per-mate result of scan_read; lives in shared memory between the kernel's phases
+struct ReadInfo {
+    int16_t len;
+    int16_t head_cut, clean_len;
+    int16_t head_hdcut, head_lqcut, tail_hdcut, tail_lqcut, adacut_pos;
+    uint16_t flags;
+};
+enum : uint16_t {
+    RF_N = 1, RF_HIGHA = 2, RF_POLYX = 4, RF_LOWQ = 8, RF_MEANQ = 16, RF_ADAPTER = 32,
+    RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256
+};
+enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
+
+// ------------------------------------------------------------------ adapter matching
+// Exact restatement of one window of adapter_pos: compare adapter[aoff+c] with read[roff+c] for
+// c < winlen, in order; a running match counter that resets on mismatch accepts at seg_thr, the
+// (budget+1)-th mismatch rejects, finishing within budget accepts. Positions outside [0,len) of
+// the read are mismatches (the reference reads out of bounds there).
+SNK_HD bool window_exact(const uint8_t* read, int len, int roff, const uint8_t* ada, int aoff, int winlen,
+                         int budget, int seg_thr)
+{
+    int mis = 0, seg = 0;
+    for (int c = 0; c < winlen; c++) {
+        int ri = roff + c;
+        bool same = (ri >= 0 && ri < len) && read[ri] == ada[aoff + c];
+        if (same) { if (++seg >= seg_thr) return true; }
+        else { mis++; seg = 0; if (mis > budget) return false; }
+    }
+    return mis <= budget;
+}
+
+// 2-bit prefilter: `win`/`winbad` hold the 16 bases starting at the window (2 bits per base, bad =
+// base that can never equal an uppercase A/C/G/T). Returns true when the window is certainly
+// rejected: more than max(budget,0) mismatches inside the first pre_k positions, and pre_k <=
+// seg_thr guarantees no run-accept can precede that rejection.
+SNK_HD bool prefilter_reject(const AdapterDev& a, uint32_t win, uint32_t winbad, int budget)
+{
+    uint32_t x = win ^ a.code0;
+    uint32_t m = (x | (x >> 1) | winbad) & a.pre_mask;
+    int b = budget < 0 ? 0 : budget;
+    return (int)popc32(m) > b;
+}
+
+// adapter_pos for one adapter (read_filter.cpp:707-790). `code`/`bad` are the read's 2-bit planes
+// (16 bases per word, MAXC+1 words, word MAXC is zero padding).
+template <int MAXC>
+SNK_HD int adapter_pos_dev(const uint8_t* seq, int len, const uint32_t* code, const uint32_t* bad, const AdapterDev& a)
+{
+    const int A = a.len;
+    if (A == 0) return -1;
+    // phase 1: adapter starts r1 = 1..5 bases before the read
+    for (int r1 = 1; r1 <= 5; r1++)
+        if (window_exact(seq, len, 0, a.seq, r1, A - r1, a.budget1[r1 - 1], a.seg_thr)) return 0;
+    // phase 2: adapter fully inside the read, smallest offset wins
+    const int last = len - A;
+    if (a.fast && a.pre_k > 0) {
+#pragma unroll(MAXC <= 16 ? MAXC : 1)
+        for (int c = 0; c < MAXC; c++) {
+            if (16 * c <= last) {
+                const uint32_t c0 = code[c], c1 = code[c + 1], b0 = bad[c], b1 = bad[c + 1];
+                for (int s = 0; s < 16; s++) {
+                    const int r1 = 16 * c + s;
+                    if (r1 > last) break;
+                    const uint32_t win = funnel_r(c0, c1, 2 * s), wbad = funnel_r(b0, b1, 2 * s);
+                    if (prefilter_reject(a, win, wbad, a.budget2)) continue;
+                    if (window_exact(seq, len, r1, a.seq, 0, A, a.budget2, a.seg_thr)) return r1;
+                }
+            }
+        }
+    } else {
+        for (int r1 = 0; r1 <= last; r1++)
+            if (window_exact(seq, len, r1, a.seq, 0, A, a.budget2, a.seg_thr)) return r1;
+    }
+    // phase 3: adapter prefix hanging over the read's 3' end, shortest overlap first
+    for (int r1 = 0; r1 < a.n3; r1++) {
+        const int base = len - r1 - a.edge;
+        if (window_exact(seq, len, base, a.seq, 0, r1 + a.edge, a.budget3[r1], a.seg_thr)) return base;
+    }
+    return -1;
+}
+
+// ------------------------------------------------------------------ per-read scan
+// Packed 4-in-a-word helpers. Bytes are ASCII (< 128).
+// 0x80 in every byte lane of w that is < k (k in 1..128)
+SNK_HD uint32_t bytes_lt(uint32_t w, uint32_t k)
+{
+    return ~((w | 0x80808080u) - k * 0x01010101u) & 0x80808080u;
+}
+// bit 0 of every byte lane gathered into 4 adjacent bits (bits 24..27 of the product)
+SNK_HD uint32_t gather1(uint32_t lanes) { return ((lanes & 0x01010101u) * 0x01020408u) >> 24; }
+// low 2 bits of every byte lane gathered into 8 adjacent bits
+SNK_HD uint32_t gather2(uint32_t lanes) { return ((lanes & 0x03030303u) * 0x01041040u) >> 24; }
+
+// longest run of set bits in the low `nbits` (<= 16) of e, plus the run touching bit 0 (lead) and
+// the run touching the top bit (tail)
+SNK_HD void runs16(uint32_t e, int nbits, int& lead, int& inner, int& tail)
+{
+    const uint32_t full = (nbits >= 32) ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
+    e &= full;
+    if (e == full) { lead = inner = tail = nbits; return; }
+    lead = ctz32(~e);
+    tail = clz32(~(e << (32 - nbits)));
+    int n = 0;
+    uint32_t x = e;
+    while (x) { x &= x >> 1; n++; }
+    inner = n;
+}
+
+template <int MAXC>
+SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P, ReadInfo& R)
+{
+    uint32_t code[MAXC + 1], bad[MAXC + 1];
+    uint32_t accC = 0, accG = 0, accT = 0, accN = 0, viol = 0;
+    uint32_t accLow = 0, qsum = 0, qviol = 0;
+    const bool want_polyx = P.polyX_num != -1;
+    const bool want_planes = P.n_adapters[mate] > 0;
+    int best_run = 0, cur_run = 0;          // runs of "same as previous base" bits
+    uint32_t prev_byte = 'Q';               // read_filter.cpp:255 last_char('Q')
+    const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
+    const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
+
+#pragma unroll(MAXC <= 16 ? MAXC : 1)
+    for (int c = 0; c < MAXC; c++) {
+        uint32_t cw = 0, bw = 0, ew = 0;
+        if (16 * c < len) {
+            const U4 sv = load16(seq + 16 * c);
+            const U4 qv = load16(qual + 16 * c);
+            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int nvalid = len - (16 * c + 4 * k);
+                if (nvalid > 0) {
+                    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+                    const uint32_t w = sw[k] & mask;
+                    const uint32_t f = w & 0xDFDFDFDFu;                  // fold case
+                    const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
+                    const uint32_t isT = ~m1 & m2 & ~m3;                 // bit0 lanes only where it matters
+                    accN += m3;
+                    accC += m1 & ~m2;
+                    accG += m1 & m2 & ~m3;
+                    accT += isT & 0x01010101u;
+                    // exact membership in {A,C,G,T,N} after folding: bits 7..5 == 010, bit4 == isT,
+                    // bit0 == !(isT|N), N implies bits 2,1 set
+                    uint32_t v = (f ^ 0x40404040u) & 0xE0E0E0E0u;
+                    v |= ((f >> 4) ^ isT) & 0x01010101u;
+                    v |= (f ^ ~(isT | m3)) & 0x01010101u;
+                    v |= m3 & ~(m1 & m2);
+                    viol |= v & mask;
+                    if (want_planes) {
+                        cw |= gather2(f >> 1) << (8 * k);
+                        bw |= gather2(((w >> 5) | m3) & 0x01010101u) << (8 * k);   // lowercase or N: bit at even position
+                    }
+                    if (want_polyx) {
+                        const uint32_t x = w ^ ((w << 8) | prev_byte);
+                        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where byte == previous
+                        ew |= gather1((z >> 7) & (mask & 0x01010101u)) << (4 * k);
+                        prev_byte = (sw[k] >> 24);
+                    }
+                    // qualities
+                    const uint32_t q = qw[k] & mask;
+                    const uint32_t qfill = q | (~mask & 0x7F7F7F7Fu);     // padding lanes read as 0x7F: never low, never < phred
+                    qsum += bytesum(q);
+                    qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
+                    if (!low_never) accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
+                }
+            }
+            if (want_polyx) {
+                const int nb = (len - 16 * c) >= 16 ? 16 : (len - 16 * c);
+                int lead, inner, tail;
+                runs16(ew, nb, lead, inner, tail);
+                if (cur_run + lead > best_run) best_run = cur_run + lead;
+                if (inner > best_run) best_run = inner;
+                cur_run = (lead == nb) ? cur_run + nb : tail;
+            }
+        }
+        code[c] = cw; bad[c] = bw;
+    }
+    code[MAXC] = 0; bad[MAXC] = 0x55555555u;
+
+    uint16_t flags = 0;
+    if (viol) flags |= RF_BAD_BASE;
+    if (qviol) flags |= RF_BAD_QUAL;
+    const int nN = (int)bytesum(accN), nC = (int)bytesum(accC), nG = (int)bytesum(accG), nT = (int)bytesum(accT);
+    const int nA = len - nN - nC - nG - nT;
+    const int nLow = (int)bytesum(accLow);
+    const int total_q = (int)qsum - len * P.phred;
+    const float flen = (float)len;
+    // read_filter.cpp:290-311: float(count)/size with IEEE fp32 division
+    const float n_ratio = (float)nN / flen, a_ratio = (float)nA / flen;
+    const float lowq_ratio = (float)nLow / flen, mean_q = (float)total_q / flen;
+    if (P.n_ratio != -1 && n_ratio >= P.n_ratio) flags |= RF_N;
+    if (P.highA_ratio != -1 && a_ratio >= P.highA_ratio) flags |= RF_HIGHA;
+    if (want_polyx && (1 + best_run) >= P.polyX_num) flags |= RF_POLYX;
+    if (P.low_qual_ratio != -1 && lowq_ratio >= P.low_qual_ratio) flags |= RF_LOWQ;
+    if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
+    if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
+
+    // adapters: first adapter in the list that hits wins (read_filter.cpp:177-188)
+    int ada_pos = -1;
+    for (int i = 0; i < P.n_adapters[mate]; i++) {
+        ada_pos = adapter_pos_dev<MAXC>(seq, len, code, bad, P.ada[mate][i]);
+        if (ada_pos >= 0) break;
+    }
+    int adacut = -1;
+    if (ada_pos >= 0) { flags |= RF_ADAPTER; adacut = len - ada_pos; }
+
+    // fastq_trim (read_filter.cpp:338-471)
+    int head_hd = -1, head_lq = -1, tail_hd = -1, tail_lq = -1;
+    int head_cut = 0, clean_len = len;
+    if (P.trimming) {
+        int hc = 0, tc = 0;
+        if (P.has_hard) { head_hd = P.hard_head[mate]; tail_hd = P.hard_tail[mate]; hc = head_hd; tc = tail_hd; }
+        if (P.has_lq) {
+            int hix = 0, tix = 0;
+            for (int ix = 0; ix < P.bad_head_max && ix < len; ix++) { if ((int)qual[ix] - P.phred < P.bad_head_thr) hix++; else break; }
+            for (int ix = 0; ix < P.bad_tail_max && ix < len; ix++) { if ((int)qual[len - ix - 1] - P.phred < P.bad_tail_thr) tix++; else break; }
+            head_lq = hix; tail_lq = tix;
+            if (hix > hc) hc = hix;
+            if (tix > tc) tc = tix;
+        }
+        if (P.ada_trim && adacut > 0 && adacut > tc) tc = adacut;
+        if (P.polyG_tail != -1) {
+            int ng = 0;
+            for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') ng++; else break; }
+            if ((float)ng >= P.polyG_tail && ng > tc) tc = ng;
+        }
+        if (hc + tc > len) { head_cut = 0; clean_len = 0; }
+        else { head_cut = hc; clean_len = len - hc - tc; }
+    }
+    R.len = (int16_t)len;
+    R.head_cut = (int16_t)head_cut; R.clean_len = (int16_t)clean_len;
+    R.head_hdcut = (int16_t)head_hd; R.head_lqcut = (int16_t)head_lq;
+    R.tail_hdcut = (int16_t)tail_hd; R.tail_lqcut = (int16_t)tail_lq;
+    R.adacut_pos = (int16_t)adacut;
+    R.flags = flags;
+}
+
+// ------------------------------------------------------------------ discard cascade
+// Returns the category; *mask = pe_dis value; *fs_base = first counter of the category's group
+// (or -1). sequence.cpp:198-387 restricted to the categories the engine implements.
+SNK_HD int decide_pair(const DevParams& P, const ReadInfo& a, const ReadInfo& b, int* mask, int* fs_base)
+{
+    bool x, y;
+#define SNK_DIS(cat, base) do { if (x || y) { *mask = (x ? 1 : 0) | (y ? 2 : 0); *fs_base = base; return cat; } } while (0)
+    if (P.min_len != -1) {
+        x = (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len; y = (uint64_t)b.clean_len < (uint64_t)(int64_t)P.min_len;
+        SNK_DIS(SNK_DROP_SHORT, SNK_FS_SHORT);
+    } else if (a.clean_len == 0 || b.clean_len == 0) { *mask = 0; *fs_base = -1; return SNK_DROP_EMPTY; }
+    if (P.max_len != -1) {
+        x = (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len; y = (uint64_t)b.clean_len > (uint64_t)(int64_t)P.max_len;
+        SNK_DIS(SNK_DROP_LONG, SNK_FS_LONG);
+    }
+    x = a.flags & RF_N; y = b.flags & RF_N; SNK_DIS(SNK_DROP_N, SNK_FS_N);
+    x = a.flags & RF_HIGHA; y = b.flags & RF_HIGHA; SNK_DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA);
+    x = a.flags & RF_POLYX; y = b.flags & RF_POLYX; SNK_DIS(SNK_DROP_POLYX, SNK_FS_POLYX);
+    x = a.flags & RF_LOWQ; y = b.flags & RF_LOWQ; SNK_DIS(SNK_DROP_LOWQ, SNK_FS_LOWQ);
+    x = a.flags & RF_MEANQ; y = b.flags & RF_MEANQ; SNK_DIS(SNK_DROP_MEANQ, SNK_FS_MEANQ);
+    if (!P.ada_trim) { x = a.flags & RF_ADAPTER; y = b.flags & RF_ADAPTER; SNK_DIS(SNK_DROP_ADAPTER, SNK_FS_ADAPTER); }
+#undef SNK_DIS
+    *mask = 0; *fs_base = -1;
+    return SNK_KEEP;
+}
+// sequence.cpp:76-178
+SNK_HD int decide_se(const DevParams& P, const ReadInfo& a, int* fs_base)
+{
+    if (P.min_len != -1 && (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len) { *fs_base = SNK_FS_SHORT; return SNK_DROP_SHORT; }
+    if (P.max_len != -1 && (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len) { *fs_base = SNK_FS_LONG; return SNK_DROP_LONG; }
+    if (a.flags & RF_N) { *fs_base = SNK_FS_N; return SNK_DROP_N; }
+    if (a.flags & RF_HIGHA) { *fs_base = SNK_FS_HIGHA; return SNK_DROP_HIGHA; }
+    if (a.flags & RF_POLYX) { *fs_base = SNK_FS_POLYX; return SNK_DROP_POLYX; }
+    if (a.flags & RF_LOWQ) { *fs_base = SNK_FS_LOWQ; return SNK_DROP_LOWQ; }
+    if (a.flags & RF_MEANQ) { *fs_base = SNK_FS_MEANQ; return SNK_DROP_MEANQ; }
+    if ((a.flags & RF_ADAPTER) && !P.ada_trim) { *fs_base = SNK_FS_ADAPTER; return SNK_DROP_ADAPTER; }
+    *fs_base = -1;
+    return SNK_KEEP;
+}
+
+// ------------------------------------------------------------------ trimming-position tables
+// Flat index into a file's ts[] block for one record, or -1 (peprocess.cpp:1107-1143).
+// which: 0 = PE fq1 (base raw_length), 1 = PE fq2 (base sequence.size()), 2 = SE.
+SNK_HD void trim_stat_indices(int which, int slen, int raw_length, int head_hd, int head_lq, int tail_hd,
+                              int tail_lq, int adacut, int* head_flat, int* tail_flat)
+{
+    *head_flat = -1; *tail_flat = -1;
+    if (head_hd > 0 || head_lq > 0)
+        *head_flat = (head_hd >= head_lq) ? SNK_TS_HT * SNK_MAX_READ_LEN + head_hd : SNK_TS_HLQ * SNK_MAX_READ_LEN + head_lq;
+    const bool ada_cond = (which == 2) ? (adacut >= 0) : (adacut > 0);
+    if (tail_hd > 0 || tail_lq > 0 || ada_cond) {
+        const int base = (which == 1) ? slen : raw_length;
+        int flat;
+        if (tail_hd >= tail_lq) {
+            if (tail_hd >= adacut) flat = SNK_TS_TT * SNK_MAX_READ_LEN + (base - tail_hd + 1);
+            else flat = SNK_TS_TA * SNK_MAX_READ_LEN + (base - adacut + 1);
+        } else {
+            if (tail_lq >= adacut) flat = SNK_TS_TLQ * SNK_MAX_READ_LEN + (base - tail_lq + 1);
+            else flat = SNK_TS_TA * SNK_MAX_READ_LEN + (base - adacut + 1);
+        }
+        if (flat >= 0 && flat < SNK_TS_WORDS) *tail_flat = flat;
+    }
+    if (*head_flat >= SNK_TS_WORDS) *head_flat = -1;
+}
+
+// ------------------------------------------------------------------ per-position histograms
+// One histogram item = 4 consecutive positions (one 32-bit word of the row) of one table.
+// The owner of an item is the only writer of its counters, so no atomics are needed.
+// Base counters are packed 4 x 8 bit per symbol (flushed by the caller before they can wrap).
+struct BaseAcc { uint32_t a, c, g, t, n; };
+
+// seq/qual: row start (16-byte aligned); off: first base of the (clean) record; n: its length;
+// w: word index of the item. qhist: this item's quality counters, qhist[(q*4 + j) * qstride].
+// Returns sticky error bits.
+template <typename CounterT>
+SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
+                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */)
+{
+    const int nvalid = n - 4 * w;
+    if (nvalid <= 0) return 0;
+    const int byte0 = off + 4 * w;
+    const int al = byte0 & ~3, sh = 8 * (byte0 & 3);
+    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+    uint32_t s = load4(seq + al), q = load4(qual + al);
+    if (sh) {                                     // record does not start on a word boundary (head trimmed)
+        s = funnel_r(s, load4(seq + al + 4), sh);
+        q = funnel_r(q, load4(qual + al + 4), sh);
+    }
+    s &= mask;
+    const uint32_t f = s & 0xDFDFDFDFu;
+    const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
+    const uint32_t valid = (f >> 6) & 0x01010101u;
+    acc.n += m3;
+    acc.c += m1 & ~m2;
+    acc.g += m1 & m2 & ~m3;
+    acc.t += ~m1 & m2 & ~m3 & 0x01010101u;
+    acc.a += valid & ~(m1 | m2 | m3);
+    uint32_t err = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (j < nvalid) {
+            const int qq = (int)((q >> (8 * j)) & 0xFFu) - phred;
+            if ((unsigned)qq < (unsigned)qb) qhist[(qq * 4 + j) * qstride] += 1;
+            else if ((unsigned)qq < (unsigned)SNK_QBINS && file_base) {
+                // bin not kept in shared memory: straight to the slot's global table (rare)
+                unsigned long long* cell = file_base + SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + qq;
+#ifdef __CUDA_ARCH__
+                atomicAdd(cell, 1ull);
+                if (qq >= 20) atomicAdd(file_base + SNK_FILE_GS_OFF + SNK_GS_Q20, 1ull);
+                if (qq >= 30) atomicAdd(file_base + SNK_FILE_GS_OFF + SNK_GS_Q30, 1ull);
+#else
+                *cell += 1;
+                if (qq >= 20) file_base[SNK_FILE_GS_OFF + SNK_GS_Q20] += 1;
+                if (qq >= 30) file_base[SNK_FILE_GS_OFF + SNK_GS_Q30] += 1;
+#endif
+            } else err |= ERR_BAD_QUAL;
+        }
+    }
+    return err;
+}
+
+} // namespace snkcore
+
+namespace snkcore {
+
+// ------------------------------------------------------------------ tile decomposition
+// A launch covers reads [first, first+n) of the input. Reads are cut into tiles of at most R reads
+// that never straddle a slot-block boundary (blocks of slot_block reads, counted from read 0 of the
+// input), so that one tile belongs to exactly one statistics slot.
+struct TileMap {
+    uint64_t first;      // global index of the batch's first read
+    uint32_t n;          // reads in the batch
+    uint32_t R;          // tile capacity
+    uint64_t sb;         // slot_block
+    uint32_t n0;         // reads of the batch that fall into its first (partial) block
+    uint32_t tiles0;     // tiles covering those
+    uint32_t tpb;        // tiles per full block
+    uint32_t ntiles;
+};
+SNK_HD TileMap make_tile_map(uint64_t first, uint32_t n, uint32_t R, uint64_t sb)
+{
+    TileMap m;
+    m.first = first; m.n = n; m.R = R; m.sb = sb;
+    const uint64_t room = sb - first % sb;
+    m.n0 = (uint64_t)n < room ? n : (uint32_t)room;
+    m.tiles0 = (m.n0 + R - 1) / R;
+    const uint64_t tpb = (sb + R - 1) / R;
+    m.tpb = tpb > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)tpb;
+    const uint32_t rest = n - m.n0;
+    const uint64_t full = rest / sb, tail = rest % sb;
+    m.ntiles = m.tiles0 + (uint32_t)(full * tpb) + (uint32_t)((tail + R - 1) / R);
+    return m;
+}
+SNK_HD void tile_range(const TileMap& m, uint32_t t, uint32_t* start, uint32_t* cnt)
+{
+    if (t < m.tiles0) {
+        *start = t * m.R;
+        const uint32_t left = m.n0 - *start;
+        *cnt = left < m.R ? left : m.R;
+        return;
+    }
+    const uint32_t tt = t - m.tiles0;
+    const uint32_t blk = tt / m.tpb, j = tt % m.tpb;
+    const uint64_t s = (uint64_t)m.n0 + (uint64_t)blk * m.sb + (uint64_t)j * m.R;
+    uint64_t c = m.sb - (uint64_t)j * m.R;
+    if (c > m.R) c = m.R;
+    if (c > m.n - s) c = m.n - s;
+    *start = (uint32_t)s; *cnt = (uint32_t)c;
+}
+SNK_HD int slot_of(uint64_t gi, uint64_t sb, int n_slots) { return (int)((gi / sb) % (uint64_t)n_slots); }
+
+} // namespace snkcore

@@ -1,0 +1,336 @@
+// filter_kernel.cuh — the fused filter + statistics kernel (sm_100a).
+//
+// One persistent CTA per SM walks a contiguous range of tiles. A tile is up to R reads (SE) or R
+// pairs (PE) of the fixed-stride SoA batch, staged into shared memory, then:
+//   phase A  one thread per read: counters, predicates, adapter search, trim   (scan_read)
+//   phase P  one thread per pair: discard cascade, result record, counters     (decide_pair/se)
+//   phase B  one thread per (table, 4 positions): per-position base x quality histograms for the
+//            raw and the clean records of the tile, owner-computes (no atomics) in shared memory
+// Histograms stay in shared memory across tiles and are added to the slot's global tables with
+// 64-bit atomics only when the CTA's slot changes and at kernel end.
+#pragma once
+#include <cuda_runtime.h>
+#include "filter_core.cuh"
+
+namespace snkcore {
+
+constexpr int kThreads = 256;
+
+struct KernelArgs {
+    const uint8_t* seq[2];
+    const uint8_t* qual[2];
+    const uint16_t* len[2];
+    snk_read_result* out[2];
+    unsigned long long* stats;      // n_slots * SNK_SLOT_WORDS
+    unsigned int* err_flags;        // sticky error bits
+    unsigned long long* err_index;  // smallest global read index that raised an error
+    uint32_t stride;                // bytes per row
+    uint32_t R;                     // tile capacity (reads or pairs)
+    uint32_t items_w;               // words per row = stride / 4
+    uint32_t X;                     // histogram row pitch (items rounded up to 32)
+    TileMap tm;
+};
+
+// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][keep][qhist u32][bhist u32]
+struct SmemPlan {
+    uint32_t off_rows[2][2];   // [mate][0 seq, 1 qual]
+    uint32_t off_len[2];
+    uint32_t off_info[2];
+    uint32_t off_keep;
+    uint32_t off_qhist;
+    uint32_t off_bhist;
+    uint32_t off_misc;
+    uint32_t total;
+};
+__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb)
+{
+    SmemPlan p;
+    uint32_t o = 0;
+    for (int m = 0; m < 2; m++)
+        for (int a = 0; a < 2; a++) {
+            p.off_rows[m][a] = o;
+            if (m < mates) o += R * stride + 16;      // +16: hist_item may read one word past the last row
+        }
+    for (int m = 0; m < 2; m++) { p.off_len[m] = o; if (m < mates) o += align_up(R * 2, 16); }
+    for (int m = 0; m < 2; m++) { p.off_info[m] = o; if (m < mates) o += align_up(R * (uint32_t)sizeof(ReadInfo), 16); }
+    p.off_keep = o; o += align_up(R, 16);
+    p.off_qhist = o; o += (uint32_t)qb * 4u * X * 4u;
+    p.off_bhist = o; o += 5u * 4u * X * 4u;
+    p.off_misc = o; o += 64;
+    p.total = o;
+    return p;
+}
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void report_error(const KernelArgs& A, uint32_t bits, uint64_t gi)
+{
+    atomicOr(A.err_flags, bits);
+    atomicMin(A.err_index, (unsigned long long)gi);
+}
+
+// add this CTA's shared-memory histograms to the slot's global tables and clear them
+__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, uint32_t* qhist, uint32_t* bhist,
+                           unsigned long long* lastkey, int slot)
+{
+    unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
+    const uint32_t X = A.X, W = A.items_w;
+    const int ntab = 2 * mates;                        // raw1,[raw2],clean1,[clean2] -> item groups
+    unsigned long long q20[4] = {0, 0, 0, 0}, q30[4] = {0, 0, 0, 0};
+    const uint32_t qent = (uint32_t)P.qb * 4u * X;
+    for (uint32_t e = threadIdx.x; e < qent; e += blockDim.x) {
+        const uint32_t v = qhist[e];
+        if (!v) continue;
+        qhist[e] = 0;
+        const uint32_t x = e % X, j = (e / X) & 3u, q = e / (4u * X);
+        const uint32_t tab = x / W, w = x % W;
+        if ((int)tab >= ntab) continue;
+        const int file = (mates == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
+        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file);
+        atomicAdd(&F[SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + q], (unsigned long long)v);
+        if (q >= 20) q20[tab] += v;
+        if (q >= 30) q30[tab] += v;
+    }
+    unsigned long long bsum[4][5];
+#pragma unroll
+    for (int t = 0; t < 4; t++)
+#pragma unroll
+        for (int b = 0; b < 5; b++) bsum[t][b] = 0;
+    const uint32_t bent = 5u * 4u * X;
+    for (uint32_t e = threadIdx.x; e < bent; e += blockDim.x) {
+        const uint32_t v = bhist[e];
+        if (!v) continue;
+        bhist[e] = 0;
+        const uint32_t x = e % X, j = (e / X) & 3u, b = e / (4u * X);
+        const uint32_t tab = x / W, w = x % W;
+        if ((int)tab >= ntab) continue;
+        const int file = (mates == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
+        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file);
+        atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b], (unsigned long long)v);
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int bb = 0; bb < 5; bb++) if ((int)tab == t && (int)b == bb) bsum[t][bb] += v;
+    }
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+        if (t >= ntab) break;
+        const int file = (mates == 2) ? t : (t == 0 ? SNK_RAW1 : SNK_CLEAN1);
+        unsigned long long* G = S + SNK_SLOT_FILE_OFF(file) + SNK_FILE_GS_OFF;
+        unsigned long long bases = 0;
+#pragma unroll
+        for (int b = 0; b < 5; b++) { if (bsum[t][b]) atomicAdd(&G[SNK_GS_A + b], bsum[t][b]); bases += bsum[t][b]; }
+        // table order is A,C,G,T,N; gs order is A,C,G,T,N as well
+        if (bases) atomicAdd(&G[SNK_GS_BASES], bases);
+        if (q20[t]) atomicAdd(&G[SNK_GS_Q20], q20[t]);
+        if (q30[t]) atomicAdd(&G[SNK_GS_Q30], q30[t]);
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int t = threadIdx.x;
+        if (t < ntab) {
+            const int file = (mates == 2) ? t : (t == 0 ? SNK_RAW1 : SNK_CLEAN1);
+            unsigned long long* G = S + SNK_SLOT_FILE_OFF(file) + SNK_FILE_GS_OFF;
+            if (lastkey[t]) atomicMax(&G[SNK_GS_LAST_KEY], lastkey[t]);
+            if (lastkey[4 + t]) atomicAdd(&G[SNK_GS_READS], lastkey[4 + t]);
+            lastkey[t] = 0; lastkey[4 + t] = 0;
+        }
+    }
+    __syncthreads();
+}
+
+template <int MAXC, int MATES>
+__global__ void __launch_bounds__(kThreads, 1)
+filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ KernelArgs A)
+{
+    extern __shared__ __align__(16) uint8_t smem[];
+    const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
+    uint32_t* qhist = reinterpret_cast<uint32_t*>(smem + sp.off_qhist);
+    uint32_t* bhist = reinterpret_cast<uint32_t*>(smem + sp.off_bhist);
+    uint8_t* keep = smem + sp.off_keep;
+    // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table
+    unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(smem + sp.off_misc);
+    const int tid = threadIdx.x;
+
+    for (uint32_t e = tid; e < (sp.off_misc + 64 - sp.off_qhist) / 4; e += blockDim.x) qhist[e] = 0;   // qhist, bhist, misc
+    __syncthreads();
+
+    const uint32_t nt = A.tm.ntiles;
+    const uint32_t t_begin = (uint32_t)((uint64_t)nt * blockIdx.x / gridDim.x);
+    const uint32_t t_end = (uint32_t)((uint64_t)nt * (blockIdx.x + 1) / gridDim.x);
+    int cur_slot = -1;
+    const uint32_t W = A.items_w;
+    const uint32_t nitems = 2u * MATES * W;
+
+    for (uint32_t t = t_begin; t < t_end; t++) {
+        uint32_t start, cnt;
+        tile_range(A.tm, t, &start, &cnt);
+        const uint64_t g0 = A.tm.first + start;
+        const int slot = slot_of(g0, (uint64_t)P.slot_block, P.n_slots);
+        if (slot != cur_slot) {
+            if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bhist, lastkey, cur_slot);
+            cur_slot = slot;
+        }
+        // ---- stage the tile: rows are contiguous in global memory, copy 16 bytes per thread-step
+        const uint32_t row_bytes = cnt * A.stride;
+#pragma unroll
+        for (int m = 0; m < MATES; m++) {
+            const uint4* gs = reinterpret_cast<const uint4*>(A.seq[m] + (size_t)start * A.stride);
+            const uint4* gq = reinterpret_cast<const uint4*>(A.qual[m] + (size_t)start * A.stride);
+            uint4* ss = reinterpret_cast<uint4*>(smem + sp.off_rows[m][0]);
+            uint4* sq = reinterpret_cast<uint4*>(smem + sp.off_rows[m][1]);
+            for (uint32_t i = tid; i < row_bytes / 16; i += blockDim.x) { ss[i] = __ldg(gs + i); sq[i] = __ldg(gq + i); }
+            uint16_t* sl = reinterpret_cast<uint16_t*>(smem + sp.off_len[m]);
+            for (uint32_t i = tid; i < cnt; i += blockDim.x) sl[i] = A.len[m][start + i];
+        }
+        __syncthreads();
+
+        // ---- phase A: one thread per read
+        for (uint32_t i = tid; i < cnt * MATES; i += blockDim.x) {
+            const int m = (MATES == 2) ? (int)(i / cnt) : 0;
+            const uint32_t r = (MATES == 2) ? i % cnt : i;
+            const uint16_t* sl = reinterpret_cast<const uint16_t*>(smem + sp.off_len[m]);
+            ReadInfo* info = reinterpret_cast<ReadInfo*>(smem + sp.off_info[m]);
+            int len = sl[r];
+            if (len > (int)A.stride) len = (int)A.stride;
+            ReadInfo ri;
+            if (len <= 0) {             // "Error:empty sequence" (read_filter.cpp:250)
+                ri.len = 0; ri.head_cut = 0; ri.clean_len = 0; ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1;
+                ri.flags = RF_BAD_BASE;
+            } else {
+                scan_read<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
+                                len, m, P, ri);
+            }
+            info[r] = ri;
+        }
+        __syncthreads();
+
+        // ---- phase P: one thread per pair / read
+        for (uint32_t r = tid; r < align_up(cnt, 32); r += blockDim.x) {
+            const bool live = r < cnt;
+            int cat = SNK_DROP_EMPTY, mask = 0, fsb = -1;
+            ReadInfo a, b;
+            const uint64_t gi = g0 + r;
+            if (live) {
+                a = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[0])[r];
+                if (MATES == 2) {
+                    b = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[1])[r];
+                    cat = decide_pair(P, a, b, &mask, &fsb);
+                    uint32_t err = 0;
+                    if ((a.flags | b.flags) & RF_BAD_BASE) err |= ERR_BAD_BASE;
+                    if ((a.flags | b.flags) & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
+                    if (cat == SNK_DROP_LOWQ && ((a.flags | b.flags) & RF_LOWQ_GT1)) err |= ERR_LOWQ_RATIO;
+                    if (err) report_error(A, err, gi);
+                } else {
+                    cat = decide_se(P, a, &fsb);
+                    mask = cat ? 1 : 0;
+                    uint32_t err = 0;
+                    if (a.flags & RF_BAD_BASE) err |= ERR_BAD_BASE;
+                    if (a.flags & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
+                    if (err) report_error(A, err, gi);
+                }
+                keep[r] = (cat == SNK_KEEP);
+                unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
+                if (fsb >= 0) {
+                    atomicAdd(&S[fsb], 1ull);
+                    if (MATES == 2) {
+                        if (mask & 1) atomicAdd(&S[fsb + 1], 1ull);
+                        if (mask & 2) atomicAdd(&S[fsb + 2], 1ull);
+                        if (mask == 3) atomicAdd(&S[fsb + 3], 1ull);
+                    }
+                }
+#pragma unroll
+                for (int m = 0; m < MATES; m++) {
+                    const ReadInfo& x = m ? b : a;
+                    // snk_read_result packed into one 8-byte store (little endian field order)
+                    const unsigned long long packed = (unsigned long long)(uint16_t)x.head_cut |
+                        ((unsigned long long)(uint16_t)x.clean_len << 16) | ((unsigned long long)(uint8_t)cat << 32) |
+                        ((unsigned long long)(uint8_t)mask << 40) | ((unsigned long long)(uint16_t)x.adacut_pos << 48);
+                    reinterpret_cast<unsigned long long*>(A.out[m])[start + r] = packed;
+                    // trimming-position tables: raw record (cut ints only if copied back, raw_length 0) and clean copy
+                    const int which = (MATES == 2) ? m : 2;
+                    int hf, tf;
+                    if (P.cutback) {
+                        trim_stat_indices(which, x.len, 0, x.head_hdcut, x.head_lqcut, x.tail_hdcut, x.tail_lqcut, x.adacut_pos, &hf, &tf);
+                        unsigned long long* T = S + SNK_SLOT_FILE_OFF(m == 0 ? SNK_RAW1 : SNK_RAW2) + SNK_FILE_TS_OFF;
+                        if (hf >= 0) atomicAdd(&T[hf], 1ull);
+                        if (tf >= 0) atomicAdd(&T[tf], 1ull);
+                    }
+                    if (cat == SNK_KEEP) {
+                        trim_stat_indices(which, x.clean_len, x.len, x.head_hdcut, x.head_lqcut, x.tail_hdcut, x.tail_lqcut, x.adacut_pos, &hf, &tf);
+                        unsigned long long* T = S + SNK_SLOT_FILE_OFF(m == 0 ? SNK_CLEAN1 : SNK_CLEAN2) + SNK_FILE_TS_OFF;
+                        if (hf >= 0) atomicAdd(&T[hf], 1ull);
+                        if (tf >= 0) atomicAdd(&T[tf], 1ull);
+                    }
+                }
+            }
+            // last record keys + record counts, one shared atomic per warp and table
+            const unsigned kept = __ballot_sync(0xFFFFFFFFu, live && cat == SNK_KEEP);
+            const unsigned lanes = __ballot_sync(0xFFFFFFFFu, live);
+            const int lane = tid & 31;
+            if (lanes && lane == 31 - __clz(lanes)) {      // last live read of this warp's group
+                atomicMax(&lastkey[0], ((gi + 1) << 16) | (unsigned long long)(uint16_t)a.len);
+                atomicAdd(&lastkey[4 + 0], (unsigned long long)__popc(lanes));
+                if (MATES == 2) {
+                    atomicMax(&lastkey[1], ((gi + 1) << 16) | (unsigned long long)(uint16_t)b.len);
+                    atomicAdd(&lastkey[4 + 1], (unsigned long long)__popc(lanes));
+                }
+            }
+            if (kept && lane == 31 - __clz(kept)) {
+                atomicMax(&lastkey[MATES], ((gi + 1) << 16) | (unsigned long long)(uint16_t)a.clean_len);
+                atomicAdd(&lastkey[4 + MATES], (unsigned long long)__popc(kept));
+                if (MATES == 2) {
+                    atomicMax(&lastkey[MATES + 1], ((gi + 1) << 16) | (unsigned long long)(uint16_t)b.clean_len);
+                    atomicAdd(&lastkey[4 + MATES + 1], (unsigned long long)__popc(kept));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- phase B: per-position histograms, owner computes
+        for (uint32_t x = tid; x < nitems; x += blockDim.x) {
+            const uint32_t tab = x / W, w = x % W;           // tab: raw mates first, then clean mates
+            const int m = (int)(tab % MATES);
+            const bool clean = tab >= (uint32_t)MATES;
+            const uint8_t* rows_s = smem + sp.off_rows[m][0];
+            const uint8_t* rows_q = smem + sp.off_rows[m][1];
+            const ReadInfo* info = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[m]);
+            const int file = (MATES == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
+            unsigned long long* gq_over = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file);
+            BaseAcc acc = {0, 0, 0, 0, 0};
+            uint32_t err = 0;
+            uint32_t since_flush = 0;
+            for (uint32_t r = 0; r < cnt; r++) {
+                int off = 0, n;
+                if (clean) {
+                    if (!keep[r]) continue;
+                    off = info[r].head_cut; n = info[r].clean_len;
+                } else n = info[r].len;
+                err |= hist_item<uint32_t>(rows_s + (size_t)r * A.stride, rows_q + (size_t)r * A.stride, off, n, (int)w,
+                                           P.phred, P.qb, acc, qhist + x, (int)A.X, gq_over);
+                if (++since_flush == 255) {
+                    since_flush = 0;
+                    const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
+#pragma unroll
+                    for (int b = 0; b < 5; b++)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) bhist[(b * 4 + j) * A.X + x] += (packed[b] >> (8 * j)) & 0xFFu;
+                    acc = {0, 0, 0, 0, 0};
+                }
+            }
+            const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
+#pragma unroll
+            for (int b = 0; b < 5; b++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) bhist[(b * 4 + j) * A.X + x] += (packed[b] >> (8 * j)) & 0xFFu;
+            if (err) report_error(A, err, g0);
+        }
+        __syncthreads();
+    }
+    if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bhist, lastkey, cur_slot);
+}
+
+#endif // __CUDACC__
+
+} // namespace snkcore

@@ -106,12 +106,13 @@ def write_fastq(path, seq, qual, length, mate, first=0, gz=False):
             f.write(data)
 
 
-def clean_fastq_bytes(seq, qual, length, results, mate, first=0, phred_shift=0):
-    """Rebuild the clean FASTQ text the reference writes (peprocess.cpp:3414) from per-read results."""
+def clean_fastq_bytes(seq, qual, length, results, mate, first=0, phred_shift=0, order=None):
+    """Rebuild the clean FASTQ text the reference writes (peprocess.cpp:3414) from per-read results.
+    `order`: emission order of the read indices (abi.ref_output_order), default input order."""
     n = seq.shape[0]
     ids = read_ids(n, mate, first)
     parts = []
-    for i in range(n):
+    for i in (range(n) if order is None else order):
         if results["category"][i] != 0:
             continue
         h = int(results["head_cut"][i]); l = int(results["clean_len"][i])
@@ -143,3 +144,31 @@ def parse_fastq(data, stride=None):
         Q[i, :l] = np.frombuffer(quals[i], dtype=np.uint8)
         Ln[i] = l
     return ids, S, Q, Ln
+
+
+def write_fastq_fixed(path, seq, qual, L, mate, first=0):
+    """Vectorised writer for uniform-length reads (bench-sized samples): fixed-width IDs
+    `@SYN:1:1101:<7 digits>:<3 digits>/<mate>` so every record has the same byte length."""
+    n = seq.shape[0]
+    idx = np.arange(first, first + n, dtype=np.int64)
+    hi, lo = idx // 1000, idx % 1000
+    head = np.frombuffer(b"@SYN:1:1101:", dtype=np.uint8)
+    idlen = head.size + 7 + 1 + 3 + 2
+    rec = np.empty((n, idlen + 1 + L + 3 + L + 1), dtype=np.uint8)
+    rec[:, :head.size] = head
+    for k in range(7):
+        rec[:, head.size + k] = (hi // 10 ** (6 - k)) % 10 + 48
+    rec[:, head.size + 7] = ord(":")
+    for k in range(3):
+        rec[:, head.size + 8 + k] = (lo // 10 ** (2 - k)) % 10 + 48
+    rec[:, head.size + 11] = ord("/")
+    rec[:, head.size + 12] = 48 + mate
+    o = idlen
+    rec[:, o] = 10
+    rec[:, o + 1:o + 1 + L] = seq[:, :L]
+    rec[:, o + 1 + L] = 10
+    rec[:, o + 2 + L] = ord("+")
+    rec[:, o + 3 + L] = 10
+    rec[:, o + 4 + L:o + 4 + 2 * L] = qual[:, :L]
+    rec[:, o + 4 + 2 * L] = 10
+    rec.tofile(path)

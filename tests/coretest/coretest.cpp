@@ -1,0 +1,217 @@
+// coretest.cpp — TEST-ONLY CPU replay of filter_kernel (soapnuke_b200/csrc/filter_kernel.cuh).
+//
+// The product runs the functions of filter_core.cuh inside a CUDA kernel. This file compiles the
+// SAME header as plain C++ and walks the same tile -> phase A -> phase P -> phase B -> flush
+// structure sequentially, so that the per-read / per-position device logic can be checked against
+// the oracle in the CPU-only test tier (no GPU in the build container). It is never linked into the
+// product and is not a fallback: it exists only under tests/.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../soapnuke_b200/csrc/filter_kernel.cuh"
+#include "../../soapnuke_b200/csrc/dev_params.h"
+
+using namespace snkcore;
+
+namespace {
+
+struct Ctx {
+    DevParams P;
+    uint64_t* stats;
+    uint32_t err = 0;
+    uint32_t stride, R, W, X;
+    int mates;
+    std::vector<uint32_t> qhist, bhist;
+    uint64_t lastkey[8] = {0};
+};
+
+int file_of(int mates, int tab) { return mates == 2 ? tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1); }
+
+void flush(Ctx& c, int slot)
+{
+    uint64_t* S = c.stats + (size_t)slot * SNK_SLOT_WORDS;
+    const int ntab = 2 * c.mates;
+    for (uint32_t e = 0; e < (uint32_t)c.P.qb * 4u * c.X; e++) {
+        uint32_t v = c.qhist[e];
+        if (!v) continue;
+        c.qhist[e] = 0;
+        uint32_t x = e % c.X, j = (e / c.X) & 3u, q = e / (4u * c.X);
+        uint32_t tab = x / c.W, w = x % c.W;
+        if ((int)tab >= ntab) continue;
+        uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
+        F[SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + q] += v;
+        if (q >= 20) F[SNK_FILE_GS_OFF + SNK_GS_Q20] += v;
+        if (q >= 30) F[SNK_FILE_GS_OFF + SNK_GS_Q30] += v;
+    }
+    for (uint32_t e = 0; e < 5u * 4u * c.X; e++) {
+        uint32_t v = c.bhist[e];
+        if (!v) continue;
+        c.bhist[e] = 0;
+        uint32_t x = e % c.X, j = (e / c.X) & 3u, b = e / (4u * c.X);
+        uint32_t tab = x / c.W, w = x % c.W;
+        if ((int)tab >= ntab) continue;
+        uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
+        F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b] += v;
+        F[SNK_FILE_GS_OFF + SNK_GS_A + b] += v;
+        F[SNK_FILE_GS_OFF + SNK_GS_BASES] += v;
+    }
+    for (int t = 0; t < ntab; t++) {
+        uint64_t* G = S + SNK_SLOT_FILE_OFF(file_of(c.mates, t)) + SNK_FILE_GS_OFF;
+        if (c.lastkey[t] > G[SNK_GS_LAST_KEY]) G[SNK_GS_LAST_KEY] = c.lastkey[t];
+        G[SNK_GS_READS] += c.lastkey[4 + t];
+        c.lastkey[t] = 0; c.lastkey[4 + t] = 0;
+    }
+}
+
+template <int MAXC>
+void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first, int grid)
+{
+    const int M = c.mates;
+    const uint32_t n = b[0]->n;
+    TileMap tm = make_tile_map(first, n, c.R, (uint64_t)c.P.slot_block);
+    std::vector<uint8_t> rows[2][2];
+    std::vector<ReadInfo> info[2];
+    std::vector<uint8_t> keep(c.R);
+    for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)c.R * c.stride + 16, 0xAB); rows[m][1].assign((size_t)c.R * c.stride + 16, 0xAB); info[m].resize(c.R); }
+    c.qhist.assign((size_t)std::max(c.P.qb, 1) * 4u * c.X, 0);
+    c.bhist.assign((size_t)5u * 4u * c.X, 0);
+    for (int cta = 0; cta < grid; cta++) {
+        const uint32_t t_begin = (uint32_t)((uint64_t)tm.ntiles * cta / grid), t_end = (uint32_t)((uint64_t)tm.ntiles * (cta + 1) / grid);
+        int cur_slot = -1;
+        for (uint32_t t = t_begin; t < t_end; t++) {
+            uint32_t start, cnt;
+            tile_range(tm, t, &start, &cnt);
+            const uint64_t g0 = first + start;
+            const int slot = slot_of(g0, (uint64_t)c.P.slot_block, c.P.n_slots);
+            if (slot != cur_slot) { if (cur_slot >= 0) flush(c, cur_slot); cur_slot = slot; }
+            uint64_t* S = c.stats + (size_t)slot * SNK_SLOT_WORDS;
+            for (int m = 0; m < M; m++) {
+                memcpy(rows[m][0].data(), b[m]->seq + (size_t)start * c.stride, (size_t)cnt * c.stride);
+                memcpy(rows[m][1].data(), b[m]->qual + (size_t)start * c.stride, (size_t)cnt * c.stride);
+            }
+            // phase A
+            for (int m = 0; m < M; m++)
+                for (uint32_t r = 0; r < cnt; r++) {
+                    int len = b[m]->len[start + r];
+                    if (len > (int)c.stride) len = (int)c.stride;
+                    ReadInfo ri;
+                    if (len <= 0) { memset(&ri, 0, sizeof ri); ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1; ri.flags = RF_BAD_BASE; }
+                    else scan_read<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, m, c.P, ri);
+                    info[m][r] = ri;
+                }
+            // phase P
+            for (uint32_t r = 0; r < cnt; r++) {
+                const uint64_t gi = g0 + r;
+                int cat, mask = 0, fsb = -1;
+                const ReadInfo& a = info[0][r];
+                const ReadInfo& bb = info[M - 1][r];
+                if (M == 2) {
+                    cat = decide_pair(c.P, a, bb, &mask, &fsb);
+                    if ((a.flags | bb.flags) & RF_BAD_BASE) c.err |= ERR_BAD_BASE;
+                    if ((a.flags | bb.flags) & RF_BAD_QUAL) c.err |= ERR_BAD_QUAL;
+                    if (cat == SNK_DROP_LOWQ && ((a.flags | bb.flags) & RF_LOWQ_GT1)) c.err |= ERR_LOWQ_RATIO;
+                } else {
+                    cat = decide_se(c.P, a, &fsb);
+                    mask = cat ? 1 : 0;
+                    if (a.flags & RF_BAD_BASE) c.err |= ERR_BAD_BASE;
+                    if (a.flags & RF_BAD_QUAL) c.err |= ERR_BAD_QUAL;
+                }
+                keep[r] = cat == SNK_KEEP;
+                if (fsb >= 0) {
+                    S[fsb]++;
+                    if (M == 2) { if (mask & 1) S[fsb + 1]++; if (mask & 2) S[fsb + 2]++; if (mask == 3) S[fsb + 3]++; }
+                }
+                for (int m = 0; m < M; m++) {
+                    const ReadInfo& x = info[m][r];
+                    snk_read_result res;
+                    res.head_cut = (uint16_t)x.head_cut; res.clean_len = (uint16_t)x.clean_len;
+                    res.category = (uint8_t)cat; res.mate_mask = (uint8_t)mask; res.adacut_pos = x.adacut_pos;
+                    out[m][start + r] = res;
+                    const int which = M == 2 ? m : 2;
+                    int hf, tf;
+                    if (c.P.cutback) {
+                        trim_stat_indices(which, x.len, 0, x.head_hdcut, x.head_lqcut, x.tail_hdcut, x.tail_lqcut, x.adacut_pos, &hf, &tf);
+                        uint64_t* T = S + SNK_SLOT_FILE_OFF(m == 0 ? SNK_RAW1 : SNK_RAW2) + SNK_FILE_TS_OFF;
+                        if (hf >= 0) T[hf]++;
+                        if (tf >= 0) T[tf]++;
+                    }
+                    if (cat == SNK_KEEP) {
+                        trim_stat_indices(which, x.clean_len, x.len, x.head_hdcut, x.head_lqcut, x.tail_hdcut, x.tail_lqcut, x.adacut_pos, &hf, &tf);
+                        uint64_t* T = S + SNK_SLOT_FILE_OFF(m == 0 ? SNK_CLEAN1 : SNK_CLEAN2) + SNK_FILE_TS_OFF;
+                        if (hf >= 0) T[hf]++;
+                        if (tf >= 0) T[tf]++;
+                    }
+                    const uint64_t kraw = ((gi + 1) << 16) | (uint64_t)(uint16_t)x.len;
+                    if (kraw > c.lastkey[m]) c.lastkey[m] = kraw;
+                    c.lastkey[4 + m]++;
+                    if (cat == SNK_KEEP) {
+                        const uint64_t kc = ((gi + 1) << 16) | (uint64_t)(uint16_t)x.clean_len;
+                        if (kc > c.lastkey[M + m]) c.lastkey[M + m] = kc;
+                        c.lastkey[4 + M + m]++;
+                    }
+                }
+            }
+            // phase B
+            const uint32_t nitems = 2u * M * c.W;
+            for (uint32_t x = 0; x < nitems; x++) {
+                const uint32_t tab = x / c.W, w = x % c.W;
+                const int m = (int)(tab % M);
+                const bool clean = tab >= (uint32_t)M;
+                unsigned long long* gq_over = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, tab)));
+                BaseAcc acc = {0, 0, 0, 0, 0};
+                auto spill = [&]() {
+                    const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
+                    for (int bsym = 0; bsym < 5; bsym++)
+                        for (int j = 0; j < 4; j++) c.bhist[(bsym * 4 + j) * c.X + x] += (packed[bsym] >> (8 * j)) & 0xFFu;
+                    acc = {0, 0, 0, 0, 0};
+                };
+                uint32_t since = 0;
+                for (uint32_t r = 0; r < cnt; r++) {
+                    int off = 0, nn;
+                    if (clean) { if (!keep[r]) continue; off = info[m][r].head_cut; nn = info[m][r].clean_len; }
+                    else nn = info[m][r].len;
+                    c.err |= hist_item<uint32_t>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, off, nn,
+                                                 (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, gq_over);
+                    if (++since == 255) { since = 0; spill(); }
+                }
+                spill();
+            }
+        }
+        if (cur_slot >= 0) flush(c, cur_slot);
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// Same contract as snk_filter_pe_host / snk_filter_se_host, on the CPU, accumulating into `stats`
+// (n_slots * SNK_SLOT_WORDS). tile_r = 0 picks the kernel's default tile size; grid = CTAs to mimic.
+int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r2, snk_read_result* out1,
+                    snk_read_result* out2, uint64_t* stats, uint64_t first, uint32_t* err, int tile_r, int grid, int qb_override)
+{
+    Ctx c;
+    prepare_params(*p, c.P);
+    if (qb_override >= 0) c.P.qb = qb_override;
+    c.stats = stats;
+    c.mates = p->is_pe ? 2 : 1;
+    c.stride = r1->stride;
+    c.W = c.stride / 4;
+    c.X = align_up(2u * c.mates * c.W, 32);
+    c.R = tile_r > 0 ? (uint32_t)tile_r : (uint32_t)(kThreads / c.mates);
+    const snk_batch* b[2] = {r1, r2};
+    snk_read_result* out[2] = {out1, out2};
+    const uint32_t chunks = c.stride / 16;
+    if (grid < 1) grid = 1;
+    if (chunks <= 4) run<4>(c, b, out, first, grid);
+    else if (chunks <= 7) run<7>(c, b, out, first, grid);
+    else if (chunks <= 10) run<10>(c, b, out, first, grid);
+    else if (chunks <= 16) run<16>(c, b, out, first, grid);
+    else run<63>(c, b, out, first, grid);
+    *err |= c.err;
+    return 0;
+}
+
+}

@@ -1,0 +1,152 @@
+"""Shared test helpers: CPU replay harness loader, engine wrappers, comparison utilities."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+from soapnuke_b200 import abi, synth  # noqa: E402
+
+A1 = synth.ADAPTER1.decode()
+A2 = synth.ADAPTER2.decode()
+# BASELINE config 2 flags as CLI arguments and as make_params kwargs
+CFG2_FLAGS = ["-f", A1, "-r", A2, "-J", "-l", "5", "-q", "0.5", "-n", "0.05", "-m", "15", "-p", "0.7",
+              "-X", "50", "-g", "10", "-y", "20,30", "-x", "20,10"]
+CFG2_KW = dict(adapter1=A1, adapter2=A2, ada_trim=True, low_qual=5, low_qual_ratio=0.5, n_ratio=0.05,
+               mean_quality=15, highA_ratio=0.7, polyX_num=50, polyG_tail=10, trim_bad_tail=(20, 30),
+               trim_bad_head=(20, 10))
+
+_CT = None
+
+
+def load_coretest():
+    """Build + load tests/coretest/libcoretest.so (CPU replay of the kernel, test-only)."""
+    global _CT
+    if _CT is None:
+        d = os.path.join(ROOT, "tests", "coretest")
+        so = os.path.join(d, "libcoretest.so")
+        deps = [os.path.join(d, "coretest.cpp")] + [os.path.join(ROOT, "soapnuke_b200", "csrc", f)
+                                                    for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h")]
+        if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared",
+                                   "-I/usr/local/cuda/include", "-o", so, deps[0]])
+        lib = C.CDLL(so)
+        lib.coretest_filter.restype = C.c_int
+        lib.coretest_filter.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Batch), C.POINTER(abi.Batch), C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int]
+        _CT = lib
+    return _CT
+
+
+def core_replay(p, d, first=0, tile_r=0, grid=3, qb=-1):
+    lib = load_coretest()
+    n = d["seq1"].shape[0]
+    b1 = abi.make_batch(d["seq1"], d["qual1"], d["len1"])
+    r1 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+    r2 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+    st = np.zeros(p.n_slots * abi.SLOT_WORDS, dtype=np.uint64)
+    err = C.c_uint32(0)
+    if p.is_pe:
+        b2 = abi.make_batch(d["seq2"], d["qual2"], d["len2"])
+        lib.coretest_filter(C.byref(p), C.byref(b1), C.byref(b2), r1.ctypes.data, r2.ctypes.data, st.ctypes.data,
+                            first, C.byref(err), tile_r, grid, qb)
+    else:
+        lib.coretest_filter(C.byref(p), C.byref(b1), None, r1.ctypes.data, None, st.ctypes.data, first,
+                            C.byref(err), tile_r, grid, qb)
+        r2 = None
+    return r1, r2, st, err.value
+
+
+def oracle_run(p, d, first=0, stats=None):
+    import oracle_py as orc
+    if p.is_pe:
+        return orc.filter_pe(p, d, stats=stats, first_index=first)
+    r1, st, err = orc.filter_se(p, d, stats=stats, first_index=first)
+    return r1, None, st, err
+
+
+class Engine:
+    """Thin RAII wrapper over the C ABI (what a reference-side binding would do)."""
+
+    def __init__(self, lib, params, device=0):
+        self.lib = lib
+        self.params = params
+        self.h = C.c_void_p()
+        rc = lib.snk_engine_create(C.byref(params), device, C.byref(self.h))
+        if rc:
+            raise RuntimeError(lib.snk_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.snk_engine_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def check(self, rc):
+        if rc:
+            raise RuntimeError(self.lib.snk_last_error().decode())
+
+    def filter_host(self, d, first=0):
+        n = d["seq1"].shape[0]
+        b1 = abi.make_batch(d["seq1"], d["qual1"], d["len1"])
+        r1 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        if self.params.is_pe:
+            b2 = abi.make_batch(d["seq2"], d["qual2"], d["len2"])
+            r2 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+            self.check(self.lib.snk_filter_pe_host(self.h, C.byref(b1), C.byref(b2), r1.ctypes.data, r2.ctypes.data, first))
+            return r1, r2
+        self.check(self.lib.snk_filter_se_host(self.h, C.byref(b1), r1.ctypes.data, first))
+        return r1, None
+
+    def stats(self):
+        st = np.zeros(self.params.n_slots * abi.SLOT_WORDS, dtype=np.uint64)
+        self.check(self.lib.snk_engine_stats(self.h, st.ctypes.data))
+        return st
+
+    def error_flags(self):
+        f = C.c_uint32(0)
+        idx = C.c_uint64(0)
+        self.check(self.lib.snk_engine_error_flags(self.h, C.byref(f), C.byref(idx)))
+        return f.value, idx.value
+
+
+def describe_stat_index(i):
+    w = int(i) % abi.SLOT_WORDS
+    slot = int(i) // abi.SLOT_WORDS
+    if w < abi.FS_COUNT:
+        return f"slot {slot} fs[{w}]"
+    f = (w - abi.FS_COUNT) // abi.FILE_WORDS
+    o = (w - abi.FS_COUNT) % abi.FILE_WORDS
+    if o < abi.FILE_BS_OFF:
+        return f"slot {slot} file {f} gs[{o}]"
+    if o < abi.FILE_QS_OFF:
+        o -= abi.FILE_BS_OFF
+        return f"slot {slot} file {f} bs[pos {o // 5}][{o % 5}]"
+    if o < abi.FILE_TS_OFF:
+        o -= abi.FILE_QS_OFF
+        return f"slot {slot} file {f} qs[pos {o // abi.QBINS}][q {o % abi.QBINS}]"
+    o -= abi.FILE_TS_OFF
+    return f"slot {slot} file {f} ts[{o // 1000}][{o % 1000}]"
+
+
+def assert_same(got, want, what):
+    """Bit-exact comparison of result records / statistics with a readable first difference."""
+    r1, r2, st = got
+    o1, o2, ost = want
+    for nm, a, b in (("mate1", r1, o1), ("mate2", r2, o2)):
+        if b is None:
+            continue
+        bad = np.nonzero(a != b)[0]
+        assert bad.size == 0, f"{what}: {nm} results differ at {bad[:5]}: got {a[bad[:3]]} want {b[bad[:3]]}"
+    bad = np.nonzero(st != ost)[0]
+    assert bad.size == 0, (f"{what}: {bad.size} statistics words differ, first: " +
+                           "; ".join(f"{describe_stat_index(i)} got {st[i]} want {ost[i]}" for i in bad[:5]))

@@ -1,0 +1,75 @@
+"""CPU tier of the kernel parity tests: the device functions of soapnuke_b200/csrc/filter_core.cuh,
+compiled as plain C++ and driven through the kernel's tile/phase structure (tests/coretest), must
+reproduce the oracle bit for bit (per-read records and every statistics word)."""
+import numpy as np
+import pytest
+
+from helpers import A1, A2, CFG2_KW, abi, assert_same, core_replay, oracle_run, synth
+
+CONFIGS = [
+    # name, pe, n, L, gen kwargs, params kwargs, replay kwargs
+    ("cfg1_se150_default", False, 20000, 150, dict(seed=1001), dict(), dict()),
+    ("cfg2_pe150_all", True, 20000, 150, dict(seed=1002), dict(CFG2_KW, threads=3, patch_size=250), dict()),
+    ("cfg2_pe150_discard", True, 10000, 150, dict(seed=1003), dict(adapter1=A1, adapter2=A2), dict(first=123456, tile_r=32)),
+    ("cfg4_se50_adapter", False, 20000, 50, dict(seed=1004, adapter1=synth.SRNA_ADAPTER3, insert_range=(15, 35)),
+     dict(adapter1=synth.SRNA_ADAPTER3.decode(), ada_trim=True, min_read_length=15), dict(grid=5)),
+    ("cfg5_pe250_polyg", True, 8000, 250, dict(seed=1005, polyg_frac=0.3), dict(adapter1=A1, adapter2=A2, ada_trim=True, polyG_tail=10), dict()),
+    ("pe120_varlen_hardtrim", True, 8000, 120, dict(seed=7, var_len=True),
+     dict(adapter1=A1, adapter2=A2, ada_trim=True, hard_trim=(3, 2, 5, 1), polyX_num=8, threads=2, patch_size=50), dict(tile_r=64, grid=5)),
+    ("pe120_small_qb", True, 4000, 120, dict(seed=8, var_len=True), dict(adapter1=A1, adapter2=A2, ada_trim=True), dict(qb=8)),
+    ("pe100_phred64_out33", True, 4000, 100, dict(seed=9), dict(adapter1=A1, adapter2=A2, mean_quality=20), dict()),
+    ("se150_two_adapters_lowercase", False, 6000, 150, dict(seed=10), dict(adapter1=[A2.lower(), A1], ada_trim=True), dict()),
+    ("pe150_minlen_off", True, 6000, 150, dict(seed=11), dict(CFG2_KW, min_read_length=-1, max_read_length=140), dict()),
+    ("pe400_long_reads", True, 1500, 400, dict(seed=12), dict(adapter1=A1, adapter2=A2, ada_trim=True), dict(tile_r=32)),
+]
+
+
+@pytest.mark.parametrize("cfg", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_core_replay_matches_oracle(cfg):
+    name, pe, n, L, gkw, pkw, rkw = cfg
+    d = synth.gen_pairs(n, L=L, se=not pe, **gkw)
+    p = abi.make_params(is_pe=pe, **pkw)
+    o1, o2, ost, oerr = oracle_run(p, d, first=rkw.get("first", 0))
+    c1, c2, cst, cerr = core_replay(p, d, **rkw)
+    assert oerr == cerr == 0
+    assert_same((c1, c2, cst), (o1, o2, ost), name)
+
+
+def test_every_byte_value_is_classified_like_the_oracle():
+    """Unrecognized bases (anything but ACGTN, any case) must raise the error flag, exactly the
+    characters the reference's switch rejects (read_filter.cpp:270-285)."""
+    L = 48
+    for b in range(1, 256):
+        if b in (10, 13):
+            continue
+        S = np.zeros((1, 48), dtype=np.uint8); Q = np.zeros_like(S)
+        S[0, :L] = np.frombuffer(b"ACGT" * 12, dtype=np.uint8)
+        S[0, 17] = b
+        Q[0, :L] = ord("I")
+        d = dict(seq1=S, qual1=Q, len1=np.array([L], dtype=np.uint16))
+        p = abi.make_params(is_pe=False)
+        _, _, _, oerr = oracle_run(p, d)
+        _, _, _, cerr = core_replay(p, d)
+        assert (oerr & 1) == (cerr & 1), f"byte {b:#x}: oracle {oerr} replay {cerr}"
+        assert bool(oerr & 1) == (chr(b) not in "ACGTNacgtn")
+
+
+def test_batches_and_first_index_compose():
+    """Feeding the input as several batches with running first_index gives the same tables as one call."""
+    d = synth.gen_pairs(9000, L=100, seed=21)
+    p = abi.make_params(is_pe=True, threads=4, patch_size=20, **CFG2_KW)
+    o1, o2, ost, _ = oracle_run(p, d)
+    st = np.zeros_like(ost)
+    import ctypes as C
+    from helpers import load_coretest
+    lib = load_coretest()
+    cuts = [0, 1000, 1003, 4200, 9000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sub = {k: (v[a:b] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+        sub = {k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in sub.items()}
+        b1 = abi.make_batch(sub["seq1"], sub["qual1"], sub["len1"]); b2 = abi.make_batch(sub["seq2"], sub["qual2"], sub["len2"])
+        r1 = np.zeros(b - a, dtype=abi.RESULT_DTYPE); r2 = np.zeros(b - a, dtype=abi.RESULT_DTYPE)
+        err = C.c_uint32(0)
+        lib.coretest_filter(C.byref(p), C.byref(b1), C.byref(b2), r1.ctypes.data, r2.ctypes.data, st.ctypes.data, a, C.byref(err), 0, 4, -1)
+        assert np.array_equal(r1, o1[a:b]) and np.array_equal(r2, o2[a:b])
+    assert np.array_equal(st, ost)

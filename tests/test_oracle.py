@@ -1,0 +1,178 @@
+"""Pins the oracle (oracle/snk_oracle.c) and the host report writer:
+  * against the golden outputs of the unmodified reference binary (tests/golden, always), and
+  * against the reference binary itself when oracle/_ref/SOAPnuke is present (it travels to the GPU box).
+Also the probe-validated known answers of SURVEY.md §9.8.
+"""
+import ctypes as C
+import filecmp
+import glob
+import gzip
+import json
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from helpers import A1, A2, CFG2_FLAGS, CFG2_KW, ROOT, abi, synth
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = sorted(d for d in os.listdir(GOLDEN) if os.path.isdir(os.path.join(GOLDEN, d)))
+
+
+def load_case(name):
+    d = os.path.join(GOLDEN, name)
+    meta = json.load(open(os.path.join(d, "case.json")))
+    data = {}
+    for m in (1, 2) if meta["pe"] else (1,):
+        ids, S, Q, Ln = synth.parse_fastq(gzip.open(os.path.join(d, f"r{m}.fq.gz")).read())
+        data[f"seq{m}"], data[f"qual{m}"], data[f"len{m}"], data[f"ids{m}"] = S, Q, Ln, ids
+    kw = dict(meta["params"])
+    for k in ("trim_bad_head", "trim_bad_tail", "hard_trim"):
+        if k in kw and kw[k] is not None:
+            kw[k] = tuple(kw[k])
+    p = abi.make_params(is_pe=meta["pe"], threads=meta["threads"], nprocs=1 << 20, patch_size=meta["patch_size"], **kw)
+    return d, meta, data, p
+
+
+def clean_bytes(data, res, m, order=None):
+    parts = []
+    S, Q, ids = data[f"seq{m}"], data[f"qual{m}"], data[f"ids{m}"]
+    if order is None:
+        order = range(len(ids))
+    for i in order:
+        if res["category"][i] != 0:
+            continue
+        h = int(res["head_cut"][i]); l = int(res["clean_len"][i])
+        parts.append(ids[i] + b"\n" + S[i, h:h + l].tobytes() + b"\n+\n" + Q[i, h:h + l].tobytes() + b"\n")
+    return b"".join(parts)
+
+
+def write_reports(lib_fn, p, stats, out_dir):
+    os.makedirs(out_dir, exist_ok=True)
+    rc = lib_fn(C.byref(p), stats.ctypes.data, out_dir.encode())
+    assert rc == 0
+
+
+def compare_reports(ref_dir, mine_dir):
+    refs = sorted(glob.glob(os.path.join(ref_dir, "*.txt")))
+    assert refs
+    for f in refs:
+        b = os.path.basename(f)
+        assert filecmp.cmp(f, os.path.join(mine_dir, b), shallow=False), f"report {b} differs from the reference"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_matches_golden(name, engine_lib, tmp_path):
+    d, meta, data, p = load_case(name)
+    if meta["pe"]:
+        r1, r2, st, err = orc.filter_pe(p, data)
+    else:
+        r1, st, err = orc.filter_se(p, data); r2 = None
+    assert err == 0
+    for m, r in ((1, r1), (2, r2)):
+        if r is None:
+            continue
+        order = abi.ref_output_order(meta["n"], meta["threads"], 1 << 20, meta["patch_size"], gz_input=False, pe=meta["pe"])
+        assert clean_bytes(data, r, m, order) == gzip.open(os.path.join(d, f"c{m}.fq.gz")).read(), f"clean fq{m} differs"
+    fn = engine_lib.snk_report_write_pe if meta["pe"] else engine_lib.snk_report_write_se
+    write_reports(fn, p, st, str(tmp_path))
+    compare_reports(d, str(tmp_path))
+
+
+LIVE = [
+    ("pe_cfg2_T1", True, 6000, 150, 1, CFG2_FLAGS, CFG2_KW, None, {}),
+    ("pe_cfg2_T3_ms", True, 6000, 150, 3, CFG2_FLAGS, CFG2_KW, 20, {}),
+    ("pe_polyg250", True, 2000, 250, 2, ["-f", A1, "-r", A2, "-J", "-g", "10"], dict(adapter1=A1, adapter2=A2, ada_trim=True, polyG_tail=10), 7, dict(polyg_frac=0.3)),
+    ("pe_hard_var", True, 3000, 120, 2, ["-f", A1, "-r", A2, "-J", "-t", "3,2,4,1"], dict(adapter1=A1, adapter2=A2, ada_trim=True, hard_trim=(3, 2, 4, 1)), 9, dict(var_len=True)),
+    ("se_default", False, 6000, 150, 1, [], {}, None, {}),
+    ("se_ada_T4_ms", False, 6000, 100, 4, ["-f", A1, "-J", "-g", "10"], dict(adapter1=A1, ada_trim=True, polyG_tail=10), 11, {}),
+]
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", LIVE, ids=[c[0] for c in LIVE])
+def test_oracle_matches_reference_binary(case, engine_lib, tmp_path):
+    name, pe, n, L, T, flags, pkw, patch, gkw = case
+    data = synth.gen_pairs(n, L=L, seed=hash(name) % 10000, se=not pe, **gkw)
+    w = str(tmp_path)
+    synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
+    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    if pe:
+        synth.write_fastq(f"{w}/r2.fq", data["seq2"], data["qual2"], data["len2"], 2)
+        args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+    if patch:
+        open(f"{w}/cfg.txt", "w").write(f"patch={patch}\n")
+        args += ["-c", f"{w}/cfg.txt"]
+    r = orc.run_reference(args + flags)
+    assert r.returncode == 0, r.stderr.decode()
+    p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
+    if pe:
+        r1, r2, st, err = orc.filter_pe(p, data)
+    else:
+        r1, st, err = orc.filter_se(p, data); r2 = None
+    assert err == 0
+    for m, rs in ((1, r1), (2, r2)):
+        if rs is None:
+            continue
+        order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
+        mine = synth.clean_fastq_bytes(data[f"seq{m}"], data[f"qual{m}"], data[f"len{m}"], rs, m, order=order)
+        assert mine == open(f"{w}/out/c{m}.fq", "rb").read(), f"clean fq{m} differs from the reference binary"
+    fn = engine_lib.snk_report_write_pe if pe else engine_lib.snk_report_write_se
+    write_reports(fn, p, st, f"{w}/mine")
+    compare_reports(f"{w}/out", f"{w}/mine")
+
+
+# ---- known answers measured on the reference binary (A=32: segThr=16, misGrad=8, misGrad5=9)
+def body(n, rng):
+    return bytes(rng.choice(np.frombuffer(b"CT", dtype=np.uint8), size=n))
+
+
+def kat_reads():
+    rng = np.random.default_rng(98)
+    ada = synth.ADAPTER1
+
+    def mut(s, idxs):
+        s = bytearray(s)
+        for i in idxs:
+            s[i] = ord("C") if s[i] != ord("C") else ord("T")
+        return bytes(s)
+    L = 100
+    cases = []
+    cases.append(("tail6", body(L - 6, rng) + ada[:6], L - 6))
+    cases.append(("tail5", body(L - 5, rng) + ada[:5], -1))
+    cases.append(("tail14_mis5", body(L - 14, rng) + mut(ada[:14], [5]), L - 14))
+    cases.append(("tail13_mis2", body(L - 13, rng) + mut(ada[:13], [2]), -1))
+    cases.append(("full_off30_2mis", body(30, rng) + mut(ada, [8, 20]) + body(L - 62, rng), 30))
+    cases.append(("full_off30_3mis", body(30, rng) + mut(ada, [8, 16, 24]) + body(L - 62, rng), -1))
+    cases.append(("prefix16_off30", body(30, rng) + ada[:16] + body(L - 46, rng), 30))
+    cases.append(("starts_ada3", ada[3:] + body(L - 29, rng), 0))
+    cases.append(("starts_ada6", ada[6:] + body(L - 26, rng), -1))
+    return cases
+
+
+@pytest.mark.parametrize("name,read,want", kat_reads(), ids=[c[0] for c in kat_reads()])
+def test_adapter_pos_known_answers(name, read, want):
+    assert orc.adapter_pos(read, synth.ADAPTER1) == want
+
+
+def test_predicate_known_answers():
+    """N ratio: 5 N in 100 is discarded (float(5)/100 >= 0.05f), 4 kept; low quality: 50 of 100 at Q5
+    discarded, 49 kept, Q6 is not low at -l 5."""
+    L = 100
+    rng = np.random.default_rng(5)
+    rows = []
+    for nN, nlow, lowq in ((5, 0, 5), (4, 0, 5), (0, 50, 5), (0, 49, 5), (0, 50, 6)):
+        s = bytearray(body(L, rng)); q = bytearray(b"I" * L)
+        for i in range(nN):
+            s[3 * i] = ord("N")
+        for i in range(nlow):
+            q[i] = 33 + lowq
+        rows.append((bytes(s), bytes(q)))
+    S = np.zeros((len(rows), 112), dtype=np.uint8); Q = np.zeros_like(S)
+    for i, (s, q) in enumerate(rows):
+        S[i, :L] = np.frombuffer(s, dtype=np.uint8); Q[i, :L] = np.frombuffer(q, dtype=np.uint8)
+    d = dict(seq1=S, qual1=Q, len1=np.full(len(rows), L, dtype=np.uint16))
+    r1, st, err = orc.filter_se(abi.make_params(is_pe=False), d)
+    assert [abi.CATEGORY_NAMES[c] for c in r1["category"]] == ["n", "keep", "lowq", "keep", "keep"]
