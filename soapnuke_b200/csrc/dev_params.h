@@ -32,23 +32,25 @@ inline void prepare_adapter(const snk_params& p, int mate, int idx, AdapterDev& 
     a.n3 = A - adaEdge > 0 ? A - adaEdge : 0;
     for (int r1 = 1; r1 <= 5; r1++) a.budget1[r1 - 1] = float_to_int_x86((float)(A - r1) / misGrad5);   // :724
     for (int r1 = 0; r1 < a.n3 && r1 < SNK_MAX_ADAPTER_LEN; r1++) a.budget3[r1] = float_to_int_x86((float)r1 / misGrad);   // :769
-    bool fast = true;
+    bool fast = A <= 64;
     for (int i = 0; i < A; i++) {
         const char ch = (char)a.seq[i];
         if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T') fast = false;
     }
     a.fast = fast ? 1 : 0;
-    int k = A < 16 ? A : 16;
-    if (a.seg_thr < k) k = a.seg_thr;
+    int k = A < 32 ? A : 32;
+    if (a.seg_thr < k) k = a.seg_thr;     // no run-accept can complete inside the prefilter window
     if (k < 0) k = 0;
     a.pre_k = k;
-    a.pre_mask = k >= 16 ? 0x55555555u : (((1u << (2 * k)) - 1u) & 0x55555555u);
-    uint32_t code = 0;
-    for (int i = 0; i < 16 && i < A; i++) {
-        const uint32_t ch = a.seq[i];
-        code |= ((ch >> 1) & 3u) << (2 * i);
+    a.pre_mask = k >= 32 ? 0xFFFFFFFFu : ((1u << k) - 1u);
+    uint64_t b0 = 0, b1 = 0;
+    for (int i = 0; i < 64 && i < A; i++) {
+        const uint64_t ch = a.seq[i];
+        b0 |= ((ch >> 1) & 1ull) << i;
+        b1 |= ((ch >> 2) & 1ull) << i;
     }
-    a.code0 = code;
+    a.a0_lo = (uint32_t)b0; a.a0_hi = (uint32_t)(b0 >> 32);
+    a.a1_lo = (uint32_t)b1; a.a1_hi = (uint32_t)(b1 >> 32);
 }
 
 inline void prepare_params(const snk_params& p, DevParams& d)

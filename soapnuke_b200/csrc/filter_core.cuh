@@ -93,16 +93,16 @@ SNK_HD uint32_t load4(const uint8_t* p)   // p 4-byte aligned
 // are evaluated once with the reference's own expression types.
 struct AdapterDev {
     int32_t  len;        // adptLen (0 => no match possible)
-    int32_t  fast;       // 1: only uppercase A/C/G/T, so the 2-bit prefilter is exact
+    int32_t  fast;       // 1: only uppercase A/C/G/T and adptLen <= 64: the bit-plane matcher applies
     int32_t  seg_thr;    // segMatchThr = (int)ceil(adptLen * adaMR)
     int32_t  budget2;    // phase 2 budget = adaMis
     int32_t  edge;       // adaEdge
     int32_t  n3;         // number of phase-3 offsets = max(0, adptLen - adaEdge)
-    int32_t  pre_k;      // prefilter window: min(16, adptLen, seg_thr); 0 disables the prefilter
-    uint32_t pre_mask;   // 0x55555555 restricted to the low 2*pre_k bits
-    uint32_t code0;      // 2-bit codes (A=0,C=1,T=2,G=3) of adapter[0..15]
+    int32_t  pre_k;      // prefilter window: min(32, adptLen, seg_thr)
+    uint32_t pre_mask;   // low pre_k bits
+    uint32_t a0_lo, a0_hi, a1_lo, a1_hi;   // bit planes of the adapter's 2-bit codes (A=0,C=1,T=2,G=3), bit c = base c
     int32_t  budget1[5]; // phase 1 budgets for r1 = 1..5
-    int32_t  pad_[2];
+    int32_t  pad_[3];
     int32_t  budget3[SNK_MAX_ADAPTER_LEN];   // phase 3 budget per r1
     uint8_t  seq[SNK_MAX_ADAPTER_LEN];
 };
@@ -160,49 +160,109 @@ SNK_HD bool window_exact(const uint8_t* read, int len, int roff, const uint8_t* 
     return mis <= budget;
 }
 
-// 2-bit prefilter: `win`/`winbad` hold the 16 bases starting at the window (2 bits per base, bad =
-// base that can never equal an uppercase A/C/G/T). Returns true when the window is certainly
-// rejected: more than max(budget,0) mismatches inside the first pre_k positions, and pre_k <=
-// seg_thr guarantees no run-accept can precede that rejection.
-SNK_HD bool prefilter_reject(const AdapterDev& a, uint32_t win, uint32_t winbad, int budget)
+SNK_HD int popc64(uint64_t x) { return (int)(popc32((uint32_t)x) + popc32((uint32_t)(x >> 32))); }
+SNK_HD int ctz64(uint64_t x)      // x != 0
 {
-    uint32_t x = win ^ a.code0;
-    uint32_t m = (x | (x >> 1) | winbad) & a.pre_mask;
-    int b = budget < 0 ? 0 : budget;
-    return (int)popc32(m) > b;
+    const uint32_t lo = (uint32_t)x;
+    return lo ? ctz32(lo) : 32 + ctz32((uint32_t)(x >> 32));
 }
 
-// adapter_pos for one adapter (read_filter.cpp:707-790). `code`/`bad` are the read's 2-bit planes
-// (16 bases per word, MAXC+1 words, word MAXC is zero padding).
-template <int MAXC>
-SNK_HD int adapter_pos_dev(const uint8_t* seq, int len, const uint32_t* code, const uint32_t* bad, const AdapterDev& a)
+// Decision of one adapter_pos window from its mismatch bit mask (bit c = position c mismatches),
+// without walking the window: equivalent to window_exact. The (max(budget,0)+1)-th mismatch is the
+// abort position; the first run of seg_thr matches that ends before it accepts; otherwise the
+// window accepts iff it finishes with mis <= budget. Loop trip counts depend only on the
+// (warp-uniform) parameters, so a warp stays converged.
+SNK_HD bool window_decide(uint64_t M, int winlen, int budget, int seg_thr)
+{
+    const uint64_t valid = winlen >= 64 ? ~0ull : ((1ull << winlen) - 1ull);
+    M &= valid;
+    const int nmis = popc64(M);
+    const int nb = budget < 0 ? 0 : budget;
+    uint64_t t = M;
+    for (int i = 0; i < nb; i++) t &= t - 1;            // drop the nb lowest mismatches
+    const int p_abort = t ? ctz64(t) : 64;
+    const int T = seg_thr < 1 ? 1 : seg_thr;
+    uint64_t run = ~M & valid;                          // bit i survives iff positions i..i+T-1 all match
+    if (T > 64) run = 0;
+    else for (int k = 1; k < T;) { const int sft = (k < T - k) ? k : T - k; run &= run >> sft; k += sft; }
+    const bool run_ok = run != 0 && (ctz64(run) + T - 1) < p_abort;
+    return run_ok || nmis <= budget;
+}
+
+// adapter_pos for one adapter (read_filter.cpp:707-790) on 1-bit planes of the read:
+// p0/p1 = the two code bits of every base (A=0,C=1,T=2,G=3), pb = "can never equal an uppercase
+// A/C/G/T" (N, lowercase, or beyond the read end); 32 bases per word, NW+2 words each.
+// Phases 2 and 3 are one forward sweep over window offsets: offsets 0..len-A are phase-2 windows
+// (full adapter, budget adaMis, smallest accepted offset wins), offsets len-A+1..len-adaEdge are
+// the phase-3 windows (adapter prefix of length len-off hanging over the 3' end; the reference
+// scans them shortest-overlap first, so the LARGEST accepted offset wins), and phase 2 beats phase 3.
+template <int NW>
+SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const AdapterDev& a)
 {
     const int A = a.len;
-    if (A == 0) return -1;
-    // phase 1: adapter starts r1 = 1..5 bases before the read
-    for (int r1 = 1; r1 <= 5; r1++)
-        if (window_exact(seq, len, 0, a.seq, r1, A - r1, a.budget1[r1 - 1], a.seg_thr)) return 0;
-    // phase 2: adapter fully inside the read, smallest offset wins
-    const int last = len - A;
-    if (a.fast && a.pre_k > 0) {
-#pragma unroll(MAXC <= 16 ? MAXC : 1)
-        for (int c = 0; c < MAXC; c++) {
-            if (16 * c <= last) {
-                const uint32_t c0 = code[c], c1 = code[c + 1], b0 = bad[c], b1 = bad[c + 1];
-                for (int s = 0; s < 16; s++) {
-                    const int r1 = 16 * c + s;
-                    if (r1 > last) break;
-                    const uint32_t win = funnel_r(c0, c1, 2 * s), wbad = funnel_r(b0, b1, 2 * s);
-                    if (prefilter_reject(a, win, wbad, a.budget2)) continue;
-                    if (window_exact(seq, len, r1, a.seq, 0, A, a.budget2, a.seg_thr)) return r1;
+    const uint64_t a0 = ((uint64_t)a.a0_hi << 32) | a.a0_lo, a1 = ((uint64_t)a.a1_hi << 32) | a.a1_lo;
+    // phase 1: adapter starts r1 = 1..5 bases before the read; read window is bases [0, A-r1)
+    {
+        const uint64_t r0 = ((uint64_t)p0[1] << 32) | p0[0], r1w = ((uint64_t)p1[1] << 32) | p1[0], rb = ((uint64_t)pb[1] << 32) | pb[0];
+        bool hit = false;
+#pragma unroll
+        for (int r1 = 1; r1 <= 5; r1++) {
+            const uint64_t M = (r0 ^ (a0 >> r1)) | (r1w ^ (a1 >> r1)) | rb;
+            const int budget = a.budget1[r1 - 1];
+            const int nb = budget < 0 ? 0 : budget;
+            const int wl = A - r1;
+            uint32_t pm = a.pre_mask;
+            if (wl < 32) pm &= wl <= 0 ? 0u : ((1u << wl) - 1u);
+            if ((int)popc32((uint32_t)M & pm) > nb) continue;
+            hit = hit || window_decide(M, wl, budget, a.seg_thr);
+        }
+        if (hit) return 0;
+    }
+    const int last2 = len - A, last3 = len - a.edge;
+    const int nb2 = a.budget2 < 0 ? 0 : a.budget2;
+    int pos2 = -1, pos3 = -1;
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int kw = 0; kw < NW; kw++) {
+        if (32 * kw <= last3 && pos2 < 0) {
+            const uint32_t l0 = p0[kw], m0 = p0[kw + 1], h0 = p0[kw + 2];
+            const uint32_t l1 = p1[kw], m1 = p1[kw + 1], h1 = p1[kw + 2];
+            const uint32_t lb = pb[kw], mb = pb[kw + 1], hb = pb[kw + 2];
+            for (int sft = 0; sft < 32; sft++) {
+                const int off = 32 * kw + sft;
+                if (off > last3 || pos2 >= 0) break;
+                // level 1: plane 0 alone (a plane-0 difference is a base mismatch)
+                const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
+                const bool ph2 = off <= last2;
+                const int winlen = ph2 ? A : len - off;
+                uint32_t pm = a.pre_mask;
+                int nb = nb2, budget = a.budget2;
+                if (!ph2) {
+                    budget = a.budget3[winlen - a.edge];
+                    nb = budget < 0 ? 0 : budget;
+                    if (winlen < 32) pm &= (1u << winlen) - 1u;
                 }
+                if ((int)popc32(x0 & pm) > nb) continue;
+                // level 2: all planes over the prefilter window
+                const uint32_t x = x0 | (funnel_r(l1, m1, sft) ^ a.a1_lo) | funnel_r(lb, mb, sft);
+                if ((int)popc32(x & pm) > nb) continue;
+                // exact decision over the whole window
+                const uint32_t xh = (funnel_r(m0, h0, sft) ^ a.a0_hi) | (funnel_r(m1, h1, sft) ^ a.a1_hi) | funnel_r(mb, hb, sft);
+                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) { if (ph2) pos2 = off; else pos3 = off; }
             }
         }
-    } else {
-        for (int r1 = 0; r1 <= last; r1++)
-            if (window_exact(seq, len, r1, a.seq, 0, A, a.budget2, a.seg_thr)) return r1;
     }
-    // phase 3: adapter prefix hanging over the read's 3' end, shortest overlap first
+    return pos2 >= 0 ? pos2 : pos3;
+}
+
+// byte-wise adapter_pos: adapters with N / lowercase / length > 64, and reads shorter than the
+// adapter (windows that start before the read). Same phase order as the reference.
+SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
+{
+    const int A = a.len;
+    for (int r1 = 1; r1 <= 5; r1++)
+        if (window_exact(seq, len, 0, a.seq, r1, A - r1, a.budget1[r1 - 1], a.seg_thr)) return 0;
+    for (int r1 = 0; r1 <= len - A; r1++)
+        if (window_exact(seq, len, r1, a.seq, 0, A, a.budget2, a.seg_thr)) return r1;
     for (int r1 = 0; r1 < a.n3; r1++) {
         const int base = len - r1 - a.edge;
         if (window_exact(seq, len, base, a.seq, 0, r1 + a.edge, a.budget3[r1], a.seg_thr)) return base;
@@ -217,43 +277,40 @@ SNK_HD uint32_t bytes_lt(uint32_t w, uint32_t k)
 {
     return ~((w | 0x80808080u) - k * 0x01010101u) & 0x80808080u;
 }
-// bit 0 of every byte lane gathered into 4 adjacent bits (bits 24..27 of the product)
+// bit 0 of every byte lane gathered into 4 adjacent bits
 SNK_HD uint32_t gather1(uint32_t lanes) { return ((lanes & 0x01010101u) * 0x01020408u) >> 24; }
-// low 2 bits of every byte lane gathered into 8 adjacent bits
-SNK_HD uint32_t gather2(uint32_t lanes) { return ((lanes & 0x03030303u) * 0x01041040u) >> 24; }
 
-// longest run of set bits in the low `nbits` (<= 16) of e, plus the run touching bit 0 (lead) and
-// the run touching the top bit (tail)
-SNK_HD void runs16(uint32_t e, int nbits, int& lead, int& inner, int& tail)
+// does the low `nbits` (<= 16) of e contain a run of at least T set bits? (T >= 1, warp-uniform)
+SNK_HD bool has_run16(uint32_t e, int T)
 {
-    const uint32_t full = (nbits >= 32) ? 0xFFFFFFFFu : ((1u << nbits) - 1u);
-    e &= full;
-    if (e == full) { lead = inner = tail = nbits; return; }
-    lead = ctz32(~e);
-    tail = clz32(~(e << (32 - nbits)));
-    int n = 0;
-    uint32_t x = e;
-    while (x) { x &= x >> 1; n++; }
-    inner = n;
+    if (T > 16) return false;
+    for (int k = 1; k < T;) { const int sft = (k < T - k) ? k : T - k; e &= e >> sft; k += sft; }
+    return e != 0;
 }
 
 template <int MAXC>
 SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P, ReadInfo& R)
 {
-    uint32_t code[MAXC + 1], bad[MAXC + 1];
+    constexpr int NW = (MAXC + 1) / 2;          // 32 bases per plane word
+    uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
     uint32_t accC = 0, accG = 0, accT = 0, accN = 0, viol = 0;
     uint32_t accLow = 0, qsum = 0, qviol = 0;
     const bool want_polyx = P.polyX_num != -1;
     const bool want_planes = P.n_adapters[mate] > 0;
-    int best_run = 0, cur_run = 0;          // runs of "same as previous base" bits
+    const int runT = P.polyX_num - 1;       // contig_base >= polyX_num  <=>  a run of >= polyX_num-1 "same as previous" bits
+    bool polyx_hit = want_polyx && runT <= 0;
+    int cur_run = 0;
     uint32_t prev_byte = 'Q';               // read_filter.cpp:255 last_char('Q')
     const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
     const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
+#pragma unroll
+    for (int i = 0; i < NW + 2; i++) { p0[i] = 0; p1[i] = 0; pb[i] = 0xFFFFFFFFu; }
 
 #pragma unroll(MAXC <= 16 ? MAXC : 1)
     for (int c = 0; c < MAXC; c++) {
-        uint32_t cw = 0, bw = 0, ew = 0;
+        uint32_t c0 = 0, c1 = 0, cb = 0xFFFFu, ew = 0;
         if (16 * c < len) {
+            cb = 0;
             const U4 sv = load16(seq + 16 * c);
             const U4 qv = load16(qual + 16 * c);
             const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
@@ -279,13 +336,14 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
                     v |= m3 & ~(m1 & m2);
                     viol |= v & mask;
                     if (want_planes) {
-                        cw |= gather2(f >> 1) << (8 * k);
-                        bw |= gather2(((w >> 5) | m3) & 0x01010101u) << (8 * k);   // lowercase or N: bit at even position
+                        c0 |= gather1(m1) << (4 * k);
+                        c1 |= gather1(m2) << (4 * k);
+                        cb |= gather1((w >> 5) | m3 | ~mask) << (4 * k);   // lowercase, N, or past the end
                     }
                     if (want_polyx) {
                         const uint32_t x = w ^ ((w << 8) | prev_byte);
                         const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where byte == previous
-                        ew |= gather1((z >> 7) & (mask & 0x01010101u)) << (4 * k);
+                        ew |= gather1((z >> 7) & mask) << (4 * k);
                         prev_byte = (sw[k] >> 24);
                     }
                     // qualities
@@ -294,20 +352,26 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
                     qsum += bytesum(q);
                     qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
                     if (!low_never) accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
+                } else if (want_planes) {
+                    cb |= 0xFu << (4 * k);
                 }
             }
-            if (want_polyx) {
+            if (want_polyx && !polyx_hit) {
                 const int nb = (len - 16 * c) >= 16 ? 16 : (len - 16 * c);
-                int lead, inner, tail;
-                runs16(ew, nb, lead, inner, tail);
-                if (cur_run + lead > best_run) best_run = cur_run + lead;
-                if (inner > best_run) best_run = inner;
-                cur_run = (lead == nb) ? cur_run + nb : tail;
+                const uint32_t full = (1u << nb) - 1u;
+                if (ew == full) { cur_run += nb; polyx_hit = cur_run >= runT; }
+                else {
+                    const int lead = ctz32(~ew);
+                    polyx_hit = (cur_run + lead >= runT) || has_run16(ew, runT);
+                    cur_run = clz32(~(ew << (32 - nb)));
+                }
             }
         }
-        code[c] = cw; bad[c] = bw;
+        if (want_planes) {
+            if (c & 1) { p0[c >> 1] |= c0 << 16; p1[c >> 1] |= c1 << 16; pb[c >> 1] = (pb[c >> 1] & 0xFFFFu) | (cb << 16); }
+            else { p0[c >> 1] = c0; p1[c >> 1] = c1; pb[c >> 1] = cb | 0xFFFF0000u; }
+        }
     }
-    code[MAXC] = 0; bad[MAXC] = 0x55555555u;
 
     uint16_t flags = 0;
     if (viol) flags |= RF_BAD_BASE;
@@ -322,7 +386,7 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     const float lowq_ratio = (float)nLow / flen, mean_q = (float)total_q / flen;
     if (P.n_ratio != -1 && n_ratio >= P.n_ratio) flags |= RF_N;
     if (P.highA_ratio != -1 && a_ratio >= P.highA_ratio) flags |= RF_HIGHA;
-    if (want_polyx && (1 + best_run) >= P.polyX_num) flags |= RF_POLYX;
+    if (polyx_hit) flags |= RF_POLYX;
     if (P.low_qual_ratio != -1 && lowq_ratio >= P.low_qual_ratio) flags |= RF_LOWQ;
     if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
     if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
@@ -330,7 +394,10 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     // adapters: first adapter in the list that hits wins (read_filter.cpp:177-188)
     int ada_pos = -1;
     for (int i = 0; i < P.n_adapters[mate]; i++) {
-        ada_pos = adapter_pos_dev<MAXC>(seq, len, code, bad, P.ada[mate][i]);
+        const AdapterDev& a = P.ada[mate][i];
+        if (a.len == 0) continue;
+        if (a.fast && len >= a.len - 1) ada_pos = adapter_pos_planes<NW>(len, p0, p1, pb, a);
+        else ada_pos = adapter_pos_bytes(seq, len, a);
         if (ada_pos >= 0) break;
     }
     int adacut = -1;

@@ -73,3 +73,68 @@ def test_batches_and_first_index_compose():
         lib.coretest_filter(C.byref(p), C.byref(b1), C.byref(b2), r1.ctypes.data, r2.ctypes.data, st.ctypes.data, a, C.byref(err), 0, 4, -1)
         assert np.array_equal(r1, o1[a:b]) and np.array_equal(r2, o2[a:b])
     assert np.array_equal(st, ost)
+
+
+def adversarial_adapter_reads(n, L, adapter, seed):
+    """Reads salted with mutated / truncated / shifted copies of the adapter, N's and lowercase:
+    every branch of adapter_pos (phase 1 shifts, phase 2 budgets and run-accepts, phase 3 overhangs)."""
+    rng = np.random.default_rng(seed)
+    A = len(adapter)
+    ada = np.frombuffer(adapter, dtype=np.uint8)
+    stride = synth.stride_for(L)
+    S = np.zeros((n, stride), dtype=np.uint8)
+    Q = np.zeros((n, stride), dtype=np.uint8)
+    Ln = rng.integers(max(A - 1, 25), L + 1, size=n).astype(np.uint16)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    for i in range(n):
+        l = int(Ln[i])
+        s = acgt[rng.integers(0, 4, size=l)].copy()
+        mode = rng.integers(0, 6)
+        if mode < 5:
+            piece = ada.copy()
+            for _ in range(int(rng.integers(0, 5))):          # 0..4 substitutions
+                piece[rng.integers(0, A)] = acgt[rng.integers(0, 4)]
+            if mode == 0:       # anywhere inside
+                off = int(rng.integers(0, max(1, l - A + 1)))
+            elif mode == 1:     # hanging over the 3' end
+                off = int(rng.integers(max(0, l - A + 1), l))
+            elif mode == 2:     # starting before the read
+                off = -int(rng.integers(1, 8))
+            elif mode == 3:     # only a prefix of the adapter, inside
+                piece = piece[: int(rng.integers(6, A))]
+                off = int(rng.integers(0, max(1, l - len(piece) + 1)))
+            else:               # exactly at the boundary lengths
+                off = l - int(rng.integers(4, 9))
+            a0, b0 = max(off, 0), min(l, off + len(piece))
+            if b0 > a0:
+                s[a0:b0] = piece[a0 - off:b0 - off]
+        if rng.random() < 0.2:
+            s[rng.integers(0, l, size=2)] = ord("N")
+        if rng.random() < 0.1:
+            j = int(rng.integers(0, l))
+            s[j] = s[j] | 0x20
+        S[i, :l] = s
+        Q[i, :l] = rng.integers(35, 74, size=l)
+    return dict(seq1=S, qual1=Q, len1=Ln, n=n, L=L, stride=stride)
+
+
+@pytest.mark.parametrize("adapter,L,kw", [
+    (synth.ADAPTER1, 100, dict()),
+    (synth.ADAPTER2, 150, dict()),
+    (synth.SRNA_ADAPTER3, 50, dict()),
+    (synth.ADAPTER1, 150, dict(ada_mis=(3, 3), ada_mr=(0.4, 0.4), ada_edge=(4, 4))),
+    (synth.ADAPTER2, 100, dict(ada_mis=(0, 0), ada_mr=(0.9, 0.9), ada_edge=(10, 10))),
+    (synth.ADAPTER1, 70, dict(ada_mis=(1, 1), ada_mr=(0.1, 0.1), ada_edge=(6, 6))),
+    (b"ACGTTGCAAC", 60, dict(ada_mis=(1, 1), ada_mr=(0.5, 0.5), ada_edge=(3, 3))),
+    (synth.ADAPTER1 + synth.ADAPTER2[:31], 150, dict()),                      # 63 bases: both plane words in use
+    (synth.ADAPTER1 + synth.ADAPTER2, 150, dict()),                           # 74 bases: byte-wise path
+    (b"AAGTCGGAGGCCAAGCGGTCTTAGGNAGACAA", 100, dict()),                       # adapter with N: byte-wise path
+], ids=["a32", "a42", "a21", "a32_loose", "a42_strict", "a32_shortrun", "a10", "a63", "a74_bytes", "a32_withN_bytes"])
+def test_adapter_matcher_adversarial(adapter, L, kw):
+    d = adversarial_adapter_reads(6000, L, adapter[:42] if len(adapter) > 64 else adapter, seed=len(adapter) * 7 + L)
+    for trim in (True, False):
+        p = abi.make_params(is_pe=False, adapter1=adapter.decode(), ada_trim=trim, min_read_length=10, **kw)
+        o1, _, ost, oerr = oracle_run(p, d)
+        c1, _, cst, cerr = core_replay(p, d)
+        assert (o1["adacut_pos"] >= 0).sum() > 500, "generator should produce many adapter hits"
+        assert_same((c1, None, cst), (o1, None, ost), f"adapter len {len(adapter)} trim={trim}")

@@ -160,3 +160,18 @@ def test_full_size_properties(engine_lib):
     assert np.array_equal(r1[: 1 << 18], r1[(1 << 18):(1 << 19)])
     o1, o2, _, _ = oracle_run(p, base)
     assert np.array_equal(r1[: 1 << 18], o1) and np.array_equal(r2[: 1 << 18], o2)
+
+
+def test_adapter_matcher_adversarial_on_gpu(engine_lib):
+    from test_core_replay import adversarial_adapter_reads
+    for adapter, L, kw in ((synth.ADAPTER1, 100, dict()), (synth.ADAPTER2, 150, dict()),
+                           (synth.ADAPTER1, 150, dict(ada_mis=(3, 3), ada_mr=(0.4, 0.4), ada_edge=(4, 4))),
+                           (synth.ADAPTER1 + synth.ADAPTER2[:31], 150, dict()),
+                           (b"AAGTCGGAGGCCAAGCGGTCTTAGGNAGACAA", 100, dict())):
+        d = adversarial_adapter_reads(20000, L, adapter, seed=len(adapter) + L)
+        p = abi.make_params(is_pe=False, adapter1=adapter.decode(), ada_trim=True, min_read_length=10, **kw)
+        o1, _, ost, _ = oracle_run(p, d)
+        with Engine(engine_lib, p) as e:
+            r1, _ = e.filter_host(d)
+            st = e.stats()
+        assert_same((r1, None, st), (o1, None, ost), f"adapter len {len(adapter)}")
