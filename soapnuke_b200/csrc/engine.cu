@@ -42,7 +42,7 @@ struct Lane {
 
 struct LaunchPlan {
     int maxc;          // template instantiation
-    uint32_t R, X, W;
+    uint32_t R, X, W, threads;
     int qb;
     size_t smem;
     int grid;
@@ -75,7 +75,7 @@ int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const L
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         smem_set = kSmemLimit;
     }
-    kern<<<lp.grid, kThreads, lp.smem, stream>>>(dp, ka);
+    kern<<<lp.grid, lp.threads, lp.smem, stream>>>(dp, ka);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     return 0;
@@ -99,23 +99,28 @@ int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t fi
     const uint32_t chunks = stride / 16;
     lp.maxc = chunks <= 4 ? 4 : chunks <= 7 ? 7 : chunks <= 10 ? 10 : chunks <= 16 ? 16 : 63;
     lp.W = stride / 4;
-    lp.X = align_up(2u * mates * lp.W, 32);
+    lp.threads = cta_threads(mates, stride);
+    lp.X = lp.threads;
     int qb = e->dev.qb;
-    const uint32_t maxR = kThreads / mates;
+    const uint32_t maxR = lp.threads / mates;          // one thread per read in phase A
+    // Prefer a tile that lets two CTAs share an SM (latency hiding across the phase barriers);
+    // fall back to one CTA per SM, then to fewer shared-memory quality bins.
     uint32_t R = 0;
+    int ctas_per_sm = 1;
     for (;;) {
-        // largest multiple of 32 (<= maxR) whose plan fits
-        for (uint32_t r = maxR; r >= 32; r -= 32) {
-            if (plan_smem(mates, r, stride, lp.X, qb).total <= kSmemLimit) { R = r; break; }
-        }
+        const size_t half = kSmemLimit / 2 - 1024;
+        if (plan_smem(mates, maxR, stride, lp.X, qb).total <= half) { R = maxR; ctas_per_sm = 2; break; }
+        for (uint32_t r = maxR; r >= 16 && !R; r -= 16)
+            if (plan_smem(mates, r, stride, lp.X, qb).total <= kSmemLimit) R = r;
         if (R) break;
         if (qb <= 0) { snk::set_error("read stride too large for the shared-memory tile"); return 1; }
-        qb = qb > 4 ? qb - 4 : 0;   // bins >= qb fall back to global atomics (hist_item gq_over)
+        qb = qb > 4 ? qb - 4 : 0;   // bins >= qb fall back to global atomics (hist_item checked path)
     }
     lp.R = R; lp.qb = qb;
     lp.smem = plan_smem(mates, R, stride, lp.X, qb).total;
     tm = make_tile_map(first, n, R, (uint64_t)e->params.slot_block);
-    lp.grid = (int)(tm.ntiles < (uint32_t)e->num_sms ? tm.ntiles : (uint32_t)e->num_sms);
+    const uint32_t max_grid = (uint32_t)e->num_sms * (uint32_t)ctas_per_sm;
+    lp.grid = (int)(tm.ntiles < max_grid ? tm.ntiles : max_grid);
     if (lp.grid < 1) lp.grid = 1;
     return 0;
 }

@@ -52,6 +52,15 @@ SNK_HD uint32_t bytesum(uint32_t w)
     return (w & 0xFF) + ((w >> 8) & 0xFF) + ((w >> 16) & 0xFF) + (w >> 24);
 #endif
 }
+// byte j (0..3) of w, zero extended
+SNK_HD uint32_t byte_of(uint32_t w, int j)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(w, 0u, 0x4440u | (uint32_t)j);
+#else
+    return (w >> (8 * j)) & 0xFFu;
+#endif
+}
 SNK_HD int ctz32(uint32_t x)   // x != 0
 {
 #ifdef __CUDA_ARCH__
@@ -138,7 +147,8 @@ struct ReadInfo {
 };
 enum : uint16_t {
     RF_N = 1, RF_HIGHA = 2, RF_POLYX = 4, RF_LOWQ = 8, RF_MEANQ = 16, RF_ADAPTER = 32,
-    RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256
+    RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256,
+    RF_QSLOW = 512        // some quality falls outside the shared-memory bins: histogram takes the checked path
 };
 enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
 
@@ -220,38 +230,54 @@ SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, c
     }
     const int last2 = len - A, last3 = len - a.edge;
     const int nb2 = a.budget2 < 0 ? 0 : a.budget2;
+    const uint32_t pm2 = a.pre_mask;
     int pos2 = -1, pos3 = -1;
+    // ---- phase 2: offsets 0..last2, first accepted offset wins
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
-        if (32 * kw <= last3 && pos2 < 0) {
-            const uint32_t l0 = p0[kw], m0 = p0[kw + 1], h0 = p0[kw + 2];
-            const uint32_t l1 = p1[kw], m1 = p1[kw + 1], h1 = p1[kw + 2];
-            const uint32_t lb = pb[kw], mb = pb[kw + 1], hb = pb[kw + 2];
-            for (int sft = 0; sft < 32; sft++) {
-                const int off = 32 * kw + sft;
-                if (off > last3 || pos2 >= 0) break;
+        if (32 * kw <= last2 && pos2 < 0) {
+            const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
+            const int send = (last2 - 32 * kw) >= 31 ? 32 : (last2 - 32 * kw + 1);
+            for (int sft = 0; sft < send; sft++) {
                 // level 1: plane 0 alone (a plane-0 difference is a base mismatch)
                 const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
-                const bool ph2 = off <= last2;
-                const int winlen = ph2 ? A : len - off;
-                uint32_t pm = a.pre_mask;
-                int nb = nb2, budget = a.budget2;
-                if (!ph2) {
-                    budget = a.budget3[winlen - a.edge];
-                    nb = budget < 0 ? 0 : budget;
-                    if (winlen < 32) pm &= (1u << winlen) - 1u;
-                }
-                if ((int)popc32(x0 & pm) > nb) continue;
+                if ((int)popc32(x0 & pm2) > nb2) continue;
                 // level 2: all planes over the prefilter window
-                const uint32_t x = x0 | (funnel_r(l1, m1, sft) ^ a.a1_lo) | funnel_r(lb, mb, sft);
-                if ((int)popc32(x & pm) > nb) continue;
+                const uint32_t x = x0 | (funnel_r(p1[kw], p1[kw + 1], sft) ^ a.a1_lo) | funnel_r(pb[kw], pb[kw + 1], sft);
+                if ((int)popc32(x & pm2) > nb2) continue;
                 // exact decision over the whole window
-                const uint32_t xh = (funnel_r(m0, h0, sft) ^ a.a0_hi) | (funnel_r(m1, h1, sft) ^ a.a1_hi) | funnel_r(mb, hb, sft);
-                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) { if (ph2) pos2 = off; else pos3 = off; }
+                const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
+                                    funnel_r(pb[kw + 1], pb[kw + 2], sft);
+                if (window_decide(((uint64_t)xh << 32) | x, A, a.budget2, a.seg_thr)) { pos2 = 32 * kw + sft; break; }
             }
         }
     }
-    return pos2 >= 0 ? pos2 : pos3;
+    if (pos2 >= 0) return pos2;
+    // ---- phase 3: offsets last2+1..last3 (window = adapter prefix of length len-off), last accepted wins
+    const int first3 = last2 + 1 < 0 ? 0 : last2 + 1;
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int kw = 0; kw < NW; kw++) {
+        if (32 * kw + 31 >= first3 && 32 * kw <= last3) {
+            const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
+            const int s0 = first3 > 32 * kw ? first3 - 32 * kw : 0;
+            const int send = (last3 - 32 * kw) >= 31 ? 32 : (last3 - 32 * kw + 1);
+            for (int sft = s0; sft < send; sft++) {
+                const int winlen = len - (32 * kw + sft);
+                const int budget = a.budget3[winlen - a.edge];
+                const int nb = budget < 0 ? 0 : budget;
+                uint32_t pm = pm2;
+                if (winlen < 32) pm &= (1u << winlen) - 1u;
+                const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
+                if ((int)popc32(x0 & pm) > nb) continue;
+                const uint32_t x = x0 | (funnel_r(p1[kw], p1[kw + 1], sft) ^ a.a1_lo) | funnel_r(pb[kw], pb[kw + 1], sft);
+                if ((int)popc32(x & pm) > nb) continue;
+                const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
+                                    funnel_r(pb[kw + 1], pb[kw + 2], sft);
+                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) pos3 = 32 * kw + sft;
+            }
+        }
+    }
+    return pos3;
 }
 
 // byte-wise adapter_pos: adapters with N / lowercase / length > 64, and reads shorter than the
@@ -294,7 +320,8 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     constexpr int NW = (MAXC + 1) / 2;          // 32 bases per plane word
     uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
     uint32_t accC = 0, accG = 0, accT = 0, accN = 0, viol = 0;
-    uint32_t accLow = 0, qsum = 0, qviol = 0;
+    uint32_t accLow = 0, qsum = 0, qviol = 0, qover = 0;
+    const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
     const bool want_polyx = P.polyX_num != -1;
     const bool want_planes = P.n_adapters[mate] > 0;
     const int runT = P.polyX_num - 1;       // contig_base >= polyX_num  <=>  a run of >= polyX_num-1 "same as previous" bits
@@ -351,6 +378,7 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
                     const uint32_t qfill = q | (~mask & 0x7F7F7F7Fu);     // padding lanes read as 0x7F: never low, never < phred
                     qsum += bytesum(q);
                     qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
+                    qover |= ~bytes_lt(q, over_k);                            // masked lanes are 0: never over
                     if (!low_never) accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
                 } else if (want_planes) {
                     cb |= 0xFu << (4 * k);
@@ -376,6 +404,7 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     uint16_t flags = 0;
     if (viol) flags |= RF_BAD_BASE;
     if (qviol) flags |= RF_BAD_QUAL;
+    if ((qover & 0x80808080u) || qviol) flags |= RF_QSLOW;
     const int nN = (int)bytesum(accN), nC = (int)bytesum(accC), nG = (int)bytesum(accG), nT = (int)bytesum(accT);
     const int nA = len - nN - nC - nG - nT;
     const int nLow = (int)bytesum(accLow);
@@ -500,29 +529,16 @@ SNK_HD void trim_stat_indices(int which, int slen, int raw_length, int head_hd, 
 }
 
 // ------------------------------------------------------------------ per-position histograms
-// One histogram item = 4 consecutive positions (one 32-bit word of the row) of one table.
-// The owner of an item is the only writer of its counters, so no atomics are needed.
-// Base counters are packed 4 x 8 bit per symbol (flushed by the caller before they can wrap).
+// One histogram item = 4 consecutive positions (one 32-bit word of the row) of one table; the
+// thread that owns an item is the only writer of its counters, so no atomics are needed.
+//   quality x position counts: shared memory, CounterT cells, index (q*4 + j) * qstride + item
+//   base x position counts:    packed 4 x 8 bit per symbol while walking a tile (BaseAcc), then
+//                              added to the owner's 20 register counters (BaseCnt) for the whole launch.
 struct BaseAcc { uint32_t a, c, g, t, n; };
+struct BaseCnt { uint32_t v[5][4]; };      // [A,C,G,T,N][j]
 
-// seq/qual: row start (16-byte aligned); off: first base of the (clean) record; n: its length;
-// w: word index of the item. qhist: this item's quality counters, qhist[(q*4 + j) * qstride].
-// Returns sticky error bits.
-template <typename CounterT>
-SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
-                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */)
+SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked */)
 {
-    const int nvalid = n - 4 * w;
-    if (nvalid <= 0) return 0;
-    const int byte0 = off + 4 * w;
-    const int al = byte0 & ~3, sh = 8 * (byte0 & 3);
-    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-    uint32_t s = load4(seq + al), q = load4(qual + al);
-    if (sh) {                                     // record does not start on a word boundary (head trimmed)
-        s = funnel_r(s, load4(seq + al + 4), sh);
-        q = funnel_r(q, load4(qual + al + 4), sh);
-    }
-    s &= mask;
     const uint32_t f = s & 0xDFDFDFDFu;
     const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
     const uint32_t valid = (f >> 6) & 0x01010101u;
@@ -531,6 +547,74 @@ SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int 
     acc.g += m1 & m2 & ~m3;
     acc.t += ~m1 & m2 & ~m3 & 0x01010101u;
     acc.a += valid & ~(m1 | m2 | m3);
+}
+SNK_HD void base_acc_spill(BaseAcc& acc, BaseCnt& cnt)
+{
+    const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
+#pragma unroll
+    for (int b = 0; b < 5; b++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) cnt.v[b][j] += (packed[b] >> (8 * j)) & 0xFFu;
+    acc.a = acc.c = acc.g = acc.t = acc.n = 0;
+}
+
+// Loads the item's 4 bases and 4 qualities of a record that starts at byte `off` of its row.
+SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, uint32_t& s, uint32_t& q)
+{
+    const int byte0 = off + 4 * w;
+    const int al = byte0 & ~3, sh = 8 * (byte0 & 3);
+    s = load4(seq + al); q = load4(qual + al);
+    if (sh) {                                     // record does not start on a word boundary (head trimmed)
+        s = funnel_r(s, load4(seq + al + 4), sh);
+        q = funnel_r(q, load4(qual + al + 4), sh);
+    }
+}
+
+// Per-read descriptor for phase B, one 32-bit word per (table, read): record length (bits 0-9),
+// first byte of the record in its row (bits 10-19), bit 31 = take the checked path. 0 = skip.
+SNK_HD uint32_t hist_desc(int n, int off, bool slow) { return n <= 0 ? 0u : ((uint32_t)n | ((uint32_t)off << 10) | (slow ? 0x80000000u : 0u)); }
+
+// Fast path: every quality of the record is known to lie inside the shared-memory bins (RF_QSLOW
+// clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at
+// qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
+template <typename CounterT>
+SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,
+                           uint8_t* qcells, int cell0, int jstep, int bstep)
+{
+    const int nvalid = n - 4 * w;
+    if (nvalid <= 0) return;
+    uint32_t s, q;
+    hist_load(seq, qual, off, w, s, q);
+    if (nvalid >= 4) {
+        base_acc_add(acc, s);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+            *cell += 1;
+        }
+    } else {
+        base_acc_add(acc, s & ((1u << (8 * nvalid)) - 1u));
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            if (j < nvalid) {
+                CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+                *cell += 1;
+            }
+    }
+}
+
+// Checked path: qualities may fall outside [0,qb). Bins not kept in shared memory go straight to
+// the slot's global table; anything outside [0,SNK_QBINS) raises the error flag. Returns error bits.
+template <typename CounterT>
+SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
+                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */)
+{
+    const int nvalid = n - 4 * w;
+    if (nvalid <= 0) return 0;
+    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+    uint32_t s, q;
+    hist_load(seq, qual, off, w, s, q);
+    base_acc_add(acc, s & mask);
     uint32_t err = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -538,7 +622,6 @@ SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int 
             const int qq = (int)((q >> (8 * j)) & 0xFFu) - phred;
             if ((unsigned)qq < (unsigned)qb) qhist[(qq * 4 + j) * qstride] += 1;
             else if ((unsigned)qq < (unsigned)SNK_QBINS && file_base) {
-                // bin not kept in shared memory: straight to the slot's global table (rare)
                 unsigned long long* cell = file_base + SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + qq;
 #ifdef __CUDA_ARCH__
                 atomicAdd(cell, 1ull);

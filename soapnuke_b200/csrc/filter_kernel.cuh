@@ -14,7 +14,20 @@
 
 namespace snkcore {
 
-constexpr int kThreads = 256;
+typedef uint16_t QCounter;                 // shared-memory quality counters; flushed before they can wrap
+constexpr uint32_t kQCounterMax = 65535;
+
+// CTA shape: one thread per histogram item (4 positions of one table), which is also the number of
+// reads a tile holds (threads / mates), so phase A and phase B both keep every thread busy.
+__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline uint32_t cta_threads(int mates, uint32_t stride)
+{
+    uint32_t t = align_up(2u * mates * (stride / 4), 32);
+    return t < 64 ? 64 : t;
+}
+template <int MAXC, int MATES> struct KernelShape {
+    static constexpr int kMaxThreads = ((2 * MATES * MAXC * 4 + 31) / 32 * 32) < 64 ? 64 : ((2 * MATES * MAXC * 4 + 31) / 32 * 32);
+};
 
 struct KernelArgs {
     const uint8_t* seq[2];
@@ -27,22 +40,22 @@ struct KernelArgs {
     uint32_t stride;                // bytes per row
     uint32_t R;                     // tile capacity (reads or pairs)
     uint32_t items_w;               // words per row = stride / 4
-    uint32_t X;                     // histogram row pitch (items rounded up to 32)
+    uint32_t X;                     // histogram row pitch = CTA threads
     TileMap tm;
 };
 
-// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][keep][qhist u32][bhist u32]
+// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][keep][qhist][misc]
 struct SmemPlan {
     uint32_t off_rows[2][2];   // [mate][0 seq, 1 qual]
     uint32_t off_len[2];
     uint32_t off_info[2];
     uint32_t off_keep;
+    uint32_t off_desc;         // hist_desc words: [raw m0][raw m1][clean m0][clean m1], R each
     uint32_t off_qhist;
-    uint32_t off_bhist;
     uint32_t off_misc;
     uint32_t total;
 };
-__host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8;      // lastkey[8] + gsum[4][8]
 __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb)
 {
     SmemPlan p;
@@ -50,14 +63,14 @@ __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t st
     for (int m = 0; m < 2; m++)
         for (int a = 0; a < 2; a++) {
             p.off_rows[m][a] = o;
-            if (m < mates) o += R * stride + 16;      // +16: hist_item may read one word past the last row
+            if (m < mates) o += R * stride + 16;      // +16: hist_load may read one word past the last row
         }
     for (int m = 0; m < 2; m++) { p.off_len[m] = o; if (m < mates) o += align_up(R * 2, 16); }
     for (int m = 0; m < 2; m++) { p.off_info[m] = o; if (m < mates) o += align_up(R * (uint32_t)sizeof(ReadInfo), 16); }
     p.off_keep = o; o += align_up(R, 16);
-    p.off_qhist = o; o += (uint32_t)qb * 4u * X * 4u;
-    p.off_bhist = o; o += 5u * 4u * X * 4u;
-    p.off_misc = o; o += 64;
+    p.off_desc = o; o += align_up(4u * R * 4u, 16);
+    p.off_qhist = o; o += align_up((uint32_t)qb * 4u * X * (uint32_t)sizeof(QCounter), 16);
+    p.off_misc = o; o += kMiscBytes;
     p.total = o;
     return p;
 }
@@ -70,14 +83,17 @@ __device__ __forceinline__ void report_error(const KernelArgs& A, uint32_t bits,
     atomicMin(A.err_index, (unsigned long long)gi);
 }
 
-// add this CTA's shared-memory histograms to the slot's global tables and clear them
-__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, uint32_t* qhist, uint32_t* bhist,
-                           unsigned long long* lastkey, int slot)
+__device__ __forceinline__ int file_of_tab(int mates, int tab) { return mates == 2 ? tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1); }
+
+// add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
+// slot's global tables and clear them
+__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt& bc,
+                           unsigned long long* lastkey, unsigned long long* gsum, int slot)
 {
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
     const uint32_t X = A.X, W = A.items_w;
     const int ntab = 2 * mates;                        // raw1,[raw2],clean1,[clean2] -> item groups
-    unsigned long long q20[4] = {0, 0, 0, 0}, q30[4] = {0, 0, 0, 0};
+    // quality cells: entry e = (q*4 + j)*X + x
     const uint32_t qent = (uint32_t)P.qb * 4u * X;
     for (uint32_t e = threadIdx.x; e < qent; e += blockDim.x) {
         const uint32_t v = qhist[e];
@@ -86,92 +102,104 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, u
         const uint32_t x = e % X, j = (e / X) & 3u, q = e / (4u * X);
         const uint32_t tab = x / W, w = x % W;
         if ((int)tab >= ntab) continue;
-        const int file = (mates == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
-        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file);
+        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
         atomicAdd(&F[SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + q], (unsigned long long)v);
-        if (q >= 20) q20[tab] += v;
-        if (q >= 30) q30[tab] += v;
+        if (q >= 20) atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)v);
+        if (q >= 30) atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)v);
     }
-    unsigned long long bsum[4][5];
-#pragma unroll
-    for (int t = 0; t < 4; t++)
-#pragma unroll
-        for (int b = 0; b < 5; b++) bsum[t][b] = 0;
-    const uint32_t bent = 5u * 4u * X;
-    for (uint32_t e = threadIdx.x; e < bent; e += blockDim.x) {
-        const uint32_t v = bhist[e];
-        if (!v) continue;
-        bhist[e] = 0;
-        const uint32_t x = e % X, j = (e / X) & 3u, b = e / (4u * X);
+    // base cells: this thread's own item
+    {
+        const uint32_t x = threadIdx.x;
         const uint32_t tab = x / W, w = x % W;
-        if ((int)tab >= ntab) continue;
-        const int file = (mates == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
-        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file);
-        atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b], (unsigned long long)v);
+        if ((int)tab < ntab) {
+            unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
+            unsigned long long bases = 0;
 #pragma unroll
-        for (int t = 0; t < 4; t++)
+            for (int b = 0; b < 5; b++) {
+                unsigned long long sym = 0;
 #pragma unroll
-            for (int bb = 0; bb < 5; bb++) if ((int)tab == t && (int)b == bb) bsum[t][bb] += v;
-    }
-#pragma unroll
-    for (int t = 0; t < 4; t++) {
-        if (t >= ntab) break;
-        const int file = (mates == 2) ? t : (t == 0 ? SNK_RAW1 : SNK_CLEAN1);
-        unsigned long long* G = S + SNK_SLOT_FILE_OFF(file) + SNK_FILE_GS_OFF;
-        unsigned long long bases = 0;
-#pragma unroll
-        for (int b = 0; b < 5; b++) { if (bsum[t][b]) atomicAdd(&G[SNK_GS_A + b], bsum[t][b]); bases += bsum[t][b]; }
-        // table order is A,C,G,T,N; gs order is A,C,G,T,N as well
-        if (bases) atomicAdd(&G[SNK_GS_BASES], bases);
-        if (q20[t]) atomicAdd(&G[SNK_GS_Q20], q20[t]);
-        if (q30[t]) atomicAdd(&G[SNK_GS_Q30], q30[t]);
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t v = bc.v[b][j];
+                    if (v) atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b], (unsigned long long)v);
+                    sym += v;
+                    bc.v[b][j] = 0;
+                }
+                if (sym) atomicAdd(&gsum[tab * 8 + b], sym);
+                bases += sym;
+            }
+            if (bases) atomicAdd(&gsum[tab * 8 + 5], bases);
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 4) {
-        const int t = threadIdx.x;
+    if (threadIdx.x < 32) {
+        const int t = threadIdx.x >> 3, k = threadIdx.x & 7;      // 4 tables x 8 sums
         if (t < ntab) {
-            const int file = (mates == 2) ? t : (t == 0 ? SNK_RAW1 : SNK_CLEAN1);
-            unsigned long long* G = S + SNK_SLOT_FILE_OFF(file) + SNK_FILE_GS_OFF;
-            if (lastkey[t]) atomicMax(&G[SNK_GS_LAST_KEY], lastkey[t]);
-            if (lastkey[4 + t]) atomicAdd(&G[SNK_GS_READS], lastkey[4 + t]);
-            lastkey[t] = 0; lastkey[4 + t] = 0;
+            unsigned long long* G = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, t)) + SNK_FILE_GS_OFF;
+            // gsum order: A,C,G,T,N,bases,q20,q30
+            const int gs_index[8] = {SNK_GS_A, SNK_GS_C, SNK_GS_G, SNK_GS_T, SNK_GS_N, SNK_GS_BASES, SNK_GS_Q20, SNK_GS_Q30};
+            const unsigned long long v = gsum[t * 8 + k];
+            if (v) atomicAdd(&G[gs_index[k]], v);
+            gsum[t * 8 + k] = 0;
+            if (k == 0) {
+                if (lastkey[t]) atomicMax(&G[SNK_GS_LAST_KEY], lastkey[t]);
+                if (lastkey[4 + t]) atomicAdd(&G[SNK_GS_READS], lastkey[4 + t]);
+                lastkey[t] = 0; lastkey[4 + t] = 0;
+            }
         }
     }
     __syncthreads();
 }
 
 template <int MAXC, int MATES>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__((KernelShape<MAXC, MATES>::kMaxThreads))
 filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ KernelArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
-    uint32_t* qhist = reinterpret_cast<uint32_t*>(smem + sp.off_qhist);
-    uint32_t* bhist = reinterpret_cast<uint32_t*>(smem + sp.off_bhist);
+    QCounter* qhist = reinterpret_cast<QCounter*>(smem + sp.off_qhist);
     uint8_t* keep = smem + sp.off_keep;
-    // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table
+    uint32_t* desc = reinterpret_cast<uint32_t*>(smem + sp.off_desc);
+    // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table, gsum[4][8]
     unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(smem + sp.off_misc);
+    unsigned long long* gsum = lastkey + 8;
     const int tid = threadIdx.x;
 
-    for (uint32_t e = tid; e < (sp.off_misc + 64 - sp.off_qhist) / 4; e += blockDim.x) qhist[e] = 0;   // qhist, bhist, misc
+    for (uint32_t e = tid; e < (sp.total - sp.off_qhist) / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(qhist)[e] = 0;   // qhist + misc
+    BaseCnt bc;
+#pragma unroll
+    for (int b = 0; b < 5; b++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) bc.v[b][j] = 0;
     __syncthreads();
 
     const uint32_t nt = A.tm.ntiles;
     const uint32_t t_begin = (uint32_t)((uint64_t)nt * blockIdx.x / gridDim.x);
     const uint32_t t_end = (uint32_t)((uint64_t)nt * (blockIdx.x + 1) / gridDim.x);
     int cur_slot = -1;
+    uint32_t reads_in_hist = 0;                     // records counted since the last flush (u16 cells)
     const uint32_t W = A.items_w;
-    const uint32_t nitems = 2u * MATES * W;
+    const uint32_t nitems = 2u * MATES * W;         // <= blockDim.x
+    // this thread's histogram item
+    const uint32_t my_tab = (uint32_t)tid / W, my_w = (uint32_t)tid % W;
+    const bool my_item = (uint32_t)tid < nitems;
+    const int my_m = (int)(my_tab % MATES);
+    const bool my_clean = my_tab >= (uint32_t)MATES;
+    // byte offsets into the quality table for hist_item_fast: cell(b, j) = cell0 + j*jstep + b*bstep
+    const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = 4 * q_jstep;
+    const int q_cell0 = tid * (int)sizeof(QCounter) - P.phred * q_bstep;
+    const uint32_t* my_desc = desc + (size_t)((my_clean ? 2 : 0) + my_m) * A.R;
 
     for (uint32_t t = t_begin; t < t_end; t++) {
         uint32_t start, cnt;
         tile_range(A.tm, t, &start, &cnt);
         const uint64_t g0 = A.tm.first + start;
         const int slot = slot_of(g0, (uint64_t)P.slot_block, P.n_slots);
-        if (slot != cur_slot) {
-            if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bhist, lastkey, cur_slot);
+        if (slot != cur_slot || reads_in_hist + cnt > kQCounterMax) {
+            if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
             cur_slot = slot;
+            reads_in_hist = 0;
         }
+        reads_in_hist += cnt;
         // ---- stage the tile: rows are contiguous in global memory, copy 16 bytes per thread-step
         const uint32_t row_bytes = cnt * A.stride;
 #pragma unroll
@@ -231,6 +259,12 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                     if (err) report_error(A, err, gi);
                 }
                 keep[r] = (cat == SNK_KEEP);
+                desc[0 * A.R + r] = hist_desc(a.len, 0, a.flags & RF_QSLOW);
+                desc[2 * A.R + r] = cat == SNK_KEEP ? hist_desc(a.clean_len, a.head_cut, a.flags & RF_QSLOW) : 0u;
+                if (MATES == 2) {
+                    desc[1 * A.R + r] = hist_desc(b.len, 0, b.flags & RF_QSLOW);
+                    desc[3 * A.R + r] = cat == SNK_KEEP ? hist_desc(b.clean_len, b.head_cut, b.flags & RF_QSLOW) : 0u;
+                }
                 unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
                 if (fsb >= 0) {
                     atomicAdd(&S[fsb], 1ull);
@@ -289,46 +323,32 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         __syncthreads();
 
         // ---- phase B: per-position histograms, owner computes
-        for (uint32_t x = tid; x < nitems; x += blockDim.x) {
-            const uint32_t tab = x / W, w = x % W;           // tab: raw mates first, then clean mates
-            const int m = (int)(tab % MATES);
-            const bool clean = tab >= (uint32_t)MATES;
-            const uint8_t* rows_s = smem + sp.off_rows[m][0];
-            const uint8_t* rows_q = smem + sp.off_rows[m][1];
-            const ReadInfo* info = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[m]);
-            const int file = (MATES == 2) ? (int)tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1);
-            unsigned long long* gq_over = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file);
+        if (my_item) {
+            const uint8_t* rows_s = smem + sp.off_rows[my_m][0];
+            const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
             BaseAcc acc = {0, 0, 0, 0, 0};
-            uint32_t err = 0;
-            uint32_t since_flush = 0;
+            uint32_t err = 0, since_spill = 0;
             for (uint32_t r = 0; r < cnt; r++) {
-                int off = 0, n;
-                if (clean) {
-                    if (!keep[r]) continue;
-                    off = info[r].head_cut; n = info[r].clean_len;
-                } else n = info[r].len;
-                err |= hist_item<uint32_t>(rows_s + (size_t)r * A.stride, rows_q + (size_t)r * A.stride, off, n, (int)w,
-                                           P.phred, P.qb, acc, qhist + x, (int)A.X, gq_over);
-                if (++since_flush == 255) {
-                    since_flush = 0;
-                    const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
-#pragma unroll
-                    for (int b = 0; b < 5; b++)
-#pragma unroll
-                        for (int j = 0; j < 4; j++) bhist[(b * 4 + j) * A.X + x] += (packed[b] >> (8 * j)) & 0xFFu;
-                    acc = {0, 0, 0, 0, 0};
+                const uint32_t d = my_desc[r];
+                const int n = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
+                if (n <= 4 * (int)my_w) continue;                       // nothing of this record in my 4 positions
+                const uint8_t* rs = rows_s + (size_t)r * A.stride;
+                const uint8_t* rq = rows_q + (size_t)r * A.stride;
+                if (!(d & 0x80000000u))
+                    hist_item_fast<QCounter>(rs, rq, off, n, (int)my_w, acc, reinterpret_cast<uint8_t*>(qhist),
+                                             q_cell0, q_jstep, q_bstep);
+                else {
+                    unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
+                    err |= hist_item<QCounter>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
                 }
+                if (++since_spill == 255) { since_spill = 0; base_acc_spill(acc, bc); }
             }
-            const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
-#pragma unroll
-            for (int b = 0; b < 5; b++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) bhist[(b * 4 + j) * A.X + x] += (packed[b] >> (8 * j)) & 0xFFu;
+            base_acc_spill(acc, bc);
             if (err) report_error(A, err, g0);
         }
         __syncthreads();
     }
-    if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bhist, lastkey, cur_slot);
+    if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
 }
 
 #endif // __CUDACC__

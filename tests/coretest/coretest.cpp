@@ -23,7 +23,8 @@ struct Ctx {
     uint32_t err = 0;
     uint32_t stride, R, W, X;
     int mates;
-    std::vector<uint32_t> qhist, bhist;
+    std::vector<QCounter> qhist;
+    std::vector<BaseCnt> bc;            // one per item (per "thread")
     uint64_t lastkey[8] = {0};
 };
 
@@ -45,17 +46,18 @@ void flush(Ctx& c, int slot)
         if (q >= 20) F[SNK_FILE_GS_OFF + SNK_GS_Q20] += v;
         if (q >= 30) F[SNK_FILE_GS_OFF + SNK_GS_Q30] += v;
     }
-    for (uint32_t e = 0; e < 5u * 4u * c.X; e++) {
-        uint32_t v = c.bhist[e];
-        if (!v) continue;
-        c.bhist[e] = 0;
-        uint32_t x = e % c.X, j = (e / c.X) & 3u, b = e / (4u * c.X);
+    for (uint32_t x = 0; x < c.X; x++) {
         uint32_t tab = x / c.W, w = x % c.W;
         if ((int)tab >= ntab) continue;
         uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
-        F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b] += v;
-        F[SNK_FILE_GS_OFF + SNK_GS_A + b] += v;
-        F[SNK_FILE_GS_OFF + SNK_GS_BASES] += v;
+        for (int b = 0; b < 5; b++)
+            for (int j = 0; j < 4; j++) {
+                uint32_t v = c.bc[x].v[b][j];
+                c.bc[x].v[b][j] = 0;
+                F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b] += v;
+                F[SNK_FILE_GS_OFF + SNK_GS_A + b] += v;
+                F[SNK_FILE_GS_OFF + SNK_GS_BASES] += v;
+            }
     }
     for (int t = 0; t < ntab; t++) {
         uint64_t* G = S + SNK_SLOT_FILE_OFF(file_of(c.mates, t)) + SNK_FILE_GS_OFF;
@@ -66,7 +68,7 @@ void flush(Ctx& c, int slot)
 }
 
 template <int MAXC>
-void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first, int grid)
+void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first, int grid, uint32_t flush_every)
 {
     const int M = c.mates;
     const uint32_t n = b[0]->n;
@@ -76,16 +78,19 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
     std::vector<uint8_t> keep(c.R);
     for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)c.R * c.stride + 16, 0xAB); rows[m][1].assign((size_t)c.R * c.stride + 16, 0xAB); info[m].resize(c.R); }
     c.qhist.assign((size_t)std::max(c.P.qb, 1) * 4u * c.X, 0);
-    c.bhist.assign((size_t)5u * 4u * c.X, 0);
+    c.bc.assign(c.X, BaseCnt());
+    for (auto& x : c.bc) memset(&x, 0, sizeof x);
     for (int cta = 0; cta < grid; cta++) {
         const uint32_t t_begin = (uint32_t)((uint64_t)tm.ntiles * cta / grid), t_end = (uint32_t)((uint64_t)tm.ntiles * (cta + 1) / grid);
         int cur_slot = -1;
+        uint32_t reads_in_hist = 0;
         for (uint32_t t = t_begin; t < t_end; t++) {
             uint32_t start, cnt;
             tile_range(tm, t, &start, &cnt);
             const uint64_t g0 = first + start;
             const int slot = slot_of(g0, (uint64_t)c.P.slot_block, c.P.n_slots);
-            if (slot != cur_slot) { if (cur_slot >= 0) flush(c, cur_slot); cur_slot = slot; }
+            if (slot != cur_slot || reads_in_hist + cnt > flush_every) { if (cur_slot >= 0) flush(c, cur_slot); cur_slot = slot; reads_in_hist = 0; }
+            reads_in_hist += cnt;
             uint64_t* S = c.stats + (size_t)slot * SNK_SLOT_WORDS;
             for (int m = 0; m < M; m++) {
                 memcpy(rows[m][0].data(), b[m]->seq + (size_t)start * c.stride, (size_t)cnt * c.stride);
@@ -153,30 +158,30 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     }
                 }
             }
-            // phase B
+            // phase B: item x is owned by "thread" x
             const uint32_t nitems = 2u * M * c.W;
             for (uint32_t x = 0; x < nitems; x++) {
                 const uint32_t tab = x / c.W, w = x % c.W;
                 const int m = (int)(tab % M);
                 const bool clean = tab >= (uint32_t)M;
-                unsigned long long* gq_over = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, tab)));
+                unsigned long long* file_base = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, tab)));
+                const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = 4 * q_jstep;
+                const int q_cell0 = (int)x * (int)sizeof(QCounter) - c.P.phred * q_bstep;
                 BaseAcc acc = {0, 0, 0, 0, 0};
-                auto spill = [&]() {
-                    const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
-                    for (int bsym = 0; bsym < 5; bsym++)
-                        for (int j = 0; j < 4; j++) c.bhist[(bsym * 4 + j) * c.X + x] += (packed[bsym] >> (8 * j)) & 0xFFu;
-                    acc = {0, 0, 0, 0, 0};
-                };
                 uint32_t since = 0;
                 for (uint32_t r = 0; r < cnt; r++) {
-                    int off = 0, nn;
-                    if (clean) { if (!keep[r]) continue; off = info[m][r].head_cut; nn = info[m][r].clean_len; }
-                    else nn = info[m][r].len;
-                    c.err |= hist_item<uint32_t>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, off, nn,
-                                                 (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, gq_over);
-                    if (++since == 255) { since = 0; spill(); }
+                    const ReadInfo ri = info[m][r];
+                    const uint32_t d = clean ? (keep[r] ? hist_desc(ri.clean_len, ri.head_cut, ri.flags & RF_QSLOW) : 0u)
+                                             : hist_desc(ri.len, 0, ri.flags & RF_QSLOW);
+                    const int nn = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
+                    if (nn <= 4 * (int)w) continue;
+                    const uint8_t* rs = rows[m][0].data() + (size_t)r * c.stride;
+                    const uint8_t* rq = rows[m][1].data() + (size_t)r * c.stride;
+                    if (!(d & 0x80000000u)) hist_item_fast<QCounter>(rs, rq, off, nn, (int)w, acc, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
+                    else c.err |= hist_item<QCounter>(rs, rq, off, nn, (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, file_base);
+                    if (++since == 255) { since = 0; base_acc_spill(acc, c.bc[x]); }
                 }
-                spill();
+                base_acc_spill(acc, c.bc[x]);
             }
         }
         if (cur_slot >= 0) flush(c, cur_slot);
@@ -192,6 +197,10 @@ extern "C" {
 int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r2, snk_read_result* out1,
                     snk_read_result* out2, uint64_t* stats, uint64_t first, uint32_t* err, int tile_r, int grid, int qb_override)
 {
+    // flush_every: the kernel flushes its 16-bit cells before kQCounterMax records; tests shrink it via the environment
+    uint32_t flush_every = kQCounterMax;
+    if (const char* fe = getenv("SNK_CORETEST_FLUSH_EVERY")) flush_every = (uint32_t)atoi(fe);
+
     Ctx c;
     prepare_params(*p, c.P);
     if (qb_override >= 0) c.P.qb = qb_override;
@@ -199,17 +208,17 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     c.mates = p->is_pe ? 2 : 1;
     c.stride = r1->stride;
     c.W = c.stride / 4;
-    c.X = align_up(2u * c.mates * c.W, 32);
-    c.R = tile_r > 0 ? (uint32_t)tile_r : (uint32_t)(kThreads / c.mates);
+    c.X = cta_threads(c.mates, c.stride);
+    c.R = tile_r > 0 ? (uint32_t)tile_r : c.X / c.mates;
     const snk_batch* b[2] = {r1, r2};
     snk_read_result* out[2] = {out1, out2};
     const uint32_t chunks = c.stride / 16;
     if (grid < 1) grid = 1;
-    if (chunks <= 4) run<4>(c, b, out, first, grid);
-    else if (chunks <= 7) run<7>(c, b, out, first, grid);
-    else if (chunks <= 10) run<10>(c, b, out, first, grid);
-    else if (chunks <= 16) run<16>(c, b, out, first, grid);
-    else run<63>(c, b, out, first, grid);
+    if (chunks <= 4) run<4>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 7) run<7>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 10) run<10>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 16) run<16>(c, b, out, first, grid, flush_every);
+    else run<63>(c, b, out, first, grid, flush_every);
     *err |= c.err;
     return 0;
 }
