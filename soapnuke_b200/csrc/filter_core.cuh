@@ -319,7 +319,7 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
 {
     constexpr int NW = (MAXC + 1) / 2;          // 32 bases per plane word
     uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
-    uint32_t accC = 0, accG = 0, accT = 0, accN = 0, viol = 0;
+    uint32_t accA = 0, accN = 0, viol = 0;
     uint32_t accLow = 0, qsum = 0, qviol = 0, qover = 0;
     const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
     const bool want_polyx = P.polyX_num != -1;
@@ -351,10 +351,8 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
                     const uint32_t f = w & 0xDFDFDFDFu;                  // fold case
                     const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
                     const uint32_t isT = ~m1 & m2 & ~m3;                 // bit0 lanes only where it matters
-                    accN += m3;
-                    accC += m1 & ~m2;
-                    accG += m1 & m2 & ~m3;
-                    accT += isT & 0x01010101u;
+                    accN += m3;                                          // only N and A feed predicates (n_ratio, highA)
+                    accA += (f >> 6) & ~(m1 | m2 | m3) & 0x01010101u;
                     // exact membership in {A,C,G,T,N} after folding: bits 7..5 == 010, bit4 == isT,
                     // bit0 == !(isT|N), N implies bits 2,1 set
                     uint32_t v = (f ^ 0x40404040u) & 0xE0E0E0E0u;
@@ -405,8 +403,7 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     if (viol) flags |= RF_BAD_BASE;
     if (qviol) flags |= RF_BAD_QUAL;
     if ((qover & 0x80808080u) || qviol) flags |= RF_QSLOW;
-    const int nN = (int)bytesum(accN), nC = (int)bytesum(accC), nG = (int)bytesum(accG), nT = (int)bytesum(accT);
-    const int nA = len - nN - nC - nG - nT;
+    const int nN = (int)bytesum(accN), nA = (int)bytesum(accA);
     const int nLow = (int)bytesum(accLow);
     const int total_q = (int)qsum - len * P.phred;
     const float flen = (float)len;
@@ -585,21 +582,14 @@ SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int
     if (nvalid <= 0) return;
     uint32_t s, q;
     hist_load(seq, qual, off, w, s, q);
-    if (nvalid >= 4) {
-        base_acc_add(acc, s);
+    // one straight-line path for full and partial words: a divergent branch here would make every
+    // warp that holds a record's last (partial) word issue the whole body twice
+    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+    base_acc_add(acc, s & mask);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
-            *cell += 1;
-        }
-    } else {
-        base_acc_add(acc, s & ((1u << (8 * nvalid)) - 1u));
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            if (j < nvalid) {
-                CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
-                *cell += 1;
-            }
+    for (int j = 0; j < 4; j++) {
+        CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+        if (j < nvalid) *cell += 1;
     }
 }
 
