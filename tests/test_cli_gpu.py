@@ -1,0 +1,112 @@
+"""GPU tier, end to end: the drop-in CLI (soapnuke_b200/bin/SOAPnuke filter ...) against the
+unmodified reference binary (oracle/_ref/SOAPnuke) on the same FASTQ files and flags: decompressed
+clean FASTQ and every report file must be byte-identical. Falls back to the committed golden
+outputs when the reference binary is not available on the box."""
+import filecmp
+import glob
+import gzip
+import json
+import os
+import shutil
+import subprocess
+
+import pytest
+
+import oracle_py as orc
+from helpers import A1, A2, CFG2_FLAGS, ROOT, synth
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    from soapnuke_b200 import build
+    build.build_all()
+    assert os.path.exists(CLI)
+    return CLI
+
+
+def read_maybe_gz(path):
+    return gzip.open(path).read() if path.endswith(".gz") else open(path, "rb").read()
+
+
+def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None):
+    w = os.path.join(str(tmp), name)
+    os.makedirs(w)
+    d = synth.gen_pairs(n, L=L, seed=abs(hash(name)) % 100000, se=not pe, **(gkw or {}))
+    ext_in = ".fq.gz" if gz_in else ".fq"
+    ext_out = ".fq.gz" if gz_out else ".fq"
+    synth.write_fastq(f"{w}/r1{ext_in}", d["seq1"], d["qual1"], d["len1"], 1, gz=gz_in)
+    base = ["-1", f"{w}/r1{ext_in}", "-C", "c1" + ext_out, "-T", str(T)]
+    if pe:
+        synth.write_fastq(f"{w}/r2{ext_in}", d["seq2"], d["qual2"], d["len2"], 2, gz=gz_in)
+        base += ["-2", f"{w}/r2{ext_in}", "-D", "c2" + ext_out]
+    if patch:
+        open(f"{w}/cfg.txt", "w").write(f"patch={patch}\n")
+        base += ["-c", f"{w}/cfg.txt"]
+    r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags)
+    assert r.returncode == 0, r.stderr.decode()
+    e = dict(os.environ)
+    e.update(env or {})
+    m = subprocess.run([cli, "filter"] + base + ["-o", f"{w}/mine"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=600)
+    assert m.returncode == 0, m.stderr.decode()
+    for mate in (1, 2) if pe else (1,):
+        a = read_maybe_gz(f"{w}/ref/c{mate}{ext_out}")
+        b = read_maybe_gz(f"{w}/mine/c{mate}{ext_out}")
+        assert a == b, f"{name}: clean fq{mate} differs ({len(a)} vs {len(b)} bytes)"
+    reports = sorted(glob.glob(f"{w}/ref/*.txt"))
+    assert len(reports) == (10 if pe else 6)
+    for f in reports:
+        assert filecmp.cmp(f, f"{w}/mine/{os.path.basename(f)}", shallow=False), f"{name}: {os.path.basename(f)} differs"
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
+@pytest.mark.parametrize("case", [
+    dict(name="pe_cfg2_plain_T1", pe=True, n=30000, L=150, T=1, flags=CFG2_FLAGS),
+    dict(name="pe_cfg2_plain_T4_multicycle", pe=True, n=30000, L=150, T=4, flags=CFG2_FLAGS, patch=25),
+    dict(name="pe_cfg2_gz_T3", pe=True, n=20000, L=150, T=3, flags=CFG2_FLAGS, patch=40, gz_in=True, gz_out=True),
+    dict(name="pe_discard_small_batches", pe=True, n=20000, L=100, T=2, flags=["-f", A1, "-r", A2], env={"SNK_BATCH_READS": "3000"}),
+    dict(name="pe_polyg250", pe=True, n=8000, L=250, T=2, flags=["-f", A1, "-r", A2, "-J", "-g", "10"], gkw=dict(polyg_frac=0.3)),
+    dict(name="pe_varlen_hardtrim", pe=True, n=12000, L=120, T=2, flags=["-f", A1, "-r", A2, "-J", "-t", "3,2,4,1"], gkw=dict(var_len=True), patch=30),
+    dict(name="se_default", pe=False, n=30000, L=150, T=1, flags=[]),
+    dict(name="se_adapter_T4", pe=False, n=30000, L=100, T=4, flags=["-f", A1, "-J", "-g", "10"], patch=11, gz_in=True),
+], ids=lambda c: c["name"])
+def test_cli_matches_reference_binary(cli, tmp_path, case):
+    run_both(cli, tmp_path, **case)
+
+
+def test_cli_reproduces_golden_outputs(cli, tmp_path):
+    golden = os.path.join(ROOT, "tests", "golden")
+    for name in sorted(os.listdir(golden)):
+        gd = os.path.join(golden, name)
+        if not os.path.isdir(gd):
+            continue
+        meta = json.load(open(os.path.join(gd, "case.json")))
+        w = tmp_path / name
+        w.mkdir()
+        args = ["-1", str(w / "r1.fq"), "-C", "c1.fq", "-o", str(w / "out"), "-T", str(meta["threads"])]
+        open(w / "r1.fq", "wb").write(gzip.open(os.path.join(gd, "r1.fq.gz")).read())
+        if meta["pe"]:
+            open(w / "r2.fq", "wb").write(gzip.open(os.path.join(gd, "r2.fq.gz")).read())
+            args += ["-2", str(w / "r2.fq"), "-D", "c2.fq"]
+        if meta["patch_size"]:
+            open(w / "cfg.txt", "w").write(f"patch={meta['patch_size']}\n")
+            args += ["-c", str(w / "cfg.txt")]
+        m = subprocess.run([cli, "filter"] + args + meta["flags"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        assert m.returncode == 0, m.stderr.decode()
+        for mate in (1, 2) if meta["pe"] else (1,):
+            assert open(w / "out" / f"c{mate}.fq", "rb").read() == gzip.open(os.path.join(gd, f"c{mate}.fq.gz")).read(), f"{name}: clean fq{mate}"
+        for f in glob.glob(os.path.join(gd, "*.txt")):
+            assert filecmp.cmp(f, str(w / "out" / os.path.basename(f)), shallow=False), f"{name}: {os.path.basename(f)}"
+
+
+def test_cli_error_convention(cli, tmp_path):
+    """Errors print `Error:...` and exit(1), like the reference (e.g. unrecognized base)."""
+    d = synth.gen_pairs(2000, L=100, seed=5, se=True)
+    d["seq1"][100, 5] = ord("X")
+    synth.write_fastq(str(tmp_path / "bad.fq"), d["seq1"], d["qual1"], d["len1"], 1)
+    m = subprocess.run([cli, "filter", "-1", str(tmp_path / "bad.fq"), "-C", "c.fq", "-o", str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert m.returncode == 1 and b"Error:unrecognized sequence" in m.stderr
+    m = subprocess.run([cli, "filter", "-C", "c.fq", "-o", str(tmp_path / "o")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert m.returncode == 1 and b"Error:input fastq1 is required" in m.stderr
