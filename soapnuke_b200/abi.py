@@ -154,8 +154,18 @@ def ref_output_order(n, threads_requested, nprocs=None, patch_size=None, gz_inpu
                 label = n // cyc            # flushed at EOF (peprocess.cpp:2166,2277)
             keyed.append((label, i, s0, s1))
     keyed.sort(key=lambda k: (k[0], k[1], k[2]))
+    # Final concat pass (peprocess.cpp:2957-2966): in the LAST cycle the temp files are appended worker
+    # by worker and the loop stops at the first worker that has no file for that cycle. A worker behind
+    # such a gap loses its last-cycle file: with plain PE input that is the mislabelled batch before the
+    # last cycle boundary whenever the input ends before worker T-2's block of the final cycle.
+    # The reads are still counted in the clean statistics; they are just never written.
+    last_label = max((k[0] for k in keyed), default=0)
+    have = {k[1] for k in keyed if k[0] == last_label}
+    first_gap = next((i for i in range(t) if i not in have), t)
     order = []
-    for _, _, s0, s1 in keyed:
+    for label, i, s0, s1 in keyed:
+        if label == last_label and i > first_gap:
+            continue
         order.extend(range(s0, s1))
     return order
 

@@ -489,8 +489,18 @@ void FilterRun::writer()
         next++;
         free_q_.push(b);
     }
+    // End of input. The reference's final concat pass (peprocess.cpp:2957-2966) walks the workers of
+    // the last cycle in order and stops at the first one without a temp file for it; the deferred
+    // batch sits in the LAST worker's file, so it is silently dropped (while still counted in the
+    // clean statistics) whenever the input ends at or before worker T-2's block of the final cycle.
+    // Reproduced for byte parity; SNK_KEEP_DEFERRED=1 writes those records instead of losing them.
+    bool drop = false;
+    if (reorder_ && total_reads_ >= cyc_ && !getenv("SNK_KEEP_DEFERRED")) {
+        const uint64_t into_last = total_reads_ - (total_reads_ / cyc_) * cyc_;
+        drop = into_last <= (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 2);
+    }
     for (int m = 0; m < mates_; m++) {
-        fwrite(pending_deferred_[m].data(), 1, pending_deferred_[m].size(), out[m]);
+        if (!drop) fwrite(pending_deferred_[m].data(), 1, pending_deferred_[m].size(), out[m]);
         if (fclose(out[m]) != 0) die("cannot write to the file," + names[m]);
     }
 }
