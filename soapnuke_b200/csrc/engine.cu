@@ -42,7 +42,7 @@ struct Lane {
 
 struct LaunchPlan {
     int maxc;          // template instantiation
-    uint32_t R, X, W, threads;
+    uint32_t R, X, W, threads, ntiles;
     int qb;
     size_t smem;
     int grid;
@@ -66,16 +66,25 @@ struct snk_engine {
 
 namespace {
 
-template <int MAXC, int MATES>
+template <int MAXC, int MATES, int J>
 int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
 {
-    auto kern = filter_kernel<MAXC, MATES>;
+    auto kern = filter_kernel<MAXC, MATES, J>;
     static size_t smem_set = 0;               // per instantiation: raise the opt-in limit only when needed
     if (lp.smem > smem_set) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
         smem_set = kSmemLimit;
     }
-    kern<<<lp.grid, lp.threads, lp.smem, stream>>>(dp, ka);
+    // persistent grid: resident CTAs per SM (shared memory / registers / threads) x SMs
+    static int occ_threads = 0, occ_blocks = 0; static size_t occ_smem = 0;
+    if (occ_threads != (int)lp.threads || occ_smem != lp.smem) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (int)lp.threads, lp.smem));
+        occ_threads = (int)lp.threads; occ_smem = lp.smem; occ_blocks = nb < 1 ? 1 : nb;
+    }
+    const uint32_t max_grid = (uint32_t)e->num_sms * (uint32_t)occ_blocks;
+    const int grid = (int)(lp.ntiles < max_grid ? (lp.ntiles ? lp.ntiles : 1) : max_grid);
+    kern<<<grid, lp.threads, lp.smem, stream>>>(dp, ka);
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     return 0;
@@ -85,11 +94,12 @@ template <int MATES>
 int launch_mates(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
 {
     switch (lp.maxc) {
-        case 4: return launch_one<4, MATES>(e, dp, ka, lp, stream);
-        case 7: return launch_one<7, MATES>(e, dp, ka, lp, stream);
-        case 10: return launch_one<10, MATES>(e, dp, ka, lp, stream);
-        case 16: return launch_one<16, MATES>(e, dp, ka, lp, stream);
-        default: return launch_one<63, MATES>(e, dp, ka, lp, stream);
+        case 4: return launch_one<4, MATES, 2>(e, dp, ka, lp, stream);
+        case 7: return launch_one<7, MATES, 2>(e, dp, ka, lp, stream);
+        case 10: return launch_one<10, MATES, 2>(e, dp, ka, lp, stream);
+        case 16: return launch_one<16, MATES, 2>(e, dp, ka, lp, stream);
+        case 32: return launch_one<32, MATES, 4>(e, dp, ka, lp, stream);
+        default: return launch_one<63, MATES, 4>(e, dp, ka, lp, stream);
     }
 }
 
@@ -97,31 +107,29 @@ int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t fi
 {
     if (stride == 0 || stride % 16 != 0 || stride > 1008) { snk::set_error("batch stride must be a multiple of 16 in [16,1008]"); return 1; }
     const uint32_t chunks = stride / 16;
-    lp.maxc = chunks <= 4 ? 4 : chunks <= 7 ? 7 : chunks <= 10 ? 10 : chunks <= 16 ? 16 : 63;
-    lp.W = stride / 4;
+    lp.maxc = chunks <= 4 ? 4 : chunks <= 7 ? 7 : chunks <= 10 ? 10 : chunks <= 16 ? 16 : chunks <= 32 ? 32 : 63;
+    lp.W = stride / hist_j(stride);
     lp.threads = cta_threads(mates, stride);
     lp.X = lp.threads;
     int qb = e->dev.qb;
-    const uint32_t maxR = lp.threads / mates;          // one thread per read in phase A
+    const uint32_t maxR = lp.threads / (mates * kNT);  // kNT threads per read in phase A
     // Prefer a tile that lets two CTAs share an SM (latency hiding across the phase barriers);
     // fall back to one CTA per SM, then to fewer shared-memory quality bins.
+    // Largest tile (<= one read per kNT threads) whose shared-memory plan fits; if even a small tile does
+    // not fit, keep fewer quality bins in shared memory (the rest go through the checked global path).
     uint32_t R = 0;
-    int ctas_per_sm = 1;
     for (;;) {
-        const size_t half = kSmemLimit / 2 - 1024;
-        if (plan_smem(mates, maxR, stride, lp.X, qb).total <= half) { R = maxR; ctas_per_sm = 2; break; }
-        for (uint32_t r = maxR; r >= 16 && !R; r -= 16)
+        for (uint32_t r = maxR; r >= 8 && !R; r -= (r > 16 ? 8 : 4))
             if (plan_smem(mates, r, stride, lp.X, qb).total <= kSmemLimit) R = r;
         if (R) break;
         if (qb <= 0) { snk::set_error("read stride too large for the shared-memory tile"); return 1; }
-        qb = qb > 4 ? qb - 4 : 0;   // bins >= qb fall back to global atomics (hist_item checked path)
+        qb = qb > 4 ? qb - 4 : 0;
     }
     lp.R = R; lp.qb = qb;
     lp.smem = plan_smem(mates, R, stride, lp.X, qb).total;
     tm = make_tile_map(first, n, R, (uint64_t)e->params.slot_block);
-    const uint32_t max_grid = (uint32_t)e->num_sms * (uint32_t)ctas_per_sm;
-    lp.grid = (int)(tm.ntiles < max_grid ? tm.ntiles : max_grid);
-    if (lp.grid < 1) lp.grid = 1;
+    lp.ntiles = tm.ntiles;
+    lp.grid = 0;       // resolved in launch_one from the kernel's real occupancy
     return 0;
 }
 

@@ -199,24 +199,170 @@ SNK_HD bool window_decide(uint64_t M, int winlen, int budget, int seg_thr)
     return run_ok || nmis <= budget;
 }
 
-// adapter_pos for one adapter (read_filter.cpp:707-790) on 1-bit planes of the read:
-// p0/p1 = the two code bits of every base (A=0,C=1,T=2,G=3), pb = "can never equal an uppercase
-// A/C/G/T" (N, lowercase, or beyond the read end); 32 bases per word, NW+2 words each.
-// Phases 2 and 3 are one forward sweep over window offsets: offsets 0..len-A are phase-2 windows
-// (full adapter, budget adaMis, smallest accepted offset wins), offsets len-A+1..len-adaEdge are
-// the phase-3 windows (adapter prefix of length len-off hanging over the 3' end; the reference
-// scans them shortest-overlap first, so the LARGEST accepted offset wins), and phase 2 beats phase 3.
+// ------------------------------------------------------------------ phase A: kNT threads per read
+// Phase A splits one read over kNT cooperating threads (adjacent lanes). Each stage below returns
+// the calling thread's PART of the result (h = thread's index within the group); the parts are
+// merged with merge_*() - on the GPU after a lane shuffle, in the CPU replay by a plain call.
+constexpr int kNT = 2;
+
+// 0x80 in every byte lane of w that is < k (bytes are ASCII < 128, k in 1..128)
+SNK_HD uint32_t bytes_lt(uint32_t w, uint32_t k)
+{
+    return ~((w | 0x80808080u) - k * 0x01010101u) & 0x80808080u;
+}
+// bit 0 of every byte lane gathered into 4 adjacent bits
+SNK_HD uint32_t gather1(uint32_t lanes) { return ((lanes & 0x01010101u) * 0x01020408u) >> 24; }
+
+// does the low 32 bits of e contain a run of at least T set bits? (T >= 1, warp-uniform)
+SNK_HD bool has_run32(uint32_t e, int T)
+{
+    if (T > 32) return false;
+    for (int k = 1; k < T;) { const int sft = (k < T - k) ? k : T - k; e &= e >> sft; k += sft; }
+    return e != 0;
+}
+
+// Bit planes of a read, 32 bases per word: p0/p1 = the two code bits (A=0,C=1,T=2,G=3 from ASCII bits
+// 1,2), pn = N, pl = lowercase. For valid bases (p0,p1,pn,pl) identifies the byte exactly.
 template <int NW>
-SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const AdapterDev& a)
+struct ScanPart {
+    uint32_t p0[NW], p1[NW], pn[NW], pl[NW];
+    uint32_t accA, accN, accLow, qsum;      // packed 4x8-bit counts (A, N, low quality), plain quality byte sum
+    uint32_t viol, qviol, qover;            // OR flags: unrecognized base, quality < phred or >= 128, quality >= qb
+};
+template <int NW>
+SNK_HD void merge_scan(ScanPart<NW>& a, const ScanPart<NW>& b)
+{
+#pragma unroll
+    for (int k = 0; k < NW; k++) { a.p0[k] |= b.p0[k]; a.p1[k] |= b.p1[k]; a.pn[k] |= b.pn[k]; a.pl[k] |= b.pl[k]; }
+    a.accA += b.accA; a.accN += b.accN; a.accLow += b.accLow; a.qsum += b.qsum;
+    a.viol |= b.viol; a.qviol |= b.qviol; a.qover |= b.qover;
+}
+
+// stage 1: packed scan of this thread's 16-byte chunks (c % kNT == h) of the bases and qualities
+template <int MAXC>
+SNK_HD void scan_chunks(const uint8_t* seq, const uint8_t* qual, int len, const DevParams& P, int h, bool want_planes,
+                        ScanPart<(MAXC + 1) / 2>& S)
+{
+    constexpr int NW = (MAXC + 1) / 2;
+#pragma unroll
+    for (int k = 0; k < NW; k++) { S.p0[k] = 0; S.p1[k] = 0; S.pn[k] = 0; S.pl[k] = 0; }
+    S.accA = S.accN = S.accLow = S.qsum = 0;
+    S.viol = S.qviol = S.qover = 0;
+    const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
+    const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
+    const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
+#pragma unroll(MAXC <= 16 ? MAXC : 1)
+    for (int c = 0; c < MAXC; c++) {
+        if ((c % kNT) != h || 16 * c >= len) continue;
+        uint32_t c0 = 0, c1 = 0, cn = 0, cl = 0;
+        const U4 sv = load16(seq + 16 * c);
+        const U4 qv = load16(qual + 16 * c);
+        const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int nvalid = len - (16 * c + 4 * k);
+            if (nvalid > 0) {
+                const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+                const uint32_t w = sw[k] & mask;
+                const uint32_t f = w & 0xDFDFDFDFu;                  // fold case
+                const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
+                const uint32_t isT = ~m1 & m2 & ~m3;                 // bit0 lanes only where it matters
+                S.accN += m3;                                        // only N and A feed predicates (n_ratio, highA)
+                S.accA += (f >> 6) & ~(m1 | m2 | m3) & 0x01010101u;
+                // exact membership in {A,C,G,T,N} after folding: bits 7..5 == 010, bit4 == isT,
+                // bit0 == !(isT|N), N implies bits 2,1 set
+                uint32_t v = (f ^ 0x40404040u) & 0xE0E0E0E0u;
+                v |= ((f >> 4) ^ isT) & 0x01010101u;
+                v |= (f ^ ~(isT | m3)) & 0x01010101u;
+                v |= m3 & ~(m1 & m2);
+                S.viol |= v & mask;
+                if (want_planes) {
+                    c0 |= gather1(m1) << (4 * k);
+                    c1 |= gather1(m2) << (4 * k);
+                    cn |= gather1(m3) << (4 * k);
+                    cl |= gather1(w >> 5) << (4 * k);
+                }
+                const uint32_t q = qw[k] & mask;
+                const uint32_t qfill = q | (~mask & 0x7F7F7F7Fu);     // padding lanes read as 0x7F: never low, never < phred
+                S.qsum += bytesum(q);
+                S.qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
+                S.qover |= ~bytes_lt(q, over_k) & 0x80808080u;        // masked lanes are 0: never over
+                if (!low_never) S.accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
+            }
+        }
+        if (want_planes) {
+            const int sh = 16 * (c & 1);
+            S.p0[c >> 1] |= c0 << sh; S.p1[c >> 1] |= c1 << sh; S.pn[c >> 1] |= cn << sh; S.pl[c >> 1] |= cl << sh;
+        }
+    }
+}
+
+// mask of the bases of plane word k that lie inside the read
+SNK_HD uint32_t plane_valid(int len, int k)
+{
+    const int nb = len - 32 * k;
+    return nb >= 32 ? 0xFFFFFFFFu : (nb <= 0 ? 0u : ((1u << nb) - 1u));
+}
+
+// stage 2 (on merged planes): is there a run of >= polyX_num identical consecutive bases?
+// (read_filter.cpp:255-268: contig_base >= polyX_num; the first base is compared with 'Q')
+template <int NW>
+SNK_HD bool polyx_hit(const ScanPart<NW>& S, int len, int polyX_num)
+{
+    const int runT = polyX_num - 1;         // run of "same as previous base" bits needed
+    if (runT <= 0) return true;
+    int cur = 0;
+    bool hit = false;
+    uint32_t c0 = 0, c1 = 0, cn = 0, cl = 0;        // bit 31 of the previous word
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int k = 0; k < NW; k++) {
+        const uint32_t vm = plane_valid(len, k);
+        if (vm == 0) break;
+        uint32_t diff = (S.p0[k] ^ ((S.p0[k] << 1) | c0)) | (S.p1[k] ^ ((S.p1[k] << 1) | c1)) |
+                        (S.pn[k] ^ ((S.pn[k] << 1) | cn)) | (S.pl[k] ^ ((S.pl[k] << 1) | cl));
+        if (k == 0) diff |= 1u;                         // first base never equals the initial 'Q'
+        const uint32_t e = ~diff & vm;
+        c0 = S.p0[k] >> 31; c1 = S.p1[k] >> 31; cn = S.pn[k] >> 31; cl = S.pl[k] >> 31;
+        if (e == vm && vm == 0xFFFFFFFFu) { cur += 32; hit = hit || cur >= runT; }
+        else {
+            const int nb = 32 - clz32(vm);              // valid bases in this word (vm is a low mask, != 0)
+            const int lead = ctz32(~e);
+            hit = hit || (cur + lead >= runT) || has_run32(e, runT);
+            cur = (e == vm) ? cur + nb : clz32(~(e << (32 - nb)));
+        }
+    }
+    return hit;
+}
+
+// stage 3: adapter_pos for one adapter (read_filter.cpp:707-790), this thread's share of the windows.
+// p0/p1 = code planes, pb = "can never equal an uppercase A/C/G/T" (N, lowercase, or beyond the read
+// end); NW+2 words each (pad words: codes 0, pb all ones).
+// Phases 2 and 3 are one forward sweep over window offsets: offsets 0..len-A are phase-2 windows
+// (full adapter, budget adaMis, smallest accepted offset wins), offsets len-A+1..len-adaEdge are the
+// phase-3 windows (adapter prefix of length len-off hanging over the 3' end; the reference scans them
+// shortest-overlap first, so the LARGEST accepted offset wins), and phase 2 beats phase 3.
+struct AdaPart { int hit1, pos2, pos3; };
+SNK_HD void merge_ada(AdaPart& a, const AdaPart& b)
+{
+    a.hit1 |= b.hit1;
+    if (b.pos2 >= 0 && (a.pos2 < 0 || b.pos2 < a.pos2)) a.pos2 = b.pos2;
+    if (b.pos3 > a.pos3) a.pos3 = b.pos3;
+}
+SNK_HD int ada_result(const AdaPart& a) { return a.hit1 ? 0 : (a.pos2 >= 0 ? a.pos2 : a.pos3); }
+
+template <int NW>
+SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const AdapterDev& a, int h, AdaPart& out)
 {
     const int A = a.len;
     const uint64_t a0 = ((uint64_t)a.a0_hi << 32) | a.a0_lo, a1 = ((uint64_t)a.a1_hi << 32) | a.a1_lo;
+    out.hit1 = 0; out.pos2 = -1; out.pos3 = -1;
     // phase 1: adapter starts r1 = 1..5 bases before the read; read window is bases [0, A-r1)
     {
         const uint64_t r0 = ((uint64_t)p0[1] << 32) | p0[0], r1w = ((uint64_t)p1[1] << 32) | p1[0], rb = ((uint64_t)pb[1] << 32) | pb[0];
-        bool hit = false;
 #pragma unroll
         for (int r1 = 1; r1 <= 5; r1++) {
+            if ((r1 % kNT) != h) continue;
             const uint64_t M = (r0 ^ (a0 >> r1)) | (r1w ^ (a1 >> r1)) | rb;
             const int budget = a.budget1[r1 - 1];
             const int nb = budget < 0 ? 0 : budget;
@@ -224,18 +370,16 @@ SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, c
             uint32_t pm = a.pre_mask;
             if (wl < 32) pm &= wl <= 0 ? 0u : ((1u << wl) - 1u);
             if ((int)popc32((uint32_t)M & pm) > nb) continue;
-            hit = hit || window_decide(M, wl, budget, a.seg_thr);
+            if (window_decide(M, wl, budget, a.seg_thr)) out.hit1 = 1;
         }
-        if (hit) return 0;
     }
     const int last2 = len - A, last3 = len - a.edge;
     const int nb2 = a.budget2 < 0 ? 0 : a.budget2;
     const uint32_t pm2 = a.pre_mask;
-    int pos2 = -1, pos3 = -1;
-    // ---- phase 2: offsets 0..last2, first accepted offset wins
+    // ---- phase 2: offsets 0..last2, first accepted offset wins (words kw % kNT == h are mine)
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
-        if (32 * kw <= last2 && pos2 < 0) {
+        if ((kw % kNT) == h && 32 * kw <= last2 && out.pos2 < 0) {
             const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
             const int send = (last2 - 32 * kw) >= 31 ? 32 : (last2 - 32 * kw + 1);
             for (int sft = 0; sft < send; sft++) {
@@ -248,16 +392,15 @@ SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, c
                 // exact decision over the whole window
                 const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
                                     funnel_r(pb[kw + 1], pb[kw + 2], sft);
-                if (window_decide(((uint64_t)xh << 32) | x, A, a.budget2, a.seg_thr)) { pos2 = 32 * kw + sft; break; }
+                if (window_decide(((uint64_t)xh << 32) | x, A, a.budget2, a.seg_thr)) { out.pos2 = 32 * kw + sft; break; }
             }
         }
     }
-    if (pos2 >= 0) return pos2;
     // ---- phase 3: offsets last2+1..last3 (window = adapter prefix of length len-off), last accepted wins
     const int first3 = last2 + 1 < 0 ? 0 : last2 + 1;
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
-        if (32 * kw + 31 >= first3 && 32 * kw <= last3) {
+        if ((kw % kNT) == h && 32 * kw + 31 >= first3 && 32 * kw <= last3) {
             const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
             const int s0 = first3 > 32 * kw ? first3 - 32 * kw : 0;
             const int send = (last3 - 32 * kw) >= 31 ? 32 : (last3 - 32 * kw + 1);
@@ -273,15 +416,14 @@ SNK_HD int adapter_pos_planes(int len, const uint32_t* p0, const uint32_t* p1, c
                 if ((int)popc32(x & pm) > nb) continue;
                 const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
                                     funnel_r(pb[kw + 1], pb[kw + 2], sft);
-                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) pos3 = 32 * kw + sft;
+                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) out.pos3 = 32 * kw + sft;
             }
         }
     }
-    return pos3;
 }
 
 // byte-wise adapter_pos: adapters with N / lowercase / length > 64, and reads shorter than the
-// adapter (windows that start before the read). Same phase order as the reference.
+// adapter (windows that start before the read). Same phase order as the reference. One thread does it.
 SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
 {
     const int A = a.len;
@@ -296,159 +438,60 @@ SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
     return -1;
 }
 
-// ------------------------------------------------------------------ per-read scan
-// Packed 4-in-a-word helpers. Bytes are ASCII (< 128).
-// 0x80 in every byte lane of w that is < k (k in 1..128)
-SNK_HD uint32_t bytes_lt(uint32_t w, uint32_t k)
+// stage 4: end scans of fastq_trim (read_filter.cpp:390-429, 454-461): thread 0 scans the head,
+// thread kNT-1 the tail and the polyG run
+struct TrimPart { int hix, tix, ng; };
+SNK_HD void merge_trim(TrimPart& a, const TrimPart& b) { a.hix += b.hix; a.tix += b.tix; a.ng += b.ng; }
+SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, const DevParams& P, int h, TrimPart& t)
 {
-    return ~((w | 0x80808080u) - k * 0x01010101u) & 0x80808080u;
-}
-// bit 0 of every byte lane gathered into 4 adjacent bits
-SNK_HD uint32_t gather1(uint32_t lanes) { return ((lanes & 0x01010101u) * 0x01020408u) >> 24; }
-
-// does the low `nbits` (<= 16) of e contain a run of at least T set bits? (T >= 1, warp-uniform)
-SNK_HD bool has_run16(uint32_t e, int T)
-{
-    if (T > 16) return false;
-    for (int k = 1; k < T;) { const int sft = (k < T - k) ? k : T - k; e &= e >> sft; k += sft; }
-    return e != 0;
-}
-
-template <int MAXC>
-SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P, ReadInfo& R)
-{
-    constexpr int NW = (MAXC + 1) / 2;          // 32 bases per plane word
-    uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
-    uint32_t accA = 0, accN = 0, viol = 0;
-    uint32_t accLow = 0, qsum = 0, qviol = 0, qover = 0;
-    const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
-    const bool want_polyx = P.polyX_num != -1;
-    const bool want_planes = P.n_adapters[mate] > 0;
-    const int runT = P.polyX_num - 1;       // contig_base >= polyX_num  <=>  a run of >= polyX_num-1 "same as previous" bits
-    bool polyx_hit = want_polyx && runT <= 0;
-    int cur_run = 0;
-    uint32_t prev_byte = 'Q';               // read_filter.cpp:255 last_char('Q')
-    const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
-    const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
-#pragma unroll
-    for (int i = 0; i < NW + 2; i++) { p0[i] = 0; p1[i] = 0; pb[i] = 0xFFFFFFFFu; }
-
-#pragma unroll(MAXC <= 16 ? MAXC : 1)
-    for (int c = 0; c < MAXC; c++) {
-        uint32_t c0 = 0, c1 = 0, cb = 0xFFFFu, ew = 0;
-        if (16 * c < len) {
-            cb = 0;
-            const U4 sv = load16(seq + 16 * c);
-            const U4 qv = load16(qual + 16 * c);
-            const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
-            const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int nvalid = len - (16 * c + 4 * k);
-                if (nvalid > 0) {
-                    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-                    const uint32_t w = sw[k] & mask;
-                    const uint32_t f = w & 0xDFDFDFDFu;                  // fold case
-                    const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
-                    const uint32_t isT = ~m1 & m2 & ~m3;                 // bit0 lanes only where it matters
-                    accN += m3;                                          // only N and A feed predicates (n_ratio, highA)
-                    accA += (f >> 6) & ~(m1 | m2 | m3) & 0x01010101u;
-                    // exact membership in {A,C,G,T,N} after folding: bits 7..5 == 010, bit4 == isT,
-                    // bit0 == !(isT|N), N implies bits 2,1 set
-                    uint32_t v = (f ^ 0x40404040u) & 0xE0E0E0E0u;
-                    v |= ((f >> 4) ^ isT) & 0x01010101u;
-                    v |= (f ^ ~(isT | m3)) & 0x01010101u;
-                    v |= m3 & ~(m1 & m2);
-                    viol |= v & mask;
-                    if (want_planes) {
-                        c0 |= gather1(m1) << (4 * k);
-                        c1 |= gather1(m2) << (4 * k);
-                        cb |= gather1((w >> 5) | m3 | ~mask) << (4 * k);   // lowercase, N, or past the end
-                    }
-                    if (want_polyx) {
-                        const uint32_t x = w ^ ((w << 8) | prev_byte);
-                        const uint32_t z = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);   // 0x80 where byte == previous
-                        ew |= gather1((z >> 7) & mask) << (4 * k);
-                        prev_byte = (sw[k] >> 24);
-                    }
-                    // qualities
-                    const uint32_t q = qw[k] & mask;
-                    const uint32_t qfill = q | (~mask & 0x7F7F7F7Fu);     // padding lanes read as 0x7F: never low, never < phred
-                    qsum += bytesum(q);
-                    qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
-                    qover |= ~bytes_lt(q, over_k);                            // masked lanes are 0: never over
-                    if (!low_never) accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
-                } else if (want_planes) {
-                    cb |= 0xFu << (4 * k);
-                }
-            }
-            if (want_polyx && !polyx_hit) {
-                const int nb = (len - 16 * c) >= 16 ? 16 : (len - 16 * c);
-                const uint32_t full = (1u << nb) - 1u;
-                if (ew == full) { cur_run += nb; polyx_hit = cur_run >= runT; }
-                else {
-                    const int lead = ctz32(~ew);
-                    polyx_hit = (cur_run + lead >= runT) || has_run16(ew, runT);
-                    cur_run = clz32(~(ew << (32 - nb)));
-                }
-            }
-        }
-        if (want_planes) {
-            if (c & 1) { p0[c >> 1] |= c0 << 16; p1[c >> 1] |= c1 << 16; pb[c >> 1] = (pb[c >> 1] & 0xFFFFu) | (cb << 16); }
-            else { p0[c >> 1] = c0; p1[c >> 1] = c1; pb[c >> 1] = cb | 0xFFFF0000u; }
-        }
+    t.hix = t.tix = t.ng = 0;
+    if (!P.trimming) return;
+    if (P.has_lq && h == 0)
+        for (int ix = 0; ix < P.bad_head_max && ix < len; ix++) { if ((int)qual[ix] - P.phred < P.bad_head_thr) t.hix++; else break; }
+    if (h == kNT - 1) {
+        if (P.has_lq)
+            for (int ix = 0; ix < P.bad_tail_max && ix < len; ix++) { if ((int)qual[len - ix - 1] - P.phred < P.bad_tail_thr) t.tix++; else break; }
+        if (P.polyG_tail != -1)
+            for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') t.ng++; else break; }
     }
+}
 
+// stage 5: everything merged -> ReadInfo (predicates of stat_read, read_filter.cpp:289-311, and the
+// cut arithmetic of fastq_trim, read_filter.cpp:383-468)
+template <int NW>
+SNK_HD void finish_read(const ScanPart<NW>& S, bool polyx, int ada_pos, const TrimPart& T, int len, int mate,
+                        const DevParams& P, ReadInfo& R)
+{
     uint16_t flags = 0;
-    if (viol) flags |= RF_BAD_BASE;
-    if (qviol) flags |= RF_BAD_QUAL;
-    if ((qover & 0x80808080u) || qviol) flags |= RF_QSLOW;
-    const int nN = (int)bytesum(accN), nA = (int)bytesum(accA);
-    const int nLow = (int)bytesum(accLow);
-    const int total_q = (int)qsum - len * P.phred;
+    if (S.viol) flags |= RF_BAD_BASE;
+    if (S.qviol) flags |= RF_BAD_QUAL;
+    if (S.qover || S.qviol) flags |= RF_QSLOW;
+    const int nN = (int)bytesum(S.accN), nA = (int)bytesum(S.accA), nLow = (int)bytesum(S.accLow);
+    const int total_q = (int)S.qsum - len * P.phred;
     const float flen = (float)len;
-    // read_filter.cpp:290-311: float(count)/size with IEEE fp32 division
+    // float(count)/size with IEEE fp32 division
     const float n_ratio = (float)nN / flen, a_ratio = (float)nA / flen;
     const float lowq_ratio = (float)nLow / flen, mean_q = (float)total_q / flen;
     if (P.n_ratio != -1 && n_ratio >= P.n_ratio) flags |= RF_N;
     if (P.highA_ratio != -1 && a_ratio >= P.highA_ratio) flags |= RF_HIGHA;
-    if (polyx_hit) flags |= RF_POLYX;
+    if (polyx) flags |= RF_POLYX;
     if (P.low_qual_ratio != -1 && lowq_ratio >= P.low_qual_ratio) flags |= RF_LOWQ;
     if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
     if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
-
-    // adapters: first adapter in the list that hits wins (read_filter.cpp:177-188)
-    int ada_pos = -1;
-    for (int i = 0; i < P.n_adapters[mate]; i++) {
-        const AdapterDev& a = P.ada[mate][i];
-        if (a.len == 0) continue;
-        if (a.fast && len >= a.len - 1) ada_pos = adapter_pos_planes<NW>(len, p0, p1, pb, a);
-        else ada_pos = adapter_pos_bytes(seq, len, a);
-        if (ada_pos >= 0) break;
-    }
     int adacut = -1;
     if (ada_pos >= 0) { flags |= RF_ADAPTER; adacut = len - ada_pos; }
-
-    // fastq_trim (read_filter.cpp:338-471)
     int head_hd = -1, head_lq = -1, tail_hd = -1, tail_lq = -1;
     int head_cut = 0, clean_len = len;
     if (P.trimming) {
         int hc = 0, tc = 0;
         if (P.has_hard) { head_hd = P.hard_head[mate]; tail_hd = P.hard_tail[mate]; hc = head_hd; tc = tail_hd; }
         if (P.has_lq) {
-            int hix = 0, tix = 0;
-            for (int ix = 0; ix < P.bad_head_max && ix < len; ix++) { if ((int)qual[ix] - P.phred < P.bad_head_thr) hix++; else break; }
-            for (int ix = 0; ix < P.bad_tail_max && ix < len; ix++) { if ((int)qual[len - ix - 1] - P.phred < P.bad_tail_thr) tix++; else break; }
-            head_lq = hix; tail_lq = tix;
-            if (hix > hc) hc = hix;
-            if (tix > tc) tc = tix;
+            head_lq = T.hix; tail_lq = T.tix;
+            if (T.hix > hc) hc = T.hix;
+            if (T.tix > tc) tc = T.tix;
         }
         if (P.ada_trim && adacut > 0 && adacut > tc) tc = adacut;
-        if (P.polyG_tail != -1) {
-            int ng = 0;
-            for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') ng++; else break; }
-            if ((float)ng >= P.polyG_tail && ng > tc) tc = ng;
-        }
+        if (P.polyG_tail != -1 && (float)T.ng >= P.polyG_tail && T.ng > tc) tc = T.ng;
         if (hc + tc > len) { head_cut = 0; clean_len = 0; }
         else { head_cut = hc; clean_len = len - hc - tc; }
     }
@@ -458,6 +501,40 @@ SNK_HD void scan_read(const uint8_t* seq, const uint8_t* qual, int len, int mate
     R.tail_hdcut = (int16_t)tail_hd; R.tail_lqcut = (int16_t)tail_lq;
     R.adacut_pos = (int16_t)adacut;
     R.flags = flags;
+}
+
+// Exchange policy for the CPU replay / documentation of the protocol: given a callable that returns
+// thread h's part, run all kNT parts and merge them. The kernel does the same with lane shuffles.
+template <int MAXC>
+SNK_HD void scan_read_serial(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P, ReadInfo& R)
+{
+    constexpr int NW = (MAXC + 1) / 2;
+    const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
+    ScanPart<NW> S, S2;
+    scan_chunks<MAXC>(seq, qual, len, P, 0, want_planes, S);
+    for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, P, h, want_planes, S2); merge_scan(S, S2); }
+    const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
+    int ada_pos = -1;
+    if (P.n_adapters[mate] > 0) {
+        uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
+        for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }
+        for (int k = NW; k < NW + 2; k++) { p0[k] = 0; p1[k] = 0; pb[k] = 0xFFFFFFFFu; }
+        for (int i = 0; i < P.n_adapters[mate]; i++) {
+            const AdapterDev& a = P.ada[mate][i];
+            if (a.len == 0) continue;
+            if (a.fast && len >= a.len - 1) {
+                AdaPart ap, ap2;
+                adapter_part<NW>(len, p0, p1, pb, a, 0, ap);
+                for (int h = 1; h < kNT; h++) { adapter_part<NW>(len, p0, p1, pb, a, h, ap2); merge_ada(ap, ap2); }
+                ada_pos = ada_result(ap);
+            } else ada_pos = adapter_pos_bytes(seq, len, a);
+            if (ada_pos >= 0) break;
+        }
+    }
+    TrimPart T, T2;
+    trim_part(seq, qual, len, P, 0, T);
+    for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, P, h, T2); merge_trim(T, T2); }
+    finish_read<NW>(S, polyx, ada_pos, T, len, mate, P, R);
 }
 
 // ------------------------------------------------------------------ discard cascade
@@ -526,15 +603,15 @@ SNK_HD void trim_stat_indices(int which, int slen, int raw_length, int head_hd, 
 }
 
 // ------------------------------------------------------------------ per-position histograms
-// One histogram item = 4 consecutive positions (one 32-bit word of the row) of one table; the
+// One histogram item = J consecutive positions of one table (J = 2, or 4 for very long reads); the
 // thread that owns an item is the only writer of its counters, so no atomics are needed.
-//   quality x position counts: shared memory, CounterT cells, index (q*4 + j) * qstride + item
-//   base x position counts:    packed 4 x 8 bit per symbol while walking a tile (BaseAcc), then
-//                              added to the owner's 20 register counters (BaseCnt) for the whole launch.
+//   quality x position counts: shared memory, CounterT cells, index (q*J + j) * qstride + item
+//   base x position counts:    packed J x 8 bit per symbol while walking a tile (BaseAcc), then
+//                              added to the owner's 5*J register counters (BaseCnt) for the whole launch.
 struct BaseAcc { uint32_t a, c, g, t, n; };
-struct BaseCnt { uint32_t v[5][4]; };      // [A,C,G,T,N][j]
+template <int J> struct BaseCnt { uint32_t v[5][J]; };      // [A,C,G,T,N][j]
 
-SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked */)
+SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked: bytes outside the item are 0 */)
 {
     const uint32_t f = s & 0xDFDFDFDFu;
     const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
@@ -545,26 +622,29 @@ SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked */)
     acc.t += ~m1 & m2 & ~m3 & 0x01010101u;
     acc.a += valid & ~(m1 | m2 | m3);
 }
-SNK_HD void base_acc_spill(BaseAcc& acc, BaseCnt& cnt)
+template <int J>
+SNK_HD void base_acc_spill(BaseAcc& acc, BaseCnt<J>& cnt)
 {
     const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
 #pragma unroll
     for (int b = 0; b < 5; b++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) cnt.v[b][j] += (packed[b] >> (8 * j)) & 0xFFu;
+        for (int j = 0; j < J; j++) cnt.v[b][j] += (packed[b] >> (8 * j)) & 0xFFu;
     acc.a = acc.c = acc.g = acc.t = acc.n = 0;
 }
 
-// Loads the item's 4 bases and 4 qualities of a record that starts at byte `off` of its row.
+// Loads the item's J bases and J qualities (low J bytes of s / q) of a record that starts at byte
+// `off` of its row; item w covers record positions J*w .. J*w+J-1.
+template <int J>
 SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, uint32_t& s, uint32_t& q)
 {
-    const int byte0 = off + 4 * w;
+    const int byte0 = off + J * w;
     const int al = byte0 & ~3, sh = 8 * (byte0 & 3);
     s = load4(seq + al); q = load4(qual + al);
-    if (sh) {                                     // record does not start on a word boundary (head trimmed)
+    if (sh + 8 * J > 32) {                        // the item straddles a word boundary
         s = funnel_r(s, load4(seq + al + 4), sh);
         q = funnel_r(q, load4(qual + al + 4), sh);
-    }
+    } else if (sh) { s >>= sh; q >>= sh; }
 }
 
 // Per-read descriptor for phase B, one 32-bit word per (table, read): record length (bits 0-9),
@@ -574,20 +654,21 @@ SNK_HD uint32_t hist_desc(int n, int off, bool slow) { return n <= 0 ? 0u : ((ui
 // Fast path: every quality of the record is known to lie inside the shared-memory bins (RF_QSLOW
 // clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at
 // qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
-template <typename CounterT>
+template <typename CounterT, int J>
 SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,
                            uint8_t* qcells, int cell0, int jstep, int bstep)
 {
-    const int nvalid = n - 4 * w;
+    const int nvalid = n - J * w;
     if (nvalid <= 0) return;
     uint32_t s, q;
-    hist_load(seq, qual, off, w, s, q);
-    // one straight-line path for full and partial words: a divergent branch here would make every
-    // warp that holds a record's last (partial) word issue the whole body twice
+    hist_load<J>(seq, qual, off, w, s, q);
+    // one straight-line path for full and partial items: a divergent branch here would make every
+    // warp that holds a record's last (partial) item issue the whole body twice
     const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-    base_acc_add(acc, s & mask);
+    const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
+    base_acc_add(acc, s & mask & jmask);
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < J; j++) {
         CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
         if (j < nvalid) *cell += 1;
     }
@@ -595,24 +676,25 @@ SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int
 
 // Checked path: qualities may fall outside [0,qb). Bins not kept in shared memory go straight to
 // the slot's global table; anything outside [0,SNK_QBINS) raises the error flag. Returns error bits.
-template <typename CounterT>
+template <typename CounterT, int J>
 SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
                           BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */)
 {
-    const int nvalid = n - 4 * w;
+    const int nvalid = n - J * w;
     if (nvalid <= 0) return 0;
     const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+    const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
     uint32_t s, q;
-    hist_load(seq, qual, off, w, s, q);
-    base_acc_add(acc, s & mask);
+    hist_load<J>(seq, qual, off, w, s, q);
+    base_acc_add(acc, s & mask & jmask);
     uint32_t err = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < J; j++) {
         if (j < nvalid) {
             const int qq = (int)((q >> (8 * j)) & 0xFFu) - phred;
-            if ((unsigned)qq < (unsigned)qb) qhist[(qq * 4 + j) * qstride] += 1;
+            if ((unsigned)qq < (unsigned)qb) qhist[(qq * J + j) * qstride] += 1;
             else if ((unsigned)qq < (unsigned)SNK_QBINS && file_base) {
-                unsigned long long* cell = file_base + SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + qq;
+                unsigned long long* cell = file_base + SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + qq;
 #ifdef __CUDA_ARCH__
                 atomicAdd(cell, 1ull);
                 if (qq >= 20) atomicAdd(file_base + SNK_FILE_GS_OFF + SNK_GS_Q20, 1ull);
@@ -627,10 +709,6 @@ SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int 
     }
     return err;
 }
-
-} // namespace snkcore
-
-namespace snkcore {
 
 // ------------------------------------------------------------------ tile decomposition
 // A launch covers reads [first, first+n) of the input. Reads are cut into tiles of at most R reads

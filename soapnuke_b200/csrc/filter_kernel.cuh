@@ -17,16 +17,21 @@ namespace snkcore {
 typedef uint16_t QCounter;                 // shared-memory quality counters; flushed before they can wrap
 constexpr uint32_t kQCounterMax = 65535;
 
-// CTA shape: one thread per histogram item (4 positions of one table), which is also the number of
-// reads a tile holds (threads / mates), so phase A and phase B both keep every thread busy.
+// CTA shape: one thread per histogram item (J positions of one table); a tile holds
+// threads / (mates * kNT) reads or pairs, so that phase A (kNT threads per read) and phase B (one
+// thread per item) both keep every thread busy. PE150: 320 threads, 80-pair tiles, 2 CTAs per SM.
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+__host__ __device__ inline int hist_j(uint32_t stride) { return stride <= 256 ? 2 : 4; }
 __host__ __device__ inline uint32_t cta_threads(int mates, uint32_t stride)
 {
-    uint32_t t = align_up(2u * mates * (stride / 4), 32);
+    uint32_t t = align_up(2u * mates * (stride / hist_j(stride)), 32);
     return t < 64 ? 64 : t;
 }
-template <int MAXC, int MATES> struct KernelShape {
-    static constexpr int kMaxThreads = ((2 * MATES * MAXC * 4 + 31) / 32 * 32) < 64 ? 64 : ((2 * MATES * MAXC * 4 + 31) / 32 * 32);
+template <int MAXC, int MATES, int J> struct KernelShape {
+    static constexpr int kItems = 2 * MATES * (16 * MAXC) / J;
+    static constexpr int kMaxThreads = ((kItems + 31) / 32 * 32) < 64 ? 64 : ((kItems + 31) / 32 * 32);
+    // register budget: keep 640 threads (20 warps) resident per SM whenever the CTA is small enough
+    static constexpr int kMinBlocks = kMaxThreads <= 320 ? 640 / kMaxThreads : 1;
 };
 
 struct KernelArgs {
@@ -39,17 +44,16 @@ struct KernelArgs {
     unsigned long long* err_index;  // smallest global read index that raised an error
     uint32_t stride;                // bytes per row
     uint32_t R;                     // tile capacity (reads or pairs)
-    uint32_t items_w;               // words per row = stride / 4
+    uint32_t items_w;               // histogram items per table = stride / J
     uint32_t X;                     // histogram row pitch = CTA threads
     TileMap tm;
 };
 
-// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][keep][qhist][misc]
+// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][desc][qhist][misc]
 struct SmemPlan {
     uint32_t off_rows[2][2];   // [mate][0 seq, 1 qual]
     uint32_t off_len[2];
     uint32_t off_info[2];
-    uint32_t off_keep;
     uint32_t off_desc;         // hist_desc words: [raw m0][raw m1][clean m0][clean m1], R each
     uint32_t off_qhist;
     uint32_t off_misc;
@@ -67,9 +71,8 @@ __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t st
         }
     for (int m = 0; m < 2; m++) { p.off_len[m] = o; if (m < mates) o += align_up(R * 2, 16); }
     for (int m = 0; m < 2; m++) { p.off_info[m] = o; if (m < mates) o += align_up(R * (uint32_t)sizeof(ReadInfo), 16); }
-    p.off_keep = o; o += align_up(R, 16);
     p.off_desc = o; o += align_up(4u * R * 4u, 16);
-    p.off_qhist = o; o += align_up((uint32_t)qb * 4u * X * (uint32_t)sizeof(QCounter), 16);
+    p.off_qhist = o; o += align_up((uint32_t)qb * (uint32_t)hist_j(stride) * X * (uint32_t)sizeof(QCounter), 16);
     p.off_misc = o; o += kMiscBytes;
     p.total = o;
     return p;
@@ -85,25 +88,83 @@ __device__ __forceinline__ void report_error(const KernelArgs& A, uint32_t bits,
 
 __device__ __forceinline__ int file_of_tab(int mates, int tab) { return mates == 2 ? tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1); }
 
+// lane exchange inside a phase-A thread group (kNT == 2: partner = lane ^ 1)
+template <int NW>
+__device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s, unsigned pm)
+{
+#pragma unroll
+    for (int k = 0; k < NW; k++) {
+        d.p0[k] = __shfl_xor_sync(pm, s.p0[k], 1); d.p1[k] = __shfl_xor_sync(pm, s.p1[k], 1);
+        d.pn[k] = __shfl_xor_sync(pm, s.pn[k], 1); d.pl[k] = __shfl_xor_sync(pm, s.pl[k], 1);
+    }
+    d.accA = __shfl_xor_sync(pm, s.accA, 1); d.accN = __shfl_xor_sync(pm, s.accN, 1);
+    d.accLow = __shfl_xor_sync(pm, s.accLow, 1); d.qsum = __shfl_xor_sync(pm, s.qsum, 1);
+    d.viol = __shfl_xor_sync(pm, s.viol, 1); d.qviol = __shfl_xor_sync(pm, s.qviol, 1); d.qover = __shfl_xor_sync(pm, s.qover, 1);
+}
+
+// phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
+template <int MAXC>
+__device__ __forceinline__ void scan_read_coop(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P,
+                                               int h, unsigned pm, ReadInfo& R)
+{
+    static_assert(kNT == 2, "lane exchange below is written for pairs");
+    constexpr int NW = (MAXC + 1) / 2;
+    const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
+    ScanPart<NW> S, O;
+    scan_chunks<MAXC>(seq, qual, len, P, h, want_planes, S);
+    shfl_scan<NW>(O, S, pm);
+    merge_scan(S, O);
+    const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
+    int ada_pos = -1;
+    if (P.n_adapters[mate] > 0) {
+        uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
+#pragma unroll
+        for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }
+        p0[NW] = p0[NW + 1] = 0; p1[NW] = p1[NW + 1] = 0; pb[NW] = pb[NW + 1] = 0xFFFFFFFFu;
+        for (int i = 0; i < P.n_adapters[mate]; i++) {
+            const AdapterDev& a = P.ada[mate][i];
+            if (a.len == 0) continue;
+            if (a.fast && len >= a.len - 1) {
+                AdaPart ap, op;
+                adapter_part<NW>(len, p0, p1, pb, a, h, ap);
+                op.hit1 = __shfl_xor_sync(pm, ap.hit1, 1); op.pos2 = __shfl_xor_sync(pm, ap.pos2, 1); op.pos3 = __shfl_xor_sync(pm, ap.pos3, 1);
+                merge_ada(ap, op);
+                ada_pos = ada_result(ap);
+            } else {
+                int pos = (h == 0) ? adapter_pos_bytes(seq, len, a) : -1;
+                const int other = __shfl_xor_sync(pm, pos, 1);
+                ada_pos = (h == 0) ? pos : other;
+            }
+            if (ada_pos >= 0) break;
+        }
+    }
+    TrimPart T, OT;
+    trim_part(seq, qual, len, P, h, T);
+    OT.hix = __shfl_xor_sync(pm, T.hix, 1); OT.tix = __shfl_xor_sync(pm, T.tix, 1); OT.ng = __shfl_xor_sync(pm, T.ng, 1);
+    merge_trim(T, OT);
+    finish_read<NW>(S, polyx, ada_pos, T, len, mate, P, R);
+}
+
 // add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
 // slot's global tables and clear them
-__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt& bc,
+template <int J>
+__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt<J>& bc,
                            unsigned long long* lastkey, unsigned long long* gsum, int slot)
 {
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
     const uint32_t X = A.X, W = A.items_w;
     const int ntab = 2 * mates;                        // raw1,[raw2],clean1,[clean2] -> item groups
-    // quality cells: entry e = (q*4 + j)*X + x
-    const uint32_t qent = (uint32_t)P.qb * 4u * X;
+    // quality cells: entry e = (q*J + j)*X + x
+    const uint32_t qent = (uint32_t)P.qb * (uint32_t)J * X;
     for (uint32_t e = threadIdx.x; e < qent; e += blockDim.x) {
         const uint32_t v = qhist[e];
         if (!v) continue;
         qhist[e] = 0;
-        const uint32_t x = e % X, j = (e / X) & 3u, q = e / (4u * X);
+        const uint32_t x = e % X, j = (e / X) % (uint32_t)J, q = e / ((uint32_t)J * X);
         const uint32_t tab = x / W, w = x % W;
         if ((int)tab >= ntab) continue;
         unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
-        atomicAdd(&F[SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + q], (unsigned long long)v);
+        atomicAdd(&F[SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q], (unsigned long long)v);
         if (q >= 20) atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)v);
         if (q >= 30) atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)v);
     }
@@ -118,9 +179,9 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
             for (int b = 0; b < 5; b++) {
                 unsigned long long sym = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < J; j++) {
                     const uint32_t v = bc.v[b][j];
-                    if (v) atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b], (unsigned long long)v);
+                    if (v) atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b], (unsigned long long)v);
                     sym += v;
                     bc.v[b][j] = 0;
                 }
@@ -150,26 +211,26 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
     __syncthreads();
 }
 
-template <int MAXC, int MATES>
-__global__ void __launch_bounds__((KernelShape<MAXC, MATES>::kMaxThreads))
+template <int MAXC, int MATES, int J>
+__global__ void __launch_bounds__((KernelShape<MAXC, MATES, J>::kMaxThreads), (KernelShape<MAXC, MATES, J>::kMinBlocks))
 filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ KernelArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
     const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
     QCounter* qhist = reinterpret_cast<QCounter*>(smem + sp.off_qhist);
-    uint8_t* keep = smem + sp.off_keep;
     uint32_t* desc = reinterpret_cast<uint32_t*>(smem + sp.off_desc);
     // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table, gsum[4][8]
     unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(smem + sp.off_misc);
     unsigned long long* gsum = lastkey + 8;
     const int tid = threadIdx.x;
+    const int lane = tid & 31;
 
     for (uint32_t e = tid; e < (sp.total - sp.off_qhist) / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(qhist)[e] = 0;   // qhist + misc
-    BaseCnt bc;
+    BaseCnt<J> bc;
 #pragma unroll
     for (int b = 0; b < 5; b++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) bc.v[b][j] = 0;
+        for (int j = 0; j < J; j++) bc.v[b][j] = 0;
     __syncthreads();
 
     const uint32_t nt = A.tm.ntiles;
@@ -185,7 +246,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     const int my_m = (int)(my_tab % MATES);
     const bool my_clean = my_tab >= (uint32_t)MATES;
     // byte offsets into the quality table for hist_item_fast: cell(b, j) = cell0 + j*jstep + b*bstep
-    const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = 4 * q_jstep;
+    const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
     const int q_cell0 = tid * (int)sizeof(QCounter) - P.phred * q_bstep;
     const uint32_t* my_desc = desc + (size_t)((my_clean ? 2 : 0) + my_m) * A.R;
 
@@ -195,7 +256,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         const uint64_t g0 = A.tm.first + start;
         const int slot = slot_of(g0, (uint64_t)P.slot_block, P.n_slots);
         if (slot != cur_slot || reads_in_hist + cnt > kQCounterMax) {
-            if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
+            if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
             cur_slot = slot;
             reads_in_hist = 0;
         }
@@ -214,10 +275,13 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         }
         __syncthreads();
 
-        // ---- phase A: one thread per read
-        for (uint32_t i = tid; i < cnt * MATES; i += blockDim.x) {
-            const int m = (MATES == 2) ? (int)(i / cnt) : 0;
-            const uint32_t r = (MATES == 2) ? i % cnt : i;
+        // ---- phase A: kNT adjacent lanes per read
+        for (uint32_t i = tid; i < cnt * MATES * kNT; i += blockDim.x) {
+            const uint32_t ir = i / kNT;
+            const int h = (int)(i % kNT);
+            const int m = (MATES == 2) ? (int)(ir / cnt) : 0;
+            const uint32_t r = (MATES == 2) ? ir % cnt : ir;
+            const unsigned pm = 3u << (lane & ~1);                  // my group's lanes
             const uint16_t* sl = reinterpret_cast<const uint16_t*>(smem + sp.off_len[m]);
             ReadInfo* info = reinterpret_cast<ReadInfo*>(smem + sp.off_info[m]);
             int len = sl[r];
@@ -227,10 +291,10 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 ri.len = 0; ri.head_cut = 0; ri.clean_len = 0; ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1;
                 ri.flags = RF_BAD_BASE;
             } else {
-                scan_read<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
-                                len, m, P, ri);
+                scan_read_coop<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
+                                     len, m, P, h, pm, ri);
             }
-            info[r] = ri;
+            if (h == 0) info[r] = ri;
         }
         __syncthreads();
 
@@ -258,7 +322,6 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                     if (a.flags & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
                     if (err) report_error(A, err, gi);
                 }
-                keep[r] = (cat == SNK_KEEP);
                 desc[0 * A.R + r] = hist_desc(a.len, 0, a.flags & RF_QSLOW);
                 desc[2 * A.R + r] = cat == SNK_KEEP ? hist_desc(a.clean_len, a.head_cut, a.flags & RF_QSLOW) : 0u;
                 if (MATES == 2) {
@@ -302,7 +365,6 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             // last record keys + record counts, one shared atomic per warp and table
             const unsigned kept = __ballot_sync(0xFFFFFFFFu, live && cat == SNK_KEEP);
             const unsigned lanes = __ballot_sync(0xFFFFFFFFu, live);
-            const int lane = tid & 31;
             if (lanes && lane == 31 - __clz(lanes)) {      // last live read of this warp's group
                 atomicMax(&lastkey[0], ((gi + 1) << 16) | (unsigned long long)(uint16_t)a.len);
                 atomicAdd(&lastkey[4 + 0], (unsigned long long)__popc(lanes));
@@ -331,24 +393,23 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             for (uint32_t r = 0; r < cnt; r++) {
                 const uint32_t d = my_desc[r];
                 const int n = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
-                if (n <= 4 * (int)my_w) continue;                       // nothing of this record in my 4 positions
+                if (n <= J * (int)my_w) continue;                       // nothing of this record in my positions
                 const uint8_t* rs = rows_s + (size_t)r * A.stride;
                 const uint8_t* rq = rows_q + (size_t)r * A.stride;
                 if (!(d & 0x80000000u))
-                    hist_item_fast<QCounter>(rs, rq, off, n, (int)my_w, acc, reinterpret_cast<uint8_t*>(qhist),
-                                             q_cell0, q_jstep, q_bstep);
+                    hist_item_fast<QCounter, J>(rs, rq, off, n, (int)my_w, acc, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
                 else {
                     unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
-                    err |= hist_item<QCounter>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
+                    err |= hist_item<QCounter, J>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
                 }
-                if (++since_spill == 255) { since_spill = 0; base_acc_spill(acc, bc); }
+                if (++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
             }
-            base_acc_spill(acc, bc);
+            base_acc_spill<J>(acc, bc);
             if (err) report_error(A, err, g0);
         }
         __syncthreads();
     }
-    if (cur_slot >= 0) flush_hist(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
+    if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
 }
 
 #endif // __CUDACC__

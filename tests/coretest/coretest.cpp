@@ -22,11 +22,20 @@ struct Ctx {
     uint64_t* stats;
     uint32_t err = 0;
     uint32_t stride, R, W, X;
-    int mates;
+    int mates, J;
     std::vector<QCounter> qhist;
-    std::vector<BaseCnt> bc;            // one per item (per "thread")
+    std::vector<BaseCnt<4>> bc;         // one per item (per "thread"); J <= 4 slots used
     uint64_t lastkey[8] = {0};
 };
+
+template <int J>
+void spill_j(BaseAcc& acc, BaseCnt<4>& cnt)
+{
+    BaseCnt<J> t;
+    memset(&t, 0, sizeof t);
+    base_acc_spill<J>(acc, t);
+    for (int b = 0; b < 5; b++) for (int j = 0; j < J; j++) cnt.v[b][j] += t.v[b][j];
+}
 
 int file_of(int mates, int tab) { return mates == 2 ? tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1); }
 
@@ -34,15 +43,16 @@ void flush(Ctx& c, int slot)
 {
     uint64_t* S = c.stats + (size_t)slot * SNK_SLOT_WORDS;
     const int ntab = 2 * c.mates;
-    for (uint32_t e = 0; e < (uint32_t)c.P.qb * 4u * c.X; e++) {
+    const uint32_t J = (uint32_t)c.J;
+    for (uint32_t e = 0; e < (uint32_t)c.P.qb * J * c.X; e++) {
         uint32_t v = c.qhist[e];
         if (!v) continue;
         c.qhist[e] = 0;
-        uint32_t x = e % c.X, j = (e / c.X) & 3u, q = e / (4u * c.X);
+        uint32_t x = e % c.X, j = (e / c.X) % J, q = e / (J * c.X);
         uint32_t tab = x / c.W, w = x % c.W;
         if ((int)tab >= ntab) continue;
         uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
-        F[SNK_FILE_QS_OFF + (size_t)(4 * w + j) * SNK_QBINS + q] += v;
+        F[SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q] += v;
         if (q >= 20) F[SNK_FILE_GS_OFF + SNK_GS_Q20] += v;
         if (q >= 30) F[SNK_FILE_GS_OFF + SNK_GS_Q30] += v;
     }
@@ -51,10 +61,10 @@ void flush(Ctx& c, int slot)
         if ((int)tab >= ntab) continue;
         uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
         for (int b = 0; b < 5; b++)
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < c.J; j++) {
                 uint32_t v = c.bc[x].v[b][j];
                 c.bc[x].v[b][j] = 0;
-                F[SNK_FILE_BS_OFF + (size_t)(4 * w + j) * 5 + b] += v;
+                F[SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b] += v;
                 F[SNK_FILE_GS_OFF + SNK_GS_A + b] += v;
                 F[SNK_FILE_GS_OFF + SNK_GS_BASES] += v;
             }
@@ -67,7 +77,7 @@ void flush(Ctx& c, int slot)
     }
 }
 
-template <int MAXC>
+template <int MAXC, int J>
 void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first, int grid, uint32_t flush_every)
 {
     const int M = c.mates;
@@ -77,8 +87,8 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
     std::vector<ReadInfo> info[2];
     std::vector<uint8_t> keep(c.R);
     for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)c.R * c.stride + 16, 0xAB); rows[m][1].assign((size_t)c.R * c.stride + 16, 0xAB); info[m].resize(c.R); }
-    c.qhist.assign((size_t)std::max(c.P.qb, 1) * 4u * c.X, 0);
-    c.bc.assign(c.X, BaseCnt());
+    c.qhist.assign((size_t)std::max(c.P.qb, 1) * (size_t)J * c.X, 0);
+    c.bc.assign(c.X, BaseCnt<4>());
     for (auto& x : c.bc) memset(&x, 0, sizeof x);
     for (int cta = 0; cta < grid; cta++) {
         const uint32_t t_begin = (uint32_t)((uint64_t)tm.ntiles * cta / grid), t_end = (uint32_t)((uint64_t)tm.ntiles * (cta + 1) / grid);
@@ -103,7 +113,7 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     if (len > (int)c.stride) len = (int)c.stride;
                     ReadInfo ri;
                     if (len <= 0) { memset(&ri, 0, sizeof ri); ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1; ri.flags = RF_BAD_BASE; }
-                    else scan_read<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, m, c.P, ri);
+                    else scan_read_serial<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, m, c.P, ri);
                     info[m][r] = ri;
                 }
             // phase P
@@ -165,7 +175,7 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                 const int m = (int)(tab % M);
                 const bool clean = tab >= (uint32_t)M;
                 unsigned long long* file_base = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, tab)));
-                const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = 4 * q_jstep;
+                const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
                 const int q_cell0 = (int)x * (int)sizeof(QCounter) - c.P.phred * q_bstep;
                 BaseAcc acc = {0, 0, 0, 0, 0};
                 uint32_t since = 0;
@@ -174,14 +184,14 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     const uint32_t d = clean ? (keep[r] ? hist_desc(ri.clean_len, ri.head_cut, ri.flags & RF_QSLOW) : 0u)
                                              : hist_desc(ri.len, 0, ri.flags & RF_QSLOW);
                     const int nn = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
-                    if (nn <= 4 * (int)w) continue;
+                    if (nn <= J * (int)w) continue;
                     const uint8_t* rs = rows[m][0].data() + (size_t)r * c.stride;
                     const uint8_t* rq = rows[m][1].data() + (size_t)r * c.stride;
-                    if (!(d & 0x80000000u)) hist_item_fast<QCounter>(rs, rq, off, nn, (int)w, acc, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
-                    else c.err |= hist_item<QCounter>(rs, rq, off, nn, (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, file_base);
-                    if (++since == 255) { since = 0; base_acc_spill(acc, c.bc[x]); }
+                    if (!(d & 0x80000000u)) hist_item_fast<QCounter, J>(rs, rq, off, nn, (int)w, acc, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
+                    else c.err |= hist_item<QCounter, J>(rs, rq, off, nn, (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, file_base);
+                    if (++since == 255) { since = 0; spill_j<J>(acc, c.bc[x]); }
                 }
-                base_acc_spill(acc, c.bc[x]);
+                spill_j<J>(acc, c.bc[x]);
             }
         }
         if (cur_slot >= 0) flush(c, cur_slot);
@@ -207,18 +217,20 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     c.stats = stats;
     c.mates = p->is_pe ? 2 : 1;
     c.stride = r1->stride;
-    c.W = c.stride / 4;
+    c.J = hist_j(c.stride);
+    c.W = c.stride / c.J;
     c.X = cta_threads(c.mates, c.stride);
-    c.R = tile_r > 0 ? (uint32_t)tile_r : c.X / c.mates;
+    c.R = tile_r > 0 ? (uint32_t)tile_r : c.X / (c.mates * kNT);
     const snk_batch* b[2] = {r1, r2};
     snk_read_result* out[2] = {out1, out2};
     const uint32_t chunks = c.stride / 16;
     if (grid < 1) grid = 1;
-    if (chunks <= 4) run<4>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 7) run<7>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 10) run<10>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 16) run<16>(c, b, out, first, grid, flush_every);
-    else run<63>(c, b, out, first, grid, flush_every);
+    if (chunks <= 4) run<4, 2>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 7) run<7, 2>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 10) run<10, 2>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 16) run<16, 2>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 32) run<32, 4>(c, b, out, first, grid, flush_every);
+    else run<63, 4>(c, b, out, first, grid, flush_every);
     *err |= c.err;
     return 0;
 }
