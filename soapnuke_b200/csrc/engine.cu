@@ -94,10 +94,10 @@ template <int MATES>
 int launch_mates(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
 {
     switch (lp.maxc) {
-        case 4: return launch_one<4, MATES, 2>(e, dp, ka, lp, stream);
-        case 7: return launch_one<7, MATES, 2>(e, dp, ka, lp, stream);
-        case 10: return launch_one<10, MATES, 2>(e, dp, ka, lp, stream);
-        case 16: return launch_one<16, MATES, 2>(e, dp, ka, lp, stream);
+        case 4: return launch_one<4, MATES, 4>(e, dp, ka, lp, stream);
+        case 7: return launch_one<7, MATES, 4>(e, dp, ka, lp, stream);
+        case 10: return launch_one<10, MATES, 4>(e, dp, ka, lp, stream);
+        case 16: return launch_one<16, MATES, 4>(e, dp, ka, lp, stream);
         case 32: return launch_one<32, MATES, 4>(e, dp, ka, lp, stream);
         default: return launch_one<63, MATES, 4>(e, dp, ka, lp, stream);
     }
@@ -110,7 +110,7 @@ int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t fi
     lp.maxc = chunks <= 4 ? 4 : chunks <= 7 ? 7 : chunks <= 10 ? 10 : chunks <= 16 ? 16 : chunks <= 32 ? 32 : 63;
     lp.W = stride / hist_j(stride);
     lp.threads = cta_threads(mates, stride);
-    lp.X = lp.threads;
+    lp.X = align_up(hist_items(mates, stride), 32);
     int qb = e->dev.qb;
     const uint32_t maxR = lp.threads / (mates * kNT);  // kNT threads per read in phase A
     // Prefer a tile that lets two CTAs share an SM (latency hiding across the phase barriers);

@@ -251,9 +251,13 @@ SNK_HD void scan_chunks(const uint8_t* seq, const uint8_t* qual, int len, const 
     const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
     const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
     const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
-#pragma unroll(MAXC <= 16 ? MAXC : 1)
-    for (int c = 0; c < MAXC; c++) {
-        if ((c % kNT) != h || 16 * c >= len) continue;
+    // Both lanes of a group run the same instruction stream on different data: step cc handles chunk
+    // c = kNT*cc + h, i.e. (kNT == 2) lane h fills half h of plane word cc.
+    static_assert(kNT == 2, "plane half-word placement below assumes two lanes per read");
+#pragma unroll(MAXC <= 16 ? NW : 1)
+    for (int cc = 0; cc < NW; cc++) {
+        const int c = kNT * cc + h;
+        if (16 * c >= len) continue;
         uint32_t c0 = 0, c1 = 0, cn = 0, cl = 0;
         const U4 sv = load16(seq + 16 * c);
         const U4 qv = load16(qual + 16 * c);
@@ -292,8 +296,8 @@ SNK_HD void scan_chunks(const uint8_t* seq, const uint8_t* qual, int len, const 
             }
         }
         if (want_planes) {
-            const int sh = 16 * (c & 1);
-            S.p0[c >> 1] |= c0 << sh; S.p1[c >> 1] |= c1 << sh; S.pn[c >> 1] |= cn << sh; S.pl[c >> 1] |= cl << sh;
+            const int sh = 16 * h;
+            S.p0[cc] = c0 << sh; S.p1[cc] = c1 << sh; S.pn[cc] = cn << sh; S.pl[cc] = cl << sh;
         }
     }
 }
@@ -354,15 +358,15 @@ SNK_HD int ada_result(const AdaPart& a) { return a.hit1 ? 0 : (a.pos2 >= 0 ? a.p
 template <int NW>
 SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const AdapterDev& a, int h, AdaPart& out)
 {
+    // The lanes of a group take the window offsets with offset % kNT == h (phase 1: r1 % kNT), so
+    // they run the same instruction stream.
     const int A = a.len;
     const uint64_t a0 = ((uint64_t)a.a0_hi << 32) | a.a0_lo, a1 = ((uint64_t)a.a1_hi << 32) | a.a1_lo;
     out.hit1 = 0; out.pos2 = -1; out.pos3 = -1;
     // phase 1: adapter starts r1 = 1..5 bases before the read; read window is bases [0, A-r1)
     {
         const uint64_t r0 = ((uint64_t)p0[1] << 32) | p0[0], r1w = ((uint64_t)p1[1] << 32) | p1[0], rb = ((uint64_t)pb[1] << 32) | pb[0];
-#pragma unroll
-        for (int r1 = 1; r1 <= 5; r1++) {
-            if ((r1 % kNT) != h) continue;
+        for (int r1 = 1 + h; r1 <= 5; r1 += kNT) {
             const uint64_t M = (r0 ^ (a0 >> r1)) | (r1w ^ (a1 >> r1)) | rb;
             const int budget = a.budget1[r1 - 1];
             const int nb = budget < 0 ? 0 : budget;
@@ -376,13 +380,13 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
     const int last2 = len - A, last3 = len - a.edge;
     const int nb2 = a.budget2 < 0 ? 0 : a.budget2;
     const uint32_t pm2 = a.pre_mask;
-    // ---- phase 2: offsets 0..last2, first accepted offset wins (words kw % kNT == h are mine)
+    // ---- phase 2: offsets 0..last2, first accepted offset wins
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
-        if ((kw % kNT) == h && 32 * kw <= last2 && out.pos2 < 0) {
+        if (32 * kw <= last2 && out.pos2 < 0) {
             const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
             const int send = (last2 - 32 * kw) >= 31 ? 32 : (last2 - 32 * kw + 1);
-            for (int sft = 0; sft < send; sft++) {
+            for (int sft = h; sft < send; sft += kNT) {
                 // level 1: plane 0 alone (a plane-0 difference is a base mismatch)
                 const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
                 if ((int)popc32(x0 & pm2) > nb2) continue;
@@ -400,11 +404,12 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
     const int first3 = last2 + 1 < 0 ? 0 : last2 + 1;
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
-        if ((kw % kNT) == h && 32 * kw + 31 >= first3 && 32 * kw <= last3) {
+        if (32 * kw + 31 >= first3 && 32 * kw <= last3) {
             const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
-            const int s0 = first3 > 32 * kw ? first3 - 32 * kw : 0;
+            int s0 = first3 > 32 * kw ? first3 - 32 * kw : 0;
+            s0 += ((s0 % kNT) != h) ? 1 : 0;                       // first offset of my parity (kNT == 2)
             const int send = (last3 - 32 * kw) >= 31 ? 32 : (last3 - 32 * kw + 1);
-            for (int sft = s0; sft < send; sft++) {
+            for (int sft = s0; sft < send; sft += kNT) {
                 const int winlen = len - (32 * kw + sft);
                 const int budget = a.budget3[winlen - a.edge];
                 const int nb = budget < 0 ? 0 : budget;
@@ -446,14 +451,20 @@ SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, const De
 {
     t.hix = t.tix = t.ng = 0;
     if (!P.trimming) return;
-    if (P.has_lq && h == 0)
-        for (int ix = 0; ix < P.bad_head_max && ix < len; ix++) { if ((int)qual[ix] - P.phred < P.bad_head_thr) t.hix++; else break; }
-    if (h == kNT - 1) {
-        if (P.has_lq)
+    const bool tail = (h == kNT - 1);
+    if (P.has_lq) {
+        // lane 0 walks from the 5' end, lane kNT-1 from the 3' end: same loop, different start/step/threshold
+        const int lim = (kNT == 1 || !tail) ? P.bad_head_max : P.bad_tail_max;
+        const int thr = (kNT == 1 || !tail) ? P.bad_head_thr : P.bad_tail_thr;
+        const int start = (kNT == 1 || !tail) ? 0 : len - 1, step = (kNT == 1 || !tail) ? 1 : -1;
+        int cnt = 0;
+        for (int ix = 0; ix < lim && ix < len; ix++) { if ((int)qual[start + step * ix] - P.phred < thr) cnt++; else break; }
+        if (kNT == 1 || !tail) t.hix = cnt; else t.tix = cnt;
+        if (kNT == 1)
             for (int ix = 0; ix < P.bad_tail_max && ix < len; ix++) { if ((int)qual[len - ix - 1] - P.phred < P.bad_tail_thr) t.tix++; else break; }
-        if (P.polyG_tail != -1)
-            for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') t.ng++; else break; }
     }
+    if (tail && P.polyG_tail != -1)
+        for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') t.ng++; else break; }
 }
 
 // stage 5: everything merged -> ReadInfo (predicates of stat_read, read_filter.cpp:289-311, and the

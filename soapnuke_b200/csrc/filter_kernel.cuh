@@ -21,15 +21,20 @@ constexpr uint32_t kQCounterMax = 65535;
 // threads / (mates * kNT) reads or pairs, so that phase A (kNT threads per read) and phase B (one
 // thread per item) both keep every thread busy. PE150: 320 threads, 80-pair tiles, 2 CTAs per SM.
 __host__ __device__ inline uint32_t align_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
-__host__ __device__ inline int hist_j(uint32_t stride) { return stride <= 256 ? 2 : 4; }
+__host__ __device__ inline int hist_j(uint32_t) { return 4; }
+// histogram items (J = 4 positions each) of all tables = threads busy in phase B; phase A runs kNT
+// threads per read, so the CTA has kNT x that many threads and a tile of threads/(mates*kNT) reads
+__host__ __device__ inline uint32_t hist_items(int mates, uint32_t stride) { return 2u * mates * (stride / 4); }
 __host__ __device__ inline uint32_t cta_threads(int mates, uint32_t stride)
 {
-    uint32_t t = align_up(2u * mates * (stride / hist_j(stride)), 32);
+    uint32_t t = align_up(kNT * hist_items(mates, stride), 32);
+    if (t > 1024) t = 1024;
     return t < 64 ? 64 : t;
 }
 template <int MAXC, int MATES, int J> struct KernelShape {
-    static constexpr int kItems = 2 * MATES * (16 * MAXC) / J;
-    static constexpr int kMaxThreads = ((kItems + 31) / 32 * 32) < 64 ? 64 : ((kItems + 31) / 32 * 32);
+    static constexpr int kItems = kNT * 2 * MATES * (16 * MAXC) / J;
+    static constexpr int kT = ((kItems + 31) / 32 * 32) < 64 ? 64 : ((kItems + 31) / 32 * 32);
+    static constexpr int kMaxThreads = kT > 1024 ? 1024 : kT;
     // register budget: keep 640 threads (20 warps) resident per SM whenever the CTA is small enough
     static constexpr int kMinBlocks = kMaxThreads <= 320 ? 640 / kMaxThreads : 1;
 };
@@ -45,7 +50,7 @@ struct KernelArgs {
     uint32_t stride;                // bytes per row
     uint32_t R;                     // tile capacity (reads or pairs)
     uint32_t items_w;               // histogram items per table = stride / J
-    uint32_t X;                     // histogram row pitch = CTA threads
+    uint32_t X;                     // histogram row pitch = items rounded up to 32
     TileMap tm;
 };
 
@@ -239,7 +244,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     int cur_slot = -1;
     uint32_t reads_in_hist = 0;                     // records counted since the last flush (u16 cells)
     const uint32_t W = A.items_w;
-    const uint32_t nitems = 2u * MATES * W;         // <= blockDim.x
+    const uint32_t nitems = 2u * MATES * W;         // <= blockDim.x / kNT
     // this thread's histogram item
     const uint32_t my_tab = (uint32_t)tid / W, my_w = (uint32_t)tid % W;
     const bool my_item = (uint32_t)tid < nitems;

@@ -219,16 +219,16 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     c.stride = r1->stride;
     c.J = hist_j(c.stride);
     c.W = c.stride / c.J;
-    c.X = cta_threads(c.mates, c.stride);
-    c.R = tile_r > 0 ? (uint32_t)tile_r : c.X / (c.mates * kNT);
+    c.X = align_up(hist_items(c.mates, c.stride), 32);
+    c.R = tile_r > 0 ? (uint32_t)tile_r : cta_threads(c.mates, c.stride) / (c.mates * kNT);
     const snk_batch* b[2] = {r1, r2};
     snk_read_result* out[2] = {out1, out2};
     const uint32_t chunks = c.stride / 16;
     if (grid < 1) grid = 1;
-    if (chunks <= 4) run<4, 2>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 7) run<7, 2>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 10) run<10, 2>(c, b, out, first, grid, flush_every);
-    else if (chunks <= 16) run<16, 2>(c, b, out, first, grid, flush_every);
+    if (chunks <= 4) run<4, 4>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 7) run<7, 4>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 10) run<10, 4>(c, b, out, first, grid, flush_every);
+    else if (chunks <= 16) run<16, 4>(c, b, out, first, grid, flush_every);
     else if (chunks <= 32) run<32, 4>(c, b, out, first, grid, flush_every);
     else run<63, 4>(c, b, out, first, grid, flush_every);
     *err |= c.err;
