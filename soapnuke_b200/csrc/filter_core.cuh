@@ -666,13 +666,8 @@ SNK_HD uint32_t hist_desc(int n, int off, bool slow) { return n <= 0 ? 0u : ((ui
 // clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at
 // qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
 template <typename CounterT, int J>
-SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,
-                           uint8_t* qcells, int cell0, int jstep, int bstep)
+SNK_HD void hist_update_fast(uint32_t s, uint32_t q, int nvalid, BaseAcc& acc, uint8_t* qcells, int cell0, int jstep, int bstep)
 {
-    const int nvalid = n - J * w;
-    if (nvalid <= 0) return;
-    uint32_t s, q;
-    hist_load<J>(seq, qual, off, w, s, q);
     // one straight-line path for full and partial items: a divergent branch here would make every
     // warp that holds a record's last (partial) item issue the whole body twice
     const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
@@ -683,6 +678,16 @@ SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int
         CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
         if (j < nvalid) *cell += 1;
     }
+}
+template <typename CounterT, int J>
+SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,
+                           uint8_t* qcells, int cell0, int jstep, int bstep)
+{
+    const int nvalid = n - J * w;
+    if (nvalid <= 0) return;
+    uint32_t s, q;
+    hist_load<J>(seq, qual, off, w, s, q);
+    hist_update_fast<CounterT, J>(s, q, nvalid, acc, qcells, cell0, jstep, bstep);
 }
 
 // Checked path: qualities may fall outside [0,qb). Bins not kept in shared memory go straight to
