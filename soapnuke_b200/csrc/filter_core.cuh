@@ -672,12 +672,19 @@ SNK_HD void hist_update_fast(uint32_t s, uint32_t q, int nvalid, BaseAcc& acc, u
     // warp that holds a record's last (partial) item issue the whole body twice
     const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
     const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
-    base_acc_add(acc, s & mask & jmask);
+    // The J cells belong to different sub-positions, so they never alias: load them all, then store
+    // them all - one shared-memory round trip per record instead of J dependent ones.
+    CounterT* cell[J];
+    CounterT val[J];
 #pragma unroll
     for (int j = 0; j < J; j++) {
-        CounterT* cell = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
-        if (j < nvalid) *cell += 1;
+        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+        val[j] = (j < nvalid) ? *cell[j] : (CounterT)0;
     }
+    base_acc_add(acc, s & mask & jmask);
+#pragma unroll
+    for (int j = 0; j < J; j++)
+        if (j < nvalid) *cell[j] = (CounterT)(val[j] + 1);
 }
 template <typename CounterT, int J>
 SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,

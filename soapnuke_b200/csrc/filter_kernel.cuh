@@ -395,28 +395,19 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
             BaseAcc acc = {0, 0, 0, 0, 0};
             uint32_t err = 0, since_spill = 0;
-            // software pipeline: descriptor two reads ahead, data one read ahead, so that the
-            // shared-memory latencies of read r+1 overlap the counter updates of read r
-            uint32_t d0 = my_desc[0], d1 = cnt > 1 ? my_desc[1] : 0u;
-            uint32_t s0 = 0, q0 = 0;
-            if ((int)(d0 & 0x3FFu) > J * (int)my_w) hist_load<J>(rows_s, rows_q, (int)((d0 >> 10) & 0x3FFu), (int)my_w, s0, q0);
             for (uint32_t r = 0; r < cnt; r++) {
-                const uint32_t d2 = (r + 2 < cnt) ? my_desc[r + 2] : 0u;
-                uint32_t s1 = 0, q1 = 0;
-                if ((int)(d1 & 0x3FFu) > J * (int)my_w)
-                    hist_load<J>(rows_s + (size_t)(r + 1) * A.stride, rows_q + (size_t)(r + 1) * A.stride, (int)((d1 >> 10) & 0x3FFu), (int)my_w, s1, q1);
-                const int nvalid = (int)(d0 & 0x3FFu) - J * (int)my_w;
-                if (nvalid > 0) {
-                    if (!(d0 & 0x80000000u))
-                        hist_update_fast<QCounter, J>(s0, q0, nvalid, acc, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
-                    else {
-                        unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
-                        err |= hist_item<QCounter, J>(rows_s + (size_t)r * A.stride, rows_q + (size_t)r * A.stride, (int)((d0 >> 10) & 0x3FFu),
-                                                      (int)(d0 & 0x3FFu), (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
-                    }
-                    if (++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
+                const uint32_t d = my_desc[r];
+                const int n = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
+                if (n <= J * (int)my_w) continue;                       // nothing of this record in my positions
+                const uint8_t* rs = rows_s + (size_t)r * A.stride;
+                const uint8_t* rq = rows_q + (size_t)r * A.stride;
+                if (!(d & 0x80000000u))
+                    hist_item_fast<QCounter, J>(rs, rq, off, n, (int)my_w, acc, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
+                else {
+                    unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
+                    err |= hist_item<QCounter, J>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
                 }
-                d0 = d1; d1 = d2; s0 = s1; q0 = q1;
+                if (++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
             }
             base_acc_spill<J>(acc, bc);
             if (err) report_error(A, err, g0);
