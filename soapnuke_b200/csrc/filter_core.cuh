@@ -644,18 +644,23 @@ SNK_HD void base_acc_spill(BaseAcc& acc, BaseCnt<J>& cnt)
     acc.a = acc.c = acc.g = acc.t = acc.n = 0;
 }
 
-// Loads the item's J bases and J qualities (low J bytes of s / q) of a record that starts at byte
-// `off` of its row; item w covers record positions J*w .. J*w+J-1.
+// Loads the J bytes (low J bytes of the result) that item w of a record starting at byte `off` of
+// its row covers (record positions J*w .. J*w+J-1).
 template <int J>
-SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, uint32_t& s, uint32_t& q)
+SNK_HD uint32_t hist_load_word(const uint8_t* row, int off, int w)
 {
     const int byte0 = off + J * w;
     const int al = byte0 & ~3, sh = 8 * (byte0 & 3);
-    s = load4(seq + al); q = load4(qual + al);
-    if (sh + 8 * J > 32) {                        // the item straddles a word boundary
-        s = funnel_r(s, load4(seq + al + 4), sh);
-        q = funnel_r(q, load4(qual + al + 4), sh);
-    } else if (sh) { s >>= sh; q >>= sh; }
+    uint32_t v = load4(row + al);
+    if (sh + 8 * J > 32) v = funnel_r(v, load4(row + al + 4), sh);     // the item straddles a word boundary
+    else if (sh) v >>= sh;
+    return v;
+}
+template <int J>
+SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, uint32_t& s, uint32_t& q)
+{
+    s = hist_load_word<J>(seq, off, w);
+    q = hist_load_word<J>(qual, off, w);
 }
 
 // Per-read descriptor for phase B, one 32-bit word per (table, read): record length (bits 0-9),
@@ -665,15 +670,19 @@ SNK_HD uint32_t hist_desc(int n, int off, bool slow) { return n <= 0 ? 0u : ((ui
 // Fast path: every quality of the record is known to lie inside the shared-memory bins (RF_QSLOW
 // clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at
 // qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
-template <typename CounterT, int J>
-SNK_HD void hist_update_fast(uint32_t s, uint32_t q, int nvalid, BaseAcc& acc, uint8_t* qcells, int cell0, int jstep, int bstep)
+template <int J>
+SNK_HD void base_update(uint32_t s, int nvalid, BaseAcc& acc)
 {
-    // one straight-line path for full and partial items: a divergent branch here would make every
-    // warp that holds a record's last (partial) item issue the whole body twice
     const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
     const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
-    // The J cells belong to different sub-positions, so they never alias: load them all, then store
-    // them all - one shared-memory round trip per record instead of J dependent ones.
+    base_acc_add(acc, s & mask & jmask);
+}
+template <typename CounterT, int J>
+SNK_HD void qual_update_fast(uint32_t q, int nvalid, uint8_t* qcells, int cell0, int jstep, int bstep)
+{
+    // One straight-line path for full and partial items (a divergent branch would make every warp that
+    // holds a record's last item issue the body twice). The J cells belong to different sub-positions,
+    // so they never alias: load them all, then store them all - one shared-memory round trip per record.
     CounterT* cell[J];
     CounterT val[J];
 #pragma unroll
@@ -681,7 +690,6 @@ SNK_HD void hist_update_fast(uint32_t s, uint32_t q, int nvalid, BaseAcc& acc, u
         cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
         val[j] = (j < nvalid) ? *cell[j] : (CounterT)0;
     }
-    base_acc_add(acc, s & mask & jmask);
 #pragma unroll
     for (int j = 0; j < J; j++)
         if (j < nvalid) *cell[j] = (CounterT)(val[j] + 1);
@@ -694,23 +702,24 @@ SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int
     if (nvalid <= 0) return;
     uint32_t s, q;
     hist_load<J>(seq, qual, off, w, s, q);
-    hist_update_fast<CounterT, J>(s, q, nvalid, acc, qcells, cell0, jstep, bstep);
+    base_update<J>(s, nvalid, acc);
+    qual_update_fast<CounterT, J>(q, nvalid, qcells, cell0, jstep, bstep);
 }
 
 // Checked path: qualities may fall outside [0,qb). Bins not kept in shared memory go straight to
 // the slot's global table; anything outside [0,SNK_QBINS) raises the error flag. Returns error bits.
 template <typename CounterT, int J>
 SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
-                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */)
+                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */,
+                          bool do_bases = true, bool do_quals = true)
 {
     const int nvalid = n - J * w;
     if (nvalid <= 0) return 0;
-    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-    const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
     uint32_t s, q;
     hist_load<J>(seq, qual, off, w, s, q);
-    base_acc_add(acc, s & mask & jmask);
+    if (do_bases) base_update<J>(s, nvalid, acc);
     uint32_t err = 0;
+    if (!do_quals) return 0;
 #pragma unroll
     for (int j = 0; j < J; j++) {
         if (j < nvalid) {

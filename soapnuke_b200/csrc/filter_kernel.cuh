@@ -153,7 +153,7 @@ __device__ __forceinline__ void scan_read_coop(const uint8_t* seq, const uint8_t
 // add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
 // slot's global tables and clear them
 template <int J>
-__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt<J>& bc,
+__device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt<J>& bc, uint32_t base_item,
                            unsigned long long* lastkey, unsigned long long* gsum, int slot)
 {
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
@@ -173,9 +173,9 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
         if (q >= 20) atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)v);
         if (q >= 30) atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)v);
     }
-    // base cells: this thread's own item
+    // base cells: the item whose base counters this thread holds (base_item = ~0u: none)
     {
-        const uint32_t x = threadIdx.x;
+        const uint32_t x = base_item;
         const uint32_t tab = x / W, w = x % W;
         if ((int)tab < ntab) {
             unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
@@ -245,14 +245,20 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     uint32_t reads_in_hist = 0;                     // records counted since the last flush (u16 cells)
     const uint32_t W = A.items_w;
     const uint32_t nitems = 2u * MATES * W;         // <= blockDim.x / kNT
-    // this thread's histogram item
-    const uint32_t my_tab = (uint32_t)tid / W, my_w = (uint32_t)tid % W;
-    const bool my_item = (uint32_t)tid < nitems;
+    // Phase B roles: the first `nitems` threads own the quality cells of one item each; when the CTA is
+    // large enough a second set of threads (starting at X, warp aligned) owns the base counters of the
+    // same items, so that both halves of the CTA work during phase B. Otherwise one thread does both.
+    const bool split = blockDim.x >= A.X + nitems;
+    const bool q_role = (uint32_t)tid < nitems;
+    const uint32_t item = (split && (uint32_t)tid >= A.X) ? (uint32_t)tid - A.X : (uint32_t)tid;
+    const bool b_role = split ? ((uint32_t)tid >= A.X && item < nitems) : q_role;
+    const uint32_t my_tab = item / W, my_w = item % W;
+    const bool my_item = q_role || b_role;
     const int my_m = (int)(my_tab % MATES);
     const bool my_clean = my_tab >= (uint32_t)MATES;
     // byte offsets into the quality table for hist_item_fast: cell(b, j) = cell0 + j*jstep + b*bstep
     const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
-    const int q_cell0 = tid * (int)sizeof(QCounter) - P.phred * q_bstep;
+    const int q_cell0 = (int)item * (int)sizeof(QCounter) - P.phred * q_bstep;
     const uint32_t* my_desc = desc + (size_t)((my_clean ? 2 : 0) + my_m) * A.R;
 
     for (uint32_t t = t_begin; t < t_end; t++) {
@@ -261,7 +267,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         const uint64_t g0 = A.tm.first + start;
         const int slot = slot_of(g0, (uint64_t)P.slot_block, P.n_slots);
         if (slot != cur_slot || reads_in_hist + cnt > kQCounterMax) {
-            if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
+            if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, b_role ? item : 0xFFFFFFFFu, lastkey, gsum, cur_slot);
             cur_slot = slot;
             reads_in_hist = 0;
         }
@@ -398,23 +404,25 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             for (uint32_t r = 0; r < cnt; r++) {
                 const uint32_t d = my_desc[r];
                 const int n = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
-                if (n <= J * (int)my_w) continue;                       // nothing of this record in my positions
+                const int nvalid = n - J * (int)my_w;
+                if (nvalid <= 0) continue;                              // nothing of this record in my positions
                 const uint8_t* rs = rows_s + (size_t)r * A.stride;
                 const uint8_t* rq = rows_q + (size_t)r * A.stride;
-                if (!(d & 0x80000000u))
-                    hist_item_fast<QCounter, J>(rs, rq, off, n, (int)my_w, acc, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
-                else {
+                if (!(d & 0x80000000u)) {
+                    if (q_role) qual_update_fast<QCounter, J>(hist_load_word<J>(rq, off, (int)my_w), nvalid, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
+                    if (b_role) base_update<J>(hist_load_word<J>(rs, off, (int)my_w), nvalid, acc);
+                } else {
                     unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
-                    err |= hist_item<QCounter, J>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + tid, (int)A.X, file_base);
+                    err |= hist_item<QCounter, J>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + item, (int)A.X, file_base, b_role, q_role);
                 }
-                if (++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
+                if (b_role && ++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
             }
             base_acc_spill<J>(acc, bc);
             if (err) report_error(A, err, g0);
         }
         __syncthreads();
     }
-    if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, lastkey, gsum, cur_slot);
+    if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, b_role ? item : 0xFFFFFFFFu, lastkey, gsum, cur_slot);
 }
 
 #endif // __CUDACC__
