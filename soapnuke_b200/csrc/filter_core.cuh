@@ -378,26 +378,48 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
         }
     }
     const int last2 = len - A, last3 = len - a.edge;
-    const int nb2 = a.budget2 < 0 ? 0 : a.budget2;
-    const uint32_t pm2 = a.pre_mask;
-    // ---- phase 2: offsets 0..last2, first accepted offset wins
+    // adapter fields used in the sweeps, in registers (the adapter is indexed dynamically in the
+    // parameter block, the compiler would otherwise reload them per offset)
+    const int budget2 = a.budget2, seg_thr = a.seg_thr, edge = a.edge;
+    const int nb2 = budget2 < 0 ? 0 : budget2;
+    const uint32_t pm2 = a.pre_mask, a0lo = a.a0_lo, a1lo = a.a1_lo, a0hi = a.a0_hi, a1hi = a.a1_hi;
+    // levels 2+3 for one candidate offset of word kw (rare): all planes over the prefilter window, then
+    // the exact decision over the whole window
+#define SNK_VERIFY(kw_, sft_, x0_, pm_, nb_, winlen_, budget_)                                                                   \
+    ([&]() -> bool {                                                                                                             \
+        const uint32_t x_ = (x0_) | (funnel_r(p1[kw_], p1[(kw_) + 1], sft_) ^ a1lo) | funnel_r(pb[kw_], pb[(kw_) + 1], sft_);    \
+        if ((int)popc32(x_ & (pm_)) > (nb_)) return false;                                                                       \
+        const uint32_t xh_ = (funnel_r(p0[(kw_) + 1], p0[(kw_) + 2], sft_) ^ a0hi) | (funnel_r(p1[(kw_) + 1], p1[(kw_) + 2], sft_) ^ a1hi) | \
+                             funnel_r(pb[(kw_) + 1], pb[(kw_) + 2], sft_);                                                        \
+        return window_decide(((uint64_t)xh_ << 32) | x_, winlen_, budget_, seg_thr);                                             \
+    }())
+    // ---- phase 2: offsets 0..last2, first accepted offset wins. Level 1 = plane 0 alone (a plane-0
+    // difference is a base mismatch); four offsets are tested per loop trip with a single branch.
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int kw = 0; kw < NW; kw++) {
         if (32 * kw <= last2 && out.pos2 < 0) {
             const uint32_t l0 = p0[kw], m0 = p0[kw + 1];
             const int send = (last2 - 32 * kw) >= 31 ? 32 : (last2 - 32 * kw + 1);
-            for (int sft = h; sft < send; sft += kNT) {
-                // level 1: plane 0 alone (a plane-0 difference is a base mismatch)
-                const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
-                if ((int)popc32(x0 & pm2) > nb2) continue;
-                // level 2: all planes over the prefilter window
-                const uint32_t x = x0 | (funnel_r(p1[kw], p1[kw + 1], sft) ^ a.a1_lo) | funnel_r(pb[kw], pb[kw + 1], sft);
-                if ((int)popc32(x & pm2) > nb2) continue;
-                // exact decision over the whole window
-                const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
-                                    funnel_r(pb[kw + 1], pb[kw + 2], sft);
-                if (window_decide(((uint64_t)xh << 32) | x, A, a.budget2, a.seg_thr)) { out.pos2 = 32 * kw + sft; break; }
+            int sft = h;
+            for (; sft + 3 * kNT < send; sft += 4 * kNT) {
+                const uint32_t xa = funnel_r(l0, m0, sft) ^ a0lo, xb = funnel_r(l0, m0, sft + kNT) ^ a0lo;
+                const uint32_t xc = funnel_r(l0, m0, sft + 2 * kNT) ^ a0lo, xd = funnel_r(l0, m0, sft + 3 * kNT) ^ a0lo;
+                const int ca = (int)popc32(xa & pm2), cb = (int)popc32(xb & pm2), cc = (int)popc32(xc & pm2), cd = (int)popc32(xd & pm2);
+                int cmin = ca < cb ? ca : cb;
+                const int cmin2 = cc < cd ? cc : cd;
+                cmin = cmin < cmin2 ? cmin : cmin2;
+                if (cmin > nb2) continue;
+                if (ca <= nb2 && SNK_VERIFY(kw, sft, xa, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft; break; }
+                if (cb <= nb2 && SNK_VERIFY(kw, sft + kNT, xb, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + kNT; break; }
+                if (cc <= nb2 && SNK_VERIFY(kw, sft + 2 * kNT, xc, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + 2 * kNT; break; }
+                if (cd <= nb2 && SNK_VERIFY(kw, sft + 3 * kNT, xd, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + 3 * kNT; break; }
             }
+            if (out.pos2 < 0)
+                for (; sft < send; sft += kNT) {
+                    const uint32_t x0 = funnel_r(l0, m0, sft) ^ a0lo;
+                    if ((int)popc32(x0 & pm2) > nb2) continue;
+                    if (SNK_VERIFY(kw, sft, x0, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft; break; }
+                }
         }
     }
     // ---- phase 3: offsets last2+1..last3 (window = adapter prefix of length len-off), last accepted wins
@@ -411,20 +433,16 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
             const int send = (last3 - 32 * kw) >= 31 ? 32 : (last3 - 32 * kw + 1);
             for (int sft = s0; sft < send; sft += kNT) {
                 const int winlen = len - (32 * kw + sft);
-                const int budget = a.budget3[winlen - a.edge];
+                const int budget = a.budget3[winlen - edge];
                 const int nb = budget < 0 ? 0 : budget;
-                uint32_t pm = pm2;
-                if (winlen < 32) pm &= (1u << winlen) - 1u;
-                const uint32_t x0 = funnel_r(l0, m0, sft) ^ a.a0_lo;
+                const uint32_t pm = winlen < 32 ? (pm2 & ((1u << winlen) - 1u)) : pm2;
+                const uint32_t x0 = funnel_r(l0, m0, sft) ^ a0lo;
                 if ((int)popc32(x0 & pm) > nb) continue;
-                const uint32_t x = x0 | (funnel_r(p1[kw], p1[kw + 1], sft) ^ a.a1_lo) | funnel_r(pb[kw], pb[kw + 1], sft);
-                if ((int)popc32(x & pm) > nb) continue;
-                const uint32_t xh = (funnel_r(m0, p0[kw + 2], sft) ^ a.a0_hi) | (funnel_r(p1[kw + 1], p1[kw + 2], sft) ^ a.a1_hi) |
-                                    funnel_r(pb[kw + 1], pb[kw + 2], sft);
-                if (window_decide(((uint64_t)xh << 32) | x, winlen, budget, a.seg_thr)) out.pos3 = 32 * kw + sft;
+                if (SNK_VERIFY(kw, sft, x0, pm, nb, winlen, budget)) out.pos3 = 32 * kw + sft;
             }
         }
     }
+#undef SNK_VERIFY
 }
 
 // byte-wise adapter_pos: adapters with N / lowercase / length > 64, and reads shorter than the
@@ -664,8 +682,9 @@ SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, u
 }
 
 // Per-read descriptor for phase B, one 32-bit word per (table, read): record length (bits 0-9),
-// first byte of the record in its row (bits 10-19), bit 31 = take the checked path. 0 = skip.
-SNK_HD uint32_t hist_desc(int n, int off, bool slow) { return n <= 0 ? 0u : ((uint32_t)n | ((uint32_t)off << 10) | (slow ? 0x80000000u : 0u)); }
+// byte address of the record's first base inside the tile's row block = r*stride + first byte
+// (bits 10-30), bit 31 = take the checked path. 0 = skip.
+SNK_HD uint32_t hist_desc(int n, uint32_t addr, bool slow) { return n <= 0 ? 0u : ((uint32_t)n | (addr << 10) | (slow ? 0x80000000u : 0u)); }
 
 // Fast path: every quality of the record is known to lie inside the shared-memory bins (RF_QSLOW
 // clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at

@@ -333,11 +333,12 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                     if (a.flags & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
                     if (err) report_error(A, err, gi);
                 }
-                desc[0 * A.R + r] = hist_desc(a.len, 0, a.flags & RF_QSLOW);
-                desc[2 * A.R + r] = cat == SNK_KEEP ? hist_desc(a.clean_len, a.head_cut, a.flags & RF_QSLOW) : 0u;
+                const uint32_t row0 = r * A.stride;
+                desc[0 * A.R + r] = hist_desc(a.len, row0, a.flags & RF_QSLOW);
+                desc[2 * A.R + r] = cat == SNK_KEEP ? hist_desc(a.clean_len, row0 + (uint32_t)a.head_cut, a.flags & RF_QSLOW) : 0u;
                 if (MATES == 2) {
-                    desc[1 * A.R + r] = hist_desc(b.len, 0, b.flags & RF_QSLOW);
-                    desc[3 * A.R + r] = cat == SNK_KEEP ? hist_desc(b.clean_len, b.head_cut, b.flags & RF_QSLOW) : 0u;
+                    desc[1 * A.R + r] = hist_desc(b.len, row0, b.flags & RF_QSLOW);
+                    desc[3 * A.R + r] = cat == SNK_KEEP ? hist_desc(b.clean_len, row0 + (uint32_t)b.head_cut, b.flags & RF_QSLOW) : 0u;
                 }
                 unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
                 if (fsb >= 0) {
@@ -395,27 +396,48 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         }
         __syncthreads();
 
-        // ---- phase B: per-position histograms, owner computes
+        // ---- phase B: per-position histograms, owner computes. Each role has its own tight loop; the
+        // descriptor carries the record's byte address, so a trip is: load descriptor, load word, update.
         if (my_item) {
             const uint8_t* rows_s = smem + sp.off_rows[my_m][0];
             const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
+            const int first_pos = J * (int)my_w;
             BaseAcc acc = {0, 0, 0, 0, 0};
-            uint32_t err = 0, since_spill = 0;
-            for (uint32_t r = 0; r < cnt; r++) {
-                const uint32_t d = my_desc[r];
-                const int n = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
-                const int nvalid = n - J * (int)my_w;
-                if (nvalid <= 0) continue;                              // nothing of this record in my positions
-                const uint8_t* rs = rows_s + (size_t)r * A.stride;
-                const uint8_t* rq = rows_q + (size_t)r * A.stride;
-                if (!(d & 0x80000000u)) {
-                    if (q_role) qual_update_fast<QCounter, J>(hist_load_word<J>(rq, off, (int)my_w), nvalid, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
-                    if (b_role) base_update<J>(hist_load_word<J>(rs, off, (int)my_w), nvalid, acc);
-                } else {
-                    unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
-                    err |= hist_item<QCounter, J>(rs, rq, off, n, (int)my_w, P.phred, P.qb, acc, qhist + item, (int)A.X, file_base, b_role, q_role);
+            uint32_t err = 0;
+            bool any_slow = false;
+            if (q_role) {
+#pragma unroll 2
+                for (uint32_t r = 0; r < cnt; r++) {
+                    const uint32_t d = my_desc[r];
+                    const int nvalid = (int)(d & 0x3FFu) - first_pos;
+                    if (nvalid <= 0) continue;
+                    if (d & 0x80000000u) { any_slow = true; continue; }
+                    qual_update_fast<QCounter, J>(hist_load_word<J>(rows_q, (int)((d >> 10) & 0x1FFFFFu), (int)my_w), nvalid,
+                                                  reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
                 }
-                if (b_role && ++since_spill == 255) { since_spill = 0; base_acc_spill<J>(acc, bc); }
+            }
+            if (b_role) {
+#pragma unroll 2
+                for (uint32_t r = 0; r < cnt; r++) {
+                    const uint32_t d = my_desc[r];
+                    const int nvalid = (int)(d & 0x3FFu) - first_pos;
+                    if (nvalid <= 0) continue;
+                    base_update<J>(hist_load_word<J>(rows_s, (int)((d >> 10) & 0x1FFFFFu), (int)my_w), nvalid, acc);
+                    if (cnt > 255 && (r & 127) == 127) base_acc_spill<J>(acc, bc);     // packed 8-bit lanes must not wrap
+                }
+            }
+            if (any_slow) {
+                // checked path for reads with qualities outside the shared-memory bins (rare): qualities only,
+                // the bases were already counted above
+                BaseAcc dummy = {0, 0, 0, 0, 0};
+                unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
+                for (uint32_t r = 0; r < cnt; r++) {
+                    const uint32_t d = my_desc[r];
+                    if (!(d & 0x80000000u)) continue;
+                    const int addr = (int)((d >> 10) & 0x1FFFFFu);
+                    err |= hist_item<QCounter, J>(rows_s, rows_q, addr, (int)(d & 0x3FFu), (int)my_w, P.phred, P.qb, dummy, qhist + item, (int)A.X,
+                                                  file_base, false, true);
+                }
             }
             base_acc_spill<J>(acc, bc);
             if (err) report_error(A, err, g0);

@@ -181,12 +181,13 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                 uint32_t since = 0;
                 for (uint32_t r = 0; r < cnt; r++) {
                     const ReadInfo ri = info[m][r];
-                    const uint32_t d = clean ? (keep[r] ? hist_desc(ri.clean_len, ri.head_cut, ri.flags & RF_QSLOW) : 0u)
-                                             : hist_desc(ri.len, 0, ri.flags & RF_QSLOW);
-                    const int nn = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x3FFu);
+                    const uint32_t row0 = r * c.stride;
+                    const uint32_t d = clean ? (keep[r] ? hist_desc(ri.clean_len, row0 + (uint32_t)ri.head_cut, ri.flags & RF_QSLOW) : 0u)
+                                             : hist_desc(ri.len, row0, ri.flags & RF_QSLOW);
+                    const int nn = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x1FFFFFu);
                     if (nn <= J * (int)w) continue;
-                    const uint8_t* rs = rows[m][0].data() + (size_t)r * c.stride;
-                    const uint8_t* rq = rows[m][1].data() + (size_t)r * c.stride;
+                    const uint8_t* rs = rows[m][0].data();
+                    const uint8_t* rq = rows[m][1].data();
                     if (!(d & 0x80000000u)) hist_item_fast<QCounter, J>(rs, rq, off, nn, (int)w, acc, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
                     else c.err |= hist_item<QCounter, J>(rs, rq, off, nn, (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, file_base);
                     if (++since == 255) { since = 0; spill_j<J>(acc, c.bc[x]); }
