@@ -36,6 +36,13 @@ namespace {
 }
 void engine_check(int rc) { if (rc) die(snk_last_error()); }
 
+double now_s()
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
 std::string local_time()
 {
     time_t t = time(nullptr);
@@ -206,6 +213,9 @@ private:
     // output routing (reference emission order)
     uint64_t cyc_ = 0, defer_len_ = 0, insert_off_ = 0;
     bool reorder_ = false;
+    // busy seconds per stage (log only)
+    double t_parse_ = 0, t_gpu_wait_ = 0, t_write_ = 0, t_setup_ = 0;
+    std::atomic<uint64_t> t_format_us_{0};
 };
 
 // ---- parse up to max_reads records of one mate into the pinned SoA rows
@@ -305,11 +315,15 @@ void FilterRun::ingest()
         if (!free_q_.pop(b)) break;
         size_t n2 = 0;
         std::thread t2;
+        const double tp0 = now_s();
         if (pe_) t2 = std::thread([&] { n2 = parse_mate(*r2, *b, 1, hp_.batch_reads); });
         const size_t n1 = parse_mate(r1, *b, 0, hp_.batch_reads);
         if (pe_) {
             t2.join();
             if (n1 != n2) die("reads number in fq1 and fq2 are different");
+        }
+        t_parse_ += now_s() - tp0;
+        if (pe_) {
             const size_t s = std::max(b->m[0].stride, b->m[1].stride);
             for (int m = 0; m < 2; m++) if (b->m[m].stride != s) b->m[m].reserve(b->m[m].cap_reads, s);
         }
@@ -336,7 +350,9 @@ void FilterRun::gpu_stage()
     const size_t depth = inflight_depth();
     auto retire = [&] {
         HostBatch* d = inflight.front(); inflight.pop_front();
+        const double t0 = now_s();
         engine_check(snk_engine_lane_sync(engines_[d->gpu], d->lane));
+        t_gpu_wait_ += now_s() - t0;
         fmt_q_.push(d);
     };
     HostBatch* b;
@@ -444,7 +460,9 @@ void FilterRun::format_worker()
 {
     HostBatch* b;
     while (fmt_q_.pop(b)) {
+        const double t0 = now_s();
         for (int m = 0; m < mates_; m++) format_mate(*b, m);
+        t_format_us_ += (uint64_t)((now_s() - t0) * 1e6);
         { std::lock_guard<std::mutex> g(done_mu_); done_[b->seq_no] = b; }
         done_cv_.notify_all();
     }
@@ -477,6 +495,7 @@ void FilterRun::writer()
             if (it == done_.end()) break;
             b = it->second; done_.erase(it);
         }
+        const double tw0 = now_s();
         for (int m = 0; m < mates_; m++) {
             for (Piece& p : b->m[m].out) {
                 if (p.kind == 0) fwrite(p.bytes.data(), 1, p.bytes.size(), out[m]);
@@ -485,6 +504,7 @@ void FilterRun::writer()
             }
             b->m[m].out.clear();
         }
+        t_write_ += now_s() - tw0;
         if (b->seq_no % 4 == 0) log_line(local_time() + " processed_reads:\t" + std::to_string(b->first_index + b->n));
         next++;
         free_q_.push(b);
@@ -507,6 +527,7 @@ void FilterRun::writer()
 
 void FilterRun::process()
 {
+    const double t_begin = now_s();
     mkdir_p(hp_.output_dir);
     log_.open(hp_.log.c_str());
     if (!log_) die("cannot open such file," + hp_.log);
@@ -525,6 +546,7 @@ void FilterRun::process()
     batches_.resize(inflight_depth() + 3);       // in flight on the GPUs + being parsed + being formatted/written
     for (auto& b : batches_) free_q_.push(&b);
 
+    t_setup_ = now_s() - t_begin;
     const int nworkers = std::max(2, hp_.threads);
     std::thread t_ingest([&] { ingest(); });
     std::thread t_gpu([&] { gpu_stage(); });
@@ -564,6 +586,13 @@ void FilterRun::process()
     engines_.clear();
     for (auto& b : batches_) for (auto& m : b.m) m.release();
     batches_.clear();
+    {
+        char buf[512];
+        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, parse(busy) %.2f, gpu-wait %.2f, format(sum over %d workers) %.2f, write %.2f, total %.2f; reads %llu",
+                 t_setup_, t_parse_, t_gpu_wait_, std::max(2, hp_.threads), t_format_us_.load() * 1e-6, t_write_, now_s() - t_begin,
+                 (unsigned long long)total_reads_);
+        log_line(buf);
+    }
     log_line(local_time() + "\tAnalysis accomplished!");
     log_.close();
 }

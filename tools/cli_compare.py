@@ -87,6 +87,10 @@ def main():
             if f.endswith(".txt"):
                 same = same and open(f"{work}/ref/{f}", "rb").read() == open(f"{work}/mine/{f}", "rb").read()
         out["outputs_identical"] = same
+    try:
+        out["b200_log"] = [l.strip() for l in open(f"{work}/mine/log") if "stage seconds" in l]
+    except Exception:
+        pass
     print(json.dumps(out))
     shutil.rmtree(work, ignore_errors=True)
 
