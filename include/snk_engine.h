@@ -173,7 +173,7 @@ int snk_engine_destroy(snk_engine* e);
  * batch. Copies the batch host->device, runs the kernels, copies the per-read results back into
  * out1/out2 (host) and accumulates the statistics on the device. Synchronous on return.
  * first_index = number of pairs (reads for SE) that precede this batch in the input; it selects
- * the slot per read and must satisfy (first_index % slot_block) % 32 == 0. */
+ * the slot per read. */
 int snk_filter_pe_host(snk_engine* e, const snk_batch* r1, const snk_batch* r2,
                        snk_read_result* out1, snk_read_result* out2, uint64_t first_index);
 int snk_filter_se_host(snk_engine* e, const snk_batch* r1, snk_read_result* out1, uint64_t first_index);
@@ -186,6 +186,56 @@ int snk_filter_pe_async(snk_engine* e, int lane, const snk_batch* r1, const snk_
                         snk_read_result* out1, snk_read_result* out2, uint64_t first_index);
 int snk_filter_se_async(snk_engine* e, int lane, const snk_batch* r1, snk_read_result* out1, uint64_t first_index);
 int snk_engine_lane_sync(snk_engine* e, int lane);
+
+/* ---- FASTQ text entry points (the steps right before and right after the path) ----
+ *
+ *   reference (file:line)                                            replaced by
+ *   ---------------------------------------------------------------  --------------------------------------
+ *   sub_thread's line loop + C_fastq fill   peprocess.cpp:2090-2131   line index + row packing kernels
+ *     (.gz: every line loses spaceNum chars), :2198-2239 (plain: 1)     (snk_text_format.strip)
+ *   fastq_trim index removal                read_filter.cpp:357-382   id_mode
+ *   preOutput (/1 /2)                       peprocess.cpp:1617-1629   pe_info
+ *   output_fastqs                           peprocess.cpp:3383-3433   format kernel: the clean records of the
+ *                                           seprocess.cpp:2302-2352     batch as one contiguous text per mate
+ *
+ * The host hands over the raw text of n_records whole records per mate (4 lines each; the last line
+ * of the input may lack its newline) and gets back the clean FASTQ/FASTA text, in input order, plus
+ * the byte offset of every record in it. Statistics accumulate on the device exactly as with the
+ * SoA entry points. Sequence: snk_filter_*_text_async -> snk_text_meta_sync (sizes, flags) ->
+ * snk_text_fetch_async into buffers of at least out_bytes[m] -> snk_engine_lane_sync. */
+typedef struct snk_text_format {
+    int32_t strip;        /* characters every input line loses at its end, newline included: 1 for plain
+                             input, spaceNum of the first line for .gz input (peprocess.cpp:2066-2076) */
+    int32_t pe_info;      /* gp.whether_add_pe_info */
+    int32_t fasta;        /* gp.output_file_type == "fasta" */
+    int32_t id_mode;      /* 0: ids unchanged; 1: gp.index_remove with seqType "0"; 2: gp.index_remove otherwise */
+    int32_t reserved[4];
+} snk_text_format;
+enum snk_text_flags {
+    SNK_TEXT_STRIDE_OVERFLOW = 1,  /* a read is longer than `stride`: nothing was filtered or counted; resubmit with
+                                      stride >= roundup16(max_len) */
+    SNK_TEXT_LEN_MISMATCH = 2,     /* sequence and quality of record bad_record differ in length */
+    SNK_TEXT_LINE_COUNT = 4,       /* the text does not hold 4 * n_records lines */
+    SNK_TEXT_TOO_LONG = 8          /* a read exceeds SNK_MAX_READ_LEN */
+};
+typedef struct snk_text_meta {
+    uint64_t out_bytes[2];  /* size of the clean text per mate */
+    uint32_t kept;          /* records (pairs) kept */
+    uint32_t max_len;       /* longest read of the batch */
+    uint32_t flags;         /* snk_text_flags */
+    uint32_t bad_record;    /* first offending record for LEN_MISMATCH / TOO_LONG */
+} snk_text_meta;
+/* text must be pinned for the copy to overlap; at most 3.75 GiB per mate and call */
+int snk_filter_pe_text_async(snk_engine* e, int lane, const char* text1, size_t bytes1, const char* text2, size_t bytes2,
+                             uint32_t n_records, uint32_t stride, const snk_text_format* fmt, uint64_t first_index);
+int snk_filter_se_text_async(snk_engine* e, int lane, const char* text1, size_t bytes1, uint32_t n_records, uint32_t stride,
+                             const snk_text_format* fmt, uint64_t first_index);
+/* waits for the lane, then reports sizes and flags of its last text submission */
+int snk_text_meta_sync(snk_engine* e, int lane, snk_text_meta* out);
+/* enqueue the copies back to the host (any pointer may be NULL): clean text, rec_off[n_records + 1]
+ * (byte offset of every record in the clean text; equal neighbours = record dropped), result records */
+int snk_text_fetch_async(snk_engine* e, int lane, char* out1, char* out2, uint32_t* rec_off1, uint32_t* rec_off2,
+                         snk_read_result* res1, snk_read_result* res2);
 
 /* Device-resident entry points: all pointers are DEVICE pointers (e.g. torch tensors' data_ptr()),
  * `stream` is a cudaStream_t (0 = legacy default stream). Asynchronous. */

@@ -248,6 +248,18 @@ def make_batch(seq, qual, length):
     return b
 
 
+class TextFormat(C.Structure):
+    _fields_ = [("strip", C.c_int32), ("pe_info", C.c_int32), ("fasta", C.c_int32), ("id_mode", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
+
+
+class TextMeta(C.Structure):
+    _fields_ = [("out_bytes", C.c_uint64 * 2), ("kept", C.c_uint32), ("max_len", C.c_uint32), ("flags", C.c_uint32),
+                ("bad_record", C.c_uint32)]
+
+
+TEXT_STRIDE_OVERFLOW, TEXT_LEN_MISMATCH, TEXT_LINE_COUNT, TEXT_TOO_LONG = 1, 2, 4, 8
+
 _PROTOS = {
     "snk_last_error": (C.c_char_p, []),
     "snk_abi_version": (C.c_int, []),
@@ -261,6 +273,12 @@ _PROTOS = {
     "snk_filter_pe_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint64]),
     "snk_filter_se_async": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(Batch), C.c_void_p, C.c_uint64]),
     "snk_engine_lane_sync": (C.c_int, [C.c_void_p, C.c_int]),
+    "snk_filter_pe_text_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                           C.POINTER(TextFormat), C.c_uint64]),
+    "snk_filter_se_text_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                           C.POINTER(TextFormat), C.c_uint64]),
+    "snk_text_meta_sync": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(TextMeta)]),
+    "snk_text_fetch_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_filter_pe_device": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "snk_filter_se_device": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_uint64, C.c_void_p]),
     "snk_engine_stats_reset": (C.c_int, [C.c_void_p]),

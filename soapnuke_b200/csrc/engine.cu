@@ -13,6 +13,7 @@
 #include <vector>
 #include <mutex>
 #include "filter_kernel.cuh"
+#include "text_kernels.cuh"
 #include "dev_params.h"
 #include "../host/host_common.h"
 
@@ -38,6 +39,14 @@ struct Lane {
     size_t cap = 0;
     // results are copied back after the kernel; remember where
     bool pending = false;
+    // text path: pinned copy of the batch's TextMeta and where the outputs of the last submission live
+    TextMeta* h_meta = nullptr;
+    TextMeta* d_meta = nullptr;
+    int text_mates = 0;
+    uint32_t text_n = 0;
+    const uint8_t* d_out[2] = {nullptr, nullptr};
+    const uint32_t* d_rec_off[2] = {nullptr, nullptr};
+    const snk_read_result* d_res[2] = {nullptr, nullptr};
 };
 
 struct LaunchPlan {
@@ -134,7 +143,8 @@ int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t fi
 }
 
 int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch* d2, snk_read_result* o1,
-                  snk_read_result* o2, uint64_t first, cudaStream_t stream)
+                  snk_read_result* o2, uint64_t first, cudaStream_t stream, const unsigned int* skip_word = nullptr,
+                  unsigned int skip_mask = 0)
 {
     if (!d1 || (mates == 2 && !d2)) { snk::set_error("null batch"); return 1; }
     if (mates == 2 && (d1->n != d2->n || d1->stride != d2->stride)) { snk::set_error("reads number in fq1 and fq2 are different"); return 1; }
@@ -152,6 +162,7 @@ int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch
             return 1;
         }
     ka.stats = e->d_stats; ka.err_flags = e->d_err; ka.err_index = e->d_err_index;
+    ka.skip_word = skip_word; ka.skip_mask = skip_mask;
     ka.stride = d1->stride; ka.R = lp.R; ka.items_w = lp.W; ka.X = lp.X; ka.tm = tm;
     DevParams dp = e->dev;
     dp.qb = lp.qb;               // may have been lowered so that this stride's histograms fit
@@ -219,6 +230,110 @@ int filter_host_async(snk_engine* e, int lane, int mates, const snk_batch* r1, c
     return 0;
 }
 
+// ------------------------------------------------------------------ FASTQ text path
+__global__ void text_meta_init_kernel(TextMeta* m)
+{
+    m->out_bytes[0] = m->out_bytes[1] = 0;
+    m->kept = 0; m->max_len = 0; m->flags = 0; m->bad_record = 0xFFFFFFFFu;
+    m->newlines[0] = m->newlines[1] = 0; m->pad_[0] = m->pad_[1] = 0;
+}
+
+inline size_t al256(size_t v) { return (v + 255) / 256 * 256; }
+
+int filter_text_async(snk_engine* e, int lane, int mates, const char* const text[2], const size_t bytes[2], uint32_t n,
+                      uint32_t stride, const snk_text_format* fmt, uint64_t first)
+{
+    if (!e) { snk::set_error("null engine"); return 1; }
+    if (lane < 0 || lane >= kLanes) { snk::set_error("lane out of range"); return 1; }
+    if (!fmt || !text[0] || (mates == 2 && !text[1])) { snk::set_error("null text or format"); return 1; }
+    if ((mates == 2) != (e->params.is_pe != 0)) { snk::set_error("engine was created for the other read layout (PE/SE)"); return 1; }
+    if (stride == 0 || stride % 16 != 0 || stride > 1008) { snk::set_error("batch stride must be a multiple of 16 in [16,1008]"); return 1; }
+    if (n == 0) { snk::set_error("empty text batch"); return 1; }
+    if (fmt->strip < 0 || fmt->id_mode < 0 || fmt->id_mode > 2) { snk::set_error("bad text format"); return 1; }
+    for (int m = 0; m < mates; m++)
+        if (bytes[m] == 0 || bytes[m] > 0xF0000000ull) { snk::set_error("a text batch must hold 1 byte .. 3.75 GiB per mate"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    Lane& L = e->lanes[lane];
+    CUDA_TRY(cudaStreamSynchronize(L.stream));        // the lane's buffers are free again
+    if (!L.h_meta) {
+        CUDA_TRY(cudaHostAlloc((void**)&L.h_meta, sizeof(TextMeta), cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc((void**)&L.d_meta, sizeof(TextMeta)));
+    }
+    // ---- carve the lane buffer
+    const size_t rows = al256((size_t)n * stride) + 256;
+    const uint32_t nblk = (n + kRecThreads - 1) / kRecThreads;
+    size_t need = 0;
+    size_t o_text[2], o_segc[2], o_segb[2], o_line[2], o_seq[2], o_qual[2], o_len[2], o_res[2], o_rec[2], o_blk[2], o_out[2];
+    uint32_t nseg[2] = {0, 0};
+    for (int m = 0; m < mates; m++) {
+        nseg[m] = (uint32_t)((bytes[m] + kSegBytes - 1) / kSegBytes);
+        o_text[m] = need; need += al256(bytes[m] + 64);
+        o_segc[m] = need; need += al256((size_t)nseg[m] * 4);
+        o_segb[m] = need; need += al256((size_t)nseg[m] * 4);
+        o_line[m] = need; need += al256(((size_t)4 * n + 2) * 4);
+        o_seq[m] = need; need += rows;
+        o_qual[m] = need; need += rows;
+        o_len[m] = need; need += al256((size_t)n * 2);
+        o_res[m] = need; need += al256((size_t)n * sizeof(snk_read_result));
+        o_rec[m] = need; need += al256(((size_t)n + 1) * 4);
+        o_blk[m] = need; need += al256((size_t)nblk * 4);
+        o_out[m] = need; need += al256(bytes[m] + 2 * (size_t)n + 64);
+    }
+    if (lane_reserve(L, need)) return 1;
+    TextArgs ta;
+    memset(&ta, 0, sizeof ta);
+    snk_batch d[2];
+    snk_read_result* dres[2] = {nullptr, nullptr};
+    for (int m = 0; m < mates; m++) {
+        uint8_t* b = L.d_buf;
+        CUDA_TRY(cudaMemcpyAsync(b + o_text[m], text[m], bytes[m], cudaMemcpyHostToDevice, L.stream));
+        ta.text[m] = b + o_text[m]; ta.bytes[m] = (uint32_t)bytes[m]; ta.nseg[m] = nseg[m];
+        ta.seg_count[m] = reinterpret_cast<uint32_t*>(b + o_segc[m]);
+        ta.seg_base[m] = reinterpret_cast<uint32_t*>(b + o_segb[m]);
+        ta.line_off[m] = reinterpret_cast<uint32_t*>(b + o_line[m]);
+        ta.seq[m] = b + o_seq[m]; ta.qual[m] = b + o_qual[m];
+        ta.len[m] = reinterpret_cast<uint16_t*>(b + o_len[m]);
+        dres[m] = reinterpret_cast<snk_read_result*>(b + o_res[m]);
+        ta.res[m] = dres[m];
+        ta.rec_off[m] = reinterpret_cast<uint32_t*>(b + o_rec[m]);
+        ta.blk_sum[m] = reinterpret_cast<uint32_t*>(b + o_blk[m]);
+        ta.out[m] = b + o_out[m];
+        d[m].seq = ta.seq[m]; d[m].qual = ta.qual[m]; d[m].len = ta.len[m]; d[m].n = n; d[m].stride = stride;
+        L.d_out[m] = ta.out[m]; L.d_rec_off[m] = ta.rec_off[m]; L.d_res[m] = dres[m];
+    }
+    ta.meta = L.d_meta; ta.n = n; ta.stride = stride; ta.mates = mates;
+    ta.fmt.strip = fmt->strip; ta.fmt.pe_info = fmt->pe_info; ta.fmt.fasta = fmt->fasta; ta.fmt.id_mode = fmt->id_mode;
+    ta.fmt.qshift = e->params.out_quality_phred - e->params.quality_phred;
+    const uint32_t seg_grid = nseg[0] > nseg[1] ? nseg[0] : nseg[1];
+    const dim3 gseg(seg_grid, mates), grec(nblk, mates);
+    text_meta_init_kernel<<<1, 1, 0, L.stream>>>(L.d_meta);
+    newline_count_kernel<<<gseg, kSegThreads, 0, L.stream>>>(ta);
+    segment_scan_kernel<<<mates, kScanThreads, 0, L.stream>>>(ta);
+    line_offset_kernel<<<gseg, kSegThreads, 0, L.stream>>>(ta);
+    {
+        const uint64_t tasks = (uint64_t)n * 2u * (stride / 16u);
+        const dim3 gpack((unsigned)((tasks + 255) / 256), mates);
+        pack_rows_kernel<<<gpack, 256, 0, L.stream>>>(ta);
+    }
+    CUDA_TRY(cudaGetLastError());
+    {
+        std::lock_guard<std::mutex> g(e->mu);
+        if (launch_filter(e, mates, &d[0], mates == 2 ? &d[1] : nullptr, dres[0], dres[1], first, L.stream, &L.d_meta->flags,
+                          TEXT_STRIDE_OVERFLOW | TEXT_LINE_COUNT))
+            return 1;
+        e->launches += 9;      // the text kernels around it
+    }
+    out_len_kernel<<<grec, kRecThreads, 0, L.stream>>>(ta);
+    block_scan_kernel<<<mates, kScanThreads, 0, L.stream>>>(ta);
+    out_offset_kernel<<<grec, kRecThreads, 0, L.stream>>>(ta);
+    format_kernel<<<dim3((n + 7) / 8, mates), 256, 0, L.stream>>>(ta);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(L.h_meta, L.d_meta, sizeof(TextMeta), cudaMemcpyDeviceToHost, L.stream));
+    L.text_mates = mates; L.text_n = n;
+    L.pending = true;
+    return 0;
+}
+
 } // namespace
 
 extern "C" {
@@ -261,6 +376,8 @@ int snk_engine_destroy(snk_engine* e)
     for (int i = 0; i < kLanes; i++) {
         if (e->lanes[i].stream) { cudaStreamSynchronize(e->lanes[i].stream); cudaStreamDestroy(e->lanes[i].stream); }
         if (e->lanes[i].d_buf) cudaFree(e->lanes[i].d_buf);
+        if (e->lanes[i].h_meta) cudaFreeHost(e->lanes[i].h_meta);
+        if (e->lanes[i].d_meta) cudaFree(e->lanes[i].d_meta);
     }
     cudaFree(e->d_stats); cudaFree(e->d_err); cudaFree(e->d_err_index);
     delete e;
@@ -296,6 +413,49 @@ int snk_filter_se_host(snk_engine* e, const snk_batch* r1, snk_read_result* out1
 {
     if (filter_host_async(e, 0, 1, r1, nullptr, out1, nullptr, first_index)) return 1;
     return snk_engine_lane_sync(e, 0);
+}
+
+int snk_filter_pe_text_async(snk_engine* e, int lane, const char* text1, size_t bytes1, const char* text2, size_t bytes2,
+                             uint32_t n_records, uint32_t stride, const snk_text_format* fmt, uint64_t first_index)
+{
+    const char* const t[2] = {text1, text2};
+    const size_t b[2] = {bytes1, bytes2};
+    return filter_text_async(e, lane, 2, t, b, n_records, stride, fmt, first_index);
+}
+int snk_filter_se_text_async(snk_engine* e, int lane, const char* text1, size_t bytes1, uint32_t n_records, uint32_t stride,
+                             const snk_text_format* fmt, uint64_t first_index)
+{
+    const char* const t[2] = {text1, nullptr};
+    const size_t b[2] = {bytes1, 0};
+    return filter_text_async(e, lane, 1, t, b, n_records, stride, fmt, first_index);
+}
+int snk_text_meta_sync(snk_engine* e, int lane, snk_text_meta* out)
+{
+    if (!e || lane < 0 || lane >= kLanes || !out) { snk::set_error("bad lane or null argument"); return 1; }
+    Lane& L = e->lanes[lane];
+    if (!L.h_meta || !L.text_n) { snk::set_error("no text batch was submitted on this lane"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(L.stream));
+    out->out_bytes[0] = L.h_meta->out_bytes[0]; out->out_bytes[1] = L.h_meta->out_bytes[1];
+    out->kept = L.h_meta->kept; out->max_len = L.h_meta->max_len; out->flags = L.h_meta->flags; out->bad_record = L.h_meta->bad_record;
+    return 0;
+}
+int snk_text_fetch_async(snk_engine* e, int lane, char* out1, char* out2, uint32_t* rec_off1, uint32_t* rec_off2,
+                         snk_read_result* res1, snk_read_result* res2)
+{
+    if (!e || lane < 0 || lane >= kLanes) { snk::set_error("bad lane"); return 1; }
+    Lane& L = e->lanes[lane];
+    if (!L.h_meta || !L.text_n) { snk::set_error("no text batch was submitted on this lane"); return 1; }
+    CUDA_TRY(cudaSetDevice(e->device));
+    CUDA_TRY(cudaStreamSynchronize(L.stream));        // meta is final
+    char* outs[2] = {out1, out2}; uint32_t* offs[2] = {rec_off1, rec_off2}; snk_read_result* ress[2] = {res1, res2};
+    for (int m = 0; m < L.text_mates; m++) {
+        if (outs[m] && L.h_meta->out_bytes[m])
+            CUDA_TRY(cudaMemcpyAsync(outs[m], L.d_out[m], L.h_meta->out_bytes[m], cudaMemcpyDeviceToHost, L.stream));
+        if (offs[m]) CUDA_TRY(cudaMemcpyAsync(offs[m], L.d_rec_off[m], ((size_t)L.text_n + 1) * 4, cudaMemcpyDeviceToHost, L.stream));
+        if (ress[m]) CUDA_TRY(cudaMemcpyAsync(ress[m], L.d_res[m], (size_t)L.text_n * sizeof(snk_read_result), cudaMemcpyDeviceToHost, L.stream));
+    }
+    return 0;
 }
 
 int snk_filter_pe_device(snk_engine* e, const snk_batch* d_r1, const snk_batch* d_r2, snk_read_result* d_out1,

@@ -47,6 +47,8 @@ struct KernelArgs {
     unsigned long long* stats;      // n_slots * SNK_SLOT_WORDS
     unsigned int* err_flags;        // sticky error bits
     unsigned long long* err_index;  // smallest global read index that raised an error
+    const unsigned int* skip_word;  // optional: when (*skip_word & skip_mask) != 0 the launch does nothing
+    unsigned int skip_mask;         //   (text path: a read did not fit the row stride, the batch is resubmitted)
     uint32_t stride;                // bytes per row
     uint32_t R;                     // tile capacity (reads or pairs)
     uint32_t items_w;               // histogram items per table = stride / J
@@ -221,6 +223,7 @@ __global__ void __launch_bounds__((KernelShape<MAXC, MATES, J>::kMaxThreads), (K
 filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ KernelArgs A)
 {
     extern __shared__ __align__(16) uint8_t smem[];
+    if (A.skip_word && (*A.skip_word & A.skip_mask)) return;
     const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
     QCounter* qhist = reinterpret_cast<QCounter*>(smem + sp.off_qhist);
     uint32_t* desc = reinterpret_cast<uint32_t*>(smem + sp.off_desc);

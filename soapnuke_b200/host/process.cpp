@@ -3,14 +3,20 @@
 //   line handling of sub_thread           peprocess.cpp:2066-2076, 2090-2131 (.gz: strip the first line's
 //                                         trailing-whitespace count from every line), :2198-2239 (plain: strip 1)
 //   first-batch pair-ID / Phred checks    peprocess.cpp:1884-1908, 1207-1319; seprocess.cpp:741-867
-//   record formatting                     peprocess.cpp:3383-3433 (output_fastqs), :1617-1629 (preOutput /1 /2),
-//                                         read_filter.cpp:357-382 (index removal)
+//   record formatting                     on the device (csrc/text_kernels.cuh): peprocess.cpp:3383-3433, :1617-1629,
+//                                         read_filter.cpp:357-382
 //   emission order of the clean records   peprocess.cpp:2141,2248,2957-2990 (see Writer::route)
 //   gzip level 2 members                  peprocess.cpp:1803-1810
 #include "process.h"
 #include "host_common.h"
 #include <zlib.h>
 #include <sys/stat.h>
+#include <fcntl.h>
+#include <unistd.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <cstdio>
@@ -83,89 +89,116 @@ private:
     bool closed_ = false;
 };
 
-// ------------------------------------------------------------------ line reader (gz or plain through zlib)
-class LineReader {
+// ------------------------------------------------------------------ raw byte source (plain via read(2), .gz via zlib)
+class ByteSource {
 public:
-    explicit LineReader(const std::string& path) : path_(path)
+    ByteSource(const std::string& path, bool gz) : path_(path), gz_(gz)
     {
-        f_ = gzopen(path.c_str(), "rb");
-        if (!f_) die("cannot open the file," + path);
-        gzbuffer(f_, 1 << 22);
-        buf_.resize(1 << 24);
-    }
-    ~LineReader() { if (f_) gzclose(f_); }
-    // next line including its '\n' when present; false at EOF
-    bool next(const char*& p, size_t& n)
-    {
-        for (;;) {
-            const char* nl = (const char*)memchr(buf_.data() + pos_, '\n', end_ - pos_);
-            if (nl) { p = buf_.data() + pos_; n = (size_t)(nl - p) + 1; pos_ += n; return true; }
-            if (eof_) {
-                if (pos_ < end_) { p = buf_.data() + pos_; n = end_ - pos_; pos_ = end_; return true; }
-                return false;
-            }
-            refill();
+        if (gz_) {
+            f_ = gzopen(path.c_str(), "rb");
+            if (!f_) die("cannot open the file," + path);
+            gzbuffer(f_, 1 << 22);
+        } else {
+            fd_ = open(path.c_str(), O_RDONLY);
+            if (fd_ < 0) die("cannot open the file," + path);
         }
     }
-private:
-    void refill()
+    ~ByteSource() { if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
+    // up to n bytes into dst; 0 at EOF
+    size_t read(char* dst, size_t n)
     {
-        if (pos_ > 0) { memmove(buf_.data(), buf_.data() + pos_, end_ - pos_); end_ -= pos_; pos_ = 0; }
-        if (end_ == buf_.size()) buf_.resize(buf_.size() * 2);
-        int got = gzread(f_, buf_.data() + end_, (unsigned)std::min<size_t>(buf_.size() - end_, 1u << 30));
+        if (gz_) {
+            int got = gzread(f_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
+            if (got < 0) die("cannot read the file," + path_);
+            return (size_t)got;
+        }
+        ssize_t got = ::read(fd_, dst, n);
         if (got < 0) die("cannot read the file," + path_);
-        if (got == 0) eof_ = true;
-        end_ += (size_t)got;
+        return (size_t)got;
     }
+    // bytes carried over from the previous batch (text after its last complete record)
+    std::vector<char> carry;
+    bool eof = false;
+private:
     std::string path_;
+    bool gz_;
     gzFile f_ = nullptr;
-    std::vector<char> buf_;
-    size_t pos_ = 0, end_ = 0;
-    bool eof_ = false;
+    int fd_ = -1;
 };
 
-// ------------------------------------------------------------------ one batch travelling through the stages
-struct Piece { int kind; std::string bytes; };   // kind: 0 main, 1 deferred, 2 flush-deferred marker
-struct MateBuf {
-    uint8_t* seq = nullptr; uint8_t* qual = nullptr; uint16_t* len = nullptr; snk_read_result* res = nullptr;
-    size_t cap_reads = 0, stride = 0;
-    std::vector<char> ids; std::vector<uint32_t> id_off;
-    std::vector<Piece> out;
-    void release()
-    {
-        if (seq) snk_host_free(seq);
-        if (qual) snk_host_free(qual);
-        if (len) snk_host_free(len);
-        if (res) snk_host_free(res);
-        seq = qual = nullptr; len = nullptr; res = nullptr;
-    }
-    void reserve(size_t reads, size_t new_stride)
-    {
-        if (reads <= cap_reads && new_stride == stride) return;
-        uint8_t *ns = nullptr, *nq = nullptr; uint16_t* nl = nullptr; snk_read_result* nr = nullptr;
-        engine_check(snk_host_alloc((void**)&ns, reads * new_stride + 64));
-        engine_check(snk_host_alloc((void**)&nq, reads * new_stride + 64));
-        engine_check(snk_host_alloc((void**)&nl, reads * sizeof(uint16_t) + 64));
-        engine_check(snk_host_alloc((void**)&nr, reads * sizeof(snk_read_result) + 64));
-        memset(ns, 0, reads * new_stride + 64); memset(nq, 0, reads * new_stride + 64);
-        if (seq) {      // re-stride what is already there (a longer read appeared: rare)
-            const size_t keep = std::min(cap_reads, reads);
-            for (size_t i = 0; i < keep; i++) {
-                memcpy(ns + i * new_stride, seq + i * stride, std::min(stride, new_stride));
-                memcpy(nq + i * new_stride, qual + i * stride, std::min(stride, new_stride));
-            }
-            memcpy(nl, len, keep * sizeof(uint16_t));
+// ------------------------------------------------------------------ newline search
+// Offset just behind the `need`-th '\n' of p[0,n), or n when there are fewer; *count = newlines seen
+// (stops counting at `need`).
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) size_t nth_newline_avx2(const char* p, size_t n, size_t need, size_t* count)
+{
+    size_t i = 0, c = 0;
+    const __m256i nl = _mm256_set1_epi8('\n');
+    while (i + 32 <= n) {
+        const uint32_t m = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), nl));
+        const size_t k = (size_t)__builtin_popcount(m);
+        if (c + k >= need) {
+            uint32_t mm = m;
+            for (size_t skip = need - c - 1; skip > 0; skip--) mm &= mm - 1;
+            *count = need;
+            return i + (size_t)__builtin_ctz(mm) + 1;
         }
-        release();
-        seq = ns; qual = nq; len = nl; res = nr; cap_reads = reads; stride = new_stride;
+        c += k;
+        i += 32;
     }
+    for (; i < n; i++)
+        if (p[i] == '\n' && ++c == need) { *count = c; return i + 1; }
+    *count = c;
+    return n;
+}
+#endif
+size_t nth_newline(const char* p, size_t n, size_t need, size_t* count)
+{
+    if (need == 0) { *count = 0; return 0; }
+#if defined(__x86_64__)
+    static const bool has_avx2 = __builtin_cpu_supports("avx2");
+    if (has_avx2) return nth_newline_avx2(p, n, need, count);
+#endif
+    size_t i = 0, c = 0;
+    while (i < n) {
+        const char* q = (const char*)memchr(p + i, '\n', n - i);
+        if (!q) break;
+        i = (size_t)(q - p) + 1;
+        if (++c == need) { *count = c; return i; }
+    }
+    *count = c;
+    return n;
+}
+
+// ------------------------------------------------------------------ one batch travelling through the stages
+struct PinnedBuf {
+    char* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes, size_t keep)          // contents [0, keep) survive
+    {
+        if (bytes <= cap) return;
+        size_t want = bytes + bytes / 4 + (1u << 20);
+        char* np = nullptr;
+        engine_check(snk_host_alloc((void**)&np, want));
+        if (p) { if (keep) memcpy(np, p, keep); snk_host_free(p); }
+        p = np; cap = want;
+    }
+    void release() { if (p) snk_host_free(p); p = nullptr; cap = 0; }
 };
+// a run of output bytes: kind 0 = in place, 1 = deferred (see FilterRun::writer), 2 = "emit the deferred bytes now"
+struct Piece { int kind; const char* p; size_t len; std::string gz; };
 struct HostBatch {
     uint64_t seq_no = 0, first_index = 0;
     uint32_t n = 0;
     int gpu = 0, lane = 0;
-    MateBuf m[2];
+    PinnedBuf in[2], out[2], off[2];      // raw text, clean text, rec_off (uint32 [n+1])
+    size_t in_bytes[2] = {0, 0};
+    snk_text_meta meta;
+    std::vector<Piece> pieces[2];
+    std::atomic<int> tasks{0};            // deflate tasks still running
+    void release() { for (int m = 0; m < 2; m++) { in[m].release(); out[m].release(); off[m].release(); } }
 };
+struct GzTask { HostBatch* b; int mate; size_t piece; };
 
 inline size_t round16(size_t v) { return (v + 15) / 16 * 16; }
 
@@ -182,6 +215,7 @@ private:
     bool pe_;
     int mates_;
     snk_params ep_;
+    snk_text_format fmt_;
     std::vector<snk_engine*> engines_;
     std::ofstream log_;
     std::mutex log_mu_;
@@ -190,23 +224,25 @@ private:
     uint64_t total_reads_ = 0;
     std::string pending_deferred_[2];  // deferred output (already encoded) waiting for its insertion point
 
-    std::vector<HostBatch> batches_;
-    Channel<HostBatch*> free_q_, gpu_q_, fmt_q_;
+    std::deque<HostBatch> batches_;
+    Channel<HostBatch*> free_q_, gpu_q_;
+    Channel<GzTask> gz_q_;
     std::mutex done_mu_;
     std::condition_variable done_cv_;
-    std::map<uint64_t, HostBatch*> done_;       // formatted batches by sequence number
-    bool fmt_finished_ = false;
+    std::map<uint64_t, HostBatch*> done_;       // finished batches by sequence number
+    bool all_submitted_ = false;
     uint64_t n_batches_total_ = 0;
 
     // stages
     void ingest();
-    size_t parse_mate(LineReader& r, HostBatch& b, int mate, size_t max_reads);
+    size_t fill_mate(ByteSource& src, HostBatch& b, int mate, size_t max_reads);
     void first_batch_checks(const HostBatch& b);
     void gpu_stage();
-    void format_worker();
-    void format_mate(HostBatch& b, int mate);
+    void make_pieces(HostBatch& b);
+    void finish_batch(HostBatch* b);
+    void gz_worker();
     void writer();
-    void encode(std::string& text);
+    void encode(const char* p, size_t n, std::string& out);
     size_t inflight_depth() const { return engines_.size() * (size_t)snk_engine_lanes(engines_[0]); }
     void log_line(const std::string& s) { std::lock_guard<std::mutex> g(log_mu_); log_ << s << std::endl; }
 
@@ -214,69 +250,91 @@ private:
     uint64_t cyc_ = 0, defer_len_ = 0, insert_off_ = 0;
     bool reorder_ = false;
     // busy seconds per stage (log only)
-    double t_parse_ = 0, t_gpu_wait_ = 0, t_write_ = 0, t_setup_ = 0;
-    std::atomic<uint64_t> t_format_us_{0};
+    double t_read_ = 0, t_gpu_wait_ = 0, t_write_ = 0, t_setup_ = 0;
+    std::atomic<uint64_t> t_gz_us_{0};
+    size_t avg_rec_bytes_[2] = {0, 0};
 };
 
-// ---- parse up to max_reads records of one mate into the pinned SoA rows
-size_t FilterRun::parse_mate(LineReader& r, HostBatch& b, int mate, size_t max_reads)
+// ---- the raw text of up to max_reads whole records of one mate, straight into the pinned buffer
+size_t FilterRun::fill_mate(ByteSource& src, HostBatch& b, int mate, size_t max_reads)
 {
-    MateBuf& mb = b.m[mate];
-    mb.ids.clear(); mb.id_off.clear(); mb.id_off.push_back(0);
-    mb.reserve(max_reads, stride_ ? stride_ : 160);
-    const size_t strip = hp_.input_gz ? (size_t)strip_gz_ : 1;     // plain: erase(size()-1) (peprocess.cpp:2206)
-    size_t n = 0;
-    const char* p; size_t ln;
-    while (n < max_reads) {
-        if (!r.next(p, ln)) break;                                       // id line
-        size_t idn = ln > strip ? ln - strip : 0;
-        mb.ids.insert(mb.ids.end(), p, p + idn);
-        mb.id_off.push_back((uint32_t)mb.ids.size());
-        const char* sp; size_t sn;
-        if (!r.next(sp, sn)) die("input fastq is truncated," + (mate ? hp_.fq2_path : hp_.fq1_path));
-        sn = sn > strip ? sn - strip : 0;
-        if (sn > SNK_MAX_READ_LEN) die("read longer than 1000 bases is not supported (READ_MAX_LEN)");
-        if (sn > mb.stride) mb.reserve(mb.cap_reads, round16(sn));
-        memcpy(mb.seq + n * mb.stride, sp, sn);
-        if (sn < mb.stride) memset(mb.seq + n * mb.stride + sn, 0, mb.stride - sn);
-        mb.len[n] = (uint16_t)sn;
-        if (!r.next(p, ln)) die("input fastq is truncated," + (mate ? hp_.fq2_path : hp_.fq1_path));   // '+'
-        const char* qp; size_t qn;
-        if (!r.next(qp, qn)) die("input fastq is truncated," + (mate ? hp_.fq2_path : hp_.fq1_path));
-        qn = qn > strip ? qn - strip : 0;
-        if (qn != sn) die("sequence and quality have different lengths," + std::string(mb.ids.data() + mb.id_off[n], idn));
-        memcpy(mb.qual + n * mb.stride, qp, qn);
-        if (qn < mb.stride) memset(mb.qual + n * mb.stride + qn, 0, mb.stride - qn);
-        n++;
+    PinnedBuf& buf = b.in[mate];
+    const size_t want_lines = 4 * max_reads;
+    const size_t guess = avg_rec_bytes_[mate] ? avg_rec_bytes_[mate] : (2 * (stride_ ? stride_ : 160) + 64);
+    size_t have = src.carry.size();
+    buf.reserve(std::max(have, max_reads * guess) + (1u << 20), 0);
+    memcpy(buf.p, src.carry.data(), have);
+    src.carry.clear();
+    size_t scanned = 0, lines = 0, end = 0;
+    bool complete = false;
+    for (;;) {
+        if (scanned < have) {
+            size_t c = 0;
+            const size_t at = nth_newline(buf.p + scanned, have - scanned, want_lines - lines, &c);
+            lines += c;
+            if (lines == want_lines) { end = scanned + at; complete = true; break; }
+            scanned = have;
+        }
+        if (src.eof) break;
+        // read about what is still missing (plus a little), never less than 1 MiB
+        size_t missing = (want_lines - lines) / 4 * guess + (256u << 10);
+        if (missing < (1u << 20)) missing = 1u << 20;
+        buf.reserve(have + missing + 64, have);
+        const size_t got = src.read(buf.p + have, missing);
+        if (got == 0) src.eof = true;
+        have += got;
+        if (have > 0xE0000000ull) die("batch text exceeds 3.5 GiB: lower SNK_BATCH_READS");
     }
+    if (!complete) {                   // end of input: everything that is left
+        end = have;
+        if (have > 0 && buf.p[have - 1] != '\n') lines++;      // last line without '\n'
+        if (lines % 4 != 0) die("input fastq is truncated," + (mate ? hp_.fq2_path : hp_.fq1_path));
+    } else {
+        src.carry.assign(buf.p + end, buf.p + have);
+    }
+    b.in_bytes[mate] = end;
+    const size_t n = lines / 4;
+    if (n) avg_rec_bytes_[mate] = end / n + 1;
     return n;
 }
 
-// peprocess.cpp:1884-1908 (pair IDs) and :1207-1319 / seprocess.cpp:741-867 (quality system sanity)
+// peprocess.cpp:1884-1908 (pair IDs) and :1207-1319 / seprocess.cpp:741-867 (quality system sanity),
+// on the first patchSize records of the run, parsed here from the raw text
 void FilterRun::first_batch_checks(const HostBatch& b)
 {
+    const size_t strip = (size_t)fmt_.strip;
+    auto line_at = [&](int m, size_t& pos, const char*& p, size_t& n) {
+        const char* base = b.in[m].p;
+        const size_t end = b.in_bytes[m];
+        const char* nl = pos < end ? (const char*)memchr(base + pos, '\n', end - pos) : nullptr;
+        const size_t raw = nl ? (size_t)(nl - (base + pos)) + 1 : end - pos;
+        p = base + pos; n = raw > strip ? raw - strip : 0;
+        pos += raw;
+    };
     if (pe_ && b.n > 0) {
-        const MateBuf &a = b.m[0], &c = b.m[1];
-        const size_t l1 = a.id_off[1] - a.id_off[0], l2 = c.id_off[1] - c.id_off[0];
+        size_t p1 = 0, p2 = 0, l1, l2; const char *a, *c;
+        line_at(0, p1, a, l1); line_at(1, p2, c, l2);
         bool warn = l1 != l2;
         if (!warn) {
             int diff = 0;
-            for (size_t i = 0; i < l1; i++) diff += a.ids[i] != c.ids[i];
+            for (size_t i = 0; i < l1; i++) diff += a[i] != c[i];
             warn = diff > 1;
         }
         if (warn) std::cerr << "Warning:read ID in fq1 and fq2 seems not in pair, please check the input files if you are not sure" << std::endl;
     }
     // the reference runs this on the first batch (patchSize reads) a worker finishes
-    const MateBuf& a = b.m[0];
     const size_t nchk = std::min<size_t>(b.n, (size_t)hp_.patch_size);
     int q1_exceed = 0, q1_normal = 0, q1_sum = 0, q2_exceed = 0, q2_normal = 0, q2_sum = 0;
     uint64_t bases = 0;
     const int other = hp_.quality_phred == 64 ? 33 : 64;
+    size_t pos = 0;
     for (size_t i = 0; i < nchk; i++) {
-        const uint8_t* q = a.qual + i * a.stride;
-        bases += a.len[i];
-        for (int k = 0; k < a.len[i]; k++) {
-            const int b1 = (int)q[k] - hp_.quality_phred, b2 = (int)q[k] - other;
+        const char *idp, *sp, *pp, *qp; size_t idn, sn, pn, qn;
+        line_at(0, pos, idp, idn); line_at(0, pos, sp, sn); line_at(0, pos, pp, pn); line_at(0, pos, qp, qn);
+        const size_t len = std::min(sn, qn);
+        bases += len;
+        for (size_t k = 0; k < len; k++) {
+            const int b1 = (int)(uint8_t)qp[k] - hp_.quality_phred, b2 = (int)(uint8_t)qp[k] - other;
             q1_sum += b1; q2_sum += b2;
             if (b1 >= 0 && b1 <= hp_.max_base_quality) q1_normal++; else if (b1 < -10 || b1 > hp_.max_base_quality + 10) q1_exceed++;
             if (b2 >= 0 && b2 <= hp_.max_base_quality) q2_normal++; else if (b2 < -10 || b2 > hp_.max_base_quality + 10) q2_exceed++;
@@ -295,19 +353,26 @@ void FilterRun::first_batch_checks(const HostBatch& b)
 
 void FilterRun::ingest()
 {
-    // spaceNum: trailing whitespace of the very first line of fq1 (peprocess.cpp:2066-2076)
+    // spaceNum: trailing whitespace of the very first line of fq1 (peprocess.cpp:2066-2076); the
+    // reference probes it with gzopen/gzgets, which also reads plain files
     {
-        LineReader probe(hp_.fq1_path);
-        const char* p; size_t n;
-        if (probe.next(p, n)) {
-            int sp = 0;
-            while (n > 0 && isspace((unsigned char)p[n - 1])) { sp++; n--; }
-            strip_gz_ = sp;
-            if (probe.next(p, n)) stride_ = std::max<size_t>(16, round16(n));      // first read sets the initial row stride
+        ByteSource probe(hp_.fq1_path, true);
+        std::vector<char> head(1 << 16);
+        const size_t got = probe.read(head.data(), head.size());
+        const char* nl = (const char*)memchr(head.data(), '\n', got);
+        size_t n = nl ? (size_t)(nl - head.data()) + 1 : got;
+        int sp = 0;
+        while (n > 0 && isspace((unsigned char)head[n - 1])) { sp++; n--; }
+        strip_gz_ = sp;
+        if (nl) {                                                  // first read sets the initial row stride
+            const char* nl2 = (const char*)memchr(nl + 1, '\n', got - (size_t)(nl + 1 - head.data()));
+            if (nl2) stride_ = std::max<size_t>(16, round16((size_t)(nl2 - nl)));
         }
     }
-    LineReader r1(hp_.fq1_path);
-    LineReader* r2 = pe_ ? new LineReader(hp_.fq2_path) : nullptr;
+    if (!stride_) stride_ = 160;
+    fmt_.strip = hp_.input_gz ? strip_gz_ : 1;                     // plain: erase(size()-1) (peprocess.cpp:2206)
+    ByteSource r1(hp_.fq1_path, hp_.input_gz);
+    ByteSource* r2 = pe_ ? new ByteSource(hp_.fq2_path, hp_.input_gz) : nullptr;
     uint64_t seq_no = 0, first = 0;
     const size_t lanes = (size_t)snk_engine_lanes(engines_[0]);
     for (;;) {
@@ -316,18 +381,13 @@ void FilterRun::ingest()
         size_t n2 = 0;
         std::thread t2;
         const double tp0 = now_s();
-        if (pe_) t2 = std::thread([&] { n2 = parse_mate(*r2, *b, 1, hp_.batch_reads); });
-        const size_t n1 = parse_mate(r1, *b, 0, hp_.batch_reads);
+        if (pe_) t2 = std::thread([&] { n2 = fill_mate(*r2, *b, 1, hp_.batch_reads); });
+        const size_t n1 = fill_mate(r1, *b, 0, hp_.batch_reads);
         if (pe_) {
             t2.join();
             if (n1 != n2) die("reads number in fq1 and fq2 are different");
         }
-        t_parse_ += now_s() - tp0;
-        if (pe_) {
-            const size_t s = std::max(b->m[0].stride, b->m[1].stride);
-            for (int m = 0; m < 2; m++) if (b->m[m].stride != s) b->m[m].reserve(b->m[m].cap_reads, s);
-        }
-        stride_ = b->m[0].stride;
+        t_read_ += now_s() - tp0;
         if (n1 == 0) { free_q_.push(b); break; }
         b->n = (uint32_t)n1; b->seq_no = seq_no; b->first_index = first;
         b->gpu = (int)(seq_no % engines_.size());
@@ -348,123 +408,134 @@ void FilterRun::gpu_stage()
 {
     std::deque<HostBatch*> inflight;
     const size_t depth = inflight_depth();
+    auto submit = [&](HostBatch* b) {
+        if (pe_) engine_check(snk_filter_pe_text_async(engines_[b->gpu], b->lane, b->in[0].p, b->in_bytes[0], b->in[1].p, b->in_bytes[1],
+                                                       b->n, (uint32_t)stride_, &fmt_, b->first_index));
+        else engine_check(snk_filter_se_text_async(engines_[b->gpu], b->lane, b->in[0].p, b->in_bytes[0], b->n, (uint32_t)stride_, &fmt_,
+                                                   b->first_index));
+    };
     auto retire = [&] {
         HostBatch* d = inflight.front(); inflight.pop_front();
         const double t0 = now_s();
+        for (;;) {
+            engine_check(snk_text_meta_sync(engines_[d->gpu], d->lane, &d->meta));
+            if (d->meta.flags & SNK_TEXT_TOO_LONG) die("read longer than 1000 bases is not supported (READ_MAX_LEN)");
+            if (d->meta.flags & SNK_TEXT_LEN_MISMATCH)
+                die("sequence and quality have different lengths, read number " + std::to_string(d->first_index + d->meta.bad_record + 1));
+            if (d->meta.flags & SNK_TEXT_LINE_COUNT) die("input fastq is truncated," + hp_.fq1_path);
+            if (!(d->meta.flags & SNK_TEXT_STRIDE_OVERFLOW)) break;
+            stride_ = std::max(stride_, round16(d->meta.max_len));       // a longer read showed up: wider rows, same batch again
+            submit(d);
+        }
+        for (int m = 0; m < mates_; m++) {
+            d->out[m].reserve((size_t)d->meta.out_bytes[m] + 64, 0);
+            d->off[m].reserve(((size_t)d->n + 1) * sizeof(uint32_t), 0);
+        }
+        engine_check(snk_text_fetch_async(engines_[d->gpu], d->lane, d->out[0].p, pe_ ? d->out[1].p : nullptr, (uint32_t*)d->off[0].p,
+                                          pe_ ? (uint32_t*)d->off[1].p : nullptr, nullptr, nullptr));
         engine_check(snk_engine_lane_sync(engines_[d->gpu], d->lane));
         t_gpu_wait_ += now_s() - t0;
-        fmt_q_.push(d);
+        finish_batch(d);
     };
     HostBatch* b;
     while (gpu_q_.pop(b)) {
         if (inflight.size() >= depth) retire();
-        snk_batch b1 = {b->m[0].seq, b->m[0].qual, b->m[0].len, b->n, (uint32_t)b->m[0].stride};
-        if (pe_) {
-            snk_batch b2 = {b->m[1].seq, b->m[1].qual, b->m[1].len, b->n, (uint32_t)b->m[1].stride};
-            engine_check(snk_filter_pe_async(engines_[b->gpu], b->lane, &b1, &b2, b->m[0].res, b->m[1].res, b->first_index));
-        } else {
-            engine_check(snk_filter_se_async(engines_[b->gpu], b->lane, &b1, b->m[0].res, b->first_index));
-        }
+        submit(b);
         inflight.push_back(b);
     }
     while (!inflight.empty()) retire();
-    fmt_q_.close();
+    { std::lock_guard<std::mutex> g(done_mu_); all_submitted_ = true; }
+    done_cv_.notify_all();
+    gz_q_.close();
 }
 
-void FilterRun::encode(std::string& text)
+void FilterRun::encode(const char* p, size_t n, std::string& out)
 {
-    if (!hp_.clean_gz || text.empty()) return;
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (deflateInit2(&zs, 2, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib deflateInit2 failed");
-    std::string out;
-    out.resize(deflateBound(&zs, (uLong)text.size()) + 32);
-    zs.next_in = (Bytef*)text.data(); zs.avail_in = (uInt)text.size();
+    out.resize(deflateBound(&zs, (uLong)n) + 32);
+    zs.next_in = (Bytef*)p; zs.avail_in = (uInt)n;
     zs.next_out = (Bytef*)&out[0]; zs.avail_out = (uInt)out.size();
     if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("zlib deflate failed");
     out.resize(zs.total_out);
     deflateEnd(&zs);
-    text.swap(out);
 }
 
-// Formats the surviving records of one mate. Output is a list of pieces so that the ordered writer
-// can reproduce the reference's emission order (see FilterRun::writer).
-void FilterRun::format_mate(HostBatch& b, int mate)
+// Cuts the batch's clean text (device-formatted, input order) into pieces at the few record
+// boundaries where the reference's emission order departs from input order (see writer()), and
+// into <= 4 MiB runs for the parallel gzip members.
+void FilterRun::make_pieces(HostBatch& b)
 {
-    MateBuf& mb = b.m[mate];
-    mb.out.clear();
-    std::string cur;
-    int cur_kind = 0;
-    auto flush_piece = [&](int kind) {
-        if (!cur.empty()) { encode(cur); mb.out.push_back({cur_kind, std::move(cur)}); cur.clear(); }
-        cur_kind = kind;
-    };
-    const int shift = hp_.out_quality_phred - hp_.quality_phred;
-    const bool fasta = hp_.output_file_type == "fasta";
-    cur.reserve((size_t)b.n * (mb.stride * 2 + 64) / 1);
-    for (uint32_t i = 0; i < b.n; i++) {
-        const uint64_t gi = b.first_index + i;
-        int kind = 0;
-        if (reorder_) {
-            const uint64_t in_cyc = gi % cyc_;
-            if (gi >= cyc_ && in_cyc == insert_off_) { flush_piece(cur_kind); mb.out.push_back({2, std::string()}); }
-            if (in_cyc >= cyc_ - defer_len_) kind = 1;     // if the input ends inside this range it is flushed at EOF: same order
-        }
-        if (kind != cur_kind) flush_piece(kind);
-        const snk_read_result& r = mb.res[i];
-        if (r.category != SNK_KEEP) continue;
-        const char* id = mb.ids.data() + mb.id_off[i];
-        size_t idn = mb.id_off[i + 1] - mb.id_off[i];
-        std::string idbuf;
-        if (hp_.index_remove) {                      // read_filter.cpp:357-382
-            if (hp_.seq_type == "0") {
-                bool cp = true;
-                for (size_t k = 0; k < idn; k++) {
-                    if (id[k] == '#') cp = false;
-                    if (cp) idbuf += id[k];
-                    else if (id[k] == '/') { cp = true; idbuf += id[k]; }
+    const size_t max_run = hp_.clean_gz ? (4u << 20) : ~(size_t)0;
+    for (int m = 0; m < mates_; m++) {
+        std::vector<Piece>& out = b.pieces[m];
+        out.clear();
+        const uint32_t* off = (const uint32_t*)b.off[m].p;
+        const char* text = b.out[m].p;
+        auto emit = [&](int kind, uint32_t r0, uint32_t r1) {         // records [r0, r1)
+            size_t a = off[r0];
+            const size_t e = off[r1];
+            while (a < e) {
+                size_t stop = e;
+                if (e - a > max_run) {                                     // cut at a record boundary near a + max_run
+                    const uint32_t* it = std::upper_bound(off + r0, off + r1 + 1, (uint32_t)(a + max_run));
+                    stop = (it == off + r0) ? e : (size_t)*(it - 1);
+                    if (stop <= a) stop = (it == off + r1 + 1) ? e : (size_t)*it;
                 }
-            } else {
-                idbuf.assign(id, idn);
-                const size_t c = idbuf.find_last_of(':');
-                idbuf = idbuf.substr(0, c);           // npos -> whole string, as substr(0, npos)
+                out.push_back({kind, text + a, stop - a, std::string()});
+                a = stop;
             }
-            id = idbuf.data(); idn = idbuf.size();
+        };
+        if (!reorder_) { emit(0, 0, b.n); continue; }
+        // walk the kind boundaries arithmetically: within a cycle of cyc_ reads, [cyc_-defer_len_, cyc_) is
+        // deferred, and (from the second cycle on) the deferred bytes are emitted before read insert_off_
+        uint32_t r = 0;
+        while (r < b.n) {
+            const uint64_t gi = b.first_index + r, in_cyc = gi % cyc_;
+            if (gi >= cyc_ && in_cyc == insert_off_) out.push_back({2, nullptr, 0, std::string()});
+            const bool deferred = in_cyc >= cyc_ - defer_len_;
+            uint64_t next = deferred ? cyc_ : cyc_ - defer_len_;          // next boundary inside the cycle
+            if (gi >= cyc_ && in_cyc < insert_off_ && insert_off_ < next) next = insert_off_;
+            else if (gi < cyc_ && !deferred) next = cyc_ - defer_len_;
+            const uint64_t run = std::min<uint64_t>(next - in_cyc, b.n - r);
+            emit(deferred ? 1 : 0, r, r + (uint32_t)run);
+            r += (uint32_t)run;
         }
-        const uint8_t* s = mb.seq + (size_t)i * mb.stride + r.head_cut;
-        const uint8_t* q = mb.qual + (size_t)i * mb.stride + r.head_cut;
-        if (fasta) {
-            std::string t(id, idn);
-            const size_t at = t.find('@');
-            if (at != std::string::npos) t[at] = '>';
-            cur += t;
-            if (hp_.pe_info) cur += mate ? "/2" : "/1";
-            cur += '\n';
-            cur.append((const char*)s, r.clean_len);
-            cur += '\n';
-            continue;
-        }
-        cur.append(id, idn);
-        if (hp_.pe_info) cur += mate ? "/2" : "/1";
-        cur += '\n';
-        cur.append((const char*)s, r.clean_len);
-        cur += "\n+\n";
-        if (shift == 0) cur.append((const char*)q, r.clean_len);
-        else for (int k = 0; k < r.clean_len; k++) cur += (char)((int)q[k] + shift);
-        cur += '\n';
     }
-    flush_piece(0);
 }
 
-void FilterRun::format_worker()
+void FilterRun::finish_batch(HostBatch* b)
 {
-    HostBatch* b;
-    while (fmt_q_.pop(b)) {
-        const double t0 = now_s();
-        for (int m = 0; m < mates_; m++) format_mate(*b, m);
-        t_format_us_ += (uint64_t)((now_s() - t0) * 1e6);
+    make_pieces(*b);
+    int tasks = 0;
+    if (hp_.clean_gz)
+        for (int m = 0; m < mates_; m++)
+            for (const Piece& p : b->pieces[m]) tasks += p.kind != 2 && p.len > 0;
+    if (tasks == 0) {
         { std::lock_guard<std::mutex> g(done_mu_); done_[b->seq_no] = b; }
         done_cv_.notify_all();
+        return;
+    }
+    b->tasks = tasks;
+    for (int m = 0; m < mates_; m++)
+        for (size_t i = 0; i < b->pieces[m].size(); i++)
+            if (b->pieces[m][i].kind != 2 && b->pieces[m][i].len > 0) gz_q_.push({b, m, i});
+}
+
+void FilterRun::gz_worker()
+{
+    GzTask t;
+    while (gz_q_.pop(t)) {
+        const double t0 = now_s();
+        Piece& p = t.b->pieces[t.mate][t.piece];
+        encode(p.p, p.len, p.gz);
+        p.p = p.gz.data(); p.len = p.gz.size();
+        t_gz_us_ += (uint64_t)((now_s() - t0) * 1e6);
+        if (--t.b->tasks == 0) {
+            { std::lock_guard<std::mutex> g(done_mu_); done_[t.b->seq_no] = t.b; }
+            done_cv_.notify_all();
+        }
     }
 }
 
@@ -478,32 +549,43 @@ void FilterRun::format_worker()
 // all .gz-input and all SE runs) is input order.
 void FilterRun::writer()
 {
-    FILE* out[2] = {nullptr, nullptr};
+    int out[2] = {-1, -1};
     const std::string names[2] = {hp_.output_dir + "/" + hp_.clean_fq1, hp_.output_dir + "/" + hp_.clean_fq2};
     for (int m = 0; m < mates_; m++) {
-        out[m] = fopen(names[m].c_str(), "wb");
-        if (!out[m]) die("cannot write to the file," + names[m]);
-        setvbuf(out[m], nullptr, _IOFBF, 1 << 22);
+        out[m] = open(names[m].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (out[m] < 0) die("cannot write to the file," + names[m]);
     }
+    auto write_all = [&](int m, const char* p, size_t n) {
+        while (n > 0) {
+            const ssize_t w = ::write(out[m], p, std::min<size_t>(n, 1u << 30));
+            if (w < 0) die("cannot write to the file," + names[m]);
+            p += w; n -= (size_t)w;
+        }
+    };
+    auto write_mate = [&](HostBatch* b, int m) {
+        for (Piece& p : b->pieces[m]) {
+            if (p.kind == 0) write_all(m, p.p, p.len);
+            else if (p.kind == 1) pending_deferred_[m].append(p.p, p.len);
+            else { write_all(m, pending_deferred_[m].data(), pending_deferred_[m].size()); pending_deferred_[m].clear(); }
+        }
+        b->pieces[m].clear();
+    };
     uint64_t next = 0;
     for (;;) {
         HostBatch* b = nullptr;
         {
             std::unique_lock<std::mutex> g(done_mu_);
-            done_cv_.wait(g, [&] { return done_.count(next) || fmt_finished_; });
+            done_cv_.wait(g, [&] { return done_.count(next) || (all_submitted_ && next >= n_batches_total_); });
             auto it = done_.find(next);
             if (it == done_.end()) break;
             b = it->second; done_.erase(it);
         }
         const double tw0 = now_s();
-        for (int m = 0; m < mates_; m++) {
-            for (Piece& p : b->m[m].out) {
-                if (p.kind == 0) fwrite(p.bytes.data(), 1, p.bytes.size(), out[m]);
-                else if (p.kind == 1) pending_deferred_[m] += p.bytes;
-                else { fwrite(pending_deferred_[m].data(), 1, pending_deferred_[m].size(), out[m]); pending_deferred_[m].clear(); }
-            }
-            b->m[m].out.clear();
-        }
+        if (pe_) {
+            std::thread t2([&] { write_mate(b, 1); });
+            write_mate(b, 0);
+            t2.join();
+        } else write_mate(b, 0);
         t_write_ += now_s() - tw0;
         if (b->seq_no % 4 == 0) log_line(local_time() + " processed_reads:\t" + std::to_string(b->first_index + b->n));
         next++;
@@ -520,8 +602,8 @@ void FilterRun::writer()
         drop = into_last <= (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 2);
     }
     for (int m = 0; m < mates_; m++) {
-        if (!drop) fwrite(pending_deferred_[m].data(), 1, pending_deferred_[m].size(), out[m]);
-        if (fclose(out[m]) != 0) die("cannot write to the file," + names[m]);
+        if (!drop) write_all(m, pending_deferred_[m].data(), pending_deferred_[m].size());
+        if (close(out[m]) != 0) die("cannot write to the file," + names[m]);
     }
 }
 
@@ -533,6 +615,12 @@ void FilterRun::process()
     if (!log_) die("cannot open such file," + hp_.log);
     log_line(local_time() + "\tAnalysis start!");
     if (snk_params_check(&ep_)) die(snk_last_error());
+    if (hp_.output_file_type != "fasta" && hp_.output_file_type != "fastq") die("output_file_type value error");
+    memset(&fmt_, 0, sizeof fmt_);
+    fmt_.strip = 1;
+    fmt_.pe_info = hp_.pe_info ? 1 : 0;
+    fmt_.fasta = hp_.output_file_type == "fasta";
+    fmt_.id_mode = hp_.index_remove ? (hp_.seq_type == "0" ? 1 : 2) : 0;
     for (int g = 0; g < hp_.n_gpus; g++) {
         snk_engine* e = nullptr;
         engine_check(snk_engine_create(&ep_, g, &e));
@@ -543,21 +631,19 @@ void FilterRun::process()
     defer_len_ = (uint64_t)hp_.patch_size;
     insert_off_ = (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 1);
     reorder_ = pe_ && !hp_.input_gz && ep_.n_slots > 1;
-    batches_.resize(inflight_depth() + 3);       // in flight on the GPUs + being parsed + being formatted/written
+    batches_.resize(inflight_depth() + 3);       // in flight on the GPUs + being read + being compressed/written
     for (auto& b : batches_) free_q_.push(&b);
 
     t_setup_ = now_s() - t_begin;
-    const int nworkers = std::max(2, hp_.threads);
+    const int nworkers = hp_.clean_gz ? std::max(2, hp_.threads) : 0;
     std::thread t_ingest([&] { ingest(); });
     std::thread t_gpu([&] { gpu_stage(); });
     std::vector<std::thread> workers;
-    for (int i = 0; i < nworkers; i++) workers.emplace_back([&] { format_worker(); });
+    for (int i = 0; i < nworkers; i++) workers.emplace_back([&] { gz_worker(); });
     std::thread t_writer([&] { writer(); });
     t_ingest.join();
     t_gpu.join();
     for (auto& w : workers) w.join();
-    { std::lock_guard<std::mutex> g(done_mu_); fmt_finished_ = true; }
-    done_cv_.notify_all();
     t_writer.join();
     free_q_.close();
 
@@ -584,12 +670,12 @@ void FilterRun::process()
     else { if (snk_report_write_se(&ep_, total.data(), hp_.output_dir.c_str())) die(snk_last_error()); }
     for (snk_engine* e : engines_) snk_engine_destroy(e);
     engines_.clear();
-    for (auto& b : batches_) for (auto& m : b.m) m.release();
+    for (auto& b : batches_) b.release();
     batches_.clear();
     {
         char buf[512];
-        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, parse(busy) %.2f, gpu-wait %.2f, format(sum over %d workers) %.2f, write %.2f, total %.2f; reads %llu",
-                 t_setup_, t_parse_, t_gpu_wait_, std::max(2, hp_.threads), t_format_us_.load() * 1e-6, t_write_, now_s() - t_begin,
+        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write %.2f, total %.2f; reads %llu",
+                 t_setup_, t_read_, t_gpu_wait_, nworkers, t_gz_us_.load() * 1e-6, t_write_, now_s() - t_begin,
                  (unsigned long long)total_reads_);
         log_line(buf);
     }

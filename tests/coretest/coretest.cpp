@@ -12,6 +12,7 @@
 #include <algorithm>
 #include "../../soapnuke_b200/csrc/filter_kernel.cuh"
 #include "../../soapnuke_b200/csrc/dev_params.h"
+#include "../../soapnuke_b200/csrc/text_core.cuh"
 
 using namespace snkcore;
 
@@ -234,6 +235,79 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     else run<63, 4>(c, b, out, first, grid, flush_every);
     *err |= c.err;
     return 0;
+}
+
+// ---- text path replay (text_core.cuh driven the way text_kernels.cuh drives it, sequentially) ----
+// text must be readable 32 bytes past `bytes`. line_off has 4n+1 entries. Returns the TextFlags.
+uint32_t coretest_text_index_pack(const uint8_t* text, uint32_t bytes, uint32_t n, uint32_t strip, uint32_t stride,
+                                  uint32_t* line_off, uint8_t* seq, uint8_t* qual, uint16_t* len, uint32_t* max_len)
+{
+    uint32_t flags = 0, k = 0;
+    const uint32_t want = 4u * n;
+    line_off[0] = 0;
+    for (uint32_t off = 0; off < bytes; off += 16) {
+        U4 v = load16(text + off);
+        uint32_t mask = newline_mask16(v, (int)std::min<int64_t>((int64_t)bytes - off, 16));
+        while (mask) {
+            const int b = ctz32(mask);
+            mask &= mask - 1u;
+            k++;
+            if (k <= want) line_off[k] = off + (uint32_t)b + 1u;
+        }
+    }
+    if (k == want) {}
+    else if (k + 1 == want && bytes > 0) line_off[want] = bytes;
+    else return TEXT_LINE_COUNT;
+    *max_len = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t* off = line_off + 4u * (size_t)i;
+        const uint32_t sn = line_visible(off, 1, strip), qn = line_visible(off, 3, strip);
+        if (sn != qn) flags |= TEXT_LEN_MISMATCH;
+        if (sn > SNK_MAX_READ_LEN) flags |= TEXT_TOO_LONG;
+        if (sn > stride) flags |= TEXT_STRIDE_OVERFLOW;
+        if (sn > *max_len) *max_len = sn;
+        len[i] = (uint16_t)std::min(sn, stride);
+        for (uint32_t c = 0; c < stride / 16; c++) {
+            const U4 a = pack_chunk(text, off[1], std::min(sn, stride), c);
+            const U4 b = pack_chunk(text, off[3], std::min(std::min(qn, sn), stride), c);
+            memcpy(seq + (size_t)i * stride + 16 * c, &a, 16);
+            memcpy(qual + (size_t)i * stride + 16 * c, &b, 16);
+        }
+    }
+    return flags;
+}
+
+// rec_off has n+1 entries; out must hold bytes + 2n + 64. `lanes` mimics the warp width. Returns the clean text size.
+uint64_t coretest_text_format(const uint8_t* text, const uint32_t* line_off, const uint8_t* seq, const uint8_t* qual,
+                              const snk_read_result* res, uint32_t n, uint32_t stride, int mate, int strip, int pe_info, int fasta,
+                              int id_mode, int qshift, uint32_t lanes, uint8_t* out, uint32_t* rec_off)
+{
+    TextFormat F = {strip, pe_info, fasta, id_mode, qshift};
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        rec_off[i] = (uint32_t)total;
+        if (res[i].category != SNK_KEEP) continue;
+        const uint32_t* off = line_off + 4u * (size_t)i;
+        uint32_t idn = line_visible(off, 0, (uint32_t)strip);
+        if (id_mode) idn = id_transform(text + off[0], idn, id_mode, nullptr);
+        total += record_out_len(idn, res[i].clean_len, F);
+    }
+    rec_off[n] = (uint32_t)total;
+    for (uint32_t i = 0; i < n; i++) {
+        if (rec_off[i + 1] == rec_off[i]) continue;
+        const uint32_t* off = line_off + 4u * (size_t)i;
+        const uint8_t* id = text + off[0];
+        const uint32_t idn = line_visible(off, 0, (uint32_t)strip);
+        uint8_t* dst = out + rec_off[i];
+        uint32_t id_out = idn;
+        if (id_mode == 0) memcpy(dst, id, idn);
+        else id_out = id_transform(id, idn, id_mode, dst);
+        const size_t row = (size_t)i * stride + res[i].head_cut;
+        for (uint32_t lane = 0; lane < lanes; lane++)
+            format_tail(dst + id_out, seq + row, qual + row, res[i].clean_len, mate, F, lane, lanes);
+        if (fasta) fasta_fix(dst, id_out + (pe_info ? 2u : 0u));
+    }
+    return total;
 }
 
 }

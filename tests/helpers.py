@@ -30,7 +30,7 @@ def load_coretest():
         d = os.path.join(ROOT, "tests", "coretest")
         so = os.path.join(d, "libcoretest.so")
         deps = [os.path.join(d, "coretest.cpp")] + [os.path.join(ROOT, "soapnuke_b200", "csrc", f)
-                                                    for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h")]
+                                                    for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h", "text_core.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared",
                                    "-I/usr/local/cuda/include", "-o", so, deps[0]])
@@ -38,6 +38,12 @@ def load_coretest():
         lib.coretest_filter.restype = C.c_int
         lib.coretest_filter.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Batch), C.POINTER(abi.Batch), C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int]
+        lib.coretest_text_index_pack.restype = C.c_uint32
+        lib.coretest_text_index_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        lib.coretest_text_format.restype = C.c_uint64
+        lib.coretest_text_format.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32] + \
+            [C.c_int] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p]
         _CT = lib
     return _CT
 
@@ -107,6 +113,28 @@ class Engine:
         self.check(self.lib.snk_filter_se_host(self.h, C.byref(b1), r1.ctypes.data, first))
         return r1, None
 
+    def filter_text(self, texts, n, stride, first=0, lane=0, strip=1, pe_info=0, fasta=0, id_mode=0, fetch=True):
+        """FASTQ text in -> (meta, [clean text per mate], [rec_off per mate], [results per mate]) through the text ABI."""
+        fmt = abi.TextFormat(strip=strip, pe_info=pe_info, fasta=fasta, id_mode=id_mode)
+        bufs = [np.frombuffer(t, dtype=np.uint8).copy() for t in texts]
+        if self.params.is_pe:
+            self.check(self.lib.snk_filter_pe_text_async(self.h, lane, bufs[0].ctypes.data, len(texts[0]), bufs[1].ctypes.data,
+                                                         len(texts[1]), n, stride, C.byref(fmt), first))
+        else:
+            self.check(self.lib.snk_filter_se_text_async(self.h, lane, bufs[0].ctypes.data, len(texts[0]), n, stride, C.byref(fmt), first))
+        meta = abi.TextMeta()
+        self.check(self.lib.snk_text_meta_sync(self.h, lane, C.byref(meta)))
+        if not fetch or meta.flags:
+            return meta, None, None, None
+        mates = 2 if self.params.is_pe else 1
+        outs = [np.zeros(max(1, meta.out_bytes[m]), dtype=np.uint8) for m in range(mates)] + [None]
+        offs = [np.zeros(n + 1, dtype=np.uint32) for m in range(mates)] + [None]
+        ress = [np.zeros(n, dtype=abi.RESULT_DTYPE) for m in range(mates)] + [None]
+        ptr = lambda a: a.ctypes.data if a is not None else None
+        self.check(self.lib.snk_text_fetch_async(self.h, lane, ptr(outs[0]), ptr(outs[1]), ptr(offs[0]), ptr(offs[1]), ptr(ress[0]), ptr(ress[1])))
+        self.check(self.lib.snk_engine_lane_sync(self.h, lane))
+        return (meta, [outs[m][:meta.out_bytes[m]].tobytes() for m in range(mates)], offs[:mates], ress[:mates])
+
     def stats(self):
         st = np.zeros(self.params.n_slots * abi.SLOT_WORDS, dtype=np.uint64)
         self.check(self.lib.snk_engine_stats(self.h, st.ctypes.data))
@@ -150,3 +178,82 @@ def assert_same(got, want, what):
     bad = np.nonzero(st != ost)[0]
     assert bad.size == 0, (f"{what}: {bad.size} statistics words differ, first: " +
                            "; ".join(f"{describe_stat_index(i)} got {st[i]} want {ost[i]}" for i in bad[:5]))
+
+
+# ---------------------------------------------------------------- FASTQ text path (test-side model)
+def fastq_text(ids, seq, qual, length, eol=b"\n", last_newline=True):
+    parts = []
+    for i in range(len(ids)):
+        l = int(length[i])
+        parts.append(ids[i] + eol + seq[i, :l].tobytes() + eol + b"+" + eol + qual[i, :l].tobytes() + eol)
+    data = b"".join(parts)
+    if not last_newline and data.endswith(b"\n"):
+        data = data[:-1]
+    return data
+
+
+def ref_id_transform(rid, mode):
+    """read_filter.cpp:357-382"""
+    if mode == 1:
+        out = bytearray()
+        cp = True
+        for ch in rid:
+            if ch == ord("#"):
+                cp = False
+            if cp:
+                out.append(ch)
+            elif ch == ord("/"):
+                cp = True
+                out.append(ch)
+        return bytes(out)
+    if mode == 2:
+        k = rid.rfind(b":")
+        return rid if k < 0 else rid[:k]
+    return rid
+
+
+def ref_clean_text(ids, seq, qual, res, mate, pe_info=0, fasta=0, id_mode=0, qshift=0):
+    """peprocess.cpp:3383-3433 + :1617-1629 on per-read results; returns (text, rec_off[n+1])."""
+    parts, off, total = [], [], 0
+    for i in range(len(ids)):
+        off.append(total)
+        if res["category"][i] != 0:
+            continue
+        rid = ref_id_transform(ids[i], id_mode)
+        if pe_info:
+            rid += b"/2" if mate else b"/1"
+        h = int(res["head_cut"][i]); l = int(res["clean_len"][i])
+        if fasta:
+            rec = rid.replace(b"@", b">", 1) + b"\n" + seq[i, h:h + l].tobytes() + b"\n"
+        else:
+            q = (qual[i, h:h + l].astype(np.int16) + qshift).astype(np.uint8)
+            rec = rid + b"\n" + seq[i, h:h + l].tobytes() + b"\n+\n" + q.tobytes() + b"\n"
+        parts.append(rec)
+        total += len(rec)
+    off.append(total)
+    return b"".join(parts), np.array(off, dtype=np.uint32)
+
+
+def text_replay_index_pack(text, n, strip, stride):
+    lib = load_coretest()
+    buf = np.zeros(len(text) + 64, dtype=np.uint8)
+    buf[:len(text)] = np.frombuffer(text, dtype=np.uint8)
+    line_off = np.zeros(4 * n + 2, dtype=np.uint32)
+    S = np.full((n, stride), 0xEE, dtype=np.uint8); Q = np.full((n, stride), 0xEE, dtype=np.uint8)
+    Ln = np.zeros(n, dtype=np.uint16)
+    mx = C.c_uint32(0)
+    flags = lib.coretest_text_index_pack(buf.ctypes.data, len(text), n, strip, stride, line_off.ctypes.data, S.ctypes.data,
+                                         Q.ctypes.data, Ln.ctypes.data, C.byref(mx))
+    return flags, line_off[:4 * n + 1], S, Q, Ln, mx.value, buf
+
+
+def text_replay_format(buf, nbytes, line_off, S, Q, res, mate, strip, pe_info=0, fasta=0, id_mode=0, qshift=0, lanes=32):
+    lib = load_coretest()
+    n = S.shape[0]
+    out = np.zeros(nbytes + 2 * n + 64, dtype=np.uint8)
+    rec_off = np.zeros(n + 1, dtype=np.uint32)
+    res = np.ascontiguousarray(res)
+    total = lib.coretest_text_format(buf.ctypes.data, line_off.ctypes.data, S.ctypes.data, Q.ctypes.data, res.ctypes.data, n,
+                                     S.shape[1], mate, strip, pe_info, fasta, id_mode, qshift, lanes, out.ctypes.data,
+                                     rec_off.ctypes.data)
+    return out[:total].tobytes(), rec_off

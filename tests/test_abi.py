@@ -32,13 +32,15 @@ def test_struct_sizes_match_the_header(tmp_path):
     import subprocess
     prog = tmp_path / "sz.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "snk_engine.h"\n'
-                    'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(snk_params), sizeof(snk_batch), sizeof(snk_read_result),'
-                    ' offsetof(snk_params, adapter), offsetof(snk_params, slot_block), offsetof(snk_params, n_slots));return 0;}\n')
+                    'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(snk_params), sizeof(snk_batch), sizeof(snk_read_result),'
+                    ' offsetof(snk_params, adapter), offsetof(snk_params, slot_block), offsetof(snk_params, n_slots),'
+                    ' sizeof(snk_text_format), sizeof(snk_text_meta), offsetof(snk_text_meta, flags));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(prog)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(abi.Params), C.sizeof(abi.Batch), C.sizeof(abi.ReadResult), abi.Params.adapter.offset,
-            abi.Params.slot_block.offset, abi.Params.n_slots.offset]
+            abi.Params.slot_block.offset, abi.Params.n_slots.offset, C.sizeof(abi.TextFormat), C.sizeof(abi.TextMeta),
+            abi.TextMeta.flags.offset]
     assert got == want
 
 
