@@ -315,6 +315,62 @@ def run_ours(args):
     h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
     d2h = sum(t.numel() * t.element_size() for t in out_pin)
 
+    # ---- e2e_text leg: raw FASTQ text in pinned host memory -> clean FASTQ text in pinned host memory
+    # (line index, row packing, filter, record formatting all on the device)
+    text_info = None
+    if not args.no_text:
+        work = tempfile.mkdtemp(prefix="snktxt_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            tsub = min(sub, host["n"])
+            tin = []
+            for m in (1, 2):
+                synth.write_fastq_fixed(f"{work}/r{m}.fq", host[f"seq{m}"][:tsub], host[f"qual{m}"][:tsub], L, m)
+                tin.append(torch.from_numpy(np.fromfile(f"{work}/r{m}.fq", dtype=np.uint8)).pin_memory())
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        tout = [[torch.empty(tin[m].numel() + 64, dtype=torch.uint8).pin_memory() for m in range(2)] for _ in range(nl)]
+        toff = [[torch.empty(tsub + 1, dtype=torch.int32).pin_memory() for m in range(2)] for _ in range(nl)]
+        fmt = abi.TextFormat(strip=1)
+        meta = abi.TextMeta()
+        nchunks = max(1, pairs // tsub)
+        moved = [0, 0]
+
+        def finish(lane):
+            check(lib.snk_text_meta_sync(h, lane, C.byref(meta)))
+            if meta.flags:
+                raise SystemExit(f"text path flags {meta.flags}")
+            check(lib.snk_text_fetch_async(h, lane, tout[lane][0].data_ptr(), tout[lane][1].data_ptr(), toff[lane][0].data_ptr(),
+                                           toff[lane][1].data_ptr(), None, None))
+            check(lib.snk_engine_lane_sync(h, lane))
+            moved[1] = meta.out_bytes[0] + meta.out_bytes[1] + 2 * 4 * (tsub + 1)
+
+        def text_step(i):
+            fifo = []
+            for ci in range(nchunks):
+                lane = ci % nl
+                if len(fifo) == nl:
+                    finish(fifo.pop(0))
+                check(lib.snk_filter_pe_text_async(h, lane, tin[0].data_ptr(), tin[0].numel(), tin[1].data_ptr(), tin[1].numel(),
+                                                   tsub, stride, C.byref(fmt), C.c_uint64((i * nchunks + ci) * tsub)))
+                fifo.append(lane)
+            while fifo:
+                finish(fifo.pop(0))
+
+        for i in range(e2e_warm):
+            text_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            text_step(i)
+        torch.cuda.synchronize()
+        text_s = max_over_ranks(time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+        text_info = {"value": 2 * tsub * nchunks * world * args.steps / text_s / 1e6, "unit": UNIT,
+                     "h2d_bytes_per_step": int(nchunks * (tin[0].numel() + tin[1].numel())), "d2h_bytes_per_step": int(nchunks * moved[1]),
+                     "sub_batch_pairs": tsub, "lanes": nl,
+                     "what": "raw FASTQ text (pinned host) -> clean FASTQ text (pinned host) through snk_filter_pe_text_async"}
+
     flags = C.c_uint32(0); bad = C.c_uint64(0)
     check(lib.snk_engine_error_flags(h, C.byref(flags), C.byref(bad)))
     if flags.value:
@@ -342,6 +398,7 @@ def run_ours(args):
                        "slots": params.n_slots, "slot_block": params.slot_block},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "sub_batch_pairs": sub, "lanes": nl, "results_match_resident": same},
+            "e2e_text": text_info,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -371,6 +428,7 @@ def main():
     ap.add_argument("--sub-pairs", type=int, default=1 << 19, help="pairs per host sub-batch in the e2e leg")
     ap.add_argument("--ref-pairs", type=int, default=1000000, help="pairs in the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -32,7 +32,7 @@ struct HostParams {
     bool is_pe = false;
     // engine-side knobs (not part of the reference CLI; environment SNK_GPUS / SNK_BATCH_READS)
     int n_gpus = 1;
-    unsigned batch_reads = 1u << 18;
+    unsigned batch_reads = 1u << 16;
 };
 
 // Parses argv exactly like global_parameter_initial + check_parameter. Returns 0 = run,

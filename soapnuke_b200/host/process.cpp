@@ -618,7 +618,7 @@ void FilterRun::process()
     if (hp_.output_file_type != "fasta" && hp_.output_file_type != "fastq") die("output_file_type value error");
     memset(&fmt_, 0, sizeof fmt_);
     fmt_.strip = 1;
-    fmt_.pe_info = hp_.pe_info ? 1 : 0;
+    fmt_.pe_info = (pe_ && hp_.pe_info) ? 1 : 0;      // seProcess::preOutput has no /1 (seprocess.cpp:919)
     fmt_.fasta = hp_.output_file_type == "fasta";
     fmt_.id_mode = hp_.index_remove ? (hp_.seq_type == "0" ? 1 : 2) : 0;
     for (int g = 0; g < hp_.n_gpus; g++) {

@@ -13,7 +13,7 @@ import subprocess
 import pytest
 
 import oracle_py as orc
-from helpers import A1, A2, CFG2_FLAGS, ROOT, synth
+from helpers import A1, A2, CFG2_FLAGS, ROOT, fastq_text, synth
 
 pytestmark = pytest.mark.gpu
 CLI = os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke")
@@ -31,19 +31,25 @@ def read_maybe_gz(path):
     return gzip.open(path).read() if path.endswith(".gz") else open(path, "rb").read()
 
 
-def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None):
+def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False):
     w = os.path.join(str(tmp), name)
     os.makedirs(w)
     d = synth.gen_pairs(n, L=L, seed=abs(hash(name)) % 100000, se=not pe, **(gkw or {}))
     ext_in = ".fq.gz" if gz_in else ".fq"
     ext_out = ".fq.gz" if gz_out else ".fq"
-    synth.write_fastq(f"{w}/r1{ext_in}", d["seq1"], d["qual1"], d["len1"], 1, gz=gz_in)
+    def write(path, m):
+        if not index_ids:
+            return synth.write_fastq(path, d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"], m, gz=gz_in)
+        ids = [b"@FCD1PB1ACXX:4:1101:%d:%d#GAAGCACG/%d" % (i // 1000, i % 1000, m) for i in range(n)]
+        data = fastq_text(ids, d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"])
+        (gzip.open(path, "wb", compresslevel=2) if gz_in else open(path, "wb")).write(data)
+    write(f"{w}/r1{ext_in}", 1)
     base = ["-1", f"{w}/r1{ext_in}", "-C", "c1" + ext_out, "-T", str(T)]
     if pe:
-        synth.write_fastq(f"{w}/r2{ext_in}", d["seq2"], d["qual2"], d["len2"], 2, gz=gz_in)
+        write(f"{w}/r2{ext_in}", 2)
         base += ["-2", f"{w}/r2{ext_in}", "-D", "c2" + ext_out]
-    if patch:
-        open(f"{w}/cfg.txt", "w").write(f"patch={patch}\n")
+    if patch or cfg:
+        open(f"{w}/cfg.txt", "w").write((f"patch={patch}\n" if patch else "") + "".join(l + "\n" for l in (cfg or [])))
         base += ["-c", f"{w}/cfg.txt"]
     r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags)
     assert r.returncode == 0, r.stderr.decode()
@@ -69,6 +75,13 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
     dict(name="pe_discard_small_batches", pe=True, n=20000, L=100, T=2, flags=["-f", A1, "-r", A2], env={"SNK_BATCH_READS": "3000"}),
     dict(name="pe_polyg250", pe=True, n=8000, L=250, T=2, flags=["-f", A1, "-r", A2, "-J", "-g", "10"], gkw=dict(polyg_frac=0.3)),
     dict(name="pe_varlen_hardtrim", pe=True, n=12000, L=120, T=2, flags=["-f", A1, "-r", A2, "-J", "-t", "3,2,4,1"], gkw=dict(var_len=True), patch=30),
+    dict(name="pe_index_peinfo_seqtype0", pe=True, n=12000, L=100, T=2, flags=["-f", A1, "-r", A2, "-J"], cfg=["index", "pe_info"], index_ids=True),
+    dict(name="pe_index_seqtype1_fasta", pe=True, n=12000, L=100, T=3, flags=["-f", A1, "-r", A2, "-J"], patch=17,
+         cfg=["index", "seqType=1", "outFileType=fasta"], index_ids=True),
+    dict(name="se_fasta_gz", pe=False, n=12000, L=100, T=2, flags=["-f", A1], cfg=["outFileType=fasta", "pe_info"], gz_in=True, gz_out=True),
+    dict(name="pe_varlen_growing_stride", pe=True, n=20000, L=150, T=2, flags=["-f", A1, "-r", A2, "-J"], gkw=dict(var_len=True),
+         env={"SNK_BATCH_READS": "2048"}, cfg=["outQualSys=1"]),
+    dict(name="pe_cfg2_gz_big_members", pe=True, n=120000, L=150, T=4, flags=CFG2_FLAGS, gz_in=True, gz_out=True),
     dict(name="se_default", pe=False, n=30000, L=150, T=1, flags=[]),
     dict(name="se_adapter_T4", pe=False, n=30000, L=100, T=4, flags=["-f", A1, "-J", "-g", "10"], patch=11, gz_in=True),
 ], ids=lambda c: c["name"])

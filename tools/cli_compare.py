@@ -55,6 +55,7 @@ def main():
     ap.add_argument("--gz", action="store_true")
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--skip-reference", action="store_true")
+    ap.add_argument("--batch-sweep", default="", help="comma list of SNK_BATCH_READS values to time the B200 CLI with")
     a = ap.parse_args()
     work = "/dev/shm/snk_cli_compare"
     shutil.rmtree(work, ignore_errors=True)
@@ -87,6 +88,15 @@ def main():
             if f.endswith(".txt"):
                 same = same and open(f"{work}/ref/{f}", "rb").read() == open(f"{work}/mine/{f}", "rb").read()
         out["outputs_identical"] = same
+    if a.batch_sweep:
+        out["batch_sweep"] = {}
+        for br in a.batch_sweep.split(","):
+            env = dict(os.environ, SNK_BATCH_READS=br)
+            shutil.rmtree(f"{work}/sweep", ignore_errors=True)
+            t = timed([os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke"), "filter"] + base + ["-o", f"{work}/sweep"] + FLAGS, env=env)
+            t["log"] = [l.strip() for l in open(f"{work}/sweep/log") if "stage seconds" in l]
+            out["batch_sweep"][br] = t
+        shutil.rmtree(f"{work}/sweep", ignore_errors=True)
     try:
         out["b200_log"] = [l.strip() for l in open(f"{work}/mine/log") if "stage seconds" in l]
     except Exception:
