@@ -66,7 +66,7 @@ struct SmemPlan {
     uint32_t off_misc;
     uint32_t total;
 };
-constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8;      // lastkey[8] + gsum[4][8]
+constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8 + 16; // lastkey[8] + gsum[4][8] + the staging mbarrier
 __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb)
 {
     SmemPlan p;
@@ -86,6 +86,37 @@ __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t st
 }
 
 #ifdef __CUDACC__
+
+// ---- TMA (bulk async copy) staging of a tile: global -> shared, completion on an mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SNK_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SNK_DONE_%=;\n"
+        "bra SNK_WAIT_%=;\n"
+        "SNK_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ void report_error(const KernelArgs& A, uint32_t bits, uint64_t gi)
 {
@@ -230,6 +261,8 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table, gsum[4][8]
     unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(smem + sp.off_misc);
     unsigned long long* gsum = lastkey + 8;
+    unsigned long long* stage_bar = gsum + 32;
+    uint32_t stage_phase = 0;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
@@ -239,6 +272,11 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     for (int b = 0; b < 5; b++)
 #pragma unroll
         for (int j = 0; j < J; j++) bc.v[b][j] = 0;
+    __syncthreads();
+    if (tid == 0) {
+        mbar_init(stage_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
 
     const uint32_t nt = A.tm.ntiles;
@@ -275,18 +313,24 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             reads_in_hist = 0;
         }
         reads_in_hist += cnt;
-        // ---- stage the tile: rows are contiguous in global memory, copy 16 bytes per thread-step
+        // ---- stage the tile: the rows of a tile are one contiguous block per array, so one elected thread
+        // hands 2*MATES bulk copies to the TMA engine and everybody waits on the mbarrier they complete on
         const uint32_t row_bytes = cnt * A.stride;
+        if (tid == 0) {
+            mbar_expect_tx(stage_bar, 2u * MATES * row_bytes);
+#pragma unroll
+            for (int m = 0; m < MATES; m++) {
+                bulk_g2s(smem + sp.off_rows[m][0], A.seq[m] + (size_t)start * A.stride, row_bytes, stage_bar);
+                bulk_g2s(smem + sp.off_rows[m][1], A.qual[m] + (size_t)start * A.stride, row_bytes, stage_bar);
+            }
+        }
 #pragma unroll
         for (int m = 0; m < MATES; m++) {
-            const uint4* gs = reinterpret_cast<const uint4*>(A.seq[m] + (size_t)start * A.stride);
-            const uint4* gq = reinterpret_cast<const uint4*>(A.qual[m] + (size_t)start * A.stride);
-            uint4* ss = reinterpret_cast<uint4*>(smem + sp.off_rows[m][0]);
-            uint4* sq = reinterpret_cast<uint4*>(smem + sp.off_rows[m][1]);
-            for (uint32_t i = tid; i < row_bytes / 16; i += blockDim.x) { ss[i] = __ldg(gs + i); sq[i] = __ldg(gq + i); }
             uint16_t* sl = reinterpret_cast<uint16_t*>(smem + sp.off_len[m]);
             for (uint32_t i = tid; i < cnt; i += blockDim.x) sl[i] = A.len[m][start + i];
         }
+        mbar_wait(stage_bar, stage_phase);
+        stage_phase ^= 1u;
         __syncthreads();
 
         // ---- phase A: kNT adjacent lanes per read

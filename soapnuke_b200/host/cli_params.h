@@ -32,7 +32,8 @@ struct HostParams {
     bool is_pe = false;
     // engine-side knobs (not part of the reference CLI; environment SNK_GPUS / SNK_BATCH_READS)
     int n_gpus = 1;
-    unsigned batch_reads = 1u << 16;
+    unsigned batch_reads = 1u << 15;
+    bool fast_exit = false;            // set by main(): skip freeing device / pinned memory, _exit after the reports are written
 };
 
 // Parses argv exactly like global_parameter_initial + check_parameter. Returns 0 = run,

@@ -3,6 +3,7 @@
 // `filterMeta`, process_argv.cpp:27,763) is served by the GPU engine.
 #include <iostream>
 #include <string>
+#include <unistd.h>
 #include "cli_params.h"
 #include "process.h"
 
@@ -25,7 +26,11 @@ int main(int argc, char** argv)
     }
     snk::HostParams hp;
     if (snk::parse_command_line(argc, argv, hp)) return 0;
-    if (hp.is_pe) { snk::peProcess p(hp); p.process(); }
-    else { snk::seProcess p(hp); p.process(); }
-    return 0;
+    hp.fast_exit = true;
+    if (hp.is_pe) { snk::peProcess* p = new snk::peProcess(hp); p->process(); }
+    else { snk::seProcess* p = new snk::seProcess(hp); p->process(); }
+    // every output file is written and closed: skip the CUDA context / pinned memory teardown
+    std::cout.flush();
+    std::cerr.flush();
+    _exit(0);
 }

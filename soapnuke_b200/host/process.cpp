@@ -27,6 +27,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -101,10 +102,12 @@ public:
         } else {
             fd_ = open(path.c_str(), O_RDONLY);
             if (fd_ < 0) die("cannot open the file," + path);
+            seekable_ = lseek(fd_, 0, SEEK_CUR) != (off_t)-1;
         }
     }
     ~ByteSource() { if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
-    // up to n bytes into dst; 0 at EOF
+    // up to n bytes into dst; 0 at EOF. Plain files: large requests are split over a few threads (the
+    // copy out of the page cache is what limits a single reader)
     size_t read(char* dst, size_t n)
     {
         if (gz_) {
@@ -112,9 +115,41 @@ public:
             if (got < 0) die("cannot read the file," + path_);
             return (size_t)got;
         }
-        ssize_t got = ::read(fd_, dst, n);
-        if (got < 0) die("cannot read the file," + path_);
-        return (size_t)got;
+        if (!seekable_) {                       // a pipe: plain sequential reads
+            const ssize_t got = ::read(fd_, dst, n);
+            if (got < 0) die("cannot read the file," + path_);
+            return (size_t)got;
+        }
+        auto pread_all = [&](char* d, size_t want, off_t at) -> size_t {
+            size_t done = 0;
+            while (done < want) {
+                const ssize_t got = ::pread(fd_, d + done, want - done, at + (off_t)done);
+                if (got < 0) die("cannot read the file," + path_);
+                if (got == 0) break;
+                done += (size_t)got;
+            }
+            return done;
+        };
+        constexpr int kParts = 4;
+        size_t total = 0;
+        if (n < (4u << 20)) total = pread_all(dst, n, off_);
+        else {
+            const size_t part = (n / kParts + 4095) & ~(size_t)4095;
+            size_t got[kParts] = {0};
+            std::thread th[kParts];
+            for (int i = 1; i < kParts; i++) {
+                const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
+                th[i] = std::thread([&, i, lo, hi] { got[i] = pread_all(dst + lo, hi - lo, off_ + (off_t)lo); });
+            }
+            got[0] = pread_all(dst, std::min(n, part), off_);
+            for (int i = 1; i < kParts; i++) th[i].join();
+            for (int i = 0; i < kParts; i++) {
+                total += got[i];
+                if (got[i] < std::min(n, part * (i + 1)) - std::min(n, part * i)) break;      // end of file inside this part
+            }
+        }
+        off_ += (off_t)total;
+        return total;
     }
     // bytes carried over from the previous batch (text after its last complete record)
     std::vector<char> carry;
@@ -124,6 +159,8 @@ private:
     bool gz_;
     gzFile f_ = nullptr;
     int fd_ = -1;
+    off_t off_ = 0;
+    bool seekable_ = true;
 };
 
 // ------------------------------------------------------------------ newline search
@@ -250,8 +287,8 @@ private:
     uint64_t cyc_ = 0, defer_len_ = 0, insert_off_ = 0;
     bool reorder_ = false;
     // busy seconds per stage (log only)
-    double t_read_ = 0, t_gpu_wait_ = 0, t_write_ = 0, t_setup_ = 0;
-    std::atomic<uint64_t> t_gz_us_{0};
+    double t_read_ = 0, t_gpu_wait_ = 0, t_setup_ = 0;
+    std::atomic<uint64_t> t_gz_us_{0}, t_write_us_{0};
     size_t avg_rec_bytes_[2] = {0, 0};
 };
 
@@ -550,27 +587,36 @@ void FilterRun::gz_worker()
 void FilterRun::writer()
 {
     int out[2] = {-1, -1};
+    off_t pos[2] = {0, 0};
     const std::string names[2] = {hp_.output_dir + "/" + hp_.clean_fq1, hp_.output_dir + "/" + hp_.clean_fq2};
     for (int m = 0; m < mates_; m++) {
         out[m] = open(names[m].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (out[m] < 0) die("cannot write to the file," + names[m]);
     }
-    auto write_all = [&](int m, const char* p, size_t n) {
+    // the order is fixed here (every run of bytes gets its file offset), the copying is done by a small pool
+    struct WriteTask { int m; const char* p; size_t len; off_t at; HostBatch* owner; std::shared_ptr<std::string> hold; };
+    Channel<WriteTask> tasks;
+    auto write_at = [&](const WriteTask& t) {
+        const char* p = t.p; size_t n = t.len; off_t at = t.at;
         while (n > 0) {
-            const ssize_t w = ::write(out[m], p, std::min<size_t>(n, 1u << 30));
-            if (w < 0) die("cannot write to the file," + names[m]);
-            p += w; n -= (size_t)w;
+            const ssize_t w = ::pwrite(out[t.m], p, std::min<size_t>(n, 1u << 30), at);
+            if (w < 0) die("cannot write to the file," + names[t.m]);
+            p += w; n -= (size_t)w; at += w;
         }
     };
-    auto write_mate = [&](HostBatch* b, int m) {
-        for (Piece& p : b->pieces[m]) {
-            if (p.kind == 0) write_all(m, p.p, p.len);
-            else if (p.kind == 1) pending_deferred_[m].append(p.p, p.len);
-            else { write_all(m, pending_deferred_[m].data(), pending_deferred_[m].size()); pending_deferred_[m].clear(); }
-        }
-        b->pieces[m].clear();
-    };
+    std::vector<std::thread> pool;
+    for (int i = 0; i < 4; i++)
+        pool.emplace_back([&] {
+            WriteTask t;
+            while (tasks.pop(t)) {
+                const double t0 = now_s();
+                write_at(t);
+                t_write_us_ += (uint64_t)((now_s() - t0) * 1e6);
+                if (t.owner && --t.owner->tasks == 0) free_q_.push(t.owner);
+            }
+        });
     uint64_t next = 0;
+    std::vector<WriteTask> mine;
     for (;;) {
         HostBatch* b = nullptr;
         {
@@ -580,17 +626,34 @@ void FilterRun::writer()
             if (it == done_.end()) break;
             b = it->second; done_.erase(it);
         }
-        const double tw0 = now_s();
-        if (pe_) {
-            std::thread t2([&] { write_mate(b, 1); });
-            write_mate(b, 0);
-            t2.join();
-        } else write_mate(b, 0);
-        t_write_ += now_s() - tw0;
-        if (b->seq_no % 4 == 0) log_line(local_time() + " processed_reads:\t" + std::to_string(b->first_index + b->n));
+        mine.clear();
+        for (int m = 0; m < mates_; m++) {
+            for (Piece& p : b->pieces[m]) {
+                if (p.kind == 0) { if (p.len) mine.push_back({m, p.p, p.len, pos[m], b, nullptr}); pos[m] += (off_t)p.len; }
+                else if (p.kind == 1) pending_deferred_[m].append(p.p, p.len);
+                else if (!pending_deferred_[m].empty()) {
+                    auto hold = std::make_shared<std::string>(std::move(pending_deferred_[m]));
+                    pending_deferred_[m].clear();
+                    mine.push_back({m, hold->data(), hold->size(), pos[m], nullptr, hold});
+                    pos[m] += (off_t)hold->size();
+                }
+            }
+        }
+        if (b->seq_no % 16 == 0) log_line(local_time() + " processed_reads:\t" + std::to_string(b->first_index + b->n));
         next++;
-        free_q_.push(b);
+        int owned = 0;
+        for (const WriteTask& t : mine) owned += t.owner != nullptr;
+        if (owned == 0) {
+            for (const WriteTask& t : mine) tasks.push(t);
+            for (int m = 0; m < mates_; m++) b->pieces[m].clear();
+            free_q_.push(b);
+        } else {
+            b->tasks = owned;                 // the batch (its pinned text and gzip strings) is recycled by the last write
+            for (const WriteTask& t : mine) tasks.push(t);
+        }
     }
+    tasks.close();
+    for (auto& t : pool) t.join();
     // End of input. The reference's final concat pass (peprocess.cpp:2957-2966) walks the workers of
     // the last cycle in order and stops at the first one without a temp file for it; the deferred
     // batch sits in the LAST worker's file, so it is silently dropped (while still counted in the
@@ -602,7 +665,7 @@ void FilterRun::writer()
         drop = into_last <= (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 2);
     }
     for (int m = 0; m < mates_; m++) {
-        if (!drop) write_all(m, pending_deferred_[m].data(), pending_deferred_[m].size());
+        if (!drop && !pending_deferred_[m].empty()) write_at({m, pending_deferred_[m].data(), pending_deferred_[m].size(), pos[m], nullptr, nullptr});
         if (close(out[m]) != 0) die("cannot write to the file," + names[m]);
     }
 }
@@ -668,14 +731,16 @@ void FilterRun::process()
     }
     if (pe_) { if (snk_report_write_pe(&ep_, total.data(), hp_.output_dir.c_str())) die(snk_last_error()); }
     else { if (snk_report_write_se(&ep_, total.data(), hp_.output_dir.c_str())) die(snk_last_error()); }
-    for (snk_engine* e : engines_) snk_engine_destroy(e);
-    engines_.clear();
-    for (auto& b : batches_) b.release();
-    batches_.clear();
+    if (!hp_.fast_exit) {                        // the CLI leaves device and pinned memory to process exit
+        for (snk_engine* e : engines_) snk_engine_destroy(e);
+        engines_.clear();
+        for (auto& b : batches_) b.release();
+        batches_.clear();
+    }
     {
         char buf[512];
-        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write %.2f, total %.2f; reads %llu",
-                 t_setup_, t_read_, t_gpu_wait_, nworkers, t_gz_us_.load() * 1e-6, t_write_, now_s() - t_begin,
+        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write(sum over 4 threads) %.2f, total %.2f; reads %llu",
+                 t_setup_, t_read_, t_gpu_wait_, nworkers, t_gz_us_.load() * 1e-6, t_write_us_.load() * 1e-6, now_s() - t_begin,
                  (unsigned long long)total_reads_);
         log_line(buf);
     }
