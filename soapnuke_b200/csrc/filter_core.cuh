@@ -8,7 +8,8 @@
 //   scan_read        stat_read counters + adapter search   read_filter.cpp:80-313, 707-790
 //                    followed by fastq_trim                 read_filter.cpp:338-482
 //   decide_pair/se   pe_discard / se_discard                sequence.cpp:198-387, 76-178
-//   hist_item        stat_pe_fqs / stat_se_fqs tables       peprocess.cpp:1144-1203, seprocess.cpp:683-739
+//   qual_update_* /  stat_pe_fqs / stat_se_fqs tables       peprocess.cpp:1144-1203, seprocess.cpp:683-739
+//   base_acc_*
 //   trim_stat_*      trimming-position tables               peprocess.cpp:1107-1143, 1325-1360; seprocess.cpp:647-682
 #pragma once
 #include <stdint.h>
@@ -17,9 +18,11 @@
 
 #if defined(__CUDACC__)
 #define SNK_HD __host__ __device__ __forceinline__
+#define SNK_HD_NOINLINE __host__ __device__ __noinline__
 #define SNK_ALIGN16 __align__(16)
 #else
 #define SNK_HD static inline
+#define SNK_HD_NOINLINE static
 #define SNK_ALIGN16 alignas(16)
 #endif
 
@@ -93,6 +96,14 @@ SNK_HD uint32_t load4(const uint8_t* p)   // p 4-byte aligned
     return *reinterpret_cast<const uint32_t*>(p);
 #else
     uint32_t v; memcpy(&v, p, 4); return v;
+#endif
+}
+SNK_HD void store16(uint8_t* p, const U4& v)   // p 16-byte aligned
+{
+#ifdef __CUDA_ARCH__
+    *reinterpret_cast<U4*>(p) = v;
+#else
+    memcpy(p, &v, 16);
 #endif
 }
 
@@ -181,8 +192,10 @@ SNK_HD int ctz64(uint64_t x)      // x != 0
 // without walking the window: equivalent to window_exact. The (max(budget,0)+1)-th mismatch is the
 // abort position; the first run of seg_thr matches that ends before it accepts; otherwise the
 // window accepts iff it finishes with mis <= budget. Loop trip counts depend only on the
-// (warp-uniform) parameters, so a warp stays converged.
-SNK_HD bool window_decide(uint64_t M, int winlen, int budget, int seg_thr)
+// (warp-uniform) parameters, so a warp stays converged. Out of line: it runs only for the few
+// offsets that pass both prefilters, and inlining it at every call site of the sweeps multiplies
+// the kernel's code size (instruction-cache pressure) for nothing.
+SNK_HD_NOINLINE bool window_decide(uint64_t M, int winlen, int budget, int seg_thr)
 {
     const uint64_t valid = winlen >= 64 ? ~0ull : ((1ull << winlen) - 1ull);
     M &= valid;
@@ -238,9 +251,13 @@ SNK_HD void merge_scan(ScanPart<NW>& a, const ScanPart<NW>& b)
     a.viol |= b.viol; a.qviol |= b.qviol; a.qover |= b.qover;
 }
 
-// stage 1: packed scan of this thread's 16-byte chunks (c % kNT == h) of the bases and qualities
+// stage 1: packed scan of this thread's 16-byte chunks (c % kNT == h) of the bases and qualities.
+// The scan also normalises the row's padding in place (the tile copy in shared memory, never the
+// caller's batch): base bytes at positions >= len become 0 (counted by nobody) and quality bytes
+// become phred+qb (the "dump" bin one past the last real bin), so that phase B can walk whole rows of
+// the raw tables without per-read length tests. nchunks = stride / 16.
 template <int MAXC>
-SNK_HD void scan_chunks(const uint8_t* seq, const uint8_t* qual, int len, const DevParams& P, int h, bool want_planes,
+SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const DevParams& P, int h, bool want_planes,
                         ScanPart<(MAXC + 1) / 2>& S)
 {
     constexpr int NW = (MAXC + 1) / 2;
@@ -251,18 +268,35 @@ SNK_HD void scan_chunks(const uint8_t* seq, const uint8_t* qual, int len, const 
     const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
     const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
     const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
+    const uint32_t qpad = (over_k & 0xFFu) * 0x01010101u;          // padding quality: the dump bin
     // Both lanes of a group run the same instruction stream on different data: step cc handles chunk
     // c = kNT*cc + h, i.e. (kNT == 2) lane h fills half h of plane word cc.
     static_assert(kNT == 2, "plane half-word placement below assumes two lanes per read");
 #pragma unroll(MAXC <= 16 ? NW : 1)
     for (int cc = 0; cc < NW; cc++) {
         const int c = kNT * cc + h;
-        if (16 * c >= len) continue;
+        if (c >= nchunks) continue;
+        if (16 * c >= len) {                                   // chunk entirely behind the read: padding only
+            const U4 z = {0u, 0u, 0u, 0u}, qp = {qpad, qpad, qpad, qpad};
+            store16(seq + 16 * c, z); store16(qual + 16 * c, qp);
+            continue;
+        }
         uint32_t c0 = 0, c1 = 0, cn = 0, cl = 0;
         const U4 sv = load16(seq + 16 * c);
         const U4 qv = load16(qual + 16 * c);
         const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+        if (len - 16 * c < 16) {                               // the read ends inside this chunk
+            uint32_t ss[4], qq[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int nv = len - (16 * c + 4 * k);
+                const uint32_t mk = nv >= 4 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
+                ss[k] = sw[k] & mk; qq[k] = (qw[k] & mk) | (qpad & ~mk);
+            }
+            const U4 s4 = {ss[0], ss[1], ss[2], ss[3]}, q4 = {qq[0], qq[1], qq[2], qq[3]};
+            store16(seq + 16 * c, s4); store16(qual + 16 * c, q4);
+        }
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int nvalid = len - (16 * c + 4 * k);
@@ -535,13 +569,13 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool polyx, int ada_pos, const Tr
 // Exchange policy for the CPU replay / documentation of the protocol: given a callable that returns
 // thread h's part, run all kNT parts and merge them. The kernel does the same with lane shuffles.
 template <int MAXC>
-SNK_HD void scan_read_serial(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P, ReadInfo& R)
+SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P, ReadInfo& R)
 {
     constexpr int NW = (MAXC + 1) / 2;
     const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
     ScanPart<NW> S, S2;
-    scan_chunks<MAXC>(seq, qual, len, P, 0, want_planes, S);
-    for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, P, h, want_planes, S2); merge_scan(S, S2); }
+    scan_chunks<MAXC>(seq, qual, len, nchunks, P, 0, want_planes, S);
+    for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, want_planes, S2); merge_scan(S, S2); }
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
     if (P.n_adapters[mate] > 0) {
@@ -632,13 +666,32 @@ SNK_HD void trim_stat_indices(int which, int slen, int raw_length, int head_hd, 
 }
 
 // ------------------------------------------------------------------ per-position histograms
-// One histogram item = J consecutive positions of one table (J = 2, or 4 for very long reads); the
-// thread that owns an item is the only writer of its counters, so no atomics are needed.
+// One histogram item = J consecutive positions of one table; the thread that owns an item is the
+// only writer of its counters, so no atomics are needed.
 //   quality x position counts: shared memory, CounterT cells, index (q*J + j) * qstride + item
 //   base x position counts:    packed J x 8 bit per symbol while walking a tile (BaseAcc), then
 //                              added to the owner's 5*J register counters (BaseCnt) for the whole launch.
+// RAW items count every record of the tile: rows are padded by scan_chunks (bases 0, qualities in the
+// dump bin), so the owner walks whole rows with no length test. The CLEAN tables are not counted
+// directly: the clean set is the raw set minus the dropped records and the trimmed-off ends, so the
+// second group of items accumulates that (usually small) difference, "removed - added", from a
+// per-tile list of DELTA entries, and the flush adds raw - delta to the clean tables.
 struct BaseAcc { uint32_t a, c, g, t, n; };
-template <int J> struct BaseCnt { uint32_t v[5][J]; };      // [A,C,G,T,N][j]
+// Per-thread base counters for one item, whole flush interval: pairs of 16-bit counters packed in
+// 32-bit registers ([symbol A,C,G,T,N][pair p]: sub-position 2p in the low half, 2p+1 in the high
+// half). raw counts records (<= kQCounterMax per interval, no carry between halves); del holds
+// "removed - added" biased by 0x8000 per half, so that neither adds nor subtracts ever carry or
+// borrow across the halves while at most kQCounterMax records are counted per interval.
+template <int J> struct BaseCnt { uint32_t raw[5][J / 2], del[5][J / 2]; };
+constexpr uint32_t kDelBias = 0x80008000u;
+template <int J>
+SNK_HD void base_cnt_reset(BaseCnt<J>& c)
+{
+#pragma unroll
+    for (int b = 0; b < 5; b++)
+#pragma unroll
+        for (int p = 0; p < J / 2; p++) { c.raw[b][p] = 0; c.del[b][p] = kDelBias; }
+}
 
 SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked: bytes outside the item are 0 */)
 {
@@ -651,19 +704,29 @@ SNK_HD void base_acc_add(BaseAcc& acc, uint32_t s /* masked: bytes outside the i
     acc.t += ~m1 & m2 & ~m3 & 0x01010101u;
     acc.a += valid & ~(m1 | m2 | m3);
 }
+// bytes 2p and 2p+1 of w, each zero-extended into a 16-bit half
+SNK_HD uint32_t byte_pair(uint32_t w, int p)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(w, 0u, 0x4140u + 0x0202u * (uint32_t)p);
+#else
+    return ((w >> (16 * p)) & 0xFFu) | (((w >> (16 * p + 8)) & 0xFFu) << 16);
+#endif
+}
+// add (sign = +1) or subtract (-1) the packed per-tile counts to/from dst (raw or del) and clear them
 template <int J>
-SNK_HD void base_acc_spill(BaseAcc& acc, BaseCnt<J>& cnt)
+SNK_HD void base_acc_spill(BaseAcc& acc, uint32_t (*dst)[J / 2], int sign = 1)
 {
     const uint32_t packed[5] = {acc.a, acc.c, acc.g, acc.t, acc.n};
 #pragma unroll
     for (int b = 0; b < 5; b++)
 #pragma unroll
-        for (int j = 0; j < J; j++) cnt.v[b][j] += (packed[b] >> (8 * j)) & 0xFFu;
+        for (int p = 0; p < J / 2; p++) dst[b][p] += (uint32_t)sign * byte_pair(packed[b], p);
     acc.a = acc.c = acc.g = acc.t = acc.n = 0;
 }
 
 // Loads the J bytes (low J bytes of the result) that item w of a record starting at byte `off` of
-// its row covers (record positions J*w .. J*w+J-1).
+// its row block covers (record positions J*w .. J*w+J-1).
 template <int J>
 SNK_HD uint32_t hist_load_word(const uint8_t* row, int off, int w)
 {
@@ -674,91 +737,227 @@ SNK_HD uint32_t hist_load_word(const uint8_t* row, int off, int w)
     else if (sh) v >>= sh;
     return v;
 }
-template <int J>
-SNK_HD void hist_load(const uint8_t* seq, const uint8_t* qual, int off, int w, uint32_t& s, uint32_t& q)
-{
-    s = hist_load_word<J>(seq, off, w);
-    q = hist_load_word<J>(qual, off, w);
-}
 
-// Per-read descriptor for phase B, one 32-bit word per (table, read): record length (bits 0-9),
-// byte address of the record's first base inside the tile's row block = r*stride + first byte
-// (bits 10-30), bit 31 = take the checked path. 0 = skip.
+// Per-record descriptor, one 32-bit word: record length n (bits 0-9), byte address of the record's
+// first base inside the tile's row block = r*stride + first byte (bits 10-30), bit 31 = some quality
+// of the record lies outside the shared-memory bins (checked path). 0 = skip.
 SNK_HD uint32_t hist_desc(int n, uint32_t addr, bool slow) { return n <= 0 ? 0u : ((uint32_t)n | (addr << 10) | (slow ? 0x80000000u : 0u)); }
 
-// Fast path: every quality of the record is known to lie inside the shared-memory bins (RF_QSLOW
-// clear). qcells = the quality table as bytes; cell of (byte value b, sub-position j) is at
-// qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
-template <int J>
-SNK_HD void base_update(uint32_t s, int nvalid, BaseAcc& acc)
+// Delta entry: positions [start, end) of the record at `addr` are REMOVED from (or, add flag, ADDED
+// to) the clean set relative to the raw set. d0 = hist_desc(end, addr, slow), d1 = start | add << 31.
+struct DeltaEnt { uint32_t d0, d1; };
+constexpr uint32_t kDeltaAdd = 0x80000000u;
+// Entries of one record (0..2): dropped -> remove everything; kept and only 3'-trimmed -> remove the
+// tail; kept with a 5' cut (clean positions shift) -> remove everything, add the clean record.
+SNK_HD int delta_entries(const ReadInfo& ri, bool keep, uint32_t row0, DeltaEnt* e)
 {
-    const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-    const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
-    base_acc_add(acc, s & mask & jmask);
+    if (ri.len <= 0) return 0;
+    const bool slow = (ri.flags & RF_QSLOW) != 0;
+    if (keep && ri.head_cut == 0) {
+        if (ri.clean_len >= ri.len) return 0;
+        e[0].d0 = hist_desc(ri.len, row0, slow); e[0].d1 = (uint32_t)(ri.clean_len < 0 ? 0 : ri.clean_len);
+        return 1;
+    }
+    e[0].d0 = hist_desc(ri.len, row0, slow); e[0].d1 = 0;
+    if (!keep || ri.clean_len <= 0) return 1;
+    e[1].d0 = hist_desc(ri.clean_len, row0 + (uint32_t)ri.head_cut, slow); e[1].d1 = kDeltaAdd;
+    return 2;
 }
-template <typename CounterT, int J>
-SNK_HD void qual_update_fast(uint32_t q, int nvalid, uint8_t* qcells, int cell0, int jstep, int bstep)
+
+// byte lanes lo <= j < hi of a word (lo, hi may lie outside [0,4])
+SNK_HD uint32_t lane_mask(int lo, int hi)
 {
-    // One straight-line path for full and partial items (a divergent branch would make every warp that
-    // holds a record's last item issue the body twice). The J cells belong to different sub-positions,
-    // so they never alias: load them all, then store them all - one shared-memory round trip per record.
+    const uint32_t mh = hi >= 4 ? 0xFFFFFFFFu : (hi <= 0 ? 0u : ((1u << (8 * hi)) - 1u));
+    const uint32_t ml = lo >= 4 ? 0xFFFFFFFFu : (lo <= 0 ? 0u : ((1u << (8 * lo)) - 1u));
+    return mh & ~ml;
+}
+template <int J>
+SNK_HD void base_update_range(uint32_t s, int lo, int hi, BaseAcc& acc)
+{
+    const uint32_t jmask = J >= 4 ? 0xFFFFFFFFu : ((1u << (8 * J)) - 1u);
+    base_acc_add(acc, s & lane_mask(lo, hi) & jmask);
+}
+
+// Quality cells: qcells = the quality table as bytes; the cell of (byte value b, sub-position j) is
+// at qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
+// The J cells belong to different sub-positions, so they never alias: load them all, then store them
+// all - one shared-memory round trip per record.
+template <typename CounterT, int J>
+SNK_HD void qual_update_all(uint32_t q, uint8_t* qcells, int cell0, int jstep, int bstep)
+{
     CounterT* cell[J];
     CounterT val[J];
 #pragma unroll
     for (int j = 0; j < J; j++) {
         cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
-        val[j] = (j < nvalid) ? *cell[j] : (CounterT)0;
+        val[j] = *cell[j];
+    }
+#pragma unroll
+    for (int j = 0; j < J; j++) *cell[j] = (CounterT)(val[j] + 1);
+}
+// sub-positions lo <= j < hi only, inc = +1 / -1 (cells wrap: delta cells are read as signed)
+template <typename CounterT, int J>
+SNK_HD void qual_update_range(uint32_t q, int lo, int hi, int inc, uint8_t* qcells, int cell0, int jstep, int bstep)
+{
+    CounterT* cell[J];
+    CounterT val[J];
+#pragma unroll
+    for (int j = 0; j < J; j++) {
+        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+        val[j] = (j >= lo && j < hi) ? *cell[j] : (CounterT)0;
     }
 #pragma unroll
     for (int j = 0; j < J; j++)
-        if (j < nvalid) *cell[j] = (CounterT)(val[j] + 1);
-}
-template <typename CounterT, int J>
-SNK_HD void hist_item_fast(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, BaseAcc& acc,
-                           uint8_t* qcells, int cell0, int jstep, int bstep)
-{
-    const int nvalid = n - J * w;
-    if (nvalid <= 0) return;
-    uint32_t s, q;
-    hist_load<J>(seq, qual, off, w, s, q);
-    base_update<J>(s, nvalid, acc);
-    qual_update_fast<CounterT, J>(q, nvalid, qcells, cell0, jstep, bstep);
+        if (j >= lo && j < hi) *cell[j] = (CounterT)(val[j] + inc);
 }
 
-// Checked path: qualities may fall outside [0,qb). Bins not kept in shared memory go straight to
-// the slot's global table; anything outside [0,SNK_QBINS) raises the error flag. Returns error bits.
+// Checked path (records whose qualities may fall outside [0,qb), RF_QSLOW): sub-positions lo <= j < hi
+// of item w of the record at `off`. Bins kept in shared memory take cell_inc; the others go straight
+// to the slot's global tables: g_inc into file_base's table and, if given, into mirror_base's too
+// (a raw record counts for the clean table as well until a delta entry removes it). Anything outside
+// [0,SNK_QBINS) raises the error flag. Returns error bits.
 template <typename CounterT, int J>
-SNK_HD uint32_t hist_item(const uint8_t* seq, const uint8_t* qual, int off, int n, int w, int phred, int qb,
-                          BaseAcc& acc, CounterT* qhist, int qstride, unsigned long long* file_base /* slot's file block, or null */,
-                          bool do_bases = true, bool do_quals = true)
+SNK_HD uint32_t qual_update_checked(const uint8_t* qual, int off, int w, int lo, int hi, int phred, int qb, int cell_inc,
+                                    CounterT* qhist /* item's first cell */, int qstride, long long g_inc,
+                                    unsigned long long* file_base, unsigned long long* mirror_base)
 {
-    const int nvalid = n - J * w;
-    if (nvalid <= 0) return 0;
-    uint32_t s, q;
-    hist_load<J>(seq, qual, off, w, s, q);
-    if (do_bases) base_update<J>(s, nvalid, acc);
+    const uint32_t q = hist_load_word<J>(qual, off, w);
     uint32_t err = 0;
-    if (!do_quals) return 0;
 #pragma unroll
     for (int j = 0; j < J; j++) {
-        if (j < nvalid) {
+        if (j >= lo && j < hi) {
             const int qq = (int)((q >> (8 * j)) & 0xFFu) - phred;
-            if ((unsigned)qq < (unsigned)qb) qhist[(qq * J + j) * qstride] += 1;
-            else if ((unsigned)qq < (unsigned)SNK_QBINS && file_base) {
-                unsigned long long* cell = file_base + SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + qq;
+            if ((unsigned)qq < (unsigned)qb) qhist[(qq * J + j) * qstride] = (CounterT)(qhist[(qq * J + j) * qstride] + cell_inc);
+            else if ((unsigned)qq < (unsigned)SNK_QBINS) {
+                const size_t cell = SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + qq;
+                unsigned long long* bases[2] = {file_base, mirror_base};
+                for (int t = 0; t < 2; t++) {
+                    unsigned long long* F = bases[t];
+                    if (!F) continue;
 #ifdef __CUDA_ARCH__
-                atomicAdd(cell, 1ull);
-                if (qq >= 20) atomicAdd(file_base + SNK_FILE_GS_OFF + SNK_GS_Q20, 1ull);
-                if (qq >= 30) atomicAdd(file_base + SNK_FILE_GS_OFF + SNK_GS_Q30, 1ull);
+                    atomicAdd(F + cell, (unsigned long long)g_inc);
+                    if (qq >= 20) atomicAdd(F + SNK_FILE_GS_OFF + SNK_GS_Q20, (unsigned long long)g_inc);
+                    if (qq >= 30) atomicAdd(F + SNK_FILE_GS_OFF + SNK_GS_Q30, (unsigned long long)g_inc);
 #else
-                *cell += 1;
-                if (qq >= 20) file_base[SNK_FILE_GS_OFF + SNK_GS_Q20] += 1;
-                if (qq >= 30) file_base[SNK_FILE_GS_OFF + SNK_GS_Q30] += 1;
+                    F[cell] += (unsigned long long)g_inc;
+                    if (qq >= 20) F[SNK_FILE_GS_OFF + SNK_GS_Q20] += (unsigned long long)g_inc;
+                    if (qq >= 30) F[SNK_FILE_GS_OFF + SNK_GS_Q30] += (unsigned long long)g_inc;
 #endif
+                }
             } else err |= ERR_BAD_QUAL;
         }
     }
     return err;
+}
+
+// ---- phase B work units. A q-unit owns JN of the J sub-positions of raw item (w of mate m) and of
+// its delta item; a b-unit owns the base counters of one item for the records r0, r0+rstep, ...
+// (and the delta entries k = r0, r0+rstep, ...). With two units per item every thread of a CTA
+// sized for phase A (two threads per read) has phase-B work.
+template <typename CounterT, int J, int JN>
+SNK_HD void unit_q_fast(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w, int j0,
+                        uint8_t* qcells, int cell0_raw, int cell0_del, int jstep, int bstep)
+{
+    const uint8_t* pq = rows_q + J * w;
+    const uint32_t sh = 8u * (uint32_t)j0;
+    const int c_raw = cell0_raw + j0 * jstep, c_del = cell0_del + j0 * jstep;
+    for (uint32_t r = 0; r < cnt; r++)
+        qual_update_all<CounterT, JN>(load4(pq + (size_t)r * stride) >> sh, qcells, c_raw, jstep, bstep);
+    const int first = J * w + j0;
+    for (uint32_t k = 0; k < nd; k++) {
+        const DeltaEnt d = dl[k];
+        const int hi = (int)(d.d0 & 0x3FFu) - first, lo = (int)(d.d1 & 0x3FFu) - first;
+        if (hi <= 0 || lo >= JN) continue;
+        qual_update_range<CounterT, JN>(hist_load_word<J>(rows_q, (int)((d.d0 >> 10) & 0x1FFFFFu), w) >> sh, lo, hi,
+                                        (d.d1 & kDeltaAdd) ? -1 : 1, qcells, c_del, jstep, bstep);
+    }
+}
+// delta entries of a b-unit (shared by the fast and the checked path)
+template <int J>
+SNK_HD void unit_b_delta(const uint8_t* rows_s, const DeltaEnt* dl, uint32_t nd, int w, uint32_t r0, uint32_t rstep, BaseCnt<J>& bc)
+{
+    BaseAcc acc = {0, 0, 0, 0, 0};
+    uint32_t since = 0;
+    const int first = J * w;
+    for (uint32_t k = r0; k < nd; k += rstep) {
+        const DeltaEnt d = dl[k];
+        const int hi = (int)(d.d0 & 0x3FFu) - first, lo = (int)(d.d1 & 0x3FFu) - first;
+        if (hi <= 0 || lo >= J) continue;
+        const uint32_t s = hist_load_word<J>(rows_s, (int)((d.d0 >> 10) & 0x1FFFFFu), w);
+        if (d.d1 & kDeltaAdd) {                  // rare: a kept record with a 5' cut
+            BaseAcc plus = {0, 0, 0, 0, 0};
+            base_update_range<J>(s, lo, hi, plus);
+            base_acc_spill<J>(plus, bc.del, -1);
+        } else {
+            base_update_range<J>(s, lo, hi, acc);
+            if (++since == 255) { since = 0; base_acc_spill<J>(acc, bc.del); }       // packed 8-bit lanes must not wrap
+        }
+    }
+    base_acc_spill<J>(acc, bc.del);
+}
+template <int J>
+SNK_HD void unit_b_fast(const uint8_t* rows_s, uint32_t stride, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w, uint32_t r0,
+                        uint32_t rstep, BaseCnt<J>& bc)
+{
+    BaseAcc acc = {0, 0, 0, 0, 0};
+    const uint8_t* ps = rows_s + J * w;
+    if (cnt <= 255u * rstep) {
+        for (uint32_t r = r0; r < cnt; r += rstep) base_acc_add(acc, load4(ps + (size_t)r * stride));
+    } else {
+        uint32_t since = 0;
+        for (uint32_t r = r0; r < cnt; r += rstep) {
+            base_acc_add(acc, load4(ps + (size_t)r * stride));
+            if (++since == 255) { since = 0; base_acc_spill<J>(acc, bc.raw); }
+        }
+    }
+    base_acc_spill<J>(acc, bc.raw);
+    unit_b_delta<J>(rows_s, dl, nd, w, r0, rstep, bc);
+}
+// Checked variants (some record of the tile has qualities outside the shared-memory bins, or a row was
+// not scanned): explicit record lengths from the raw descriptors, out-of-bin qualities straight to
+// the slot's global tables. Returns error bits.
+template <typename CounterT, int J>
+SNK_HD uint32_t unit_q_checked(const uint8_t* rows_q, const uint32_t* desc, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w,
+                               int j0, int jn, int phred, int qb, CounterT* cell_raw /* raw item's first cell */, uint32_t nraw,
+                               int qstride, unsigned long long* f_raw, unsigned long long* f_clean)
+{
+    uint32_t err = 0;
+    const int first = J * w;
+    for (uint32_t r = 0; r < cnt; r++) {
+        const uint32_t d0 = desc[r];
+        int hi = (int)(d0 & 0x3FFu) - first;
+        if (hi > j0 + jn) hi = j0 + jn;
+        if (hi <= j0) continue;
+        err |= qual_update_checked<CounterT, J>(rows_q, (int)((d0 >> 10) & 0x1FFFFFu), w, j0, hi, phred, qb, 1, cell_raw, qstride, 1ll, f_raw, f_clean);
+    }
+    for (uint32_t k = 0; k < nd; k++) {
+        const DeltaEnt d = dl[k];
+        int hi = (int)(d.d0 & 0x3FFu) - first, lo = (int)(d.d1 & 0x3FFu) - first;
+        if (hi > j0 + jn) hi = j0 + jn;
+        if (lo < j0) lo = j0;
+        if (hi <= lo) continue;
+        const bool add = (d.d1 & kDeltaAdd) != 0;
+        err |= qual_update_checked<CounterT, J>(rows_q, (int)((d.d0 >> 10) & 0x1FFFFFu), w, lo, hi, phred, qb, add ? -1 : 1, cell_raw + nraw,
+                                                qstride, add ? 1ll : -1ll, f_clean, nullptr);
+    }
+    return err;
+}
+template <int J>
+SNK_HD void unit_b_checked(const uint8_t* rows_s, const uint32_t* desc, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w,
+                           uint32_t r0, uint32_t rstep, BaseCnt<J>& bc)
+{
+    BaseAcc acc = {0, 0, 0, 0, 0};
+    uint32_t since = 0;
+    const int first = J * w;
+    for (uint32_t r = r0; r < cnt; r += rstep) {
+        const uint32_t d0 = desc[r];
+        const int hi = (int)(d0 & 0x3FFu) - first;
+        if (hi <= 0) continue;
+        base_update_range<J>(hist_load_word<J>(rows_s, (int)((d0 >> 10) & 0x1FFFFFu), w), 0, hi, acc);
+        if (++since == 255) { since = 0; base_acc_spill<J>(acc, bc.raw); }
+    }
+    base_acc_spill<J>(acc, bc.raw);
+    unit_b_delta<J>(rows_s, dl, nd, w, r0, rstep, bc);
 }
 
 // ------------------------------------------------------------------ tile decomposition

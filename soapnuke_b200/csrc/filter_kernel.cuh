@@ -15,7 +15,7 @@
 namespace snkcore {
 
 typedef uint16_t QCounter;                 // shared-memory quality counters; flushed before they can wrap
-constexpr uint32_t kQCounterMax = 65535;
+constexpr uint32_t kQCounterMax = 32767;   // delta cells are read back as signed 16-bit values
 
 // CTA shape: one thread per histogram item (J positions of one table); a tile holds
 // threads / (mates * kNT) reads or pairs, so that phase A (kNT threads per read) and phase B (one
@@ -56,17 +56,19 @@ struct KernelArgs {
     TileMap tm;
 };
 
-// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][desc][qhist][misc]
+// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][desc][delta][qhist][misc]
 struct SmemPlan {
     uint32_t off_rows[2][2];   // [mate][0 seq, 1 qual]
     uint32_t off_len[2];
     uint32_t off_info[2];
-    uint32_t off_desc;         // hist_desc words: [raw m0][raw m1][clean m0][clean m1], R each
-    uint32_t off_qhist;
+    uint32_t off_desc;         // hist_desc words of the raw records: [m0][m1], R each (checked path only)
+    uint32_t off_delta;        // DeltaEnt lists: [m0][m1], 2R entries each
+    uint32_t off_qhist;        // (qb + 1) * J rows of X cells; row group qb is the padding dump bin
     uint32_t off_misc;
     uint32_t total;
 };
-constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8 + 16; // lastkey[8] + gsum[4][8] + the staging mbarrier
+// misc: lastkey[8] + gsum[4][8] + the staging mbarrier (8) + ndelta[2] + tile_slow + pad
+constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8 + 8 + 2 * 4 + 4 + 12;
 __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb)
 {
     SmemPlan p;
@@ -78,8 +80,9 @@ __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t st
         }
     for (int m = 0; m < 2; m++) { p.off_len[m] = o; if (m < mates) o += align_up(R * 2, 16); }
     for (int m = 0; m < 2; m++) { p.off_info[m] = o; if (m < mates) o += align_up(R * (uint32_t)sizeof(ReadInfo), 16); }
-    p.off_desc = o; o += align_up(4u * R * 4u, 16);
-    p.off_qhist = o; o += align_up((uint32_t)qb * (uint32_t)hist_j(stride) * X * (uint32_t)sizeof(QCounter), 16);
+    p.off_desc = o; o += align_up((uint32_t)mates * R * 4u, 16);
+    p.off_delta = o; o += align_up((uint32_t)mates * 2u * R * (uint32_t)sizeof(DeltaEnt), 16);
+    p.off_qhist = o; o += align_up((uint32_t)(qb + 1) * (uint32_t)hist_j(stride) * X * (uint32_t)sizeof(QCounter), 16);
     p.off_misc = o; o += kMiscBytes;
     p.total = o;
     return p;
@@ -142,14 +145,14 @@ __device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s
 
 // phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
 template <int MAXC>
-__device__ __forceinline__ void scan_read_coop(const uint8_t* seq, const uint8_t* qual, int len, int mate, const DevParams& P,
+__device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P,
                                                int h, unsigned pm, ReadInfo& R)
 {
     static_assert(kNT == 2, "lane exchange below is written for pairs");
     constexpr int NW = (MAXC + 1) / 2;
     const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
     ScanPart<NW> S, O;
-    scan_chunks<MAXC>(seq, qual, len, P, h, want_planes, S);
+    scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, want_planes, S);
     shfl_scan<NW>(O, S, pm);
     merge_scan(S, O);
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
@@ -184,55 +187,67 @@ __device__ __forceinline__ void scan_read_coop(const uint8_t* seq, const uint8_t
 }
 
 // add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
-// slot's global tables and clear them
+// slot's global tables and clear them. Raw cells count all records, delta cells "removed - added":
+// raw table += raw, clean table += raw - delta (64-bit wrap-around arithmetic, the sums are exact).
 template <int J>
 __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, QCounter* qhist, BaseCnt<J>& bc, uint32_t base_item,
                            unsigned long long* lastkey, unsigned long long* gsum, int slot)
 {
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
     const uint32_t X = A.X, W = A.items_w;
-    const int ntab = 2 * mates;                        // raw1,[raw2],clean1,[clean2] -> item groups
+    const uint32_t nraw = (uint32_t)mates * W;         // raw items; the delta item of raw item x is x + nraw
     // quality cells: entry e = (q*J + j)*X + x
-    const uint32_t qent = (uint32_t)P.qb * (uint32_t)J * X;
-    for (uint32_t e = threadIdx.x; e < qent; e += blockDim.x) {
-        const uint32_t v = qhist[e];
-        if (!v) continue;
-        qhist[e] = 0;
-        const uint32_t x = e % X, j = (e / X) % (uint32_t)J, q = e / ((uint32_t)J * X);
+    const uint32_t qent = (uint32_t)P.qb * (uint32_t)J * nraw;
+    for (uint32_t i = threadIdx.x; i < qent; i += blockDim.x) {
+        const uint32_t x = i % nraw, qj = i / nraw;
+        const uint32_t e = qj * X + x;
+        const uint32_t vr = qhist[e];
+        const int vd = (int)(int16_t)qhist[e + nraw];
+        if (!vr && !vd) continue;
+        qhist[e] = 0; qhist[e + nraw] = 0;
+        const uint32_t j = qj % (uint32_t)J, q = qj / (uint32_t)J;
         const uint32_t tab = x / W, w = x % W;
-        if ((int)tab >= ntab) continue;
-        unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
-        atomicAdd(&F[SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q], (unsigned long long)v);
-        if (q >= 20) atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)v);
-        if (q >= 30) atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)v);
+        const size_t cell = SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q;
+        const unsigned long long vc = (unsigned long long)((long long)vr - (long long)vd);
+        if (vr) atomicAdd(&S[SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab)) + cell], (unsigned long long)vr);
+        if (vc) atomicAdd(&S[SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates)) + cell], vc);
+        if (q >= 20) { atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)vr); atomicAdd(&gsum[(tab + mates) * 8 + 6], vc); }
+        if (q >= 30) { atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)vr); atomicAdd(&gsum[(tab + mates) * 8 + 7], vc); }
     }
-    // base cells: the item whose base counters this thread holds (base_item = ~0u: none)
+    // base cells: the raw item whose base counters this thread holds (base_item = ~0u: none)
     {
         const uint32_t x = base_item;
         const uint32_t tab = x / W, w = x % W;
-        if ((int)tab < ntab) {
-            unsigned long long* F = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
-            unsigned long long bases = 0;
+        if ((int)tab < mates) {
+            unsigned long long* FR = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
+            unsigned long long* FC = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates));
+            unsigned long long bases_r = 0, bases_c = 0;
 #pragma unroll
             for (int b = 0; b < 5; b++) {
-                unsigned long long sym = 0;
+                unsigned long long sym_r = 0, sym_c = 0;
 #pragma unroll
                 for (int j = 0; j < J; j++) {
-                    const uint32_t v = bc.v[b][j];
-                    if (v) atomicAdd(&F[SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b], (unsigned long long)v);
-                    sym += v;
-                    bc.v[b][j] = 0;
+                    const uint32_t vr = (bc.raw[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu;
+                    const int vd = (int)((bc.del[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu) - 0x8000;
+                    const unsigned long long vc = (unsigned long long)((long long)vr - (long long)vd);
+                    const size_t cell = SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b;
+                    if (vr) atomicAdd(&FR[cell], (unsigned long long)vr);
+                    if (vc) atomicAdd(&FC[cell], vc);
+                    sym_r += vr; sym_c += vc;
                 }
-                if (sym) atomicAdd(&gsum[tab * 8 + b], sym);
-                bases += sym;
+                if (sym_r) atomicAdd(&gsum[tab * 8 + b], sym_r);
+                if (sym_c) atomicAdd(&gsum[(tab + mates) * 8 + b], sym_c);
+                bases_r += sym_r; bases_c += sym_c;
             }
-            if (bases) atomicAdd(&gsum[tab * 8 + 5], bases);
+            if (bases_r) atomicAdd(&gsum[tab * 8 + 5], bases_r);
+            if (bases_c) atomicAdd(&gsum[(tab + mates) * 8 + 5], bases_c);
+            base_cnt_reset<J>(bc);
         }
     }
     __syncthreads();
     if (threadIdx.x < 32) {
         const int t = threadIdx.x >> 3, k = threadIdx.x & 7;      // 4 tables x 8 sums
-        if (t < ntab) {
+        if (t < 2 * mates) {
             unsigned long long* G = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, t)) + SNK_FILE_GS_OFF;
             // gsum order: A,C,G,T,N,bases,q20,q30
             const int gs_index[8] = {SNK_GS_A, SNK_GS_C, SNK_GS_G, SNK_GS_T, SNK_GS_N, SNK_GS_BASES, SNK_GS_Q20, SNK_GS_Q30};
@@ -258,20 +273,20 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
     QCounter* qhist = reinterpret_cast<QCounter*>(smem + sp.off_qhist);
     uint32_t* desc = reinterpret_cast<uint32_t*>(smem + sp.off_desc);
+    DeltaEnt* dlist = reinterpret_cast<DeltaEnt*>(smem + sp.off_delta);
     // misc: lastkey[0..3] = max key per table, lastkey[4..7] = record counts per table, gsum[4][8]
     unsigned long long* lastkey = reinterpret_cast<unsigned long long*>(smem + sp.off_misc);
     unsigned long long* gsum = lastkey + 8;
     unsigned long long* stage_bar = gsum + 32;
+    uint32_t* ndelta = reinterpret_cast<uint32_t*>(stage_bar + 1);     // [2] entries in each mate's delta list
+    uint32_t* tile_slow = ndelta + 2;                                    // some record of the tile needs the checked path
     uint32_t stage_phase = 0;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
 
     for (uint32_t e = tid; e < (sp.total - sp.off_qhist) / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(qhist)[e] = 0;   // qhist + misc
     BaseCnt<J> bc;
-#pragma unroll
-    for (int b = 0; b < 5; b++)
-#pragma unroll
-        for (int j = 0; j < J; j++) bc.v[b][j] = 0;
+    base_cnt_reset<J>(bc);
     __syncthreads();
     if (tid == 0) {
         mbar_init(stage_bar, 1);
@@ -283,35 +298,46 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     const uint32_t t_begin = (uint32_t)((uint64_t)nt * blockIdx.x / gridDim.x);
     const uint32_t t_end = (uint32_t)((uint64_t)nt * (blockIdx.x + 1) / gridDim.x);
     int cur_slot = -1;
-    uint32_t reads_in_hist = 0;                     // records counted since the last flush (u16 cells)
+    uint32_t reads_in_hist = 0;                     // records counted since the last flush (16-bit cells)
     const uint32_t W = A.items_w;
-    const uint32_t nitems = 2u * MATES * W;         // <= blockDim.x / kNT
-    // Phase B roles: the first `nitems` threads own the quality cells of one item each; when the CTA is
-    // large enough a second set of threads (starting at X, warp aligned) owns the base counters of the
-    // same items, so that both halves of the CTA work during phase B. Otherwise one thread does both.
-    const bool split = blockDim.x >= A.X + nitems;
-    const bool q_role = (uint32_t)tid < nitems;
-    const uint32_t item = (split && (uint32_t)tid >= A.X) ? (uint32_t)tid - A.X : (uint32_t)tid;
-    const bool b_role = split ? ((uint32_t)tid >= A.X && item < nitems) : q_role;
-    const uint32_t my_tab = item / W, my_w = item % W;
+    const int nchunks = (int)(A.stride / 16);
+    // Phase B roles (work units of filter_core.cuh). nraw raw items = MATES tables x W items; the delta
+    // item of raw item x is x + nraw. "wide" CTAs (4*nraw threads, the size phase A wants) run two
+    // q-units per item (half of the J sub-positions each) on threads [0, 2*nraw) and two b-units per item
+    // (every other record each) on threads [2*nraw, 4*nraw); CTAs capped at 1024 threads run one unit
+    // per item.
+    const uint32_t nraw = (uint32_t)MATES * W;
+    const bool wide = blockDim.x >= 4u * nraw;
+    const uint32_t n_units = wide ? 2u * nraw : nraw;
+    const uint32_t b_first = wide ? 2u * nraw : ((blockDim.x >= align_up(nraw, 32) + nraw) ? align_up(nraw, 32) : 0u);
+    const bool q_role = (uint32_t)tid < n_units;
+    const bool b_role = (uint32_t)tid >= b_first && (uint32_t)tid < b_first + n_units;
+    const uint32_t unit = b_role ? (uint32_t)tid - b_first : (uint32_t)tid;     // a thread with both roles has b_first == 0
+    const uint32_t item = wide ? unit % nraw : unit;                             // raw item
+    const uint32_t half = wide ? unit / nraw : 0u;                               // q: which J/2 sub-positions; b: record parity
+    const uint32_t my_w = item % W;
+    const int my_m = (int)(item / W) % MATES;
     const bool my_item = q_role || b_role;
-    const int my_m = (int)(my_tab % MATES);
-    const bool my_clean = my_tab >= (uint32_t)MATES;
-    // byte offsets into the quality table for hist_item_fast: cell(b, j) = cell0 + j*jstep + b*bstep
+    // byte offsets into the quality table: cell(b, j) = cell0 + j*jstep + b*bstep
     const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
     const int q_cell0 = (int)item * (int)sizeof(QCounter) - P.phred * q_bstep;
-    const uint32_t* my_desc = desc + (size_t)((my_clean ? 2 : 0) + my_m) * A.R;
+    const int q_cell0_del = q_cell0 + (int)nraw * (int)sizeof(QCounter);
+    const uint32_t* my_desc = desc + (size_t)my_m * A.R;
+    const DeltaEnt* my_dlist = dlist + (size_t)my_m * 2u * A.R;
+    const uint32_t flush_item = b_role ? item : 0xFFFFFFFFu;
 
-    for (uint32_t t = t_begin; t < t_end; t++) {
-        uint32_t start, cnt;
-        tile_range(A.tm, t, &start, &cnt);
+    for (uint32_t t = t_begin; t <= t_end; t++) {
+        // (the trip t == t_end only flushes: one inlined copy of flush_hist instead of two)
+        uint32_t start = 0, cnt = 0;
+        if (t < t_end) tile_range(A.tm, t, &start, &cnt);
         const uint64_t g0 = A.tm.first + start;
-        const int slot = slot_of(g0, (uint64_t)P.slot_block, P.n_slots);
+        const int slot = t < t_end ? slot_of(g0, (uint64_t)P.slot_block, P.n_slots) : -1;
         if (slot != cur_slot || reads_in_hist + cnt > kQCounterMax) {
-            if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, b_role ? item : 0xFFFFFFFFu, lastkey, gsum, cur_slot);
+            if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, flush_item, lastkey, gsum, cur_slot);
             cur_slot = slot;
             reads_in_hist = 0;
         }
+        if (t == t_end) break;
         reads_in_hist += cnt;
         // ---- stage the tile: the rows of a tile are one contiguous block per array, so one elected thread
         // hands 2*MATES bulk copies to the TMA engine and everybody waits on the mbarrier they complete on
@@ -323,6 +349,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 bulk_g2s(smem + sp.off_rows[m][0], A.seq[m] + (size_t)start * A.stride, row_bytes, stage_bar);
                 bulk_g2s(smem + sp.off_rows[m][1], A.qual[m] + (size_t)start * A.stride, row_bytes, stage_bar);
             }
+            ndelta[0] = 0; ndelta[1] = 0; *tile_slow = 0;
         }
 #pragma unroll
         for (int m = 0; m < MATES; m++) {
@@ -347,12 +374,15 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             ReadInfo ri;
             if (len <= 0) {             // "Error:empty sequence" (read_filter.cpp:250)
                 ri.len = 0; ri.head_cut = 0; ri.clean_len = 0; ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1;
-                ri.flags = RF_BAD_BASE;
+                ri.flags = RF_BAD_BASE | RF_QSLOW;      // row left as staged: not safe for the unchecked histogram walk
             } else {
                 scan_read_coop<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
-                                     len, m, P, h, pm, ri);
+                                     len, nchunks, m, P, h, pm, ri);
             }
-            if (h == 0) info[r] = ri;
+            if (h == 0) {
+                info[r] = ri;
+                if (ri.flags & RF_QSLOW) *tile_slow = 1u;
+            }
         }
         __syncthreads();
 
@@ -361,6 +391,8 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             const bool live = r < cnt;
             int cat = SNK_DROP_EMPTY, mask = 0, fsb = -1;
             ReadInfo a, b;
+            DeltaEnt de[2][2];
+            int nde[2] = {0, 0};
             const uint64_t gi = g0 + r;
             if (live) {
                 a = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[0])[r];
@@ -382,10 +414,10 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 }
                 const uint32_t row0 = r * A.stride;
                 desc[0 * A.R + r] = hist_desc(a.len, row0, a.flags & RF_QSLOW);
-                desc[2 * A.R + r] = cat == SNK_KEEP ? hist_desc(a.clean_len, row0 + (uint32_t)a.head_cut, a.flags & RF_QSLOW) : 0u;
+                nde[0] = delta_entries(a, cat == SNK_KEEP, row0, de[0]);
                 if (MATES == 2) {
                     desc[1 * A.R + r] = hist_desc(b.len, row0, b.flags & RF_QSLOW);
-                    desc[3 * A.R + r] = cat == SNK_KEEP ? hist_desc(b.clean_len, row0 + (uint32_t)b.head_cut, b.flags & RF_QSLOW) : 0u;
+                    nde[1] = delta_entries(b, cat == SNK_KEEP, row0, de[1]);
                 }
                 unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
                 if (fsb >= 0) {
@@ -421,6 +453,20 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                     }
                 }
             }
+            // append this warp's delta entries to the tile's lists: one shared atomic per warp and mate
+            const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int m = 0; m < MATES; m++) {
+                const unsigned b1 = __ballot_sync(0xFFFFFFFFu, nde[m] >= 1), b2 = __ballot_sync(0xFFFFFFFFu, nde[m] >= 2);
+                if (b1) {
+                    uint32_t base = 0;
+                    if (lane == 0) base = atomicAdd(&ndelta[m], (uint32_t)(__popc(b1) + __popc(b2)));
+                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                    DeltaEnt* dl = dlist + (size_t)m * 2u * A.R + base + __popc(b1 & lt) + __popc(b2 & lt);
+                    if (nde[m] >= 1) dl[0] = de[m][0];
+                    if (nde[m] >= 2) dl[1] = de[m][1];
+                }
+            }
             // last record keys + record counts, one shared atomic per warp and table
             const unsigned kept = __ballot_sync(0xFFFFFFFFu, live && cat == SNK_KEEP);
             const unsigned lanes = __ballot_sync(0xFFFFFFFFu, live);
@@ -443,56 +489,38 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         }
         __syncthreads();
 
-        // ---- phase B: per-position histograms, owner computes. Each role has its own tight loop; the
-        // descriptor carries the record's byte address, so a trip is: load descriptor, load word, update.
+        // ---- phase B: per-position histograms, owner computes. Raw items walk every (padded) row of the
+        // tile; delta items walk the tile's short list of removed / added record parts.
         if (my_item) {
             const uint8_t* rows_s = smem + sp.off_rows[my_m][0];
             const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
-            const int first_pos = J * (int)my_w;
-            BaseAcc acc = {0, 0, 0, 0, 0};
-            uint32_t err = 0;
-            bool any_slow = false;
-            if (q_role) {
-#pragma unroll 2
-                for (uint32_t r = 0; r < cnt; r++) {
-                    const uint32_t d = my_desc[r];
-                    const int nvalid = (int)(d & 0x3FFu) - first_pos;
-                    if (nvalid <= 0) continue;
-                    if (d & 0x80000000u) { any_slow = true; continue; }
-                    qual_update_fast<QCounter, J>(hist_load_word<J>(rows_q, (int)((d >> 10) & 0x1FFFFFu), (int)my_w), nvalid,
-                                                  reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
+            const uint32_t nd = ndelta[my_m];
+            if (*tile_slow == 0u) {
+                if (q_role) {
+                    if (wide)
+                        unit_q_fast<QCounter, J, J / 2>(rows_q, A.stride, cnt, my_dlist, nd, (int)my_w, (int)half * (J / 2),
+                                                        reinterpret_cast<uint8_t*>(qhist), q_cell0, q_cell0_del, q_jstep, q_bstep);
+                    else
+                        unit_q_fast<QCounter, J, J>(rows_q, A.stride, cnt, my_dlist, nd, (int)my_w, 0, reinterpret_cast<uint8_t*>(qhist),
+                                                    q_cell0, q_cell0_del, q_jstep, q_bstep);
                 }
+                if (b_role) unit_b_fast<J>(rows_s, A.stride, cnt, my_dlist, nd, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
+            } else {
+                unsigned long long* slot_base = A.stats + (size_t)slot * SNK_SLOT_WORDS;
+                unsigned long long* f_raw = slot_base + SNK_SLOT_FILE_OFF(file_of_tab(MATES, my_m));
+                unsigned long long* f_clean = slot_base + SNK_SLOT_FILE_OFF(file_of_tab(MATES, my_m + MATES));
+                uint32_t err = 0;
+                if (q_role)
+                    err = unit_q_checked<QCounter, J>(rows_q, my_desc, cnt, my_dlist, nd, (int)my_w, wide ? (int)half * (J / 2) : 0, wide ? J / 2 : J,
+                                                      P.phred, P.qb, qhist + item, nraw, (int)A.X, f_raw, f_clean);
+                if (b_role) unit_b_checked<J>(rows_s, my_desc, cnt, my_dlist, nd, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
+                if (err) report_error(A, err, g0);
             }
-            if (b_role) {
-#pragma unroll 2
-                for (uint32_t r = 0; r < cnt; r++) {
-                    const uint32_t d = my_desc[r];
-                    const int nvalid = (int)(d & 0x3FFu) - first_pos;
-                    if (nvalid <= 0) continue;
-                    base_update<J>(hist_load_word<J>(rows_s, (int)((d >> 10) & 0x1FFFFFu), (int)my_w), nvalid, acc);
-                    if (cnt > 255 && (r & 127) == 127) base_acc_spill<J>(acc, bc);     // packed 8-bit lanes must not wrap
-                }
-            }
-            if (any_slow) {
-                // checked path for reads with qualities outside the shared-memory bins (rare): qualities only,
-                // the bases were already counted above
-                BaseAcc dummy = {0, 0, 0, 0, 0};
-                unsigned long long* file_base = A.stats + (size_t)slot * SNK_SLOT_WORDS + SNK_SLOT_FILE_OFF(file_of_tab(MATES, (int)my_tab));
-                for (uint32_t r = 0; r < cnt; r++) {
-                    const uint32_t d = my_desc[r];
-                    if (!(d & 0x80000000u)) continue;
-                    const int addr = (int)((d >> 10) & 0x1FFFFFu);
-                    err |= hist_item<QCounter, J>(rows_s, rows_q, addr, (int)(d & 0x3FFu), (int)my_w, P.phred, P.qb, dummy, qhist + item, (int)A.X,
-                                                  file_base, false, true);
-                }
-            }
-            base_acc_spill<J>(acc, bc);
-            if (err) report_error(A, err, g0);
         }
         __syncthreads();
     }
-    if (cur_slot >= 0) flush_hist<J>(A, P, MATES, qhist, bc, b_role ? item : 0xFFFFFFFFu, lastkey, gsum, cur_slot);
 }
+
 
 #endif // __CUDACC__
 

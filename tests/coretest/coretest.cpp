@@ -25,18 +25,10 @@ struct Ctx {
     uint32_t stride, R, W, X;
     int mates, J;
     std::vector<QCounter> qhist;
-    std::vector<BaseCnt<4>> bc;         // one per item (per "thread"); J <= 4 slots used
+    std::vector<BaseCnt<4>> bc;         // one per b-unit (per "thread")
+    uint32_t threads = 0;               // CTA size the kernel would use (decides one or two units per item)
     uint64_t lastkey[8] = {0};
 };
-
-template <int J>
-void spill_j(BaseAcc& acc, BaseCnt<4>& cnt)
-{
-    BaseCnt<J> t;
-    memset(&t, 0, sizeof t);
-    base_acc_spill<J>(acc, t);
-    for (int b = 0; b < 5; b++) for (int j = 0; j < J; j++) cnt.v[b][j] += t.v[b][j];
-}
 
 int file_of(int mates, int tab) { return mates == 2 ? tab : (tab == 0 ? SNK_RAW1 : SNK_CLEAN1); }
 
@@ -45,30 +37,39 @@ void flush(Ctx& c, int slot)
     uint64_t* S = c.stats + (size_t)slot * SNK_SLOT_WORDS;
     const int ntab = 2 * c.mates;
     const uint32_t J = (uint32_t)c.J;
-    for (uint32_t e = 0; e < (uint32_t)c.P.qb * J * c.X; e++) {
-        uint32_t v = c.qhist[e];
-        if (!v) continue;
-        c.qhist[e] = 0;
-        uint32_t x = e % c.X, j = (e / c.X) % J, q = e / (J * c.X);
-        uint32_t tab = x / c.W, w = x % c.W;
-        if ((int)tab >= ntab) continue;
-        uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
-        F[SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q] += v;
-        if (q >= 20) F[SNK_FILE_GS_OFF + SNK_GS_Q20] += v;
-        if (q >= 30) F[SNK_FILE_GS_OFF + SNK_GS_Q30] += v;
-    }
-    for (uint32_t x = 0; x < c.X; x++) {
-        uint32_t tab = x / c.W, w = x % c.W;
-        if ((int)tab >= ntab) continue;
-        uint64_t* F = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
+    const uint32_t nraw = (uint32_t)c.mates * c.W;
+    // raw cells count all records, delta cells "removed - added": raw += raw, clean += raw - delta
+    for (uint32_t qj = 0; qj < (uint32_t)c.P.qb * J; qj++)
+        for (uint32_t x = 0; x < nraw; x++) {
+            const uint32_t e = qj * c.X + x;
+            const uint32_t vr = c.qhist[e];
+            const int vd = (int)(int16_t)c.qhist[e + nraw];
+            c.qhist[e] = 0; c.qhist[e + nraw] = 0;
+            const uint32_t j = qj % J, q = qj / J;
+            const uint32_t tab = x / c.W, w = x % c.W;
+            const uint64_t vc = (uint64_t)((int64_t)vr - (int64_t)vd);
+            uint64_t* FR = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
+            uint64_t* FC = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab + c.mates));
+            const size_t cell = SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q;
+            FR[cell] += vr; FC[cell] += vc;
+            if (q >= 20) { FR[SNK_FILE_GS_OFF + SNK_GS_Q20] += vr; FC[SNK_FILE_GS_OFF + SNK_GS_Q20] += vc; }
+            if (q >= 30) { FR[SNK_FILE_GS_OFF + SNK_GS_Q30] += vr; FC[SNK_FILE_GS_OFF + SNK_GS_Q30] += vc; }
+        }
+    for (size_t u = 0; u < c.bc.size(); u++) {
+        const uint32_t x = (uint32_t)(u % nraw);            // unit u counts for raw item x (two units per item when wide)
+        const uint32_t tab = x / c.W, w = x % c.W;
+        uint64_t* FR = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
+        uint64_t* FC = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab + c.mates));
         for (int b = 0; b < 5; b++)
             for (int j = 0; j < c.J; j++) {
-                uint32_t v = c.bc[x].v[b][j];
-                c.bc[x].v[b][j] = 0;
-                F[SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b] += v;
-                F[SNK_FILE_GS_OFF + SNK_GS_A + b] += v;
-                F[SNK_FILE_GS_OFF + SNK_GS_BASES] += v;
+                const uint32_t vr = (c.bc[u].raw[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu;
+                const int vd = (int)((c.bc[u].del[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu) - 0x8000;
+                const uint64_t vc = (uint64_t)((int64_t)vr - (int64_t)vd);
+                const size_t cell = SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b;
+                FR[cell] += vr; FR[SNK_FILE_GS_OFF + SNK_GS_A + b] += vr; FR[SNK_FILE_GS_OFF + SNK_GS_BASES] += vr;
+                FC[cell] += vc; FC[SNK_FILE_GS_OFF + SNK_GS_A + b] += vc; FC[SNK_FILE_GS_OFF + SNK_GS_BASES] += vc;
             }
+        base_cnt_reset<4>(c.bc[u]);
     }
     for (int t = 0; t < ntab; t++) {
         uint64_t* G = S + SNK_SLOT_FILE_OFF(file_of(c.mates, t)) + SNK_FILE_GS_OFF;
@@ -87,10 +88,14 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
     std::vector<uint8_t> rows[2][2];
     std::vector<ReadInfo> info[2];
     std::vector<uint8_t> keep(c.R);
+    std::vector<DeltaEnt> dlist[2];
+    const int nchunks = (int)(c.stride / 16);
     for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)c.R * c.stride + 16, 0xAB); rows[m][1].assign((size_t)c.R * c.stride + 16, 0xAB); info[m].resize(c.R); }
-    c.qhist.assign((size_t)std::max(c.P.qb, 1) * (size_t)J * c.X, 0);
-    c.bc.assign(c.X, BaseCnt<4>());
-    for (auto& x : c.bc) memset(&x, 0, sizeof x);
+    c.qhist.assign((size_t)(c.P.qb + 1) * (size_t)J * c.X, 0);
+    const uint32_t nraw = (uint32_t)M * c.W;
+    const bool wide = c.threads >= 4u * nraw;               // same rule as the kernel
+    c.bc.assign(wide ? 2u * nraw : nraw, BaseCnt<4>());
+    for (auto& x : c.bc) base_cnt_reset<4>(x);
     for (int cta = 0; cta < grid; cta++) {
         const uint32_t t_begin = (uint32_t)((uint64_t)tm.ntiles * cta / grid), t_end = (uint32_t)((uint64_t)tm.ntiles * (cta + 1) / grid);
         int cur_slot = -1;
@@ -108,16 +113,19 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                 memcpy(rows[m][1].data(), b[m]->qual + (size_t)start * c.stride, (size_t)cnt * c.stride);
             }
             // phase A
+            bool tile_slow = false;
             for (int m = 0; m < M; m++)
                 for (uint32_t r = 0; r < cnt; r++) {
                     int len = b[m]->len[start + r];
                     if (len > (int)c.stride) len = (int)c.stride;
                     ReadInfo ri;
-                    if (len <= 0) { memset(&ri, 0, sizeof ri); ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1; ri.flags = RF_BAD_BASE; }
-                    else scan_read_serial<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, m, c.P, ri);
+                    if (len <= 0) { memset(&ri, 0, sizeof ri); ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1; ri.flags = RF_BAD_BASE | RF_QSLOW; }
+                    else scan_read_serial<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, nchunks, m, c.P, ri);
                     info[m][r] = ri;
+                    if (ri.flags & RF_QSLOW) tile_slow = true;
                 }
             // phase P
+            for (int m = 0; m < M; m++) dlist[m].clear();
             for (uint32_t r = 0; r < cnt; r++) {
                 const uint64_t gi = g0 + r;
                 int cat, mask = 0, fsb = -1;
@@ -135,6 +143,11 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     if (a.flags & RF_BAD_QUAL) c.err |= ERR_BAD_QUAL;
                 }
                 keep[r] = cat == SNK_KEEP;
+                for (int m = 0; m < M; m++) {
+                    DeltaEnt de[2];
+                    const int nde = delta_entries(info[m][r], cat == SNK_KEEP, r * c.stride, de);
+                    for (int i = 0; i < nde; i++) dlist[m].push_back(de[i]);
+                }
                 if (fsb >= 0) {
                     S[fsb]++;
                     if (M == 2) { if (mask & 1) S[fsb + 1]++; if (mask & 2) S[fsb + 2]++; if (mask == 3) S[fsb + 3]++; }
@@ -169,31 +182,35 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     }
                 }
             }
-            // phase B: item x is owned by "thread" x
-            const uint32_t nitems = 2u * M * c.W;
-            for (uint32_t x = 0; x < nitems; x++) {
-                const uint32_t tab = x / c.W, w = x % c.W;
-                const int m = (int)(tab % M);
-                const bool clean = tab >= (uint32_t)M;
-                unsigned long long* file_base = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, tab)));
-                const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
+            // phase B: the kernel's work units, one after the other (q-units then b-units)
+            std::vector<uint32_t> rawdesc[2];
+            for (int m = 0; m < M; m++) {
+                rawdesc[m].resize(cnt);
+                for (uint32_t r = 0; r < cnt; r++) rawdesc[m][r] = hist_desc(info[m][r].len, r * c.stride, info[m][r].flags & RF_QSLOW);
+            }
+            const uint32_t n_units = wide ? 2u * nraw : nraw;
+            const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
+            for (uint32_t u = 0; u < n_units; u++) {
+                const uint32_t x = wide ? u % nraw : u, half = wide ? u / nraw : 0u;
+                const uint32_t w = x % c.W;
+                const int m = (int)(x / c.W) % M;
+                unsigned long long* f_raw = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, m)));
+                unsigned long long* f_clean = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, m + M)));
                 const int q_cell0 = (int)x * (int)sizeof(QCounter) - c.P.phred * q_bstep;
-                BaseAcc acc = {0, 0, 0, 0, 0};
-                uint32_t since = 0;
-                for (uint32_t r = 0; r < cnt; r++) {
-                    const ReadInfo ri = info[m][r];
-                    const uint32_t row0 = r * c.stride;
-                    const uint32_t d = clean ? (keep[r] ? hist_desc(ri.clean_len, row0 + (uint32_t)ri.head_cut, ri.flags & RF_QSLOW) : 0u)
-                                             : hist_desc(ri.len, row0, ri.flags & RF_QSLOW);
-                    const int nn = (int)(d & 0x3FFu), off = (int)((d >> 10) & 0x1FFFFFu);
-                    if (nn <= J * (int)w) continue;
-                    const uint8_t* rs = rows[m][0].data();
-                    const uint8_t* rq = rows[m][1].data();
-                    if (!(d & 0x80000000u)) hist_item_fast<QCounter, J>(rs, rq, off, nn, (int)w, acc, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
-                    else c.err |= hist_item<QCounter, J>(rs, rq, off, nn, (int)w, c.P.phred, c.P.qb, acc, c.qhist.data() + x, (int)c.X, file_base);
-                    if (++since == 255) { since = 0; spill_j<J>(acc, c.bc[x]); }
+                const int q_cell0_del = q_cell0 + (int)nraw * (int)sizeof(QCounter);
+                const uint8_t* rs = rows[m][0].data();
+                const uint8_t* rq = rows[m][1].data();
+                const DeltaEnt* dl = dlist[m].data();
+                const uint32_t nd = (uint32_t)dlist[m].size();
+                if (!tile_slow) {
+                    if (wide) unit_q_fast<QCounter, J, J / 2>(rq, c.stride, cnt, dl, nd, (int)w, (int)half * (J / 2), (uint8_t*)c.qhist.data(), q_cell0, q_cell0_del, q_jstep, q_bstep);
+                    else unit_q_fast<QCounter, J, J>(rq, c.stride, cnt, dl, nd, (int)w, 0, (uint8_t*)c.qhist.data(), q_cell0, q_cell0_del, q_jstep, q_bstep);
+                    unit_b_fast<J>(rs, c.stride, cnt, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
+                } else {
+                    c.err |= unit_q_checked<QCounter, J>(rq, rawdesc[m].data(), cnt, dl, nd, (int)w, wide ? (int)half * (J / 2) : 0, wide ? J / 2 : J,
+                                                         c.P.phred, c.P.qb, c.qhist.data() + x, nraw, (int)c.X, f_raw, f_clean);
+                    unit_b_checked<J>(rs, rawdesc[m].data(), cnt, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
                 }
-                spill_j<J>(acc, c.bc[x]);
             }
         }
         if (cur_slot >= 0) flush(c, cur_slot);
@@ -222,7 +239,8 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     c.J = hist_j(c.stride);
     c.W = c.stride / c.J;
     c.X = align_up(hist_items(c.mates, c.stride), 32);
-    c.R = tile_r > 0 ? (uint32_t)tile_r : cta_threads(c.mates, c.stride) / (c.mates * kNT);
+    c.threads = cta_threads(c.mates, c.stride);
+    c.R = tile_r > 0 ? (uint32_t)tile_r : c.threads / (c.mates * kNT);
     const snk_batch* b[2] = {r1, r2};
     snk_read_result* out[2] = {out1, out2};
     const uint32_t chunks = c.stride / 16;

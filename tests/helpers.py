@@ -257,3 +257,17 @@ def text_replay_format(buf, nbytes, line_off, S, Q, res, mate, strip, pe_info=0,
                                      S.shape[1], mate, strip, pe_info, fasta, id_mode, qshift, lanes, out.ctypes.data,
                                      rec_off.ctypes.data)
     return out[:total].tobytes(), rec_off
+
+
+def high_quality_mix(n=6000, L=100, seed=31, every=97):
+    """PE batch where a few scattered records carry qualities above the shared-memory bins (Q42..Q60):
+    most tiles take the unchecked histogram walk, some the checked one, and the two must add up."""
+    d = synth.gen_pairs(n, L=L, seed=seed, var_len=True)
+    rng = np.random.default_rng(seed)
+    for key, lk in (("qual1", "len1"), ("qual2", "len2")):
+        Q = d[key]
+        for i in range(int(rng.integers(0, every)), n, every):
+            l = int(d[lk][i])
+            pos = rng.integers(0, l, size=max(1, l // 5))
+            Q[i, pos] = 33 + rng.integers(42, 61, size=pos.size).astype(np.uint8)
+    return d

@@ -21,6 +21,8 @@ CONFIGS = [
     ("se150_two_adapters_lowercase", False, 6000, 150, dict(seed=10), dict(adapter1=[A2.lower(), A1], ada_trim=True), dict()),
     ("pe150_minlen_off", True, 6000, 150, dict(seed=11), dict(CFG2_KW, min_read_length=-1, max_read_length=140), dict()),
     ("pe400_long_reads", True, 1500, 400, dict(seed=12), dict(adapter1=A1, adapter2=A2, ada_trim=True), dict(tile_r=32)),
+    # stride 1008: the CTA is capped at 1024 threads -> one phase-B unit per item instead of two
+    ("pe1000_max_len", True, 300, 1000, dict(seed=13), dict(adapter1=A1, adapter2=A2, ada_trim=True, polyG_tail=10, trim_bad_head=(20, 10)), dict()),
 ]
 
 
@@ -33,6 +35,23 @@ def test_core_replay_matches_oracle(cfg):
     c1, c2, cst, cerr = core_replay(p, d, **rkw)
     assert oerr == cerr == 0
     assert_same((c1, c2, cst), (o1, o2, ost), name)
+
+
+def test_mixed_checked_and_unchecked_tiles(monkeypatch):
+    """A few records with qualities above the shared-memory bins: their tiles take the checked
+    histogram path (out-of-bin qualities go straight to the global tables, mirrored into the clean
+    table and taken back by delta entries), all other tiles the unchecked walk; head and tail trims
+    on, and a small flush period so that raw/delta cells are flushed many times."""
+    from helpers import high_quality_mix
+    monkeypatch.setenv("SNK_CORETEST_FLUSH_EVERY", "300")
+    d = high_quality_mix()
+    p = abi.make_params(is_pe=True, adapter1=A1, adapter2=A2, ada_trim=True, trim_bad_head=(25, 12), trim_bad_tail=(25, 40),
+                        hard_trim=(2, 0, 0, 3), polyG_tail=8, threads=3, patch_size=40)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    c1, c2, cst, cerr = core_replay(p, d, tile_r=16, grid=7)
+    assert oerr == cerr == 0
+    assert (o1["category"] == 0).sum() > 1000 and (o1["head_cut"] > 2).sum() > 50
+    assert_same((c1, c2, cst), (o1, o2, ost), "mixed tiles")
 
 
 def test_every_byte_value_is_classified_like_the_oracle():

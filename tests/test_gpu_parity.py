@@ -46,6 +46,22 @@ def test_engine_matches_oracle(cfg, engine_lib):
     assert_same((r1, r2, st), (o1, o2, ost), name)
 
 
+def test_mixed_checked_and_unchecked_tiles(engine_lib):
+    """Records with qualities above the shared-memory bins scattered through the batch (see the CPU
+    tier's test of the same name): checked and unchecked tiles, raw and delta cells must add up."""
+    from helpers import high_quality_mix
+    d = high_quality_mix(n=40000)
+    p = abi.make_params(is_pe=True, adapter1=A1, adapter2=A2, ada_trim=True, trim_bad_head=(25, 12), trim_bad_tail=(25, 40),
+                        hard_trim=(2, 0, 0, 3), polyG_tail=8, threads=3, patch_size=40)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    with Engine(engine_lib, p) as e:
+        r1, r2 = e.filter_host(d)
+        st = e.stats()
+        flags, _ = e.error_flags()
+    assert flags == oerr == 0
+    assert_same((r1, r2, st), (o1, o2, ost), "mixed tiles")
+
+
 def test_batches_compose_and_empty_batch(engine_lib):
     d = synth.gen_pairs(30000, L=100, seed=21)
     p = abi.make_params(is_pe=True, threads=4, patch_size=20, **CFG2_KW)
