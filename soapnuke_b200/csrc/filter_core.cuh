@@ -64,6 +64,29 @@ SNK_HD uint32_t byte_of(uint32_t w, int j)
     return (w >> (8 * j)) & 0xFFu;
 #endif
 }
+// general byte permute (PRMT, default mode): result byte k = byte (selector nibble k & 7) of the 8-byte
+// pool {a (bytes 0-3), b (bytes 4-7)}; selector nibbles must have bit 3 clear
+SNK_HD uint32_t perm8(uint32_t a, uint32_t b, uint32_t sel)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(a, b, sel);
+#else
+    const uint64_t pool = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int k = 0; k < 4; k++) r |= (uint32_t)((pool >> (8 * ((sel >> (4 * k)) & 7u))) & 0xFFu) << (8 * k);
+    return r;
+#endif
+}
+// acc + sum over the four byte lanes of a[k] * b[k] (unsigned bytes)
+SNK_HD uint32_t dot4(uint32_t a, uint32_t b, uint32_t acc)
+{
+#ifdef __CUDA_ARCH__
+    return __dp4a(a, b, acc);
+#else
+    for (int k = 0; k < 4; k++) acc += ((a >> (8 * k)) & 0xFFu) * ((b >> (8 * k)) & 0xFFu);
+    return acc;
+#endif
+}
 SNK_HD int ctz32(uint32_t x)   // x != 0
 {
 #ifdef __CUDA_ARCH__
@@ -223,8 +246,6 @@ SNK_HD uint32_t bytes_lt(uint32_t w, uint32_t k)
 {
     return ~((w | 0x80808080u) - k * 0x01010101u) & 0x80808080u;
 }
-// bit 0 of every byte lane gathered into 4 adjacent bits
-SNK_HD uint32_t gather1(uint32_t lanes) { return ((lanes & 0x01010101u) * 0x01020408u) >> 24; }
 
 // does the low 32 bits of e contain a run of at least T set bits? (T >= 1, warp-uniform)
 SNK_HD bool has_run32(uint32_t e, int T)
@@ -239,16 +260,75 @@ SNK_HD bool has_run32(uint32_t e, int T)
 template <int NW>
 struct ScanPart {
     uint32_t p0[NW], p1[NW], pn[NW], pl[NW];
-    uint32_t accA, accN, accLow, qsum;      // packed 4x8-bit counts (A, N, low quality), plain quality byte sum
-    uint32_t viol, qviol, qover;            // OR flags: unrecognized base, quality < phred or >= 128, quality >= qb
+    uint32_t low128, qsum;                  // 128 x (number of low-quality bases), plain quality byte sum
+    uint32_t viol, qbad;                    // OR flags: unrecognized base; quality byte outside [phred, phred+qb)
 };
 template <int NW>
 SNK_HD void merge_scan(ScanPart<NW>& a, const ScanPart<NW>& b)
 {
 #pragma unroll
     for (int k = 0; k < NW; k++) { a.p0[k] |= b.p0[k]; a.p1[k] |= b.p1[k]; a.pn[k] |= b.pn[k]; a.pl[k] |= b.pl[k]; }
-    a.accA += b.accA; a.accN += b.accN; a.accLow += b.accLow; a.qsum += b.qsum;
-    a.viol |= b.viol; a.qviol |= b.qviol; a.qover |= b.qover;
+    a.low128 += b.low128; a.qsum += b.qsum;
+    a.viol |= b.viol; a.qbad |= b.qbad;
+}
+
+// byte lanes 0 .. nv-1 of a word (nv may be <= 0 or >= 4)
+SNK_HD uint32_t low_lanes(int nv) { return nv >= 4 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u)); }
+
+struct ScanConst { uint32_t phred4, over4, low4, qpad; };
+SNK_HD ScanConst scan_const(const DevParams& P)
+{
+    ScanConst c;
+    int low_k = P.low_qual + P.phred + 1;                          // q <= lowQual  <=>  byte < low_k
+    low_k = low_k < 0 ? 0 : (low_k > 128 ? 128 : low_k);           // 0: never low, 128: always (bytes are < 128)
+    const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
+    c.phred4 = (uint32_t)P.phred * 0x01010101u;
+    c.over4 = over_k * 0x01010101u;
+    c.low4 = (uint32_t)low_k * 0x01010101u;
+    c.qpad = (over_k & 0xFFu) * 0x01010101u;                        // padding quality: the dump bin
+    return c;
+}
+
+// One 16-byte chunk (4 words of bases sw, 4 of qualities qw) of which the first nv bytes (1..16) lie
+// inside the read; FULL = (nv == 16) drops all masking. Per word:
+//   bases      fold case, look the expected byte up by bits 3..1 (A 000, C 001, T 010, G 011, N 111;
+//              100/101/110 -> 0) with one PRMT and compare: exact membership in {A,C,G,T,N,a,c,g,t,n}
+//   qualities  three packed subtractions on (q | 0x80) give "q >= phred", "q >= phred+qb", "q >= low_k"
+//              per byte lane in bit 7 (no borrow between lanes); DP4A sums the flags and the bytes
+// and per pair of words one DP4A per plane gathers bit b of 8 consecutive bytes into 8 adjacent bits.
+template <bool FULL>
+SNK_HD void scan_chunk16(const uint32_t* sw, const uint32_t* qw, int nv, const ScanConst& K, uint32_t& c0, uint32_t& c1, uint32_t& cn,
+                         uint32_t& cl, uint32_t& low128, uint32_t& qsum, uint32_t& viol, uint32_t& qbad)
+{
+    uint32_t w[4], f[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t mk = FULL ? 0xFFFFFFFFu : low_lanes(nv - 4 * k);
+        w[k] = FULL ? sw[k] : (sw[k] & mk);
+        f[k] = w[k] & 0xDFDFDFDFu;                                   // fold case
+        const uint32_t t = (f[k] >> 1) & 0x07070707u;
+        const uint32_t u = t | (t >> 4);
+        const uint32_t e = perm8(0x47544341u, 0x4E000000u, perm8(u, 0u, 0x4420u));
+        viol |= FULL ? (e ^ f[k]) : ((e ^ f[k]) & mk);
+        const uint32_t q = FULL ? qw[k] : (qw[k] & mk);
+        const uint32_t qin = FULL ? q : (q | (K.phred4 & ~mk));     // padding lanes read as phred: in range
+        const uint32_t g = qin | 0x80808080u;
+        qbad |= (~(g - K.phred4) | (g - K.over4) | qin) & 0x80808080u;
+        const uint32_t lowf = ~(g - K.low4) & 0x80808080u;
+        low128 = dot4(FULL ? lowf : (lowf & mk), 0x01010101u, low128);
+        qsum = dot4(q, 0x01010101u, qsum);
+    }
+#pragma unroll
+    for (int pr = 0; pr < 2; pr++) {
+        // bits 3..1 of word 2pr in the low nibbles, of word 2pr+1 in the high nibbles; weights 1,2,4,8 turn
+        // bit b of the 8 bytes into 8 adjacent bits starting at bit b
+        const uint32_t x = (f[2 * pr] & 0x0E0E0E0Eu) | ((f[2 * pr + 1] & 0x0E0E0E0Eu) << 4);
+        const uint32_t y = ((w[2 * pr] >> 4) & 0x02020202u) | (w[2 * pr + 1] & 0x20202020u);     // bit 5: lowercase
+        c0 |= (dot4(x & 0x22222222u, 0x08040201u, 0u) >> 1) << (8 * pr);
+        c1 |= (dot4(x & 0x44444444u, 0x08040201u, 0u) >> 2) << (8 * pr);
+        cn |= (dot4(x & 0x88888888u, 0x08040201u, 0u) >> 3) << (8 * pr);
+        cl |= (dot4(y, 0x08040201u, 0u) >> 1) << (8 * pr);
+    }
 }
 
 // stage 1: packed scan of this thread's 16-byte chunks (c % kNT == h) of the bases and qualities.
@@ -257,18 +337,14 @@ SNK_HD void merge_scan(ScanPart<NW>& a, const ScanPart<NW>& b)
 // become phred+qb (the "dump" bin one past the last real bin), so that phase B can walk whole rows of
 // the raw tables without per-read length tests. nchunks = stride / 16.
 template <int MAXC>
-SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const DevParams& P, int h, bool want_planes,
-                        ScanPart<(MAXC + 1) / 2>& S)
+SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const DevParams& P, int h, ScanPart<(MAXC + 1) / 2>& S)
 {
     constexpr int NW = (MAXC + 1) / 2;
 #pragma unroll
     for (int k = 0; k < NW; k++) { S.p0[k] = 0; S.p1[k] = 0; S.pn[k] = 0; S.pl[k] = 0; }
-    S.accA = S.accN = S.accLow = S.qsum = 0;
-    S.viol = S.qviol = S.qover = 0;
-    const uint32_t low_k = (uint32_t)(P.low_qual + P.phred + 1);   // q <= lowQual  <=>  byte < low_k
-    const bool low_never = (P.low_qual + P.phred + 1) <= 0, low_always = (P.low_qual + P.phred + 1) > 128;
-    const uint32_t over_k = (uint32_t)(P.qb + P.phred);            // q >= qb  <=>  byte >= over_k  (<= 128)
-    const uint32_t qpad = (over_k & 0xFFu) * 0x01010101u;          // padding quality: the dump bin
+    S.low128 = S.qsum = 0;
+    S.viol = S.qbad = 0;
+    const ScanConst K = scan_const(P);
     // Both lanes of a group run the same instruction stream on different data: step cc handles chunk
     // c = kNT*cc + h, i.e. (kNT == 2) lane h fills half h of plane word cc.
     static_assert(kNT == 2, "plane half-word placement below assumes two lanes per read");
@@ -277,7 +353,7 @@ SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const
         const int c = kNT * cc + h;
         if (c >= nchunks) continue;
         if (16 * c >= len) {                                   // chunk entirely behind the read: padding only
-            const U4 z = {0u, 0u, 0u, 0u}, qp = {qpad, qpad, qpad, qpad};
+            const U4 z = {0u, 0u, 0u, 0u}, qp = {K.qpad, K.qpad, K.qpad, K.qpad};
             store16(seq + 16 * c, z); store16(qual + 16 * c, qp);
             continue;
         }
@@ -286,53 +362,21 @@ SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const
         const U4 qv = load16(qual + 16 * c);
         const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
-        if (len - 16 * c < 16) {                               // the read ends inside this chunk
+        const int nv = len - 16 * c;
+        if (nv >= 16) scan_chunk16<true>(sw, qw, 16, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
+        else {                                                 // the read ends inside this chunk
             uint32_t ss[4], qq[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int nv = len - (16 * c + 4 * k);
-                const uint32_t mk = nv >= 4 ? 0xFFFFFFFFu : (nv <= 0 ? 0u : ((1u << (8 * nv)) - 1u));
-                ss[k] = sw[k] & mk; qq[k] = (qw[k] & mk) | (qpad & ~mk);
+                const uint32_t mk = low_lanes(nv - 4 * k);
+                ss[k] = sw[k] & mk; qq[k] = (qw[k] & mk) | (K.qpad & ~mk);
             }
             const U4 s4 = {ss[0], ss[1], ss[2], ss[3]}, q4 = {qq[0], qq[1], qq[2], qq[3]};
             store16(seq + 16 * c, s4); store16(qual + 16 * c, q4);
+            scan_chunk16<false>(sw, qw, nv, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int nvalid = len - (16 * c + 4 * k);
-            if (nvalid > 0) {
-                const uint32_t mask = nvalid >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
-                const uint32_t w = sw[k] & mask;
-                const uint32_t f = w & 0xDFDFDFDFu;                  // fold case
-                const uint32_t m1 = (f >> 1) & 0x01010101u, m2 = (f >> 2) & 0x01010101u, m3 = (f >> 3) & 0x01010101u;
-                const uint32_t isT = ~m1 & m2 & ~m3;                 // bit0 lanes only where it matters
-                S.accN += m3;                                        // only N and A feed predicates (n_ratio, highA)
-                S.accA += (f >> 6) & ~(m1 | m2 | m3) & 0x01010101u;
-                // exact membership in {A,C,G,T,N} after folding: bits 7..5 == 010, bit4 == isT,
-                // bit0 == !(isT|N), N implies bits 2,1 set
-                uint32_t v = (f ^ 0x40404040u) & 0xE0E0E0E0u;
-                v |= ((f >> 4) ^ isT) & 0x01010101u;
-                v |= (f ^ ~(isT | m3)) & 0x01010101u;
-                v |= m3 & ~(m1 & m2);
-                S.viol |= v & mask;
-                if (want_planes) {
-                    c0 |= gather1(m1) << (4 * k);
-                    c1 |= gather1(m2) << (4 * k);
-                    cn |= gather1(m3) << (4 * k);
-                    cl |= gather1(w >> 5) << (4 * k);
-                }
-                const uint32_t q = qw[k] & mask;
-                const uint32_t qfill = q | (~mask & 0x7F7F7F7Fu);     // padding lanes read as 0x7F: never low, never < phred
-                S.qsum += bytesum(q);
-                S.qviol |= (qfill & 0x80808080u) | bytes_lt(qfill, (uint32_t)P.phred);
-                S.qover |= ~bytes_lt(q, over_k) & 0x80808080u;        // masked lanes are 0: never over
-                if (!low_never) S.accLow += (low_always ? (mask & 0x80808080u) : bytes_lt(qfill, low_k)) >> 7;
-            }
-        }
-        if (want_planes) {
-            const int sh = 16 * h;
-            S.p0[cc] = c0 << sh; S.p1[cc] = c1 << sh; S.pn[cc] = cn << sh; S.pl[cc] = cl << sh;
-        }
+        const int sh = 16 * h;
+        S.p0[cc] = c0 << sh; S.p1[cc] = c1 << sh; S.pn[cc] = cn << sh; S.pl[cc] = cl << sh;
     }
 }
 
@@ -496,40 +540,102 @@ SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
 }
 
 // stage 4: end scans of fastq_trim (read_filter.cpp:390-429, 454-461): thread 0 scans the head,
-// thread kNT-1 the tail and the polyG run
+// thread kNT-1 the tail and the polyG run. The scans go a word (4 bytes) at a time: `nm` flags (bit 7
+// of a byte lane) mark the bytes that END a run; most reads leave after one word.
+// 0x80 in every byte lane of w that is NOT a 'G'/'g'
+SNK_HD uint32_t not_g_lanes(uint32_t w)
+{
+    const uint32_t x = (w | 0x20202020u) ^ 0x67676767u;            // zero byte <=> g or G
+    return (((x | 0x80808080u) - 0x01010101u) | x) & 0x80808080u;
+}
+SNK_HD int lead_bytes(uint32_t nm)      // number of byte lanes, from lane 3 downwards, before the first flag
+{
+    return nm ? clz32(nm) >> 3 : 4;
+}
+SNK_HD int trail_bytes(uint32_t nm)     // number of byte lanes, from lane 0 upwards, before the first flag
+{
+    return nm ? ctz32(nm) >> 3 : 4;
+}
+// run of bytes at the 3' end of row[0..len) whose lanes are not flagged by NM(word); len >= 1
+template <class NM>
+SNK_HD int tail_run(const uint8_t* row, int len, int limit, NM nm_of)
+{
+    int run = 0;
+    int wi = (len - 1) >> 2, nv = ((len - 1) & 3) + 1;            // word of the last byte, valid bytes in it
+    for (;;) {
+        const uint32_t nm = nm_of(load4(row + 4 * wi)) << (8 * (4 - nv));   // last valid byte -> lane 3
+        int r = lead_bytes(nm);
+        if (r > nv) r = nv;
+        run += r;
+        if (r < nv || wi == 0 || run >= limit) break;
+        wi--; nv = 4;
+    }
+    return run < limit ? run : limit;
+}
+template <class NM>
+SNK_HD int head_run(const uint8_t* row, int len, int limit, NM nm_of)
+{
+    int run = 0;
+    for (int wi = 0;; wi++) {
+        const int nv = len - 4 * wi >= 4 ? 4 : len - 4 * wi;
+        int r = trail_bytes(nm_of(load4(row + 4 * wi)));
+        if (r > nv) r = nv;
+        run += r;
+        if (r < 4 || 4 * (wi + 1) >= len || run >= limit) break;
+    }
+    return run < limit ? run : limit;
+}
 struct TrimPart { int hix, tix, ng; };
 SNK_HD void merge_trim(TrimPart& a, const TrimPart& b) { a.hix += b.hix; a.tix += b.tix; a.ng += b.ng; }
 SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, const DevParams& P, int h, TrimPart& t)
 {
     t.hix = t.tix = t.ng = 0;
     if (!P.trimming) return;
-    const bool tail = (h == kNT - 1);
+    const bool tail = (h == kNT - 1), head = (h == 0);
     if (P.has_lq) {
-        // lane 0 walks from the 5' end, lane kNT-1 from the 3' end: same loop, different start/step/threshold
-        const int lim = (kNT == 1 || !tail) ? P.bad_head_max : P.bad_tail_max;
-        const int thr = (kNT == 1 || !tail) ? P.bad_head_thr : P.bad_tail_thr;
-        const int start = (kNT == 1 || !tail) ? 0 : len - 1, step = (kNT == 1 || !tail) ? 1 : -1;
-        int cnt = 0;
-        for (int ix = 0; ix < lim && ix < len; ix++) { if ((int)qual[start + step * ix] - P.phred < thr) cnt++; else break; }
-        if (kNT == 1 || !tail) t.hix = cnt; else t.tix = cnt;
-        if (kNT == 1)
-            for (int ix = 0; ix < P.bad_tail_max && ix < len; ix++) { if ((int)qual[len - ix - 1] - P.phred < P.bad_tail_thr) t.tix++; else break; }
+        // q - phred < thr  <=>  byte < thr + phred (clamped to [0,128]: bytes are < 128)
+        if (head && P.bad_head_max > 0) {
+            int k = P.bad_head_thr + P.phred; k = k < 0 ? 0 : (k > 128 ? 128 : k);
+            const uint32_t kk = (uint32_t)k;
+            t.hix = head_run(qual, len, P.bad_head_max, [kk](uint32_t w) { return ~bytes_lt(w, kk) & 0x80808080u; });
+        }
+        if (tail && P.bad_tail_max > 0) {
+            int k = P.bad_tail_thr + P.phred; k = k < 0 ? 0 : (k > 128 ? 128 : k);
+            const uint32_t kk = (uint32_t)k;
+            t.tix = tail_run(qual, len, P.bad_tail_max, [kk](uint32_t w) { return ~bytes_lt(w, kk) & 0x80808080u; });
+        }
     }
-    if (tail && P.polyG_tail != -1)
-        for (int i = len - 1; i >= 0; i--) { if ((seq[i] | 0x20) == 'g') t.ng++; else break; }
+    if (tail && P.polyG_tail != -1) t.ng = tail_run(seq, len, len, [](uint32_t w) { return not_g_lanes(w); });
+}
+
+// rare path behind ScanPart::qbad: is some quality byte >= 128 or below the Phred base? (the other way to
+// be flagged, q >= qb, is legal and only sends the record's histogram through the checked path)
+SNK_HD_NOINLINE bool qual_violation(const uint8_t* qual, int len, int phred)
+{
+    for (int i = 0; i < len; i++)
+        if (qual[i] >= 128 || (int)qual[i] < phred) return true;
+    return false;
 }
 
 // stage 5: everything merged -> ReadInfo (predicates of stat_read, read_filter.cpp:289-311, and the
 // cut arithmetic of fastq_trim, read_filter.cpp:383-468)
 template <int NW>
-SNK_HD void finish_read(const ScanPart<NW>& S, bool polyx, int ada_pos, const TrimPart& T, int len, int mate,
+SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, const TrimPart& T, int len, int mate,
                         const DevParams& P, ReadInfo& R)
 {
     uint16_t flags = 0;
     if (S.viol) flags |= RF_BAD_BASE;
-    if (S.qviol) flags |= RF_BAD_QUAL;
-    if (S.qover || S.qviol) flags |= RF_QSLOW;
-    const int nN = (int)bytesum(S.accN), nA = (int)bytesum(S.accA), nLow = (int)bytesum(S.accLow);
+    if (qviol) flags |= RF_BAD_QUAL;
+    if (S.qbad) flags |= RF_QSLOW;
+    // A and N counts from the planes (only A and N feed predicates: highA, n_ratio)
+    int nN = 0, nA = 0;
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int k = 0; k < NW; k++) {
+        const uint32_t vm = plane_valid(len, k);
+        nN += (int)popc32(S.pn[k] & vm);
+        nA += (int)popc32(~(S.p0[k] | S.p1[k] | S.pn[k]) & vm);
+    }
+    const int nLow = (int)(S.low128 >> 7);
     const int total_q = (int)S.qsum - len * P.phred;
     const float flen = (float)len;
     // float(count)/size with IEEE fp32 division
@@ -572,10 +678,9 @@ template <int MAXC>
 SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P, ReadInfo& R)
 {
     constexpr int NW = (MAXC + 1) / 2;
-    const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
     ScanPart<NW> S, S2;
-    scan_chunks<MAXC>(seq, qual, len, nchunks, P, 0, want_planes, S);
-    for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, want_planes, S2); merge_scan(S, S2); }
+    scan_chunks<MAXC>(seq, qual, len, nchunks, P, 0, S);
+    for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, S2); merge_scan(S, S2); }
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
     if (P.n_adapters[mate] > 0) {
@@ -597,7 +702,7 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
     TrimPart T, T2;
     trim_part(seq, qual, len, P, 0, T);
     for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, P, h, T2); merge_trim(T, T2); }
-    finish_read<NW>(S, polyx, ada_pos, T, len, mate, P, R);
+    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, T, len, mate, P, R);
 }
 
 // ------------------------------------------------------------------ discard cascade

@@ -138,9 +138,8 @@ __device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s
         d.p0[k] = __shfl_xor_sync(pm, s.p0[k], 1); d.p1[k] = __shfl_xor_sync(pm, s.p1[k], 1);
         d.pn[k] = __shfl_xor_sync(pm, s.pn[k], 1); d.pl[k] = __shfl_xor_sync(pm, s.pl[k], 1);
     }
-    d.accA = __shfl_xor_sync(pm, s.accA, 1); d.accN = __shfl_xor_sync(pm, s.accN, 1);
-    d.accLow = __shfl_xor_sync(pm, s.accLow, 1); d.qsum = __shfl_xor_sync(pm, s.qsum, 1);
-    d.viol = __shfl_xor_sync(pm, s.viol, 1); d.qviol = __shfl_xor_sync(pm, s.qviol, 1); d.qover = __shfl_xor_sync(pm, s.qover, 1);
+    d.low128 = __shfl_xor_sync(pm, s.low128, 1); d.qsum = __shfl_xor_sync(pm, s.qsum, 1);
+    d.viol = __shfl_xor_sync(pm, s.viol, 1); d.qbad = __shfl_xor_sync(pm, s.qbad, 1);
 }
 
 // phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
@@ -150,9 +149,8 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
 {
     static_assert(kNT == 2, "lane exchange below is written for pairs");
     constexpr int NW = (MAXC + 1) / 2;
-    const bool want_planes = P.n_adapters[mate] > 0 || P.polyX_num != -1;
     ScanPart<NW> S, O;
-    scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, want_planes, S);
+    scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, S);
     shfl_scan<NW>(O, S, pm);
     merge_scan(S, O);
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
@@ -183,7 +181,7 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     trim_part(seq, qual, len, P, h, T);
     OT.hix = __shfl_xor_sync(pm, T.hix, 1); OT.tix = __shfl_xor_sync(pm, T.tix, 1); OT.ng = __shfl_xor_sync(pm, T.ng, 1);
     merge_trim(T, OT);
-    finish_read<NW>(S, polyx, ada_pos, T, len, mate, P, R);
+    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, T, len, mate, P, R);
 }
 
 // add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
@@ -196,23 +194,34 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
     const uint32_t X = A.X, W = A.items_w;
     const uint32_t nraw = (uint32_t)mates * W;         // raw items; the delta item of raw item x is x + nraw
-    // quality cells: entry e = (q*J + j)*X + x
-    const uint32_t qent = (uint32_t)P.qb * (uint32_t)J * nraw;
-    for (uint32_t i = threadIdx.x; i < qent; i += blockDim.x) {
-        const uint32_t x = i % nraw, qj = i / nraw;
-        const uint32_t e = qj * X + x;
-        const uint32_t vr = qhist[e];
-        const int vd = (int)(int16_t)qhist[e + nraw];
-        if (!vr && !vd) continue;
-        qhist[e] = 0; qhist[e + nraw] = 0;
-        const uint32_t j = qj % (uint32_t)J, q = qj / (uint32_t)J;
-        const uint32_t tab = x / W, w = x % W;
-        const size_t cell = SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + q;
-        const unsigned long long vc = (unsigned long long)((long long)vr - (long long)vd);
-        if (vr) atomicAdd(&S[SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab)) + cell], (unsigned long long)vr);
-        if (vc) atomicAdd(&S[SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates)) + cell], vc);
-        if (q >= 20) { atomicAdd(&gsum[tab * 8 + 6], (unsigned long long)vr); atomicAdd(&gsum[(tab + mates) * 8 + 6], vc); }
-        if (q >= 30) { atomicAdd(&gsum[tab * 8 + 7], (unsigned long long)vr); atomicAdd(&gsum[(tab + mates) * 8 + 7], vc); }
+    // quality cells: entry e = (q*J + j)*X + x. A thread keeps one raw item x (hence one table) and strides
+    // over the (q, j) rows, so the q20/q30 totals stay in registers until one 32-bit shared atomic each
+    // (all per-interval sums fit 32 bits: at most kQCounterMax records x 1008 positions).
+    const uint32_t qrows = (uint32_t)P.qb * (uint32_t)J;
+    const uint32_t rows_par = blockDim.x / nraw;            // >= 2: the CTA has at least 2*nraw threads
+    if (threadIdx.x < rows_par * nraw) {
+        const uint32_t x = threadIdx.x % nraw, tab = x / W, w = x % W;
+        unsigned long long* FR = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab)) + SNK_FILE_QS_OFF + (size_t)(J * w) * SNK_QBINS;
+        unsigned long long* FC = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates)) + SNK_FILE_QS_OFF + (size_t)(J * w) * SNK_QBINS;
+        uint32_t r20 = 0, r30 = 0, c20 = 0, c30 = 0;
+        for (uint32_t qj = threadIdx.x / nraw; qj < qrows; qj += rows_par) {
+            const uint32_t e = qj * X + x;
+            const uint32_t vr = qhist[e];
+            const int vd = (int)(int16_t)qhist[e + nraw];
+            if (!vr && !vd) continue;
+            qhist[e] = 0; qhist[e + nraw] = 0;
+            const uint32_t j = qj % (uint32_t)J, q = qj / (uint32_t)J;
+            const uint32_t vc = (uint32_t)((int)vr - vd);      // records of the clean set in this cell: never negative
+            if (vr) atomicAdd(&FR[(size_t)j * SNK_QBINS + q], (unsigned long long)vr);
+            if (vc) atomicAdd(&FC[(size_t)j * SNK_QBINS + q], (unsigned long long)vc);
+            if (q >= 20) { r20 += vr; c20 += vc; }
+            if (q >= 30) { r30 += vr; c30 += vc; }
+        }
+        uint32_t* g32 = reinterpret_cast<uint32_t*>(gsum);  // low words (little endian); high words stay 0
+        if (r20) atomicAdd(&g32[2 * (tab * 8 + 6)], r20);
+        if (r30) atomicAdd(&g32[2 * (tab * 8 + 7)], r30);
+        if (c20) atomicAdd(&g32[2 * ((tab + mates) * 8 + 6)], c20);
+        if (c30) atomicAdd(&g32[2 * ((tab + mates) * 8 + 7)], c30);
     }
     // base cells: the raw item whose base counters this thread holds (base_item = ~0u: none)
     {
@@ -221,26 +230,29 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
         if ((int)tab < mates) {
             unsigned long long* FR = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab));
             unsigned long long* FC = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates));
-            unsigned long long bases_r = 0, bases_c = 0;
+            uint32_t* g32 = reinterpret_cast<uint32_t*>(gsum);
+            uint32_t bases_r = 0, bases_c = 0;
 #pragma unroll
             for (int b = 0; b < 5; b++) {
-                unsigned long long sym_r = 0, sym_c = 0;
+                uint32_t sym_r = 0, sym_c = 0;
 #pragma unroll
                 for (int j = 0; j < J; j++) {
                     const uint32_t vr = (bc.raw[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu;
                     const int vd = (int)((bc.del[b][j / 2] >> (16 * (j & 1))) & 0xFFFFu) - 0x8000;
-                    const unsigned long long vc = (unsigned long long)((long long)vr - (long long)vd);
+                    // this thread's share of the clean count may be negative when two b-units split an item's
+                    // records (one saw the record, the other its delta entry): 64-bit wrap-around add
+                    const long long vc = (long long)vr - (long long)vd;
                     const size_t cell = SNK_FILE_BS_OFF + (size_t)(J * w + j) * 5 + b;
                     if (vr) atomicAdd(&FR[cell], (unsigned long long)vr);
-                    if (vc) atomicAdd(&FC[cell], vc);
-                    sym_r += vr; sym_c += vc;
+                    if (vc) atomicAdd(&FC[cell], (unsigned long long)vc);
+                    sym_r += vr; sym_c += (uint32_t)vc;
                 }
-                if (sym_r) atomicAdd(&gsum[tab * 8 + b], sym_r);
-                if (sym_c) atomicAdd(&gsum[(tab + mates) * 8 + b], sym_c);
+                if (sym_r) atomicAdd(&g32[2 * (tab * 8 + b)], sym_r);
+                if (sym_c) atomicAdd(&g32[2 * ((tab + mates) * 8 + b)], sym_c);      // mod 2^32: the table's total is non-negative
                 bases_r += sym_r; bases_c += sym_c;
             }
-            if (bases_r) atomicAdd(&gsum[tab * 8 + 5], bases_r);
-            if (bases_c) atomicAdd(&gsum[(tab + mates) * 8 + 5], bases_c);
+            if (bases_r) atomicAdd(&g32[2 * (tab * 8 + 5)], bases_r);
+            if (bases_c) atomicAdd(&g32[2 * ((tab + mates) * 8 + 5)], bases_c);
             base_cnt_reset<J>(bc);
         }
     }

@@ -73,6 +73,28 @@ def test_every_byte_value_is_classified_like_the_oracle():
         assert bool(oerr & 1) == (chr(b) not in "ACGTNacgtn")
 
 
+def test_every_quality_byte_value_flags_like_the_oracle():
+    """Quality bytes below the Phred base or above the table's bins raise the bad-quality flag on both
+    sides; bytes inside [phred, phred+64) never do, whether or not they fit the shared-memory bins."""
+    L = 40
+    for phred in (33, 64):
+        for b in list(range(1, 10)) + list(range(10, 256, 3)) + [phred - 1, phred, phred + 41, phred + 42, phred + 63, phred + 64, 127, 128, 255]:
+            if b in (10, 13) or b > 255:
+                continue
+            S = np.zeros((3, 48), dtype=np.uint8); Q = np.zeros_like(S)
+            S[:, :L] = np.frombuffer(b"ACGT" * 10, dtype=np.uint8)
+            Q[:, :L] = phred + 30
+            Q[1, 23] = b
+            d = dict(seq1=S, qual1=Q, len1=np.array([L, L, L - 7], dtype=np.uint16))
+            p = abi.make_params(is_pe=False, quality_phred=phred)
+            o1, _, ost, oerr = oracle_run(p, d)
+            c1, _, cst, cerr = core_replay(p, d)
+            assert oerr == cerr, f"phred {phred} byte {b}: oracle {oerr} replay {cerr}"
+            assert bool(oerr & 2) == (not (phred <= b < phred + 64)), (phred, b, oerr)
+            if oerr == 0:
+                assert_same((c1, None, cst), (o1, None, ost), f"phred {phred} byte {b}")
+
+
 def test_batches_and_first_index_compose():
     """Feeding the input as several batches with running first_index gives the same tables as one call."""
     d = synth.gen_pairs(9000, L=100, seed=21)
