@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNK_ABI_VERSION 1
+#define SNK_ABI_VERSION 2
 
 /* ---- limits (global_variable.h:9-11 READ_MAX_LEN / MAX_QUAL) ---- */
 #define SNK_MAX_READ_LEN   1000   /* READ_MAX_LEN: per-position tables have this many rows        */
@@ -80,7 +80,16 @@ typedef struct snk_params {
      * partition-dependent merge (peprocess.cpp:732-1069) can be replayed on the host. */
     int32_t n_slots;              /* gp.threads_num after clamping; >=1 */
     int64_t slot_block;           /* gp.patchSize * patch ; >=1 */
-    int32_t reserved[8];
+    /* filtersRNA module (seProcess with the sRNA branches: read_filter.cpp:170-174, 432-438,
+     * seprocess.cpp:899-902). adapter[0][0] is the 5' adapter (-f), adapter[1][0] the 3' adapter (-r).
+     * Defaults global_parameter.h:54-58. */
+    int32_t srna;                 /* gp.module_name == "filtersRNA" (SE only) */
+    int32_t ada_rctg;             /* gp.adaRCtg: min 5' adapter continuous alignment length (6) */
+    float   ada_rar;              /* gp.adaRAr: min alignment rate when finding the 5' adapter (0.8) */
+    int32_t ada_rma;              /* gp.adaRMa: min alignment length when finding the 3' adapter (5) */
+    float   ada_rer;              /* gp.adaREr: max error rate mismatch/match for the 3' adapter (0.4) */
+    int32_t ada_rmm;              /* gp.adaRMm: max mismatches for the 3' adapter (4) */
+    int32_t reserved[2];
 } snk_params;
 
 /* ---- one mate of a batch, fixed-stride SoA ---- */
@@ -104,7 +113,9 @@ enum snk_category {
     SNK_DROP_LOWQ = 6,           /* "Reads with low quality" */
     SNK_DROP_MEANQ = 7,          /* "Reads with low mean quality" */
     SNK_DROP_ADAPTER = 8,        /* "Reads with adapter" */
-    SNK_DROP_EMPTY = 9           /* min_read_length==-1 and a mate was emptied (sequence.cpp:245-249), uncounted */
+    SNK_DROP_EMPTY = 9,          /* min_read_length==-1 and a mate was emptied (sequence.cpp:245-249), uncounted */
+    SNK_DROP_NO3ADAPTER = 10,    /* filtersRNA: no 3' adapter found (sequence.cpp:36-39), counted but never reported */
+    SNK_DROP_INSERTNULL = 11     /* filtersRNA: 3' adapter within the first 3 bases (sequence.cpp:40-44), never reported */
 };
 typedef struct snk_read_result {
     uint16_t head_cut;     /* bases removed from the 5' end of this mate */
@@ -125,7 +136,9 @@ enum snk_fs {
     SNK_FS_MEANQ, SNK_FS_MEANQ1, SNK_FS_MEANQ2, SNK_FS_MEANQ_OV,
     SNK_FS_SHORT, SNK_FS_SHORT1, SNK_FS_SHORT2, SNK_FS_SHORT_OV,
     SNK_FS_LONG, SNK_FS_LONG1, SNK_FS_LONG2, SNK_FS_LONG_OV,
-    SNK_FS_COUNT = 32
+    SNK_FS_NO3ADAPTER,           /* fs.no_3_adapter_num (filtersRNA) */
+    SNK_FS_INSERTNULL,           /* fs.int_insertNull_num (filtersRNA) */
+    SNK_FS_COUNT = 40
 };
 /* C_general_stat (global_variable.h:88-100), index into a file block's gs[] */
 enum snk_gs {

@@ -78,7 +78,7 @@ def have_reference():
     return os.path.exists(REF_BIN) and os.access(REF_BIN, os.X_OK)
 
 
-def run_reference(args, cwd=None, timeout=600):
-    """Run the unmodified reference binary: `SOAPnuke filter <args>`."""
-    return subprocess.run([REF_BIN, "filter"] + list(args), cwd=cwd, timeout=timeout,
+def run_reference(args, cwd=None, timeout=600, module="filter"):
+    """Run the unmodified reference binary: `SOAPnuke <module> <args>` (filter | filtersRNA)."""
+    return subprocess.run([REF_BIN, module] + list(args), cwd=cwd, timeout=timeout,
                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)

@@ -73,6 +73,64 @@ ORC_EXPORT int orc_adapter_pos(const uint8_t* read, int readLen, const uint8_t* 
     return -1;
 }
 
+/* read_filter.cpp:791-862 sRNA_findAdapter(): ungapped alignments of the 3' adapter against the read,
+ * first with the adapter's offsets 2,1,0 at read position 0, then adapter offset 0 at read positions
+ * 1..readLen-adaRMa. 'N' in the read is neither a match nor a mismatch. Returns the read position of the
+ * preferred accepted alignment (a later one replaces the current one only if it has no more mismatches
+ * and no fewer matches) or -1. */
+ORC_EXPORT int orc_srna_find_adapter(const uint8_t* read, int readLen, const uint8_t* adapter, int adptLen,
+                                     int adaRMa, int adaRMm, float adaREr)
+{
+    int startPos = -1;
+    if (adptLen == 0) return -1;
+    int a1 = 2, flagType = 0, misTmp = 0, totalMapTmp = 0;
+    for (int r1 = 0; r1 <= readLen - adaRMa;) {
+        int len1 = adptLen - a1, len2 = readLen - r1;
+        int len = len1 < len2 ? len1 : len2;
+        int mis = 0, totalMap = 0;
+        for (int c = 0; c < len; c++) {
+            if (read[r1 + c] == 'N') continue;
+            if (adapter[a1 + c] == read[r1 + c]) totalMap++;
+            else mis++;
+        }
+        int misAndMap = mis + totalMap;
+        float rate = 1.0 * mis / totalMap;                 /* double division, then float (:832) */
+        if (mis <= adaRMm && misAndMap >= adaRMa && rate <= adaREr) {
+            if (flagType) {
+                if (mis <= misTmp && totalMap >= totalMapTmp) { startPos = r1; misTmp = mis; totalMapTmp = totalMap; }
+            } else { startPos = r1; flagType = 1; misTmp = mis; totalMapTmp = totalMap; }
+        }
+        if (a1 > 0) a1--; else r1++;
+    }
+    return startPos;
+}
+
+/* read_filter.cpp:863-926 sRNA_hasAdapter(): is the 5' adapter's tail (at least adaRCtg bases) present?
+ * adapter offsets adptLen-adaRCtg .. 0 at read position 0, then offset 0 at read positions
+ * 1..max(0,readLen-adaRCtg); accepts at most 4 mismatches, a run of adaRCtg matches (or a read shorter
+ * than 12) and a match fraction of adaRAr relative to the read or to the adapter. */
+ORC_EXPORT int orc_srna_has_adapter(const uint8_t* read, int readLen, const uint8_t* adapter, int adptLen,
+                                    int adaRCtg, float adaRAr)
+{
+    if (adptLen == 0) return 0;
+    int a1 = adptLen - adaRCtg;
+    int readLenSmall = (readLen - adaRCtg < 0) ? 0 : (readLen - adaRCtg);
+    for (int r1 = 0; r1 <= readLenSmall;) {
+        int len1 = adptLen - a1, len2 = readLen - r1;
+        int len = len1 < len2 ? len1 : len2;
+        int mis = 0, totalMap = 0, run = 0, max_map = 0;
+        for (int c = 0; c < len; c++) {
+            if (adapter[a1 + c] == read[r1 + c]) { totalMap++; if (++run > max_map) max_map = run; }
+            else { mis++; run = 0; }
+        }
+        if (mis <= 4 && (max_map >= adaRCtg || readLen < 12) &&
+            (1.0 * totalMap / readLen >= adaRAr || 1.0 * totalMap / adptLen >= adaRAr))
+            return 1;
+        if (a1 > 0) a1--; else r1++;
+    }
+    return 0;
+}
+
 /* everything stat_read / fastq_trim leave behind for one mate */
 typedef struct {
     int len;
@@ -80,6 +138,7 @@ typedef struct {
     int contig;
     float n_ratio, a_ratio, lowq_ratio, mean_q;
     int has_adapter;
+    int include_3_adapter;      /* filtersRNA: sRNA_findAdapter() of the raw read */
     /* C_fastq cut bookkeeping (sequence.h:69), -1 as set by C_fastq_init (peprocess.cpp:1674-1689) */
     int head_hdcut, head_lqcut, tail_hdcut, tail_lqcut, adacut_pos;
     int head_cut, clean_len;    /* result of fastq_trim */
@@ -107,12 +166,20 @@ static void orc_stat_and_trim(const snk_params* p, int mate, const uint8_t* seq,
     r->head_hdcut = r->head_lqcut = r->tail_hdcut = r->tail_lqcut = r->adacut_pos = -1;
     /* :175-188 first adapter in the list that hits wins */
     int ada_pos = -1;
-    for (int i = 0; i < p->n_adapters[mate]; i++) {
-        ada_pos = orc_adapter_pos(seq, len, (const uint8_t*)p->adapter[mate][i], p->adapter_len[mate][i],
-                                  p->ada_mis[mate], p->ada_mr[mate], p->ada_edge[mate]);
-        if (ada_pos >= 0) break;
+    if (p->srna) {
+        /* :170-174: 3' adapter = adapter2_seq, 5' adapter = adapter1_seq; adacut_pos stays -1 */
+        r->include_3_adapter = orc_srna_find_adapter(seq, len, (const uint8_t*)p->adapter[1][0], p->n_adapters[1] ? p->adapter_len[1][0] : 0,
+                                                     p->ada_rma, p->ada_rmm, p->ada_rer);
+        r->has_adapter = orc_srna_has_adapter(seq, len, (const uint8_t*)p->adapter[0][0], p->n_adapters[0] ? p->adapter_len[0][0] : 0,
+                                              p->ada_rctg, p->ada_rar);
+    } else {
+        for (int i = 0; i < p->n_adapters[mate]; i++) {
+            ada_pos = orc_adapter_pos(seq, len, (const uint8_t*)p->adapter[mate][i], p->adapter_len[mate][i],
+                                      p->ada_mis[mate], p->ada_mr[mate], p->ada_edge[mate]);
+            if (ada_pos >= 0) break;
+        }
+        if (ada_pos >= 0) { r->has_adapter = 1; r->adacut_pos = len - ada_pos; }
     }
-    if (ada_pos >= 0) { r->has_adapter = 1; r->adacut_pos = len - ada_pos; }
     /* :255-287 base loop */
     int last_char = 'Q', contig = 0, max_contig = 1;
     for (int i = 0; i < len; i++) {
@@ -167,16 +234,23 @@ static void orc_stat_and_trim(const snk_params* p, int mate, const uint8_t* seq,
         if (hix > head_cut) head_cut = hix;
         if (tix > tail_cut) tail_cut = tix;
     }
+    int cur = len;                                  /* read.sequence.size() as the function goes on */
     if (p->ada_trim) {                              /* :430-442 */
+        if (p->srna) {
+            /* :432-438 the read is cut at the 3' adapter BEFORE the head/tail cuts are applied (the same
+               search as in stat_read: the sequence has not been modified yet) */
+            int pos3 = r->include_3_adapter;
+            if (pos3 > 2 && pos3 < cur) cur = pos3;
+        }
         if (r->adacut_pos > 0 && r->adacut_pos > tail_cut) tail_cut = r->adacut_pos;
     }
     if (p->polyG_tail != -1) {                      /* :454-461, polyG_number :472-482 */
         int ng = 0;
-        for (int i = len - 1; i >= 0; i--) { if (seq[i] == 'G' || seq[i] == 'g') ng++; else break; }
+        for (int i = cur - 1; i >= 0; i--) { if (seq[i] == 'G' || seq[i] == 'g') ng++; else break; }
         if ((float)ng >= p->polyG_tail) { if (ng > tail_cut) tail_cut = ng; }
     }
-    if (head_cut + tail_cut > len) { r->head_cut = 0; r->clean_len = 0; }   /* :462-464 */
-    else { r->head_cut = head_cut; r->clean_len = len - head_cut - tail_cut; }
+    if (head_cut + tail_cut > cur) { r->head_cut = 0; r->clean_len = 0; }   /* :462-464 */
+    else { r->head_cut = head_cut; r->clean_len = cur - head_cut - tail_cut; }
 }
 
 static void ts_bump(uint64_t* ts, int arr, long idx)
@@ -287,6 +361,21 @@ static int orc_se_discard(const snk_params* p, const orc_read* r, uint64_t* fs)
     return SNK_KEEP;
 }
 
+/* sequence.cpp:19-75 sRNA_discard */
+static int orc_srna_discard(const snk_params* p, const orc_read* r, uint64_t* fs, uint32_t* err)
+{
+    if (p->max_read_length != -1 && (uint64_t)r->clean_len > (uint64_t)(int64_t)p->max_read_length) { fs[SNK_FS_LONG]++; return SNK_DROP_LONG; }
+    if (p->low_qual_ratio != -1 && r->lowq_ratio >= p->low_qual_ratio) { fs[SNK_FS_LOWQ]++; return SNK_DROP_LOWQ; }
+    if (r->include_3_adapter == -1) { fs[SNK_FS_NO3ADAPTER]++; return SNK_DROP_NO3ADAPTER; }
+    if (r->include_3_adapter <= 2) { fs[SNK_FS_INSERTNULL]++; return SNK_DROP_INSERTNULL; }
+    if (r->has_adapter) { fs[SNK_FS_ADAPTER]++; return SNK_DROP_ADAPTER; }
+    if (p->highA_ratio != -1 && r->a_ratio >= p->highA_ratio) { fs[SNK_FS_HIGHA]++; return SNK_DROP_HIGHA; }
+    if (p->polyX_num != -1 && r->contig >= p->polyX_num) { fs[SNK_FS_POLYX]++; return SNK_DROP_POLYX; }
+    if ((uint64_t)r->clean_len < (uint64_t)(int64_t)p->min_read_length) { fs[SNK_FS_SHORT]++; return SNK_DROP_SHORT; }   /* :68 no -1 test */
+    (void)err;
+    return SNK_KEEP;
+}
+
 static void fill_result(snk_read_result* o, const orc_read* r, int cat, int mask)
 {
     o->head_cut = (uint16_t)r->head_cut;
@@ -349,7 +438,7 @@ ORC_EXPORT int orc_filter_se(const snk_params* p, const snk_batch* b1, snk_read_
         orc_read r1;
         orc_stat_and_trim(p, 0, s1, q1, b1->len[i], &r1);
         if (r1.bad_base) *err |= 1u;
-        int cat = orc_se_discard(p, &r1, S);
+        int cat = p->srna ? orc_srna_discard(p, &r1, S, err) : orc_se_discard(p, &r1, S);
         fill_result(&out1[i], &r1, cat, cat ? 1 : 0);
         orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_RAW1), 2, s1, q1, r1.len, 0,
                         cutback ? r1.head_hdcut : -1, cutback ? r1.head_lqcut : -1, cutback ? r1.tail_hdcut : -1,

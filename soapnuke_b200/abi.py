@@ -11,14 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ENGINE_LIB = os.path.join(HERE, "lib", "libsnk_engine.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_READ_LEN = 1000
 QBINS = 64
 MAX_ADAPTERS = 8
 MAX_ADAPTER_LEN = 128
 MAX_SLOTS = 256
 
-FS_COUNT = 32
+FS_COUNT = 40
 GS_COUNT = 16
 FILE_COUNT = 4
 TS_COUNT = 5
@@ -79,7 +79,13 @@ class Params(C.Structure):
         ("max_base_quality", C.c_int32),
         ("n_slots", C.c_int32),
         ("slot_block", C.c_int64),
-        ("reserved", C.c_int32 * 8),
+        ("srna", C.c_int32),
+        ("ada_rctg", C.c_int32),
+        ("ada_rar", C.c_float),
+        ("ada_rma", C.c_int32),
+        ("ada_rer", C.c_float),
+        ("ada_rmm", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -175,7 +181,8 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
                 min_read_length=30, max_read_length=-1, quality_phred=33, out_quality_phred=33,
                 ada_mis=(2, 2), ada_mr=(0.5, 0.5), ada_edge=(6, 6), hard_trim=None,
                 trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
-                contam_trim=False, index_remove=False, patch_size=None):
+                contam_trim=False, index_remove=False, patch_size=None, srna=False, ada_rctg=6, ada_rar=0.8,
+                ada_rma=5, ada_rer=0.4, ada_rmm=4):
     """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
     Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
     p = Params()
@@ -227,6 +234,8 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
         p.has_trim_bad_tail = 1
         p.bad_tail_thr, p.bad_tail_max = trim_bad_tail
     p.max_base_quality = max_base_quality
+    p.srna = 1 if srna else 0       # filtersRNA: adapter1 = 5' adapter, adapter2 = 3' adapter, SE only
+    p.ada_rctg, p.ada_rar, p.ada_rma, p.ada_rer, p.ada_rmm = ada_rctg, ada_rar, ada_rma, ada_rer, ada_rmm
     n_slots, block, _ = ref_threads_partition(threads, nprocs, patch_size)
     p.n_slots = n_slots
     p.slot_block = block

@@ -72,6 +72,9 @@ inline void prepare_params(const snk_params& p, DevParams& d)
     for (int m = 0; m < 2; m++) { d.hard_head[m] = p.hard_head[m]; d.hard_tail[m] = p.hard_tail[m]; }
     d.bad_head_thr = p.has_trim_bad_head ? p.bad_head_thr : 0; d.bad_head_max = p.has_trim_bad_head ? p.bad_head_max : 0;
     d.bad_tail_thr = p.has_trim_bad_tail ? p.bad_tail_thr : 0; d.bad_tail_max = p.has_trim_bad_tail ? p.bad_tail_max : 0;
+    d.srna = p.srna;
+    d.ada_rctg = p.ada_rctg; d.ada_rma = p.ada_rma; d.ada_rmm = p.ada_rmm;
+    d.ada_rar = p.ada_rar; d.ada_rer = p.ada_rer;
     d.n_slots = p.n_slots;
     d.slot_block = p.slot_block;
     int qb = p.max_base_quality + 1;

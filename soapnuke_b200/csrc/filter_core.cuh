@@ -167,6 +167,9 @@ struct DevParams {
     int32_t bad_head_thr, bad_head_max, bad_tail_thr, bad_tail_max;
     int32_t n_adapters[2];
     int32_t n_slots;
+    int32_t srna;          // filtersRNA: ada[0][0] = 5' adapter, ada[1][0] = 3' adapter (bytes only)
+    int32_t ada_rctg, ada_rma, ada_rmm;
+    float   ada_rar, ada_rer;
     int32_t qb;            // quality bins kept in shared memory (max_base_quality+1, <= SNK_QBINS)
     int64_t slot_block;
     AdapterDev ada[2][SNK_MAX_ADAPTERS];
@@ -182,7 +185,8 @@ struct ReadInfo {
 enum : uint16_t {
     RF_N = 1, RF_HIGHA = 2, RF_POLYX = 4, RF_LOWQ = 8, RF_MEANQ = 16, RF_ADAPTER = 32,
     RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256,
-    RF_QSLOW = 512        // some quality falls outside the shared-memory bins: histogram takes the checked path
+    RF_QSLOW = 512,       // some quality falls outside the shared-memory bins: histogram takes the checked path
+    RF_NO3 = 1024, RF_INSNULL = 2048     // filtersRNA: no 3' adapter / 3' adapter within the first three bases
 };
 enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
 
@@ -539,6 +543,56 @@ SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
     return -1;
 }
 
+// ---- filtersRNA adapter finders (byte-wise ungapped alignments; reads are short)
+// read_filter.cpp:791-862 sRNA_findAdapter: 3' adapter. Alignments in the reference's order: adapter
+// offsets 2,1,0 at read position 0, then offset 0 at read positions 1..len-adaRMa; an 'N' of the read is
+// neither match nor mismatch; a later accepted alignment replaces the current one only if it has no more
+// mismatches and no fewer matches. Returns the read position or -1.
+SNK_HD int srna_find_adapter(const uint8_t* read, int len, const uint8_t* ada, int alen, int rma, int rmm, float rer)
+{
+    if (alen == 0) return -1;
+    int start = -1, a1 = 2, mis_best = 0, map_best = 0;
+    bool have = false;
+    for (int r1 = 0; r1 <= len - rma;) {
+        const int l1 = alen - a1, l2 = len - r1;
+        const int n = l1 < l2 ? l1 : l2;
+        int mis = 0, tot = 0;
+        for (int c = 0; c < n; c++) {
+            const uint8_t b = read[r1 + c];
+            if (b == 'N') continue;
+            if (ada[a1 + c] == b) tot++; else mis++;
+        }
+        if (mis <= rmm && mis + tot >= rma) {
+            const float rate = (float)((double)mis / (double)tot);      // `float rate = 1.0*mis/totalMap` (:832)
+            if (rate <= rer && (!have || (mis <= mis_best && tot >= map_best))) { start = r1; have = true; mis_best = mis; map_best = tot; }
+        }
+        if (a1 > 0) a1--; else r1++;
+    }
+    return start;
+}
+// read_filter.cpp:863-926 sRNA_hasAdapter: 5' adapter tail. Adapter offsets alen-adaRCtg..0 at read
+// position 0, then offset 0 at read positions 1..max(0,len-adaRCtg).
+SNK_HD bool srna_has_adapter(const uint8_t* read, int len, const uint8_t* ada, int alen, int rctg, float rar)
+{
+    if (alen == 0) return false;
+    int a1 = alen - rctg;
+    if (a1 < 0) a1 = 0;                 // adapters shorter than adaRCtg are rejected by the host (reference: out-of-bounds read)
+    const int last = len - rctg < 0 ? 0 : len - rctg;
+    for (int r1 = 0; r1 <= last;) {
+        const int l1 = alen - a1, l2 = len - r1;
+        const int n = l1 < l2 ? l1 : l2;
+        int mis = 0, tot = 0, run = 0, best = 0;
+        for (int c = 0; c < n; c++) {
+            if (ada[a1 + c] == read[r1 + c]) { tot++; run++; best = run > best ? run : best; }
+            else { mis++; run = 0; }
+        }
+        if (mis <= 4 && (best >= rctg || len < 12) &&
+            ((double)tot / (double)len >= (double)rar || (double)tot / (double)alen >= (double)rar)) return true;
+        if (a1 > 0) a1--; else r1++;
+    }
+    return false;
+}
+
 // stage 4: end scans of fastq_trim (read_filter.cpp:390-429, 454-461): thread 0 scans the head,
 // thread kNT-1 the tail and the polyG run. The scans go a word (4 bytes) at a time: `nm` flags (bit 7
 // of a byte lane) mark the bytes that END a run; most reads leave after one word.
@@ -587,7 +641,8 @@ SNK_HD int head_run(const uint8_t* row, int len, int limit, NM nm_of)
 }
 struct TrimPart { int hix, tix, ng; };
 SNK_HD void merge_trim(TrimPart& a, const TrimPart& b) { a.hix += b.hix; a.tix += b.tix; a.ng += b.ng; }
-SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, const DevParams& P, int h, TrimPart& t)
+// glen = length of the sequence the polyG scan sees (filtersRNA cuts the read at the 3' adapter first)
+SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, int glen, const DevParams& P, int h, TrimPart& t)
 {
     t.hix = t.tix = t.ng = 0;
     if (!P.trimming) return;
@@ -605,7 +660,7 @@ SNK_HD void trim_part(const uint8_t* seq, const uint8_t* qual, int len, const De
             t.tix = tail_run(qual, len, P.bad_tail_max, [kk](uint32_t w) { return ~bytes_lt(w, kk) & 0x80808080u; });
         }
     }
-    if (tail && P.polyG_tail != -1) t.ng = tail_run(seq, len, len, [](uint32_t w) { return not_g_lanes(w); });
+    if (tail && P.polyG_tail != -1 && glen > 0) t.ng = tail_run(seq, glen, glen, [](uint32_t w) { return not_g_lanes(w); });
 }
 
 // rare path behind ScanPart::qbad: is some quality byte >= 128 or below the Phred base? (the other way to
@@ -617,11 +672,20 @@ SNK_HD_NOINLINE bool qual_violation(const uint8_t* qual, int len, int phred)
     return false;
 }
 
+// read_filter.cpp:432-438: with adapter trimming on, filtersRNA cuts the read at the 3' adapter (position
+// > 2) before the head / tail cuts are applied; returns the sequence length fastq_trim goes on with
+SNK_HD int srna_cut_len(const DevParams& P, int ada_pos, int len)
+{
+    return (P.srna && P.ada_trim && ada_pos > 2 && ada_pos < len) ? ada_pos : len;
+}
+
 // stage 5: everything merged -> ReadInfo (predicates of stat_read, read_filter.cpp:289-311, and the
 // cut arithmetic of fastq_trim, read_filter.cpp:383-468)
 template <int NW>
-SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, const TrimPart& T, int len, int mate,
-                        const DevParams& P, ReadInfo& R)
+// ada_pos: adapter_pos() result (filter) or sRNA_findAdapter() result (filtersRNA); has5: sRNA_hasAdapter();
+// cur = sequence length fastq_trim applies the cuts to (len, or the 3' adapter position in filtersRNA)
+SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, bool has5, int cur, const TrimPart& T, int len,
+                        int mate, const DevParams& P, ReadInfo& R)
 {
     uint16_t flags = 0;
     if (S.viol) flags |= RF_BAD_BASE;
@@ -648,7 +712,10 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
     if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
     if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
     int adacut = -1;
-    if (ada_pos >= 0) { flags |= RF_ADAPTER; adacut = len - ada_pos; }
+    if (P.srna) {
+        if (ada_pos == -1) flags |= RF_NO3; else if (ada_pos <= 2) flags |= RF_INSNULL;
+        if (has5) flags |= RF_ADAPTER;
+    } else if (ada_pos >= 0) { flags |= RF_ADAPTER; adacut = len - ada_pos; }
     int head_hd = -1, head_lq = -1, tail_hd = -1, tail_lq = -1;
     int head_cut = 0, clean_len = len;
     if (P.trimming) {
@@ -661,8 +728,8 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
         }
         if (P.ada_trim && adacut > 0 && adacut > tc) tc = adacut;
         if (P.polyG_tail != -1 && (float)T.ng >= P.polyG_tail && T.ng > tc) tc = T.ng;
-        if (hc + tc > len) { head_cut = 0; clean_len = 0; }
-        else { head_cut = hc; clean_len = len - hc - tc; }
+        if (hc + tc > cur) { head_cut = 0; clean_len = 0; }
+        else { head_cut = hc; clean_len = cur - hc - tc; }
     }
     R.len = (int16_t)len;
     R.head_cut = (int16_t)head_cut; R.clean_len = (int16_t)clean_len;
@@ -683,7 +750,11 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
     for (int h = 1; h < kNT; h++) { scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, S2); merge_scan(S, S2); }
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
-    if (P.n_adapters[mate] > 0) {
+    bool has5 = false;
+    if (P.srna) {
+        ada_pos = srna_find_adapter(seq, len, P.ada[1][0].seq, P.n_adapters[1] > 0 ? P.ada[1][0].len : 0, P.ada_rma, P.ada_rmm, P.ada_rer);
+        has5 = srna_has_adapter(seq, len, P.ada[0][0].seq, P.n_adapters[0] > 0 ? P.ada[0][0].len : 0, P.ada_rctg, P.ada_rar);
+    } else if (P.n_adapters[mate] > 0) {
         uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
         for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }
         for (int k = NW; k < NW + 2; k++) { p0[k] = 0; p1[k] = 0; pb[k] = 0xFFFFFFFFu; }
@@ -699,10 +770,11 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
             if (ada_pos >= 0) break;
         }
     }
+    const int cur = srna_cut_len(P, ada_pos, len);
     TrimPart T, T2;
-    trim_part(seq, qual, len, P, 0, T);
-    for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, P, h, T2); merge_trim(T, T2); }
-    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, T, len, mate, P, R);
+    trim_part(seq, qual, len, cur, P, 0, T);
+    for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, cur, P, h, T2); merge_trim(T, T2); }
+    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, cur, T, len, mate, P, R);
 }
 
 // ------------------------------------------------------------------ discard cascade
@@ -741,6 +813,21 @@ SNK_HD int decide_se(const DevParams& P, const ReadInfo& a, int* fs_base)
     if (a.flags & RF_LOWQ) { *fs_base = SNK_FS_LOWQ; return SNK_DROP_LOWQ; }
     if (a.flags & RF_MEANQ) { *fs_base = SNK_FS_MEANQ; return SNK_DROP_MEANQ; }
     if ((a.flags & RF_ADAPTER) && !P.ada_trim) { *fs_base = SNK_FS_ADAPTER; return SNK_DROP_ADAPTER; }
+    *fs_base = -1;
+    return SNK_KEEP;
+}
+
+// sequence.cpp:19-75 sRNA_discard
+SNK_HD int decide_srna(const DevParams& P, const ReadInfo& a, int* fs_base)
+{
+    if (P.max_len != -1 && (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len) { *fs_base = SNK_FS_LONG; return SNK_DROP_LONG; }
+    if (a.flags & RF_LOWQ) { *fs_base = SNK_FS_LOWQ; return SNK_DROP_LOWQ; }
+    if (a.flags & RF_NO3) { *fs_base = SNK_FS_NO3ADAPTER; return SNK_DROP_NO3ADAPTER; }
+    if (a.flags & RF_INSNULL) { *fs_base = SNK_FS_INSERTNULL; return SNK_DROP_INSERTNULL; }
+    if (a.flags & RF_ADAPTER) { *fs_base = SNK_FS_ADAPTER; return SNK_DROP_ADAPTER; }
+    if (a.flags & RF_HIGHA) { *fs_base = SNK_FS_HIGHA; return SNK_DROP_HIGHA; }
+    if (a.flags & RF_POLYX) { *fs_base = SNK_FS_POLYX; return SNK_DROP_POLYX; }
+    if ((uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len) { *fs_base = SNK_FS_SHORT; return SNK_DROP_SHORT; }   // no -1 test (:68)
     *fs_base = -1;
     return SNK_KEEP;
 }

@@ -155,7 +155,15 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     merge_scan(S, O);
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
-    if (P.n_adapters[mate] > 0) {
+    bool has5 = false;
+    if (P.srna) {
+        // filtersRNA: the group's first lane aligns the 3' adapter, the second the 5' adapter
+        int v = (h == 0) ? srna_find_adapter(seq, len, P.ada[1][0].seq, P.n_adapters[1] > 0 ? P.ada[1][0].len : 0, P.ada_rma, P.ada_rmm, P.ada_rer)
+                         : (int)srna_has_adapter(seq, len, P.ada[0][0].seq, P.n_adapters[0] > 0 ? P.ada[0][0].len : 0, P.ada_rctg, P.ada_rar);
+        const int o = __shfl_xor_sync(pm, v, 1);
+        ada_pos = (h == 0) ? v : o;
+        has5 = ((h == 0) ? o : v) != 0;
+    } else if (P.n_adapters[mate] > 0) {
         uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
 #pragma unroll
         for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }
@@ -177,11 +185,12 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
             if (ada_pos >= 0) break;
         }
     }
+    const int cur = srna_cut_len(P, ada_pos, len);
     TrimPart T, OT;
-    trim_part(seq, qual, len, P, h, T);
+    trim_part(seq, qual, len, cur, P, h, T);
     OT.hix = __shfl_xor_sync(pm, T.hix, 1); OT.tix = __shfl_xor_sync(pm, T.tix, 1); OT.ng = __shfl_xor_sync(pm, T.ng, 1);
     merge_trim(T, OT);
-    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, T, len, mate, P, R);
+    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, cur, T, len, mate, P, R);
 }
 
 // add this CTA's histograms (shared-memory quality counters, per-thread base counters) to the
@@ -417,7 +426,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                     if (cat == SNK_DROP_LOWQ && ((a.flags | b.flags) & RF_LOWQ_GT1)) err |= ERR_LOWQ_RATIO;
                     if (err) report_error(A, err, gi);
                 } else {
-                    cat = decide_se(P, a, &fsb);
+                    cat = P.srna ? decide_srna(P, a, &fsb) : decide_se(P, a, &fsb);
                     mask = cat ? 1 : 0;
                     uint32_t err = 0;
                     if (a.flags & RF_BAD_BASE) err |= ERR_BAD_BASE;

@@ -116,6 +116,9 @@ void init_from_config(HostParams& hp, const char* path)
         else if (key == "pe_info") hp.pe_info = true;
         else if (key == "patch") hp.patch_size = atoi(value.c_str());
         else if (key == "maxReadLen") hp.max_read_length = atoi(value.c_str());
+        else if (hp.srna && (key == "adaMis" || key == "adaMR" || key == "adaEdge"))       // process_argv.cpp:1380,1403,1426 + :774-782
+            die(std::string("these parameters should not appear in the module,") +
+                (key == "adaMis" ? "-M|--adaMis" : key == "adaMR" ? "-A|adaMR" : "-9|--adaEdge"));
         else if (key == "adaMis") pair_int(hp.ada_mis, hp.ada_mis2);
         else if (key == "adaEdge") pair_int(hp.ada_edge, hp.ada_edge2);
         else if (key == "adaMR") {
@@ -126,8 +129,14 @@ void init_from_config(HostParams& hp, const char* path)
         else if (key == "trim") hp.trim = value;
         else if (key == "trimBadHead") hp.trim_bad_head = value;
         else if (key == "trimBadTail") hp.trim_bad_tail = value;
-        else if (key == "adaRCtg" || key == "adaRAr" || key == "adaRMa" || key == "adaREr" || key == "adaRMm")
-            die("these parameters should not appear in the module,--" + key);      // filtersRNA-only (process_argv.cpp:763-770)
+        else if (key == "adaRCtg" || key == "adaRAr" || key == "adaRMa" || key == "adaREr" || key == "adaRMm") {
+            if (!hp.srna) die("these parameters should not appear in the module,--" + key);      // filtersRNA-only (process_argv.cpp:763-770)
+            if (key == "adaRCtg") hp.ada_rctg = atoi(value.c_str());                               // process_argv.cpp:1447-1470
+            else if (key == "adaRAr") hp.ada_rar = (float)atof(value.c_str());
+            else if (key == "adaRMa") hp.ada_rma = atoi(value.c_str());
+            else if (key == "adaREr") hp.ada_rer = (float)atof(value.c_str());
+            else hp.ada_rmm = atoi(value.c_str());
+        }
         else unsupported(key);
     }
 }
@@ -151,6 +160,7 @@ void print_usage(const std::string& module)
               << "  -h, --help   -v, --version\n"
               << "config file keys: seqType outFileType index qualSys outQualSys maxBaseQuality pe_info patch maxReadLen\n"
               << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log\n"
+              << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
 }
 
@@ -166,6 +176,11 @@ int parse_command_line(int argc, char** argv, HostParams& hp)
         {"trim", 1, nullptr, 't'}, {"thread", 1, nullptr, 'T'}, {"minReadLen", 1, nullptr, '4'}, {"output_clean", 1, nullptr, 'w'},
         {"help", 0, nullptr, 'h'}, {"version", 0, nullptr, 'v'}, {nullptr, 0, nullptr, 0}};
     hp.module_name = argv[1];
+    if (hp.module_name == "filtersRNA") {        // process_argv.cpp:174-178
+        hp.srna = true;
+        hp.min_read_length = 18;
+        hp.max_read_length = 49;
+    }
     int opt;
     while ((opt = getopt_long(argc, argv, short_opts, long_opts, nullptr)) != -1) {
         switch (opt) {
@@ -218,8 +233,13 @@ int parse_command_line(int argc, char** argv, HostParams& hp)
         if (ends_with_gz(hp.clean_fq1) != ends_with_gz(hp.clean_fq2)) die("the format of clean fastq1 is inconsistent with fastq2");
         if (ends_with_gz(hp.fq1_path) != ends_with_gz(hp.fq2_path)) die("the format of input fastq1 is inconsistent with fastq2");
     } else {
-        if (!hp.adapter2_seq.empty()) die("no need adapter2");
+        if (!hp.srna && !hp.adapter2_seq.empty()) die("no need adapter2");       // process_argv.cpp:625
         if (!hp.clean_fq2.empty()) die("input file is not pe data");
+    }
+    if (hp.srna) {
+        if (hp.is_pe) die("filtersRNA with paired input is not served by the GPU filter engine (seProcess path only)");
+        // sRNA_hasAdapter starts at adapter offset adptLen-adaRCtg (read_filter.cpp:872): negative = out-of-bounds read in the reference
+        if (!hp.ada1s.empty() && (int)hp.ada1s[0].size() < hp.ada_rctg) die("adapter1 is shorter than adaRCtg");
     }
     if (hp.seq_type != "0" && hp.seq_type != "1") die("seq_type value should be 0 or 1");
     if (hp.output_file_type != "fastq" && hp.output_file_type != "fasta") die("output_file_type value should be fastq or fasta");
@@ -296,6 +316,8 @@ void to_engine_params(const HostParams& hp, snk_params& p)
     }
     p.index_remove = hp.index_remove;
     p.max_base_quality = hp.max_base_quality;
+    p.srna = hp.srna;
+    p.ada_rctg = hp.ada_rctg; p.ada_rar = hp.ada_rar; p.ada_rma = hp.ada_rma; p.ada_rer = hp.ada_rer; p.ada_rmm = hp.ada_rmm;
     p.n_slots = hp.threads;                                       // logical reference threads
     p.slot_block = (int64_t)hp.patch_size * (160 / hp.threads);   // peprocess.cpp:81, :2063
 }

@@ -1,4 +1,4 @@
-// cli_params.h — `SOAPnuke filter` command line and config-file surface (process_argv.cpp:72-917,
+// cli_params.h — `SOAPnuke filter` / `SOAPnuke filtersRNA` command line and config-file surface (process_argv.cpp:72-917,
 // 1158-1638, defaults global_parameter.h:20-83), parsed once into an immutable HostParams and the
 // engine's snk_params POD.
 #ifndef SNK_CLI_PARAMS_H
@@ -30,6 +30,10 @@ struct HostParams {
     int ada_mis = 2, ada_mis2 = 2, ada_edge = 6, ada_edge2 = 6;
     float ada_mr = 0.5f, ada_mr2 = 0.5f;
     bool is_pe = false;
+    // filtersRNA module (global_parameter.h:54-58)
+    bool srna = false;
+    int ada_rctg = 6, ada_rma = 5, ada_rmm = 4;
+    float ada_rar = 0.8f, ada_rer = 0.4f;
     // engine-side knobs (not part of the reference CLI; environment SNK_GPUS / SNK_BATCH_READS)
     int n_gpus = 1;
     unsigned batch_reads = 1u << 15;

@@ -26,6 +26,11 @@ int params_check(const snk_params& p)
             if ((int)strnlen(p.adapter[m][i], SNK_MAX_ADAPTER_LEN) < L) { set_error("adapter_len exceeds adapter string"); return 1; }
         }
     }
+    if (p.srna) {
+        if (p.is_pe) { set_error("filtersRNA runs on single-end input (seProcess)"); return 1; }
+        // sRNA_hasAdapter starts at adapter offset adptLen - adaRCtg (read_filter.cpp:872)
+        if (p.n_adapters[0] > 0 && p.adapter_len[0][0] < p.ada_rctg) { set_error("adapter1 is shorter than adaRCtg"); return 1; }
+    }
     if (p.has_hard_trim) for (int m = 0; m < 2; m++)
         if (p.hard_head[m] < 0 || p.hard_tail[m] < 0) { set_error("trim value format error"); return 1; }
     return 0;

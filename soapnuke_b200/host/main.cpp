@@ -1,6 +1,6 @@
 // main.cpp — `SOAPnuke <module> [options]` (reference main.cpp:17-68): module dispatch, parameter
-// parsing, then peProcess / seProcess ::process(). Only the `filter` module (and its alias
-// `filterMeta`, process_argv.cpp:27,763) is served by the GPU engine.
+// parsing, then peProcess / seProcess ::process(). The `filter` module (and its alias `filterMeta`,
+// process_argv.cpp:27,763) and `filtersRNA` (seProcess with the sRNA branches) are served by the GPU engine.
 #include <iostream>
 #include <string>
 #include <unistd.h>
@@ -11,15 +11,15 @@ int main(int argc, char** argv)
 {
     if (argc < 2) {
         std::cout << "\nProgram: SOAPnuke (b200 filter engine)\nCommand:\n         filter        preprocessing normal Fastq files\n"
-                     "         filterMeta    preprocessing Meta Fastq files\n\n";
+                     "         filterMeta    preprocessing Meta Fastq files\n         filtersRNA    preprocessing sRNA Fastq files\n\n";
         return 1;
     }
     const std::string module = argv[1];
     if (module == "-h" || module == "--help") { snk::print_usage("filter"); return 0; }
     if (module == "-v" || module == "--version") { snk::print_version(); return 0; }
-    if (module != "filter" && module != "filterMeta") {
-        if (module == "filterStLFR" || module == "filtersRNA" || module == "filterHts")
-            std::cerr << "Error:module " << module << " is not served by the GPU filter engine (only filter / filterMeta)" << std::endl;
+    if (module != "filter" && module != "filterMeta" && module != "filtersRNA") {
+        if (module == "filterStLFR" || module == "filterHts")
+            std::cerr << "Error:module " << module << " is not served by the GPU filter engine (only filter / filterMeta / filtersRNA)" << std::endl;
         else
             std::cerr << "Error:no such module," << module << std::endl;
         return 1;

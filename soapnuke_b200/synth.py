@@ -11,6 +11,8 @@ ADAPTER1 = b"AAGTCGGAGGCCAAGCGGTCTTAGGAAGACAA"            # -f, process_argv.cpp
 ADAPTER2 = b"AAGTCGGATCGTAGCCATGTCGTTCTGTGAGCCAAGGAGTTG"  # -r
 SRNA_ADAPTER3 = b"TCGTATGCCGTCTTCTGCTTG"
 
+SRNA_ADAPTER5 = b"GTTCAGAGTTCTACAGTCCGACGATC"
+
 _ACGT = np.frombuffer(b"ACGT", dtype=np.uint8)
 
 
@@ -83,6 +85,54 @@ def gen_pairs(n, L=150, seed=1002, polyg_frac=0.04, adapter1=ADAPTER1, adapter2=
     out["L"] = L
     out["stride"] = stride
     return out
+
+
+def gen_srna(n, L=50, seed=1004, adapter5=SRNA_ADAPTER5, adapter3=SRNA_ADAPTER3, var_len=False):
+    """SE small-RNA reads for the filtersRNA module: insert, then the 3' adapter (sometimes mutated), then
+    random bases; classes without a 3' adapter, with an empty insert, with the 5' adapter's tail in front,
+    with low qualities and with N's. Same dict layout as gen_pairs(se=True)."""
+    rng = np.random.default_rng(seed)
+    stride = stride_for(L)
+    seq, qual = gen_mate_arrays(rng, n, L)
+    a3 = np.frombuffer(adapter3, dtype=np.uint8)
+    a5 = np.frombuffer(adapter5, dtype=np.uint8)
+    u = rng.random(n)
+    for i in range(n):
+        if u[i] < 0.08:
+            continue                                            # no 3' adapter
+        if u[i] < 0.14:
+            k = int(rng.integers(0, 4))                         # (nearly) empty insert
+        else:
+            k = int(rng.integers(15, min(36, L - 5)))
+        piece = a3.copy()
+        for _ in range(int(rng.integers(0, 3))):                # 0..2 substitutions
+            piece[rng.integers(0, piece.size)] = _ACGT[rng.integers(0, 4)]
+        e = min(L, k + piece.size)
+        seq[i, k:e] = piece[: e - k]
+        if 0.14 <= u[i] < 0.22:                                 # tail of the 5' adapter in front of the insert
+            t = int(rng.integers(16, a5.size + 1))              # sRNA_hasAdapter wants >= adaRAr * adapter length matches
+            t = min(t, L)
+            seq[i, :t] = a5[-t:]
+            if rng.random() < 0.5:
+                seq[i, int(rng.integers(0, t))] = _ACGT[rng.integers(0, 4)]
+        if 0.22 <= u[i] < 0.27:
+            qual[i] = rng.integers(2, 8, size=L, dtype=np.uint8)
+        if 0.27 <= u[i] < 0.32:
+            seq[i, rng.integers(0, L, size=3)] = ord("N")
+        if 0.32 <= u[i] < 0.36:
+            seq[i, k - min(k, 12):k] = ord("G")                 # G-rich insert end (polyG after the adapter cut)
+    length = np.full(n, L, dtype=np.uint16)
+    if var_len:
+        length = rng.integers(max(8, L // 3), L + 1, size=n).astype(np.uint16)
+    S = np.zeros((n, stride), dtype=np.uint8)
+    Q = np.zeros((n, stride), dtype=np.uint8)
+    S[:, :L] = seq
+    Q[:, :L] = qual + 33
+    col = np.arange(stride)[None, :]
+    pad = col >= length[:, None]
+    S[pad] = 0
+    Q[pad] = 0
+    return dict(seq1=S, qual1=Q, len1=length, n=n, L=L, stride=stride)
 
 
 def read_ids(n, mate, first=0):

@@ -137,7 +137,7 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     if ((a.flags | bb.flags) & RF_BAD_QUAL) c.err |= ERR_BAD_QUAL;
                     if (cat == SNK_DROP_LOWQ && ((a.flags | bb.flags) & RF_LOWQ_GT1)) c.err |= ERR_LOWQ_RATIO;
                 } else {
-                    cat = decide_se(c.P, a, &fsb);
+                    cat = c.P.srna ? decide_srna(c.P, a, &fsb) : decide_se(c.P, a, &fsb);
                     mask = cat ? 1 : 0;
                     if (a.flags & RF_BAD_BASE) c.err |= ERR_BAD_BASE;
                     if (a.flags & RF_BAD_QUAL) c.err |= ERR_BAD_QUAL;

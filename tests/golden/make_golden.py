@@ -30,18 +30,28 @@ CASES = {
     "se_default": (False, 1000, 100, 4244, dict(), [], dict(), 1, None),
     "se_trim_var": (False, 800, 120, 4245, dict(var_len=True), ["-f", A1, "-J", "-g", "8", "-4", "20"],
                     dict(adapter1=A1, ada_trim=True, polyG_tail=8, min_read_length=20), 3, "patch=3\n"),
+    # filtersRNA module (generator gen_srna; params carry srna=True and the module defaults 18/49)
+    "srna_trim": (False, 1000, 50, 4246, dict(var_len=True, srna=True),
+                  ["-f", synth.SRNA_ADAPTER5.decode(), "-r", synth.SRNA_ADAPTER3.decode(), "-J", "-g", "6"],
+                  dict(srna=True, adapter1=synth.SRNA_ADAPTER5.decode(), adapter2=synth.SRNA_ADAPTER3.decode(), ada_trim=True,
+                       polyG_tail=6, min_read_length=18, max_read_length=49), 2, "patch=7\n"),
 }
 
 
 def main():
+    only = set(sys.argv[1:])          # python make_golden.py [case ...]: regenerate only the named cases
     for name, (pe, n, L, seed, gkw, flags, pkw, T, cfg) in CASES.items():
+        if only and name not in only:
+            continue
         d = os.path.join(HERE, name)
         shutil.rmtree(d, ignore_errors=True)
         os.makedirs(d)
         work = os.path.join("/tmp", "golden_" + name)
         shutil.rmtree(work, ignore_errors=True)
         os.makedirs(work)
-        data = synth.gen_pairs(n, L=L, seed=seed, se=not pe, **gkw)
+        gkw = dict(gkw)
+        module = "filtersRNA" if gkw.pop("srna", False) else "filter"
+        data = synth.gen_srna(n, L=L, seed=seed, **gkw) if module == "filtersRNA" else synth.gen_pairs(n, L=L, seed=seed, se=not pe, **gkw)
         synth.write_fastq(os.path.join(work, "r1.fq"), data["seq1"], data["qual1"], data["len1"], 1)
         args = ["-1", os.path.join(work, "r1.fq"), "-C", "c1.fq", "-o", os.path.join(work, "out"), "-T", str(T)]
         if pe:
@@ -53,7 +63,7 @@ def main():
                 f.write(cfg)
             args += ["-c", os.path.join(work, "cfg.txt")]
             patch = int(cfg.split("=")[1])
-        subprocess.check_call([REF, "filter"] + args + flags, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        subprocess.check_call([REF, module] + args + flags, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         for m in (1, 2) if pe else (1,):
             for src, dst in ((os.path.join(work, f"r{m}.fq"), f"r{m}.fq.gz"), (os.path.join(work, "out", f"c{m}.fq"), f"c{m}.fq.gz")):
                 with open(src, "rb") as fi, gzip.GzipFile(os.path.join(d, dst), "wb", compresslevel=9, mtime=0) as fo:
@@ -61,7 +71,7 @@ def main():
         for f in sorted(os.listdir(os.path.join(work, "out"))):
             if f.endswith(".txt"):
                 shutil.copy(os.path.join(work, "out", f), os.path.join(d, f))
-        meta = dict(pe=pe, n=n, L=L, seed=seed, flags=flags, params=pkw, threads=T, patch_size=patch,
+        meta = dict(pe=pe, n=n, L=L, seed=seed, module=module, flags=flags, params=pkw, threads=T, patch_size=patch,
                     nprocs=os.cpu_count(), reference="SOAPnuke 2.1.9 @ 2d5b727, g++ -O3 -std=c++11 -include cstdint")
         with open(os.path.join(d, "case.json"), "w") as f:
             json.dump(meta, f, indent=1)

@@ -31,10 +31,14 @@ def read_maybe_gz(path):
     return gzip.open(path).read() if path.endswith(".gz") else open(path, "rb").read()
 
 
-def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False):
+def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False,
+             module="filter"):
     w = os.path.join(str(tmp), name)
     os.makedirs(w)
-    d = synth.gen_pairs(n, L=L, seed=abs(hash(name)) % 100000, se=not pe, **(gkw or {}))
+    if module == "filtersRNA":
+        d = synth.gen_srna(n, L=L, seed=abs(hash(name)) % 100000, **(gkw or {}))
+    else:
+        d = synth.gen_pairs(n, L=L, seed=abs(hash(name)) % 100000, se=not pe, **(gkw or {}))
     ext_in = ".fq.gz" if gz_in else ".fq"
     ext_out = ".fq.gz" if gz_out else ".fq"
     def write(path, m):
@@ -51,11 +55,11 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
     if patch or cfg:
         open(f"{w}/cfg.txt", "w").write((f"patch={patch}\n" if patch else "") + "".join(l + "\n" for l in (cfg or [])))
         base += ["-c", f"{w}/cfg.txt"]
-    r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags)
+    r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags, module=module)
     assert r.returncode == 0, r.stderr.decode()
     e = dict(os.environ)
     e.update(env or {})
-    m = subprocess.run([cli, "filter"] + base + ["-o", f"{w}/mine"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=600)
+    m = subprocess.run([cli, module] + base + ["-o", f"{w}/mine"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=600)
     assert m.returncode == 0, m.stderr.decode()
     for mate in (1, 2) if pe else (1,):
         a = read_maybe_gz(f"{w}/ref/c{mate}{ext_out}")
@@ -89,6 +93,23 @@ def test_cli_matches_reference_binary(cli, tmp_path, case):
     run_both(cli, tmp_path, **case)
 
 
+SA5, SA3 = synth.SRNA_ADAPTER5.decode(), synth.SRNA_ADAPTER3.decode()
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
+@pytest.mark.parametrize("case", [
+    dict(name="srna_trim_T1", n=40000, L=50, T=1, flags=["-f", SA5, "-r", SA3, "-J"]),
+    dict(name="srna_trim_polyg_T3_gz", n=30000, L=50, T=3, flags=["-f", SA5, "-r", SA3, "-J", "-g", "6", "-p", "0.6", "-X", "12"],
+         gkw=dict(var_len=True), patch=15, gz_in=True, gz_out=True),
+    dict(name="srna_discard_L44", n=20000, L=44, T=2, flags=["-f", SA5, "-r", SA3]),
+    dict(name="srna_hard_cfg", n=20000, L=75, T=2, flags=["-f", SA5, "-r", SA3, "-J", "-t", "2,1", "-4", "15"],
+         cfg=["maxReadLen=60", "adaRCtg=7", "adaRAr=0.7", "adaRMa=6", "adaREr=0.3", "adaRMm=3"], env={"SNK_BATCH_READS": "3000"}),
+], ids=lambda c: c["name"])
+def test_cli_filtersRNA_matches_reference_binary(cli, tmp_path, case):
+    """`SOAPnuke filtersRNA` (seProcess + sRNA_findAdapter / sRNA_hasAdapter / sRNA_discard)."""
+    run_both(cli, tmp_path, pe=False, module="filtersRNA", **case)
+
+
 def test_cli_reproduces_golden_outputs(cli, tmp_path):
     golden = os.path.join(ROOT, "tests", "golden")
     for name in sorted(os.listdir(golden)):
@@ -106,7 +127,7 @@ def test_cli_reproduces_golden_outputs(cli, tmp_path):
         if meta["patch_size"]:
             open(w / "cfg.txt", "w").write(f"patch={meta['patch_size']}\n")
             args += ["-c", str(w / "cfg.txt")]
-        m = subprocess.run([cli, "filter"] + args + meta["flags"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
+        m = subprocess.run([cli, meta.get("module", "filter")] + args + meta["flags"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=600)
         assert m.returncode == 0, m.stderr.decode()
         for mate in (1, 2) if meta["pe"] else (1,):
             assert open(w / "out" / f"c{mate}.fq", "rb").read() == gzip.open(os.path.join(gd, f"c{mate}.fq.gz")).read(), f"{name}: clean fq{mate}"

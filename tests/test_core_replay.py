@@ -37,6 +37,30 @@ def test_core_replay_matches_oracle(cfg):
     assert_same((c1, c2, cst), (o1, o2, ost), name)
 
 
+SRNA_CONFIGS = [
+    ("srna_discard_L44", 12000, 44, dict(), dict()),
+    ("srna_trim_polyg_varlen", 12000, 50, dict(var_len=True), dict(ada_trim=True, polyG_tail=6, highA_ratio=0.6, polyX_num=12)),
+    ("srna_trim_hard_params", 8000, 75, dict(), dict(ada_trim=True, hard_trim=(2, 1), min_read_length=15, max_read_length=60,
+                                                     ada_rctg=7, ada_rar=0.7, ada_rma=6, ada_rer=0.3, ada_rmm=3)),
+    ("srna_minlen_off", 6000, 50, dict(var_len=True), dict(ada_trim=True, min_read_length=-1, max_read_length=-1)),
+]
+
+
+@pytest.mark.parametrize("cfg", SRNA_CONFIGS, ids=[c[0] for c in SRNA_CONFIGS])
+def test_core_replay_matches_oracle_filtersRNA(cfg):
+    """filtersRNA: sRNA_findAdapter / sRNA_hasAdapter, the cut at the 3' adapter and sRNA_discard."""
+    name, n, L, gkw, pkw = cfg
+    d = synth.gen_srna(n, L=L, seed=len(name) * 31 + L, **gkw)
+    kw = dict(min_read_length=18, max_read_length=49)
+    kw.update(pkw)
+    p = abi.make_params(is_pe=False, srna=True, adapter1=synth.SRNA_ADAPTER5, adapter2=synth.SRNA_ADAPTER3, threads=2, patch_size=100, **kw)
+    o1, _, ost, oerr = oracle_run(p, d)
+    c1, _, cst, cerr = core_replay(p, d, grid=5)
+    assert oerr == cerr == 0
+    assert (np.bincount(o1["category"], minlength=12) > 0).sum() >= 4
+    assert_same((c1, None, cst), (o1, None, ost), name)
+
+
 def test_mixed_checked_and_unchecked_tiles(monkeypatch):
     """A few records with qualities above the shared-memory bins: their tiles take the checked
     histogram path (out-of-bin qualities go straight to the global tables, mirrored into the clean

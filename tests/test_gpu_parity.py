@@ -46,6 +46,28 @@ def test_engine_matches_oracle(cfg, engine_lib):
     assert_same((r1, r2, st), (o1, o2, ost), name)
 
 
+@pytest.mark.parametrize("cfg", [
+    ("srna_discard_L44", 60000, 44, dict(), dict()),
+    ("srna_trim_polyg_varlen", 60000, 50, dict(var_len=True), dict(ada_trim=True, polyG_tail=6, highA_ratio=0.6, polyX_num=12)),
+    ("srna_trim_hard_params", 30000, 75, dict(), dict(ada_trim=True, hard_trim=(2, 1), min_read_length=15, max_read_length=60,
+                                                      ada_rctg=7, ada_rar=0.7, ada_rma=6, ada_rer=0.3, ada_rmm=3)),
+], ids=lambda c: c[0])
+def test_engine_matches_oracle_filtersRNA(cfg, engine_lib):
+    """filtersRNA module on the engine (sRNA_findAdapter, sRNA_hasAdapter, cut at the 3' adapter, sRNA_discard)."""
+    name, n, L, gkw, pkw = cfg
+    d = synth.gen_srna(n, L=L, seed=len(name) * 31 + L, **gkw)
+    kw = dict(min_read_length=18, max_read_length=49)
+    kw.update(pkw)
+    p = abi.make_params(is_pe=False, srna=True, adapter1=synth.SRNA_ADAPTER5, adapter2=synth.SRNA_ADAPTER3, threads=2, patch_size=1000, **kw)
+    o1, _, ost, oerr = oracle_run(p, d)
+    with Engine(engine_lib, p) as e:
+        r1, _ = e.filter_host(d)
+        st = e.stats()
+        flags, _ = e.error_flags()
+    assert flags == oerr == 0
+    assert_same((r1, None, st), (o1, None, ost), name)
+
+
 def test_mixed_checked_and_unchecked_tiles(engine_lib):
     """Records with qualities above the shared-memory bins scattered through the batch (see the CPU
     tier's test of the same name): checked and unchecked tiles, raw and delta cells must add up."""

@@ -124,6 +124,52 @@ def test_oracle_matches_reference_binary(case, engine_lib, tmp_path):
     compare_reports(f"{w}/out", f"{w}/mine")
 
 
+# ---- filtersRNA module (seProcess with the sRNA branches): oracle vs the reference binary
+A5, A3 = synth.SRNA_ADAPTER5.decode(), synth.SRNA_ADAPTER3.decode()
+SRNA_LIVE = [
+    # name, n, L, T, flags, params kwargs, generator kwargs, config-file lines
+    ("srna_default", 6000, 44, 1, ["-f", A5, "-r", A3], dict(), {}, []),          # discard mode: reads must fit maxReadLen=49
+    ("srna_trim_T3", 6000, 50, 3, ["-f", A5, "-r", A3, "-J", "-g", "6", "-p", "0.6", "-X", "12"],
+     dict(ada_trim=True, polyG_tail=6, highA_ratio=0.6, polyX_num=12), dict(var_len=True), ["patch=15"]),
+    # (-x/-y cannot be used with SE input: check_parameter wants one field, fastq_trim two)
+    ("srna_trim_hard_cfg", 4000, 75, 2, ["-f", A5, "-r", A3, "-J", "-t", "2,1", "-4", "15"],
+     dict(ada_trim=True, hard_trim=(2, 1), min_read_length=15, max_read_length=60,
+          ada_rctg=7, ada_rar=0.7, ada_rma=6, ada_rer=0.3, ada_rmm=3), {},
+     ["maxReadLen=60", "adaRCtg=7", "adaRAr=0.7", "adaRMa=6", "adaREr=0.3", "adaRMm=3"]),
+]
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", SRNA_LIVE, ids=[c[0] for c in SRNA_LIVE])
+def test_oracle_matches_reference_binary_filtersRNA(case, engine_lib, tmp_path):
+    name, n, L, T, flags, pkw, gkw, cfg = case
+    data = synth.gen_srna(n, L=L, seed=sum(map(ord, name)), **gkw)
+    w = str(tmp_path)
+    synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
+    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    patch = None
+    if cfg:
+        open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg))
+        args += ["-c", f"{w}/cfg.txt"]
+        for l in cfg:
+            if l.startswith("patch="):
+                patch = int(l.split("=")[1])
+    r = orc.run_reference(args + flags, module="filtersRNA")
+    assert r.returncode == 0, r.stderr.decode()
+    kw = dict(min_read_length=18, max_read_length=49)       # filtersRNA defaults (process_argv.cpp:174-178)
+    kw.update(pkw)
+    p = abi.make_params(is_pe=False, srna=True, adapter1=A5, adapter2=A3, threads=T, patch_size=patch, **kw)
+    r1, st, err = orc.filter_se(p, data)
+    assert err == 0
+    cats = np.bincount(r1["category"], minlength=12)
+    assert cats[0] > n // 4 and (cats > 0).sum() >= 5, cats     # keep + several of: long, lowq, no 3', empty insert, 5' adapter, short
+    order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=False)
+    mine = synth.clean_fastq_bytes(data["seq1"], data["qual1"], data["len1"], r1, 1, order=order)
+    assert mine == open(f"{w}/out/c1.fq", "rb").read(), "clean fq differs from the reference binary"
+    write_reports(engine_lib.snk_report_write_se, p, st, f"{w}/mine")
+    compare_reports(f"{w}/out", f"{w}/mine")
+
+
 # ---- known answers measured on the reference binary (A=32: segThr=16, misGrad=8, misGrad5=9)
 def body(n, rng):
     return bytes(rng.choice(np.frombuffer(b"CT", dtype=np.uint8), size=n))
