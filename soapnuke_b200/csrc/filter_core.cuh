@@ -19,10 +19,12 @@
 #if defined(__CUDACC__)
 #define SNK_HD __host__ __device__ __forceinline__
 #define SNK_HD_NOINLINE __host__ __device__ __noinline__
+#define SNK_HD_MEMBER static __host__ __device__ __forceinline__
 #define SNK_ALIGN16 __align__(16)
 #else
 #define SNK_HD static inline
 #define SNK_HD_NOINLINE static
+#define SNK_HD_MEMBER static inline
 #define SNK_ALIGN16 alignas(16)
 #endif
 
@@ -593,6 +595,122 @@ SNK_HD bool srna_has_adapter(const uint8_t* read, int len, const uint8_t* ada, i
     return false;
 }
 
+// ---- bit-plane versions of the two aligners (adapter of uppercase A/C/G/T, at most 64 bases: `fast`).
+// q0/q1/qn/ql = the read's planes padded with two zero words. One alignment = a few funnel shifts, one
+// XOR/OR tree and popcounts instead of a byte loop: equality with an uppercase adapter base means equal
+// 2-bit code, not N, not lowercase.
+// window of the read's plane starting at position 32*kw + sft: 32 bases (adapters up to 32 bases) or 64
+template <typename W> struct PlaneWin;
+template <> struct PlaneWin<uint32_t> {
+    SNK_HD_MEMBER uint32_t get(const uint32_t* q, int kw, int sft) { return funnel_r(q[kw], q[kw + 1], (uint32_t)sft); }
+    SNK_HD_MEMBER uint32_t low(int n) { return n >= 32 ? 0xFFFFFFFFu : (n <= 0 ? 0u : ((1u << n) - 1u)); }
+    SNK_HD_MEMBER int popc(uint32_t x) { return (int)popc32(x); }
+    SNK_HD_MEMBER uint32_t ada(uint32_t lo, uint32_t) { return lo; }
+};
+template <> struct PlaneWin<uint64_t> {
+    SNK_HD_MEMBER uint64_t get(const uint32_t* q, int kw, int sft)
+    {
+        return ((uint64_t)funnel_r(q[kw + 1], q[kw + 2], (uint32_t)sft) << 32) | funnel_r(q[kw], q[kw + 1], (uint32_t)sft);
+    }
+    SNK_HD_MEMBER uint64_t low(int n) { return n >= 64 ? ~0ull : (n <= 0 ? 0ull : ((1ull << n) - 1ull)); }
+    SNK_HD_MEMBER int popc(uint64_t x) { return popc64(x); }
+    SNK_HD_MEMBER uint64_t ada(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+};
+// does x contain a run of at least T set bits? (T >= 1)
+template <typename W>
+SNK_HD bool has_run_bits(W x, int T)
+{
+    if (T > (int)(8 * sizeof(W))) return false;
+    for (int k = 1; k < T;) { const int sft = (k < T - k) ? k : T - k; x &= x >> sft; k += sft; }
+    return x != 0;
+}
+// The alignments come in the reference's order: adapter offsets a_first..0 at read position 0, then
+// adapter offset 0 at read positions 1..r_last. The position loop is unrolled over plane words (static
+// register indices) with a dynamic bit offset inside.
+struct SrnaFindState { int start, mis_best, map_best; bool have; };
+template <typename W>
+SNK_HD void srna_find_eval(SrnaFindState& st, W w0, W w1, W wn, W wl, W A0, W A1, int alen, int a1, int r1, int len, int rma, int rmm, float rer)
+{
+    const int l1 = alen - a1, l2 = len - r1;
+    const W wm = PlaneWin<W>::low(l1 < l2 ? l1 : l2);
+    const W neq = (w0 ^ (A0 >> a1)) | (w1 ^ (A1 >> a1)) | wn | wl;
+    const int tot = PlaneWin<W>::popc(~neq & wm);
+    const int mis = PlaneWin<W>::popc(neq & ~(wn & ~wl) & wm);     // an uppercase 'N' of the read is skipped (:816)
+    if (mis <= rmm && mis + tot >= rma) {
+        const float rate = (float)((double)mis / (double)tot);      // `float rate = 1.0*mis/totalMap` (:832)
+        if (rate <= rer && (!st.have || (mis <= st.mis_best && tot >= st.map_best))) { st.start = r1; st.have = true; st.mis_best = mis; st.map_best = tot; }
+    }
+}
+template <int NW, typename W>
+SNK_HD int srna_find_planes(const uint32_t* q0, const uint32_t* q1, const uint32_t* qn, const uint32_t* ql, int len,
+                            const AdapterDev& a, int rma, int rmm, float rer)
+{
+    const int alen = a.len;
+    const int r_last = len - rma;
+    if (alen == 0 || r_last < 0) return -1;
+    const W A0 = PlaneWin<W>::ada(a.a0_lo, a.a0_hi), A1 = PlaneWin<W>::ada(a.a1_lo, a.a1_hi);
+    SrnaFindState st = {-1, 0, 0, false};
+    {
+        const W w0 = PlaneWin<W>::get(q0, 0, 0), w1 = PlaneWin<W>::get(q1, 0, 0), wn = PlaneWin<W>::get(qn, 0, 0), wl = PlaneWin<W>::get(ql, 0, 0);
+        for (int a1 = 2; a1 >= 0; a1--) srna_find_eval<W>(st, w0, w1, wn, wl, A0, A1, alen, a1, 0, len, rma, rmm, rer);
+    }
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int kw = 0; kw < NW; kw++) {
+        if (32 * kw <= r_last) {
+            const int send = (r_last - 32 * kw) >= 31 ? 32 : (r_last - 32 * kw + 1);
+            for (int sft = kw == 0 ? 1 : 0; sft < send; sft++)
+                srna_find_eval<W>(st, PlaneWin<W>::get(q0, kw, sft), PlaneWin<W>::get(q1, kw, sft), PlaneWin<W>::get(qn, kw, sft),
+                                  PlaneWin<W>::get(ql, kw, sft), A0, A1, alen, 0, 32 * kw + sft, len, rma, rmm, rer);
+        }
+    }
+    return st.start;
+}
+// min_tot = smallest match count that satisfies one of the two rate tests (see srna_has_planes)
+template <typename W>
+SNK_HD bool srna_has_eval(W w0, W w1, W wn, W wl, W A0, W A1, int alen, int a1, int r1, int len, int rctg, int min_tot)
+{
+    const int l1 = alen - a1, l2 = len - r1;
+    const W wm = PlaneWin<W>::low(l1 < l2 ? l1 : l2);
+    const W neq = (w0 ^ (A0 >> a1)) | (w1 ^ (A1 >> a1)) | wn | wl;
+    const W eq = ~neq & wm;
+    const int tot = PlaneWin<W>::popc(eq), mis = PlaneWin<W>::popc(neq & wm);
+    return mis <= 4 && tot >= min_tot && (len < 12 || has_run_bits<W>(eq, rctg < 1 ? 1 : rctg));
+}
+template <int NW, typename W>
+SNK_HD bool srna_has_planes(const uint32_t* q0, const uint32_t* q1, const uint32_t* qn, const uint32_t* ql, int len,
+                            const AdapterDev& a, int rctg, float rar)
+{
+    const int alen = a.len;
+    if (alen == 0) return false;
+    // `1.0*totalMap/readLen >= adaRAr || 1.0*totalMap/adptLen >= adaRAr` (:911): with integers below 2^10 and a
+    // threshold that is a float, the rounded quotient compares like the exact one, and tot/len >= r is
+    // tot >= r*len with the product exact in double; so the test is tot >= ceil(r * min(len, alen)) for
+    // r > 0 (r <= 0: always true)
+    const int shorter = len < alen ? len : alen;
+    const double need = (double)rar * (double)shorter;
+    int min_tot = need <= 0.0 ? 0 : (int)need;
+    if ((double)min_tot < need) min_tot++;
+    const W A0 = PlaneWin<W>::ada(a.a0_lo, a.a0_hi), A1 = PlaneWin<W>::ada(a.a1_lo, a.a1_hi);
+    const int a_first = alen - rctg < 0 ? 0 : alen - rctg;
+    const int r_last = len - rctg < 0 ? 0 : len - rctg;
+    {
+        const W w0 = PlaneWin<W>::get(q0, 0, 0), w1 = PlaneWin<W>::get(q1, 0, 0), wn = PlaneWin<W>::get(qn, 0, 0), wl = PlaneWin<W>::get(ql, 0, 0);
+        for (int a1 = a_first; a1 >= 0; a1--)
+            if (srna_has_eval<W>(w0, w1, wn, wl, A0, A1, alen, a1, 0, len, rctg, min_tot)) return true;
+    }
+    bool found = false;
+#pragma unroll(NW <= 8 ? NW : 1)
+    for (int kw = 0; kw < NW; kw++) {
+        if (32 * kw <= r_last && !found) {
+            const int send = (r_last - 32 * kw) >= 31 ? 32 : (r_last - 32 * kw + 1);
+            for (int sft = kw == 0 ? 1 : 0; sft < send; sft++)
+                if (srna_has_eval<W>(PlaneWin<W>::get(q0, kw, sft), PlaneWin<W>::get(q1, kw, sft), PlaneWin<W>::get(qn, kw, sft),
+                                     PlaneWin<W>::get(ql, kw, sft), A0, A1, alen, 0, 32 * kw + sft, len, rctg, min_tot)) { found = true; break; }
+        }
+    }
+    return found;
+}
+
 // stage 4: end scans of fastq_trim (read_filter.cpp:390-429, 454-461): thread 0 scans the head,
 // thread kNT-1 the tail and the polyG run. The scans go a word (4 bytes) at a time: `nm` flags (bit 7
 // of a byte lane) mark the bytes that END a run; most reads leave after one word.
@@ -739,6 +857,24 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
     R.flags = flags;
 }
 
+// filtersRNA aligner dispatch: which = 1 -> sRNA_findAdapter with the 3' adapter (ada[1][0]), returns the
+// position or -1; which = 0 -> sRNA_hasAdapter with the 5' adapter (ada[0][0]), returns 0/1. Plane
+// versions for `fast` adapters, the byte loops otherwise.
+template <int NW>
+SNK_HD int srna_find(const uint8_t* seq, const uint32_t* q0, const uint32_t* q1, const uint32_t* qn, const uint32_t* ql, int len,
+                     const DevParams& P, int which)
+{
+    const AdapterDev& a = P.ada[which][0];
+    const int alen = P.n_adapters[which] > 0 ? a.len : 0;
+    if (alen == 0) return which ? -1 : 0;
+    if (!a.fast) return which ? srna_find_adapter(seq, len, a.seq, alen, P.ada_rma, P.ada_rmm, P.ada_rer)
+                              : (int)srna_has_adapter(seq, len, a.seq, alen, P.ada_rctg, P.ada_rar);
+    if (alen <= 32) return which ? srna_find_planes<NW, uint32_t>(q0, q1, qn, ql, len, a, P.ada_rma, P.ada_rmm, P.ada_rer)
+                                 : (int)srna_has_planes<NW, uint32_t>(q0, q1, qn, ql, len, a, P.ada_rctg, P.ada_rar);
+    return which ? srna_find_planes<NW, uint64_t>(q0, q1, qn, ql, len, a, P.ada_rma, P.ada_rmm, P.ada_rer)
+                 : (int)srna_has_planes<NW, uint64_t>(q0, q1, qn, ql, len, a, P.ada_rctg, P.ada_rar);
+}
+
 // Exchange policy for the CPU replay / documentation of the protocol: given a callable that returns
 // thread h's part, run all kNT parts and merge them. The kernel does the same with lane shuffles.
 template <int MAXC>
@@ -752,8 +888,10 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
     int ada_pos = -1;
     bool has5 = false;
     if (P.srna) {
-        ada_pos = srna_find_adapter(seq, len, P.ada[1][0].seq, P.n_adapters[1] > 0 ? P.ada[1][0].len : 0, P.ada_rma, P.ada_rmm, P.ada_rer);
-        has5 = srna_has_adapter(seq, len, P.ada[0][0].seq, P.n_adapters[0] > 0 ? P.ada[0][0].len : 0, P.ada_rctg, P.ada_rar);
+        uint32_t q0[NW + 2], q1[NW + 2], qn[NW + 2], ql[NW + 2];
+        for (int k = 0; k < NW + 2; k++) { q0[k] = k < NW ? S.p0[k] : 0; q1[k] = k < NW ? S.p1[k] : 0; qn[k] = k < NW ? S.pn[k] : 0; ql[k] = k < NW ? S.pl[k] : 0; }
+        ada_pos = srna_find<NW>(seq, q0, q1, qn, ql, len, P, 1);
+        has5 = srna_find<NW>(seq, q0, q1, qn, ql, len, P, 0) != 0;
     } else if (P.n_adapters[mate] > 0) {
         uint32_t p0[NW + 2], p1[NW + 2], pb[NW + 2];
         for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }

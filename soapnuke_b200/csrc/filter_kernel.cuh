@@ -158,8 +158,10 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     bool has5 = false;
     if (P.srna) {
         // filtersRNA: the group's first lane aligns the 3' adapter, the second the 5' adapter
-        int v = (h == 0) ? srna_find_adapter(seq, len, P.ada[1][0].seq, P.n_adapters[1] > 0 ? P.ada[1][0].len : 0, P.ada_rma, P.ada_rmm, P.ada_rer)
-                         : (int)srna_has_adapter(seq, len, P.ada[0][0].seq, P.n_adapters[0] > 0 ? P.ada[0][0].len : 0, P.ada_rctg, P.ada_rar);
+        uint32_t q0[NW + 2], q1[NW + 2], qn[NW + 2], ql[NW + 2];
+#pragma unroll
+        for (int k = 0; k < NW + 2; k++) { q0[k] = k < NW ? S.p0[k] : 0u; q1[k] = k < NW ? S.p1[k] : 0u; qn[k] = k < NW ? S.pn[k] : 0u; ql[k] = k < NW ? S.pl[k] : 0u; }
+        const int v = srna_find<NW>(seq, q0, q1, qn, ql, len, P, h == 0 ? 1 : 0);
         const int o = __shfl_xor_sync(pm, v, 1);
         ada_pos = (h == 0) ? v : o;
         has5 = ((h == 0) ? o : v) != 0;

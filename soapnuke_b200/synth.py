@@ -121,6 +121,9 @@ def gen_srna(n, L=50, seed=1004, adapter5=SRNA_ADAPTER5, adapter3=SRNA_ADAPTER3,
             seq[i, rng.integers(0, L, size=3)] = ord("N")
         if 0.32 <= u[i] < 0.36:
             seq[i, k - min(k, 12):k] = ord("G")                 # G-rich insert end (polyG after the adapter cut)
+        if 0.36 <= u[i] < 0.40:
+            j = int(rng.integers(0, L))
+            seq[i, j] = seq[i, j] | 0x20                        # a lowercase base (never equals an uppercase adapter base)
     length = np.full(n, L, dtype=np.uint16)
     if var_len:
         length = rng.integers(max(8, L // 3), L + 1, size=n).astype(np.uint16)

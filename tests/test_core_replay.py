@@ -46,6 +46,22 @@ SRNA_CONFIGS = [
 ]
 
 
+def test_filtersRNA_other_adapter_shapes():
+    """Adapters with an N or longer than 64 bases cannot use the bit-plane aligners (byte loops);
+    adapters of 33..64 bases use the 64-bit windows."""
+    d = synth.gen_srna(6000, L=50, seed=77, var_len=True)
+    a5 = synth.SRNA_ADAPTER5[:10] + b"N" + synth.SRNA_ADAPTER5[11:]
+    a3 = synth.SRNA_ADAPTER3[:14] + b"N" + synth.SRNA_ADAPTER3[15:]
+    for ada5, ada3 in ((a5, a3), (synth.SRNA_ADAPTER5 * 3, synth.SRNA_ADAPTER3),
+                       (synth.SRNA_ADAPTER5[:6] + synth.SRNA_ADAPTER5 + synth.SRNA_ADAPTER5[:14], synth.SRNA_ADAPTER3 + synth.SRNA_ADAPTER3)):
+        p = abi.make_params(is_pe=False, srna=True, adapter1=ada5, adapter2=ada3, ada_trim=True, min_read_length=18, max_read_length=49)
+        o1, _, ost, oerr = oracle_run(p, d)
+        c1, _, cst, cerr = core_replay(p, d)
+        assert oerr == cerr == 0
+        assert (o1["category"] == 0).sum() > 500
+        assert_same((c1, None, cst), (o1, None, ost), "srna byte path")
+
+
 @pytest.mark.parametrize("cfg", SRNA_CONFIGS, ids=[c[0] for c in SRNA_CONFIGS])
 def test_core_replay_matches_oracle_filtersRNA(cfg):
     """filtersRNA: sRNA_findAdapter / sRNA_hasAdapter, the cut at the 3' adapter and sRNA_discard."""
