@@ -1185,14 +1185,19 @@ SNK_HD uint32_t qual_update_checked(const uint8_t* qual, int off, int w, int lo,
 // (and the delta entries k = r0, r0+rstep, ...). With two units per item every thread of a CTA
 // sized for phase A (two threads per read) has phase-B work.
 template <typename CounterT, int J, int JN>
-SNK_HD void unit_q_fast(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w, int j0,
-                        uint8_t* qcells, int cell0_raw, int cell0_del, int jstep, int bstep)
+SNK_HD void unit_q_raw(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, int w, int j0, uint8_t* qcells, int cell0_raw, int jstep, int bstep)
 {
     const uint8_t* pq = rows_q + J * w;
     const uint32_t sh = 8u * (uint32_t)j0;
-    const int c_raw = cell0_raw + j0 * jstep, c_del = cell0_del + j0 * jstep;
+    const int c_raw = cell0_raw + j0 * jstep;
     for (uint32_t r = 0; r < cnt; r++)
         qual_update_all<CounterT, JN>(load4(pq + (size_t)r * stride) >> sh, qcells, c_raw, jstep, bstep);
+}
+template <typename CounterT, int J, int JN>
+SNK_HD void unit_q_delta(const uint8_t* rows_q, const DeltaEnt* dl, uint32_t nd, int w, int j0, uint8_t* qcells, int cell0_del, int jstep, int bstep)
+{
+    const uint32_t sh = 8u * (uint32_t)j0;
+    const int c_del = cell0_del + j0 * jstep;
     const int first = J * w + j0;
     for (uint32_t k = 0; k < nd; k++) {
         const DeltaEnt d = dl[k];
@@ -1226,8 +1231,7 @@ SNK_HD void unit_b_delta(const uint8_t* rows_s, const DeltaEnt* dl, uint32_t nd,
     base_acc_spill<J>(acc, bc.del);
 }
 template <int J>
-SNK_HD void unit_b_fast(const uint8_t* rows_s, uint32_t stride, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w, uint32_t r0,
-                        uint32_t rstep, BaseCnt<J>& bc)
+SNK_HD void unit_b_raw(const uint8_t* rows_s, uint32_t stride, uint32_t cnt, int w, uint32_t r0, uint32_t rstep, BaseCnt<J>& bc)
 {
     BaseAcc acc = {0, 0, 0, 0, 0};
     const uint8_t* ps = rows_s + J * w;
@@ -1241,7 +1245,6 @@ SNK_HD void unit_b_fast(const uint8_t* rows_s, uint32_t stride, uint32_t cnt, co
         }
     }
     base_acc_spill<J>(acc, bc.raw);
-    unit_b_delta<J>(rows_s, dl, nd, w, r0, rstep, bc);
 }
 // Checked variants (some record of the tile has qualities outside the shared-memory bins, or a row was
 // not scanned): explicit record lengths from the raw descriptors, out-of-bin qualities straight to

@@ -3,9 +3,9 @@
 // One persistent CTA per SM walks a contiguous range of tiles. A tile is up to R reads (SE) or R
 // pairs (PE) of the fixed-stride SoA batch, staged into shared memory, then:
 //   phase A  one thread per read: counters, predicates, adapter search, trim   (scan_read)
-//   phase P  one thread per pair: discard cascade, result record, counters     (decide_pair/se)
-//   phase B  one thread per (table, 4 positions): per-position base x quality histograms for the
-//            raw and the clean records of the tile, owner-computes (no atomics) in shared memory
+//   phase P  one thread per read: discard cascade, result record, counters, delta list  (decide_pair/se)
+//   phase B  work units per (table, 4 positions): per-position base x quality histograms, owner-computes
+//            (no atomics) in shared memory: raw records counted directly, clean = raw - delta entries
 // Histograms stay in shared memory across tiles and are added to the slot's global tables with
 // 64-bit atomics only when the CTA's slot changes and at kernel end.
 #pragma once
@@ -409,51 +409,55 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         }
         __syncthreads();
 
-        // ---- phase P: one thread per pair / read
-        for (uint32_t r = tid; r < align_up(cnt, 32); r += blockDim.x) {
-            const bool live = r < cnt;
-            int cat = SNK_DROP_EMPTY, mask = 0, fsb = -1;
-            ReadInfo a, b;
-            DeltaEnt de[2][2];
-            int nde[2] = {0, 0};
-            const uint64_t gi = g0 + r;
-            if (live) {
-                a = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[0])[r];
-                if (MATES == 2) {
-                    b = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[1])[r];
-                    cat = decide_pair(P, a, b, &mask, &fsb);
+        // ---- phase P: one thread per read (pair r, mate m on adjacent lanes): discard cascade (both lanes of a
+        // pair evaluate it), result record, counters, trim-position tables, raw descriptor, delta entries.
+        // Wide CTAs run it on the b-unit warps only: the q-unit warps go straight on to the raw histogram
+        // walk, which does not depend on anything phase P produces.
+        const uint32_t p_first = wide ? (b_first & ~31u) : 0u;       // whole warps (the ballots below use full masks)
+        if ((uint32_t)tid >= p_first) {
+            const unsigned par_mask = MATES == 2 ? 0x55555555u : 0xFFFFFFFFu;         // lanes of mate 0
+            for (uint32_t i = (uint32_t)tid - p_first; i < align_up(cnt * MATES, 32); i += blockDim.x - p_first) {
+                const uint32_t r = i / MATES;
+                const int m = (int)(i % MATES);
+                const bool live = r < cnt;
+                int cat = SNK_DROP_EMPTY, mask = 0, fsb = -1;
+                ReadInfo x;
+                x.len = 0; x.clean_len = 0;
+                DeltaEnt de[2];
+                int nde = 0;
+                const uint64_t gi = g0 + r;
+                if (live) {
+                    const ReadInfo a = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[0])[r];
                     uint32_t err = 0;
-                    if ((a.flags | b.flags) & RF_BAD_BASE) err |= ERR_BAD_BASE;
-                    if ((a.flags | b.flags) & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
-                    if (cat == SNK_DROP_LOWQ && ((a.flags | b.flags) & RF_LOWQ_GT1)) err |= ERR_LOWQ_RATIO;
-                    if (err) report_error(A, err, gi);
-                } else {
-                    cat = P.srna ? decide_srna(P, a, &fsb) : decide_se(P, a, &fsb);
-                    mask = cat ? 1 : 0;
-                    uint32_t err = 0;
-                    if (a.flags & RF_BAD_BASE) err |= ERR_BAD_BASE;
-                    if (a.flags & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
-                    if (err) report_error(A, err, gi);
-                }
-                const uint32_t row0 = r * A.stride;
-                desc[0 * A.R + r] = hist_desc(a.len, row0, a.flags & RF_QSLOW);
-                nde[0] = delta_entries(a, cat == SNK_KEEP, row0, de[0]);
-                if (MATES == 2) {
-                    desc[1 * A.R + r] = hist_desc(b.len, row0, b.flags & RF_QSLOW);
-                    nde[1] = delta_entries(b, cat == SNK_KEEP, row0, de[1]);
-                }
-                unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
-                if (fsb >= 0) {
-                    atomicAdd(&S[fsb], 1ull);
                     if (MATES == 2) {
-                        if (mask & 1) atomicAdd(&S[fsb + 1], 1ull);
-                        if (mask & 2) atomicAdd(&S[fsb + 2], 1ull);
-                        if (mask == 3) atomicAdd(&S[fsb + 3], 1ull);
+                        const ReadInfo b = reinterpret_cast<const ReadInfo*>(smem + sp.off_info[1])[r];
+                        cat = decide_pair(P, a, b, &mask, &fsb);
+                        if ((a.flags | b.flags) & RF_BAD_BASE) err |= ERR_BAD_BASE;
+                        if ((a.flags | b.flags) & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
+                        if (cat == SNK_DROP_LOWQ && ((a.flags | b.flags) & RF_LOWQ_GT1)) err |= ERR_LOWQ_RATIO;
+                        x = m ? b : a;
+                    } else {
+                        cat = P.srna ? decide_srna(P, a, &fsb) : decide_se(P, a, &fsb);
+                        mask = cat ? 1 : 0;
+                        if (a.flags & RF_BAD_BASE) err |= ERR_BAD_BASE;
+                        if (a.flags & RF_BAD_QUAL) err |= ERR_BAD_QUAL;
+                        x = a;
                     }
-                }
-#pragma unroll
-                for (int m = 0; m < MATES; m++) {
-                    const ReadInfo& x = m ? b : a;
+                    unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
+                    if (m == 0) {                                   // once per pair
+                        if (err) report_error(A, err, gi);
+                        if (fsb >= 0) {
+                            atomicAdd(&S[fsb], 1ull);
+                            if (MATES == 2) {
+                                if (mask & 1) atomicAdd(&S[fsb + 1], 1ull);
+                                if (mask & 2) atomicAdd(&S[fsb + 2], 1ull);
+                                if (mask == 3) atomicAdd(&S[fsb + 3], 1ull);
+                            }
+                        }
+                    }
+                    const uint32_t row0 = r * A.stride;
+                    desc[(size_t)m * A.R + r] = hist_desc(x.len, row0, x.flags & RF_QSLOW);
+                    nde = delta_entries(x, cat == SNK_KEEP, row0, de);
                     // snk_read_result packed into one 8-byte store (little endian field order)
                     const unsigned long long packed = (unsigned long long)(uint16_t)x.head_cut |
                         ((unsigned long long)(uint16_t)x.clean_len << 16) | ((unsigned long long)(uint8_t)cat << 32) |
@@ -475,59 +479,55 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                         if (tf >= 0) atomicAdd(&T[tf], 1ull);
                     }
                 }
-            }
-            // append this warp's delta entries to the tile's lists: one shared atomic per warp and mate
-            const unsigned lt = (1u << lane) - 1u;
-#pragma unroll
-            for (int m = 0; m < MATES; m++) {
-                const unsigned b1 = __ballot_sync(0xFFFFFFFFu, nde[m] >= 1), b2 = __ballot_sync(0xFFFFFFFFu, nde[m] >= 2);
-                if (b1) {
-                    uint32_t base = 0;
-                    if (lane == 0) base = atomicAdd(&ndelta[m], (uint32_t)(__popc(b1) + __popc(b2)));
-                    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                // per-mate warp aggregation: the lanes of mate m are those with lane % MATES == m
+                const unsigned mine = par_mask << m;
+                const unsigned lt = ((1u << lane) - 1u) & mine;
+                // append the delta entries to the tile's lists: one shared atomic per warp and mate
+                const unsigned b1 = __ballot_sync(0xFFFFFFFFu, nde >= 1) & mine, b2 = __ballot_sync(0xFFFFFFFFu, nde >= 2) & mine;
+                uint32_t base = 0;
+                if (lane == m && b1) base = atomicAdd(&ndelta[m], (uint32_t)(__popc(b1) + __popc(b2)));
+                base = __shfl_sync(0xFFFFFFFFu, base, m);
+                if (nde >= 1) {
                     DeltaEnt* dl = dlist + (size_t)m * 2u * A.R + base + __popc(b1 & lt) + __popc(b2 & lt);
-                    if (nde[m] >= 1) dl[0] = de[m][0];
-                    if (nde[m] >= 2) dl[1] = de[m][1];
+                    dl[0] = de[0];
+                    if (nde >= 2) dl[1] = de[1];
                 }
-            }
-            // last record keys + record counts, one shared atomic per warp and table
-            const unsigned kept = __ballot_sync(0xFFFFFFFFu, live && cat == SNK_KEEP);
-            const unsigned lanes = __ballot_sync(0xFFFFFFFFu, live);
-            if (lanes && lane == 31 - __clz(lanes)) {      // last live read of this warp's group
-                atomicMax(&lastkey[0], ((gi + 1) << 16) | (unsigned long long)(uint16_t)a.len);
-                atomicAdd(&lastkey[4 + 0], (unsigned long long)__popc(lanes));
-                if (MATES == 2) {
-                    atomicMax(&lastkey[1], ((gi + 1) << 16) | (unsigned long long)(uint16_t)b.len);
-                    atomicAdd(&lastkey[4 + 1], (unsigned long long)__popc(lanes));
+                // last record keys + record counts, one shared atomic per warp and table
+                const unsigned lanes_live = __ballot_sync(0xFFFFFFFFu, live) & mine;
+                const unsigned kept = __ballot_sync(0xFFFFFFFFu, live && cat == SNK_KEEP) & mine;
+                if (lanes_live && lane == 31 - __clz(lanes_live)) {      // last live read of this mate in the warp
+                    atomicMax(&lastkey[m], ((gi + 1) << 16) | (unsigned long long)(uint16_t)x.len);
+                    atomicAdd(&lastkey[4 + m], (unsigned long long)__popc(lanes_live));
                 }
-            }
-            if (kept && lane == 31 - __clz(kept)) {
-                atomicMax(&lastkey[MATES], ((gi + 1) << 16) | (unsigned long long)(uint16_t)a.clean_len);
-                atomicAdd(&lastkey[4 + MATES], (unsigned long long)__popc(kept));
-                if (MATES == 2) {
-                    atomicMax(&lastkey[MATES + 1], ((gi + 1) << 16) | (unsigned long long)(uint16_t)b.clean_len);
-                    atomicAdd(&lastkey[4 + MATES + 1], (unsigned long long)__popc(kept));
+                if (kept && lane == 31 - __clz(kept)) {
+                    atomicMax(&lastkey[MATES + m], ((gi + 1) << 16) | (unsigned long long)(uint16_t)x.clean_len);
+                    atomicAdd(&lastkey[4 + MATES + m], (unsigned long long)__popc(kept));
                 }
             }
         }
-        __syncthreads();
 
         // ---- phase B: per-position histograms, owner computes. Raw items walk every (padded) row of the
-        // tile; delta items walk the tile's short list of removed / added record parts.
+        // tile (no dependency on phase P); after a barrier the delta items walk the tile's short list of
+        // removed / added record parts.
+        const uint8_t* rows_s = smem + sp.off_rows[my_m][0];
+        const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
+        const bool slow_tile = *tile_slow != 0u;           // written in phase A, CTA-uniform here
+        if (!slow_tile) {
+            if (q_role) {
+                if (wide) unit_q_raw<QCounter, J, J / 2>(rows_q, A.stride, cnt, (int)my_w, (int)half * (J / 2), reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
+                else unit_q_raw<QCounter, J, J>(rows_q, A.stride, cnt, (int)my_w, 0, reinterpret_cast<uint8_t*>(qhist), q_cell0, q_jstep, q_bstep);
+            }
+            if (b_role) unit_b_raw<J>(rows_s, A.stride, cnt, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
+        }
+        __syncthreads();                                    // phase P done: descriptors and delta lists are complete
         if (my_item) {
-            const uint8_t* rows_s = smem + sp.off_rows[my_m][0];
-            const uint8_t* rows_q = smem + sp.off_rows[my_m][1];
             const uint32_t nd = ndelta[my_m];
-            if (*tile_slow == 0u) {
+            if (!slow_tile) {
                 if (q_role) {
-                    if (wide)
-                        unit_q_fast<QCounter, J, J / 2>(rows_q, A.stride, cnt, my_dlist, nd, (int)my_w, (int)half * (J / 2),
-                                                        reinterpret_cast<uint8_t*>(qhist), q_cell0, q_cell0_del, q_jstep, q_bstep);
-                    else
-                        unit_q_fast<QCounter, J, J>(rows_q, A.stride, cnt, my_dlist, nd, (int)my_w, 0, reinterpret_cast<uint8_t*>(qhist),
-                                                    q_cell0, q_cell0_del, q_jstep, q_bstep);
+                    if (wide) unit_q_delta<QCounter, J, J / 2>(rows_q, my_dlist, nd, (int)my_w, (int)half * (J / 2), reinterpret_cast<uint8_t*>(qhist), q_cell0_del, q_jstep, q_bstep);
+                    else unit_q_delta<QCounter, J, J>(rows_q, my_dlist, nd, (int)my_w, 0, reinterpret_cast<uint8_t*>(qhist), q_cell0_del, q_jstep, q_bstep);
                 }
-                if (b_role) unit_b_fast<J>(rows_s, A.stride, cnt, my_dlist, nd, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
+                if (b_role) unit_b_delta<J>(rows_s, my_dlist, nd, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
             } else {
                 unsigned long long* slot_base = A.stats + (size_t)slot * SNK_SLOT_WORDS;
                 unsigned long long* f_raw = slot_base + SNK_SLOT_FILE_OFF(file_of_tab(MATES, my_m));
@@ -543,7 +543,6 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         __syncthreads();
     }
 }
-
 
 #endif // __CUDACC__
 

@@ -203,9 +203,15 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                 const DeltaEnt* dl = dlist[m].data();
                 const uint32_t nd = (uint32_t)dlist[m].size();
                 if (!tile_slow) {
-                    if (wide) unit_q_fast<QCounter, J, J / 2>(rq, c.stride, cnt, dl, nd, (int)w, (int)half * (J / 2), (uint8_t*)c.qhist.data(), q_cell0, q_cell0_del, q_jstep, q_bstep);
-                    else unit_q_fast<QCounter, J, J>(rq, c.stride, cnt, dl, nd, (int)w, 0, (uint8_t*)c.qhist.data(), q_cell0, q_cell0_del, q_jstep, q_bstep);
-                    unit_b_fast<J>(rs, c.stride, cnt, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
+                    if (wide) {
+                        unit_q_raw<QCounter, J, J / 2>(rq, c.stride, cnt, (int)w, (int)half * (J / 2), (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
+                        unit_q_delta<QCounter, J, J / 2>(rq, dl, nd, (int)w, (int)half * (J / 2), (uint8_t*)c.qhist.data(), q_cell0_del, q_jstep, q_bstep);
+                    } else {
+                        unit_q_raw<QCounter, J, J>(rq, c.stride, cnt, (int)w, 0, (uint8_t*)c.qhist.data(), q_cell0, q_jstep, q_bstep);
+                        unit_q_delta<QCounter, J, J>(rq, dl, nd, (int)w, 0, (uint8_t*)c.qhist.data(), q_cell0_del, q_jstep, q_bstep);
+                    }
+                    unit_b_raw<J>(rs, c.stride, cnt, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
+                    unit_b_delta<J>(rs, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
                 } else {
                     c.err |= unit_q_checked<QCounter, J>(rq, rawdesc[m].data(), cnt, dl, nd, (int)w, wide ? (int)half * (J / 2) : 0, wide ? J / 2 : J,
                                                          c.P.phred, c.P.qb, c.qhist.data() + x, nraw, (int)c.X, f_raw, f_clean);
