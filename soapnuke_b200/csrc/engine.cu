@@ -127,15 +127,20 @@ int make_plan(snk_engine* e, int mates, uint32_t stride, uint32_t n, uint64_t fi
     // Largest tile (<= one read per kNT threads) whose shared-memory plan fits; if even a small tile does
     // not fit, keep fewer quality bins in shared memory (the rest go through the checked global path).
     uint32_t R = 0;
-    for (;;) {
+    // two CTAs per SM hide each other's phase barriers and staging waits: accept a tile up to a quarter
+    // smaller than the largest one if that is what it takes to fit twice (228 KB per SM, 1 KB reserved per CTA)
+    constexpr size_t kSmemTwoPerSm = (228 * 1024) / 2 - 1024;
+    for (uint32_t r = maxR; r >= 8 && 4 * r >= 3 * maxR && !R; r -= (r > 16 ? 8 : 4))
+        if (plan_smem(mates, r, stride, lp.X, qb, ada_slots(e->dev.n_adapters)).total <= kSmemTwoPerSm) R = r;
+    for (; !R;) {
         for (uint32_t r = maxR; r >= 8 && !R; r -= (r > 16 ? 8 : 4))
-            if (plan_smem(mates, r, stride, lp.X, qb).total <= kSmemLimit) R = r;
+            if (plan_smem(mates, r, stride, lp.X, qb, ada_slots(e->dev.n_adapters)).total <= kSmemLimit) R = r;
         if (R) break;
         if (qb <= 0) { snk::set_error("read stride too large for the shared-memory tile"); return 1; }
         qb = qb > 4 ? qb - 4 : 0;
     }
     lp.R = R; lp.qb = qb;
-    lp.smem = plan_smem(mates, R, stride, lp.X, qb).total;
+    lp.smem = plan_smem(mates, R, stride, lp.X, qb, ada_slots(e->dev.n_adapters)).total;
     tm = make_tile_map(first, n, R, (uint64_t)e->params.slot_block);
     lp.ntiles = tm.ntiles;
     lp.grid = 0;       // resolved in launch_one from the kernel's real occupancy

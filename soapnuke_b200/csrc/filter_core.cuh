@@ -152,6 +152,26 @@ struct AdapterDev {
     uint8_t  seq[SNK_MAX_ADAPTER_LEN];
 };
 
+// The fields of a `fast` adapter the bit-plane sweep reads, compact enough to keep one per mate in shared
+// memory. Budgets are clamped to [-1, 64]: any negative budget behaves like -1 and, windows being at most
+// 64 bases, any budget above 64 like 64.
+struct AdaHot {
+    int32_t  len, seg_thr, budget2, edge;
+    uint32_t pre_mask, a0_lo, a0_hi, a1_lo, a1_hi;
+    int32_t  budget1[5];
+    int32_t  fast, pad_;
+    int8_t   budget3[64];
+};
+SNK_HD int8_t clamp_budget(int32_t b) { return (int8_t)(b < 0 ? -1 : (b > 64 ? 64 : b)); }
+SNK_HD void make_ada_hot(const AdapterDev& a, AdaHot& h)
+{
+    h.len = a.len; h.seg_thr = a.seg_thr; h.budget2 = a.budget2; h.edge = a.edge;
+    h.pre_mask = a.pre_mask; h.a0_lo = a.a0_lo; h.a0_hi = a.a0_hi; h.a1_lo = a.a1_lo; h.a1_hi = a.a1_hi;
+    for (int i = 0; i < 5; i++) h.budget1[i] = a.budget1[i];
+    h.fast = a.fast; h.pad_ = 0;
+    for (int i = 0; i < 64; i++) h.budget3[i] = clamp_budget(a.budget3[i]);
+}
+
 struct DevParams {
     int32_t is_pe;
     int32_t phred;
@@ -439,8 +459,8 @@ SNK_HD void merge_ada(AdaPart& a, const AdaPart& b)
 }
 SNK_HD int ada_result(const AdaPart& a) { return a.hit1 ? 0 : (a.pos2 >= 0 ? a.pos2 : a.pos3); }
 
-template <int NW>
-SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const AdapterDev& a, int h, AdaPart& out)
+template <int NW, class ADA /* AdapterDev or AdaHot */>
+SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const uint32_t* pb, const ADA& a, int h, AdaPart& out)
 {
     // The lanes of a group take the window offsets with offset % kNT == h (phase 1: r1 % kNT), so
     // they run the same instruction stream.

@@ -56,7 +56,7 @@ struct KernelArgs {
     TileMap tm;
 };
 
-// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][desc][delta][qhist][misc]
+// shared memory layout (dynamic): [tile seq/qual rows][len][ReadInfo][desc][delta][qhist][adapters][misc]
 struct SmemPlan {
     uint32_t off_rows[2][2];   // [mate][0 seq, 1 qual]
     uint32_t off_len[2];
@@ -64,12 +64,14 @@ struct SmemPlan {
     uint32_t off_desc;         // hist_desc words of the raw records: [m0][m1], R each (checked path only)
     uint32_t off_delta;        // DeltaEnt lists: [m0][m1], 2R entries each
     uint32_t off_qhist;        // (qb + 1) * J rows of X cells; row group qb is the padding dump bin
+    uint32_t off_ada;          // AdaHot[ada_slots]: the sweep constants of every adapter, mate 0's first, built at kernel start
     uint32_t off_misc;
     uint32_t total;
 };
 // misc: lastkey[8] + gsum[4][8] + the staging mbarrier (8) + ndelta[2] + tile_slow + pad
 constexpr uint32_t kMiscBytes = 8 * 8 + 4 * 8 * 8 + 8 + 2 * 4 + 4 + 12;
-__host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb)
+// nada = adapters staged in shared memory (see ada_slots)
+__host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t stride, uint32_t X, int qb, uint32_t nada)
 {
     SmemPlan p;
     uint32_t o = 0;
@@ -83,10 +85,15 @@ __host__ __device__ inline SmemPlan plan_smem(int mates, uint32_t R, uint32_t st
     p.off_desc = o; o += align_up((uint32_t)mates * R * 4u, 16);
     p.off_delta = o; o += align_up((uint32_t)mates * 2u * R * (uint32_t)sizeof(DeltaEnt), 16);
     p.off_qhist = o; o += align_up((uint32_t)(qb + 1) * (uint32_t)hist_j(stride) * X * (uint32_t)sizeof(QCounter), 16);
+    p.off_ada = o; o += align_up(nada * (uint32_t)sizeof(AdaHot), 16);
     p.off_misc = o; o += kMiscBytes;
     p.total = o;
     return p;
 }
+
+// adapters of mate 0 occupy AdaHot slots [0, max(1,n0)), those of mate 1 follow
+__host__ __device__ inline uint32_t ada_first_slot(const int32_t* n_adapters, int mate) { return mate ? (uint32_t)(n_adapters[0] > 1 ? n_adapters[0] : 1) : 0u; }
+__host__ __device__ inline uint32_t ada_slots(const int32_t* n_adapters) { return ada_first_slot(n_adapters, 1) + (uint32_t)(n_adapters[1] > 1 ? n_adapters[1] : 1); }
 
 #ifdef __CUDACC__
 
@@ -144,8 +151,10 @@ __device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s
 
 // phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
 template <int MAXC>
+// ada0 = shared-memory AdaHot array of the mate's adapters (the compiler re-derives the parameter-space
+// address of a dynamically indexed adapter at every use; a shared copy costs one pointer register)
 __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P,
-                                               int h, unsigned pm, ReadInfo& R)
+                                               const AdaHot* ada0, int h, unsigned pm, ReadInfo& R)
 {
     static_assert(kNT == 2, "lane exchange below is written for pairs");
     constexpr int NW = (MAXC + 1) / 2;
@@ -171,7 +180,7 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
         for (int k = 0; k < NW; k++) { p0[k] = S.p0[k]; p1[k] = S.p1[k]; pb[k] = S.pn[k] | S.pl[k] | ~plane_valid(len, k); }
         p0[NW] = p0[NW + 1] = 0; p1[NW] = p1[NW + 1] = 0; pb[NW] = pb[NW + 1] = 0xFFFFFFFFu;
         for (int i = 0; i < P.n_adapters[mate]; i++) {
-            const AdapterDev& a = P.ada[mate][i];
+            const AdaHot& a = ada0[i];
             if (a.len == 0) continue;
             if (a.fast && len >= a.len - 1) {
                 AdaPart ap, op;
@@ -180,9 +189,9 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
                 merge_ada(ap, op);
                 ada_pos = ada_result(ap);
             } else {
-                int pos = (h == 0) ? adapter_pos_bytes(seq, len, a) : -1;
-                const int other = __shfl_xor_sync(pm, pos, 1);
-                ada_pos = (h == 0) ? pos : other;
+                int pos = (h == 0) ? adapter_pos_bytes(seq, len, P.ada[mate][i]) : -1;
+                const int other_pos = __shfl_xor_sync(pm, pos, 1);
+                ada_pos = (h == 0) ? pos : other_pos;
             }
             if (ada_pos >= 0) break;
         }
@@ -293,7 +302,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
 {
     extern __shared__ __align__(16) uint8_t smem[];
     if (A.skip_word && (*A.skip_word & A.skip_mask)) return;
-    const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb);
+    const SmemPlan sp = plan_smem(MATES, A.R, A.stride, A.X, P.qb, ada_slots(P.n_adapters));
     QCounter* qhist = reinterpret_cast<QCounter*>(smem + sp.off_qhist);
     uint32_t* desc = reinterpret_cast<uint32_t*>(smem + sp.off_desc);
     DeltaEnt* dlist = reinterpret_cast<DeltaEnt*>(smem + sp.off_delta);
@@ -311,6 +320,10 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     BaseCnt<J> bc;
     base_cnt_reset<J>(bc);
     __syncthreads();
+    for (uint32_t e = tid; e < ada_slots(P.n_adapters); e += blockDim.x) {
+        const int m = e >= ada_first_slot(P.n_adapters, 1) ? 1 : 0;
+        make_ada_hot(P.ada[m][e - ada_first_slot(P.n_adapters, m)], reinterpret_cast<AdaHot*>(smem + sp.off_ada)[e]);
+    }
     if (tid == 0) {
         mbar_init(stage_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -400,7 +413,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 ri.flags = RF_BAD_BASE | RF_QSLOW;      // row left as staged: not safe for the unchecked histogram walk
             } else {
                 scan_read_coop<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
-                                     len, nchunks, m, P, h, pm, ri);
+                                     len, nchunks, m, P, reinterpret_cast<const AdaHot*>(smem + sp.off_ada) + ada_first_slot(P.n_adapters, m), h, pm, ri);
             }
             if (h == 0) {
                 info[r] = ri;
