@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNK_ABI_VERSION 2
+#define SNK_ABI_VERSION 3
 
 /* ---- limits (global_variable.h:9-11 READ_MAX_LEN / MAX_QUAL) ---- */
 #define SNK_MAX_READ_LEN   1000   /* READ_MAX_LEN: per-position tables have this many rows        */
@@ -42,6 +42,8 @@ extern "C" {
 #define SNK_MAX_ADAPTERS   8      /* adapters per mate (-f/-r list files), read_filter.cpp:177     */
 #define SNK_MAX_ADAPTER_LEN 128
 #define SNK_MAX_SLOTS      256    /* logical reference threads whose tables are kept apart         */
+#define SNK_MAX_ID_FILTERS 64     /* entries of the tile / fov removal lists                        */
+#define SNK_ID_FILTER_LEN  8      /* a tile is up to 4 digits, a fov 8 characters (C001R003)        */
 
 /* ---- parameters: the subset of C_global_parameter (global_parameter.h:20-190) the hot path reads ---- */
 typedef struct snk_params {
@@ -90,16 +92,31 @@ typedef struct snk_params {
     float   ada_rer;              /* gp.adaREr: max error rate mismatch/match for the 3' adapter (0.4) */
     int32_t ada_rmm;              /* gp.adaRMm: max mismatches for the 3' adapter (4) */
     int32_t reserved[2];
+    /* tile / fov removal lists (config keys `tile`, `fov`; check_tile_or_fov read_filter.cpp:14-79): a read
+     * is dropped when the tile (fov) parsed from its id (stat_read, read_filter.cpp:86-148) equals a list
+     * entry. IDs never cross the SoA boundary: callers of the SoA entry points mark such reads with
+     * SNK_PRE_TILE / SNK_PRE_FOV in len[]; the FASTQ text entry points parse the ids on the device with
+     * these lists. Entries are NUL padded. */
+    int32_t seq_type1;            /* gp.seq_type == "1": the tile follows the 4th ':' instead of the 2nd */
+    int32_t n_tile, n_fov;
+    char    tile[SNK_MAX_ID_FILTERS][SNK_ID_FILTER_LEN];
+    char    fov[SNK_MAX_ID_FILTERS][SNK_ID_FILTER_LEN];
 } snk_params;
 
 /* ---- one mate of a batch, fixed-stride SoA ---- */
 typedef struct snk_batch {
     const uint8_t*  seq;     /* [n][stride] bases, ASCII */
     const uint8_t*  qual;    /* [n][stride] qualities, ASCII */
-    const uint16_t* len;     /* [n] read lengths (1..stride) */
+    const uint16_t* len;     /* [n] read lengths (1..stride) in bits 0-13; bits 14/15 = SNK_PRE_TILE / SNK_PRE_FOV */
     uint32_t        n;       /* reads in this batch */
     uint32_t        stride;  /* bytes per row, multiple of 16, <= 1008 */
 } snk_batch;
+
+/* len[] flag bits: the read's id selected it for removal by the tile / fov lists (for a pair only mate 1's
+ * flags count, sequence.cpp:213-230) */
+#define SNK_LEN_MASK  0x3FFFu
+#define SNK_PRE_TILE  0x4000u
+#define SNK_PRE_FOV   0x8000u
 
 /* ---- per-read result record (8 bytes) ---- */
 /* category codes, in pe_discard / se_discard priority order (sequence.cpp:198-387, 76-178) */
@@ -115,7 +132,9 @@ enum snk_category {
     SNK_DROP_ADAPTER = 8,        /* "Reads with adapter" */
     SNK_DROP_EMPTY = 9,          /* min_read_length==-1 and a mate was emptied (sequence.cpp:245-249), uncounted */
     SNK_DROP_NO3ADAPTER = 10,    /* filtersRNA: no 3' adapter found (sequence.cpp:36-39), counted but never reported */
-    SNK_DROP_INSERTNULL = 11     /* filtersRNA: 3' adapter within the first 3 bases (sequence.cpp:40-44), never reported */
+    SNK_DROP_INSERTNULL = 11,    /* filtersRNA: 3' adapter within the first 3 bases (sequence.cpp:40-44), never reported */
+    SNK_DROP_TILE = 12,          /* "Reads with filtered tile" (first test of pe_discard / se_discard) */
+    SNK_DROP_FOV = 13            /* "Reads with filtered fov" */
 };
 typedef struct snk_read_result {
     uint16_t head_cut;     /* bases removed from the 5' end of this mate */
@@ -138,6 +157,8 @@ enum snk_fs {
     SNK_FS_LONG, SNK_FS_LONG1, SNK_FS_LONG2, SNK_FS_LONG_OV,
     SNK_FS_NO3ADAPTER,           /* fs.no_3_adapter_num (filtersRNA) */
     SNK_FS_INSERTNULL,           /* fs.int_insertNull_num (filtersRNA) */
+    SNK_FS_TILE,                 /* fs.tile_num */
+    SNK_FS_FOV,                  /* fs.fov_num */
     SNK_FS_COUNT = 40
 };
 /* C_general_stat (global_variable.h:88-100), index into a file block's gs[] */

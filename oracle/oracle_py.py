@@ -29,6 +29,8 @@ def lib():
         L.orc_adapter_pos.restype = C.c_int
         L.orc_adapter_pos.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.c_int, C.c_float, C.c_int]
         L.orc_filter_pe.restype = C.c_int
+        L.orc_id_flags.restype = C.c_uint32
+        L.orc_id_flags.argtypes = [C.POINTER(abi.Params), C.c_char_p, C.c_int]
         L.orc_filter_pe.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Batch), C.POINTER(abi.Batch),
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32)]
         L.orc_filter_se.restype = C.c_int
@@ -40,6 +42,11 @@ def lib():
 
 def adapter_pos(read: bytes, adapter: bytes, ada_mis=2, ada_mr=0.5, ada_edge=6):
     return lib().orc_adapter_pos(read, len(read), adapter, len(adapter), ada_mis, ada_mr, ada_edge)
+
+
+def id_flags(params, ids):
+    """SNK_PRE_TILE / SNK_PRE_FOV bits (uint16 array) of the record ids (list of bytes), to be OR-ed into len[]."""
+    return np.array([lib().orc_id_flags(C.byref(params), i, len(i)) for i in ids], dtype=np.uint16)
 
 
 def new_stats(params):

@@ -13,6 +13,7 @@
  * It works on the same fixed-stride SoA batches and fills the same result/statistics layouts as the
  * engine (include/snk_engine.h supplies only those POD definitions).
  */
+#define _GNU_SOURCE
 #include <math.h>
 #include <limits.h>
 #include <string.h>
@@ -129,6 +130,47 @@ ORC_EXPORT int orc_srna_has_adapter(const uint8_t* read, int readLen, const uint
         if (a1 > 0) a1--; else r1++;
     }
     return 0;
+}
+
+/* stat_read's id parse (read_filter.cpp:86-148) + check_tile_or_fov (:14-79): SNK_PRE_TILE / SNK_PRE_FOV
+ * bits for one record id (idlen bytes, no terminator needed). The tile is the (up to) 4 digits behind the
+ * 2nd ':' (seqType 0) or the 4th ':' (seqType 1); the fov the 8 bytes from the first 'C' that has an 'R'
+ * four bytes later (and at least 9 bytes to the end of the id). A read is selected when that string equals
+ * an entry of the removal list (ranges with '-' never match anything in the reference). */
+ORC_EXPORT uint32_t orc_id_flags(const snk_params* p, const uint8_t* id, int idlen)
+{
+    uint32_t flags = 0;
+    if (p->n_tile > 0) {
+        int i = 0, num = 0;
+        const int want = p->seq_type1 ? 4 : 2;
+        for (; i < idlen; i++) {
+            if (id[i] == ':') num++;
+            if (num >= want) break;
+        }
+        char tile[5];
+        int tn = 0;
+        for (int j = 0; j != 4; j++) {
+            int k = i + j + 1;
+            int ch = k < idlen ? id[k] : 0;                      /* std::string: id[size()] is '\0', beyond is UB */
+            if (ch >= '0' && ch <= '9') tile[tn++] = (char)ch;
+        }
+        tile[tn] = 0;
+        for (int e = 0; e < p->n_tile; e++) {
+            int el = (int)strnlen(p->tile[e], SNK_ID_FILTER_LEN);
+            if (el == tn && memcmp(p->tile[e], tile, (size_t)tn) == 0) { flags |= SNK_PRE_TILE; break; }
+        }
+    }
+    if (p->n_fov > 0) {
+        int i = 0;
+        for (i = 0; i < idlen; i++)
+            if (id[i] == 'C' && i + 8 < idlen && id[i + 4] == 'R') break;
+        int fn = idlen - i; if (fn > 8) fn = 8; if (fn < 0) fn = 0;   /* substr(i, 8) */
+        for (int e = 0; e < p->n_fov; e++) {
+            int el = (int)strnlen(p->fov[e], SNK_ID_FILTER_LEN);
+            if (el == fn && memcmp(p->fov[e], id + i, (size_t)fn) == 0) { flags |= SNK_PRE_FOV; break; }
+        }
+    }
+    return flags;
 }
 
 /* everything stat_read / fastq_trim leave behind for one mate */
@@ -316,10 +358,13 @@ static void fs_dis(uint64_t* fs, int base, int a, int b)
 }
 
 /* sequence.cpp:198-387 pe_discard (contam/tile/fov/dup/overlap branches are out of scope) */
-static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_read* r2, uint64_t* fs,
+static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_read* r2, uint32_t pre, uint64_t* fs,
                           int* mask, uint32_t* err)
 {
     int a, b;
+    /* :213-230 tile / fov of fastq1 only, plain counters */
+    if (pre & SNK_PRE_TILE) { fs[SNK_FS_TILE]++; *mask = 0; return SNK_DROP_TILE; }
+    if (pre & SNK_PRE_FOV) { fs[SNK_FS_FOV]++; *mask = 0; return SNK_DROP_FOV; }
 #define DIS(cat, base) do { if (a || b) { fs_dis(fs, base, a, b); *mask = (a ? 1 : 0) | (b ? 2 : 0); return cat; } } while (0)
     if (p->min_read_length != -1) {
         /* size_t < int comparison: negative thresholds other than -1 convert to huge unsigned */
@@ -348,8 +393,10 @@ static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_rea
 }
 
 /* sequence.cpp:76-178 se_discard */
-static int orc_se_discard(const snk_params* p, const orc_read* r, uint64_t* fs)
+static int orc_se_discard(const snk_params* p, const orc_read* r, uint32_t pre, uint64_t* fs)
 {
+    if (pre & SNK_PRE_TILE) { fs[SNK_FS_TILE]++; return SNK_DROP_TILE; }      /* :84-98 */
+    if (pre & SNK_PRE_FOV) { fs[SNK_FS_FOV]++; return SNK_DROP_FOV; }
     if (p->min_read_length != -1 && (uint64_t)r->clean_len < (uint64_t)(int64_t)p->min_read_length) { fs[SNK_FS_SHORT]++; return SNK_DROP_SHORT; }
     if (p->max_read_length != -1 && (uint64_t)r->clean_len > (uint64_t)(int64_t)p->max_read_length) { fs[SNK_FS_LONG]++; return SNK_DROP_LONG; }
     if (p->n_ratio != -1 && r->n_ratio >= p->n_ratio) { fs[SNK_FS_N]++; return SNK_DROP_N; }
@@ -400,11 +447,11 @@ ORC_EXPORT int orc_filter_pe(const snk_params* p, const snk_batch* b1, const snk
         const uint8_t* s1 = b1->seq + (size_t)i * b1->stride; const uint8_t* q1 = b1->qual + (size_t)i * b1->stride;
         const uint8_t* s2 = b2->seq + (size_t)i * b2->stride; const uint8_t* q2 = b2->qual + (size_t)i * b2->stride;
         orc_read r1, r2;
-        orc_stat_and_trim(p, 0, s1, q1, b1->len[i], &r1);
-        orc_stat_and_trim(p, 1, s2, q2, b2->len[i], &r2);
+        orc_stat_and_trim(p, 0, s1, q1, b1->len[i] & SNK_LEN_MASK, &r1);
+        orc_stat_and_trim(p, 1, s2, q2, b2->len[i] & SNK_LEN_MASK, &r2);
         if (r1.bad_base || r2.bad_base) *err |= 1u;
         int mask = 0;
-        int cat = orc_pe_discard(p, &r1, &r2, S, &mask, err);
+        int cat = orc_pe_discard(p, &r1, &r2, b1->len[i] & ~SNK_LEN_MASK, S, &mask, err);
         fill_result(&out1[i], &r1, cat, mask);
         fill_result(&out2[i], &r2, cat, mask);
         /* raw tables: raw records keep raw_length==0 and -1 cuts unless copied back (peprocess.cpp:1441-1459) */
@@ -436,9 +483,9 @@ ORC_EXPORT int orc_filter_se(const snk_params* p, const snk_batch* b1, snk_read_
         uint64_t* S = stats + (size_t)slot * SNK_SLOT_WORDS;
         const uint8_t* s1 = b1->seq + (size_t)i * b1->stride; const uint8_t* q1 = b1->qual + (size_t)i * b1->stride;
         orc_read r1;
-        orc_stat_and_trim(p, 0, s1, q1, b1->len[i], &r1);
+        orc_stat_and_trim(p, 0, s1, q1, b1->len[i] & SNK_LEN_MASK, &r1);
         if (r1.bad_base) *err |= 1u;
-        int cat = p->srna ? orc_srna_discard(p, &r1, S, err) : orc_se_discard(p, &r1, S);
+        int cat = p->srna ? orc_srna_discard(p, &r1, S, err) : orc_se_discard(p, &r1, b1->len[i] & ~SNK_LEN_MASK, S);
         fill_result(&out1[i], &r1, cat, cat ? 1 : 0);
         orc_stat_record(p, S + SNK_SLOT_FILE_OFF(SNK_RAW1), 2, s1, q1, r1.len, 0,
                         cutback ? r1.head_hdcut : -1, cutback ? r1.head_lqcut : -1, cutback ? r1.tail_hdcut : -1,

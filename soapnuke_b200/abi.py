@@ -11,12 +11,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ENGINE_LIB = os.path.join(HERE, "lib", "libsnk_engine.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_READ_LEN = 1000
 QBINS = 64
 MAX_ADAPTERS = 8
 MAX_ADAPTER_LEN = 128
 MAX_SLOTS = 256
+MAX_ID_FILTERS = 64
+ID_FILTER_LEN = 8
+LEN_MASK, PRE_TILE, PRE_FOV = 0x3FFF, 0x4000, 0x8000
 
 FS_COUNT = 40
 GS_COUNT = 16
@@ -35,7 +38,8 @@ SLOT_WORDS = FS_COUNT + FILE_COUNT * FILE_WORDS
 RAW1, RAW2, CLEAN1, CLEAN2 = 0, 1, 2, 3
 GS_READS, GS_BASES, GS_A, GS_C, GS_G, GS_T, GS_N, GS_Q20, GS_Q30, GS_LAST_KEY = range(10)
 
-CATEGORY_NAMES = ["keep", "short", "long", "n", "highA", "polyX", "lowq", "meanq", "adapter", "empty"]
+CATEGORY_NAMES = ["keep", "short", "long", "n", "highA", "polyX", "lowq", "meanq", "adapter", "empty", "no3adapter", "insertnull",
+                  "tile", "fov"]
 FS_BASE = {"adapter": 0, "n": 4, "highA": 8, "polyX": 12, "lowq": 16, "meanq": 20, "short": 24, "long": 28}
 
 
@@ -86,6 +90,11 @@ class Params(C.Structure):
         ("ada_rer", C.c_float),
         ("ada_rmm", C.c_int32),
         ("reserved", C.c_int32 * 2),
+        ("seq_type1", C.c_int32),
+        ("n_tile", C.c_int32),
+        ("n_fov", C.c_int32),
+        ("tile", (C.c_char * ID_FILTER_LEN) * MAX_ID_FILTERS),
+        ("fov", (C.c_char * ID_FILTER_LEN) * MAX_ID_FILTERS),
     ]
 
 
@@ -182,7 +191,7 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
                 ada_mis=(2, 2), ada_mr=(0.5, 0.5), ada_edge=(6, 6), hard_trim=None,
                 trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
                 contam_trim=False, index_remove=False, patch_size=None, srna=False, ada_rctg=6, ada_rar=0.8,
-                ada_rma=5, ada_rer=0.4, ada_rmm=4):
+                ada_rma=5, ada_rer=0.4, ada_rmm=4, tile=None, fov=None, seq_type1=False):
     """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
     Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
     p = Params()
@@ -236,6 +245,13 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
     p.max_base_quality = max_base_quality
     p.srna = 1 if srna else 0       # filtersRNA: adapter1 = 5' adapter, adapter2 = 3' adapter, SE only
     p.ada_rctg, p.ada_rar, p.ada_rma, p.ada_rer, p.ada_rmm = ada_rctg, ada_rar, ada_rma, ada_rer, ada_rmm
+    p.seq_type1 = 1 if seq_type1 else 0
+    for name, val in (("tile", tile), ("fov", fov)):          # config keys tile= / fov= (comma separated)
+        ents = [e for e in (val.split(",") if val else []) if 0 < len(e) <= ID_FILTER_LEN]
+        assert len(ents) <= MAX_ID_FILTERS
+        setattr(p, "n_" + name, len(ents))
+        for i, e in enumerate(ents):
+            getattr(p, name)[i].value = e.encode()
     n_slots, block, _ = ref_threads_partition(threads, nprocs, patch_size)
     p.n_slots = n_slots
     p.slot_block = block

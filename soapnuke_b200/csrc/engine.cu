@@ -307,6 +307,7 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
         L.d_out[m] = ta.out[m]; L.d_rec_off[m] = ta.rec_off[m]; L.d_res[m] = dres[m];
     }
     ta.meta = L.d_meta; ta.n = n; ta.stride = stride; ta.mates = mates;
+    make_id_filter(e->params, ta.idf);
     ta.fmt.strip = fmt->strip; ta.fmt.pe_info = fmt->pe_info; ta.fmt.fasta = fmt->fasta; ta.fmt.id_mode = fmt->id_mode;
     ta.fmt.qshift = e->params.out_quality_phred - e->params.quality_phred;
     const uint32_t seg_grid = nseg[0] > nseg[1] ? nseg[0] : nseg[1];

@@ -208,8 +208,10 @@ enum : uint16_t {
     RF_N = 1, RF_HIGHA = 2, RF_POLYX = 4, RF_LOWQ = 8, RF_MEANQ = 16, RF_ADAPTER = 32,
     RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256,
     RF_QSLOW = 512,       // some quality falls outside the shared-memory bins: histogram takes the checked path
-    RF_NO3 = 1024, RF_INSNULL = 2048     // filtersRNA: no 3' adapter / 3' adapter within the first three bases
+    RF_NO3 = 1024, RF_INSNULL = 2048,    // filtersRNA: no 3' adapter / 3' adapter within the first three bases
+    RF_TILE = 4096, RF_FOV = 8192        // the id selected the read for removal (SNK_PRE_TILE / SNK_PRE_FOV of len[])
 };
+SNK_HD uint16_t pre_flags(uint32_t len_word) { return (uint16_t)(((len_word & SNK_PRE_TILE) ? RF_TILE : 0) | ((len_word & SNK_PRE_FOV) ? RF_FOV : 0)); }
 enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
 
 // ------------------------------------------------------------------ adapter matching
@@ -941,6 +943,9 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
 SNK_HD int decide_pair(const DevParams& P, const ReadInfo& a, const ReadInfo& b, int* mask, int* fs_base)
 {
     bool x, y;
+    // sequence.cpp:213-230: tile / fov of fastq1 only; plain counters (fs_base + 1.. are not touched: mask 0)
+    if (a.flags & RF_TILE) { *mask = 0; *fs_base = SNK_FS_TILE; return SNK_DROP_TILE; }
+    if (a.flags & RF_FOV) { *mask = 0; *fs_base = SNK_FS_FOV; return SNK_DROP_FOV; }
 #define SNK_DIS(cat, base) do { if (x || y) { *mask = (x ? 1 : 0) | (y ? 2 : 0); *fs_base = base; return cat; } } while (0)
     if (P.min_len != -1) {
         x = (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len; y = (uint64_t)b.clean_len < (uint64_t)(int64_t)P.min_len;
@@ -963,6 +968,8 @@ SNK_HD int decide_pair(const DevParams& P, const ReadInfo& a, const ReadInfo& b,
 // sequence.cpp:76-178
 SNK_HD int decide_se(const DevParams& P, const ReadInfo& a, int* fs_base)
 {
+    if (a.flags & RF_TILE) { *fs_base = SNK_FS_TILE; return SNK_DROP_TILE; }      // sequence.cpp:84-98
+    if (a.flags & RF_FOV) { *fs_base = SNK_FS_FOV; return SNK_DROP_FOV; }
     if (P.min_len != -1 && (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len) { *fs_base = SNK_FS_SHORT; return SNK_DROP_SHORT; }
     if (P.max_len != -1 && (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len) { *fs_base = SNK_FS_LONG; return SNK_DROP_LONG; }
     if (a.flags & RF_N) { *fs_base = SNK_FS_N; return SNK_DROP_N; }

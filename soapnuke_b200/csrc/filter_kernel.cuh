@@ -405,7 +405,8 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             const unsigned pm = 3u << (lane & ~1);                  // my group's lanes
             const uint16_t* sl = reinterpret_cast<const uint16_t*>(smem + sp.off_len[m]);
             ReadInfo* info = reinterpret_cast<ReadInfo*>(smem + sp.off_info[m]);
-            int len = sl[r];
+            const uint32_t len_word = sl[r];
+            int len = (int)(len_word & SNK_LEN_MASK);
             if (len > (int)A.stride) len = (int)A.stride;
             ReadInfo ri;
             if (len <= 0) {             // "Error:empty sequence" (read_filter.cpp:250)
@@ -416,6 +417,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                                      len, nchunks, m, P, reinterpret_cast<const AdaHot*>(smem + sp.off_ada) + ada_first_slot(P.n_adapters, m), h, pm, ri);
             }
             if (h == 0) {
+                ri.flags |= pre_flags(len_word);
                 info[r] = ri;
                 if (ri.flags & RF_QSLOW) *tile_slow = 1u;
             }

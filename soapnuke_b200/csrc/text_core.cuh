@@ -110,6 +110,57 @@ SNK_HD uint32_t id_transform(const uint8_t* id, uint32_t n, int mode, uint8_t* d
     return keep;
 }
 
+// ---- tile / fov removal lists (config keys `tile`, `fov`). stat_read parses the tile / fov out of the record
+// id (read_filter.cpp:86-148) and check_tile_or_fov (:14-79) compares it with the comma separated list:
+// only exact equality with an entry ever selects a read. Entries and the parsed strings are held as 8
+// bytes, NUL padded, in one 64-bit word.
+struct IdFilter {
+    int32_t n_tile, n_fov, seq_type1, pad_;
+    unsigned long long tile[SNK_MAX_ID_FILTERS], fov[SNK_MAX_ID_FILTERS];
+};
+SNK_HD void make_id_filter(const snk_params& p, IdFilter& F)
+{
+    F.n_tile = p.n_tile; F.n_fov = p.n_fov; F.seq_type1 = p.seq_type1; F.pad_ = 0;
+    for (int e = 0; e < SNK_MAX_ID_FILTERS; e++) {
+        unsigned long long t = 0, f = 0;
+        for (int k = SNK_ID_FILTER_LEN - 1; k >= 0; k--) { t = (t << 8) | (uint8_t)p.tile[e][k]; f = (f << 8) | (uint8_t)p.fov[e][k]; }
+        F.tile[e] = t; F.fov[e] = f;
+    }
+}
+// SNK_PRE_TILE / SNK_PRE_FOV bits of one record id (n visible bytes)
+SNK_HD uint32_t id_prefilter(const uint8_t* id, uint32_t n, const IdFilter& F)
+{
+    uint32_t flags = 0;
+    if (F.n_tile > 0) {
+        uint32_t i = 0;
+        int num = 0;
+        const int want = F.seq_type1 ? 4 : 2;
+        for (; i < n; i++) {
+            if (id[i] == ':') num++;
+            if (num >= want) break;
+        }
+        unsigned long long tile = 0;
+        int tn = 0;
+        for (uint32_t j = 0; j != 4; j++) {
+            const uint32_t k = i + j + 1;
+            const uint8_t ch = k < n ? id[k] : (uint8_t)0;
+            if (ch >= '0' && ch <= '9') { tile |= (unsigned long long)ch << (8 * tn); tn++; }
+        }
+        for (int e = 0; e < F.n_tile; e++)
+            if (F.tile[e] == tile) { flags |= SNK_PRE_TILE; break; }
+    }
+    if (F.n_fov > 0) {
+        uint32_t i = 0;
+        for (; i < n; i++)
+            if (id[i] == 'C' && i + 8 < n && id[i + 4] == 'R') break;
+        unsigned long long fov = 0;
+        for (uint32_t k = 0; k < 8 && i + k < n; k++) fov |= (unsigned long long)id[i + k] << (8 * k);      // substr(i, 8)
+        for (int e = 0; e < F.n_fov; e++)
+            if (F.fov[e] == fov) { flags |= SNK_PRE_FOV; break; }
+    }
+    return flags;
+}
+
 // bytes a kept record adds to the clean file
 SNK_HD uint32_t record_out_len(uint32_t id_out, uint32_t clean_len, const TextFormat& F)
 {

@@ -53,6 +53,7 @@ struct TextArgs {
     uint32_t stride;
     int mates;
     TextFormat fmt;
+    IdFilter idf;                 // tile / fov removal lists (ids are parsed while packing)
 };
 
 #ifdef __CUDACC__
@@ -181,7 +182,9 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ 
             atomicOr(&A.meta->flags, bad);
             if (bad & (TEXT_LEN_MISMATCH | TEXT_TOO_LONG)) atomicMin(&A.meta->bad_record, i);
         }
-        A.len[m][i] = (uint16_t)(sn < A.stride ? sn : A.stride);
+        uint32_t pre = 0;           // only mate 1's id decides for a pair (sequence.cpp:213-230)
+        if (m == 0 && (A.idf.n_tile > 0 || A.idf.n_fov > 0)) pre = id_prefilter(A.text[m] + off[0], line_visible(off, 0, strip), A.idf);
+        A.len[m][i] = (uint16_t)((sn < A.stride ? sn : A.stride) | pre);
     }
     const uint32_t len = which ? (qn < sn ? qn : sn) : sn;
     const U4 v = pack_chunk(A.text[m], off[which ? 3 : 1], len < A.stride ? len : A.stride, c);

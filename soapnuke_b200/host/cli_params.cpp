@@ -125,6 +125,8 @@ void init_from_config(HostParams& hp, const char* path)
             if (value.find(",") == std::string::npos) { hp.ada_mr = (float)atof(value.c_str()); hp.ada_mr2 = hp.ada_mr; }
             else { auto v = split(value, ','); if (v.size() < 2) die("expected two values in -A parameter"); hp.ada_mr = (float)atof(v[0].c_str()); hp.ada_mr2 = (float)atof(v[1].c_str()); }
         }
+        else if (key == "tile") hp.tile = value;                                           // process_argv.cpp:1314-1320
+        else if (key == "fov") hp.fov = value;
         else if (key == "log") hp.log = value;
         else if (key == "trim") hp.trim = value;
         else if (key == "trimBadHead") hp.trim_bad_head = value;
@@ -159,7 +161,7 @@ void print_usage(const std::string& module)
               << "  -T, --thread INT [6]    logical worker partition of the reference (statistics/ordering parity) and host threads\n"
               << "  -h, --help   -v, --version\n"
               << "config file keys: seqType outFileType index qualSys outQualSys maxBaseQuality pe_info patch maxReadLen\n"
-              << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log\n"
+              << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log tile fov\n"
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
 }
@@ -243,6 +245,17 @@ int parse_command_line(int argc, char** argv, HostParams& hp)
     }
     if (hp.seq_type != "0" && hp.seq_type != "1") die("seq_type value should be 0 or 1");
     if (hp.output_file_type != "fastq" && hp.output_file_type != "fasta") die("output_file_type value should be fastq or fasta");
+    if (!hp.tile.empty()) {                     // process_argv.cpp:717-751
+        // a '-' sends the reference into `for (size_type ix = size-1; ix >= 0; ix--)` (never terminates, reads out of
+        // bounds); ranges never match a tile anyway (check_tile_or_fov compares the tile with the whole "a-b" string)
+        if (hp.tile.find("-") != std::string::npos) die("tile ranges (a-b) are not usable in SOAPnuke 2.1.9 (process_argv.cpp:724 never terminates); list the tiles");
+        for (char ch : hp.tile)
+            if (!isalnum((unsigned char)ch) && ch != ',') die("tile value format error");
+    }
+    if (!hp.fov.empty()) {
+        if (hp.seq_type != "0") { std::cerr << "Warning:Zebra-500 data(--fov), --seqType is 0" << std::endl; exit(1); }   // read_filter.cpp:131-134
+        if (hp.fov.find("-") != std::string::npos) die("input tile parameter format error," + hp.fov);
+    }
     if (hp.quality_phred != 64 && hp.quality_phred != 33) die("qualityPhred value error");
     if (hp.out_quality_phred != 64 && hp.out_quality_phred != 33) die("outputQualityPhred value error");
     if (!hp.trim.empty()) {
@@ -316,6 +329,20 @@ void to_engine_params(const HostParams& hp, snk_params& p)
     }
     p.index_remove = hp.index_remove;
     p.max_base_quality = hp.max_base_quality;
+    p.seq_type1 = hp.seq_type != "0";
+    {
+        struct { const std::string* src; int32_t* n; char (*dst)[SNK_ID_FILTER_LEN]; } lists[2] = {{&hp.tile, &p.n_tile, p.tile}, {&hp.fov, &p.n_fov, p.fov}};
+        for (auto& l : lists) {
+            *l.n = 0;
+            if (l.src->empty()) continue;
+            for (const std::string& e : split(*l.src, ',')) {
+                if (e.empty() || e.size() > SNK_ID_FILTER_LEN) continue;       // can never equal a 4-digit tile / 8-character fov
+                if (*l.n >= SNK_MAX_ID_FILTERS) die("too many entries in the tile / fov list");
+                memcpy(l.dst[*l.n], e.data(), e.size());
+                (*l.n)++;
+            }
+        }
+    }
     p.srna = hp.srna;
     p.ada_rctg = hp.ada_rctg; p.ada_rar = hp.ada_rar; p.ada_rma = hp.ada_rma; p.ada_rer = hp.ada_rer; p.ada_rmm = hp.ada_rmm;
     p.n_slots = hp.threads;                                       // logical reference threads

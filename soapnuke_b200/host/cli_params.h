@@ -30,6 +30,7 @@ struct HostParams {
     int ada_mis = 2, ada_mis2 = 2, ada_edge = 6, ada_edge2 = 6;
     float ada_mr = 0.5f, ada_mr2 = 0.5f;
     bool is_pe = false;
+    std::string tile, fov;             // config keys tile= / fov= (removal lists, comma separated)
     // filtersRNA module (global_parameter.h:54-58)
     bool srna = false;
     int ada_rctg = 6, ada_rma = 5, ada_rmm = 4;

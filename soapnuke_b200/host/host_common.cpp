@@ -31,6 +31,8 @@ int params_check(const snk_params& p)
         // sRNA_hasAdapter starts at adapter offset adptLen - adaRCtg (read_filter.cpp:872)
         if (p.n_adapters[0] > 0 && p.adapter_len[0][0] < p.ada_rctg) { set_error("adapter1 is shorter than adaRCtg"); return 1; }
     }
+    if (p.n_tile < 0 || p.n_tile > SNK_MAX_ID_FILTERS || p.n_fov < 0 || p.n_fov > SNK_MAX_ID_FILTERS) { set_error("too many tile / fov entries"); return 1; }
+    if (p.n_fov > 0 && p.seq_type1) { set_error("Zebra-500 data(--fov), --seqType is 0"); return 1; }     // read_filter.cpp:131-134
     if (p.has_hard_trim) for (int m = 0; m < 2; m++)
         if (p.hard_head[m] < 0 || p.hard_tail[m] < 0) { set_error("trim value format error"); return 1; }
     return 0;

@@ -167,13 +167,14 @@ Quartiles quartiles(const Merged& m, uint64_t pos, int len)
 struct FilterRow { const char* label; int fs_base; };
 // label order of peprocess.cpp:226-241 restricted to the categories the engine produces
 const FilterRow kPeRows[] = {
+    {"Reads with filtered tile", SNK_FS_TILE}, {"Reads with filtered fov", SNK_FS_FOV},
     {"Reads too short", SNK_FS_SHORT}, {"Reads too long", SNK_FS_LONG},
     {"Reads with n rate exceed", SNK_FS_N}, {"Reads with highA", SNK_FS_HIGHA},
     {"Reads with polyX", SNK_FS_POLYX}, {"Reads with low quality", SNK_FS_LOWQ},
     {"Reads with low mean quality", SNK_FS_MEANQ}, {"Reads with adapter", SNK_FS_ADAPTER}};
 // seprocess.cpp:136-150 has the same relative order for these categories
 const FilterRow* const kSeRows = kPeRows;
-const int kRows = 8;
+const int kRows = 10;
 
 uint64_t filtered_total(const Global& G)
 {
@@ -320,7 +321,9 @@ int report_write_pe(const snk_params& p, const uint64_t* stats, const std::strin
         if (c[0] == 0) continue;
         f_filter << kPeRows[i].label << "\t" << c[0] << "\t";
         f_filter << std::setprecision(2) << 100 * (float)c[0] / total << "%\t";
-        f_filter << c[1] << "\t" << c[2] << "\t" << c[3] << std::endl;
+        // tile / fov have no per-mate counters: the reference prints the same number four times (peprocess.cpp:271-304)
+        const bool plain = kPeRows[i].fs_base == SNK_FS_TILE || kPeRows[i].fs_base == SNK_FS_FOV;
+        f_filter << (plain ? c[0] : c[1]) << "\t" << (plain ? c[0] : c[2]) << "\t" << (plain ? c[0] : c[3]) << std::endl;
     }
     f_filter.close();
 
@@ -412,7 +415,9 @@ int report_write_se(const snk_params& p, const uint64_t* stats, const std::strin
         !open_out(f_q1, dir + "/Distribution_of_Q20_Q30_bases_by_read_position_1.txt") ||
         !open_out(f_t1, dir + "/Statistics_of_Trimming_Position_of_Reads_1.txt")) { delete Gp; return 1; }
 
-    // seprocess.cpp:135-181
+    // seprocess.cpp:135-181. The SE update_stat merges tile_num but not fov_num (seprocess.cpp:495): reads removed
+    // by the fov list never reach the report (neither their row nor the totals)
+    G.fs[SNK_FS_FOV] = 0;
     const uint64_t total = filtered_total(G);
     f_filter << "Item\tTotal\tPercentage" << std::endl;
     f_filter << std::setiosflags(std::ios::fixed);

@@ -142,10 +142,21 @@ def read_ids(n, mate, first=0):
     return [b"@SYN:1:1101:%d:%d/%d" % ((first + i) // 1000, (first + i) % 1000, mate) for i in range(n)]
 
 
-def write_fastq(path, seq, qual, length, mate, first=0, gz=False):
+def tile_ids(n, mate, tiles=(1101, 1102, 1103, 1104, 2201)):
+    """Old-style ids whose tile field (behind the 2nd ':') cycles irregularly through `tiles`."""
+    return [b"@SYN:1:%d:%d:%d/%d" % (tiles[(i * 7 + i // 5) % len(tiles)], i // 1000, i % 1000, mate) for i in range(n)]
+
+
+def fov_ids(n, mate):
+    """Zebra-platform style ids with a CxxxRyyy field of view."""
+    return [b"@V300012345L1C%03dR%03d%07d/%d" % (1 + (i * 3 + i // 7) % 4, 1 + (i // 3) % 5, i, mate) for i in range(n)]
+
+
+def write_fastq(path, seq, qual, length, mate, first=0, gz=False, ids=None):
     import gzip
     n = seq.shape[0]
-    ids = read_ids(n, mate, first)
+    if ids is None:
+        ids = read_ids(n, mate, first)
     parts = []
     for i in range(n):
         l = int(length[i])
@@ -159,11 +170,12 @@ def write_fastq(path, seq, qual, length, mate, first=0, gz=False):
             f.write(data)
 
 
-def clean_fastq_bytes(seq, qual, length, results, mate, first=0, phred_shift=0, order=None):
+def clean_fastq_bytes(seq, qual, length, results, mate, first=0, phred_shift=0, order=None, ids=None):
     """Rebuild the clean FASTQ text the reference writes (peprocess.cpp:3414) from per-read results.
     `order`: emission order of the read indices (abi.ref_output_order), default input order."""
     n = seq.shape[0]
-    ids = read_ids(n, mate, first)
+    if ids is None:
+        ids = read_ids(n, mate, first)
     parts = []
     for i in (range(n) if order is None else order):
         if results["category"][i] != 0:

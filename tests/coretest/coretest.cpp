@@ -116,11 +116,13 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
             bool tile_slow = false;
             for (int m = 0; m < M; m++)
                 for (uint32_t r = 0; r < cnt; r++) {
-                    int len = b[m]->len[start + r];
+                    const uint32_t len_word = b[m]->len[start + r];
+                    int len = (int)(len_word & SNK_LEN_MASK);
                     if (len > (int)c.stride) len = (int)c.stride;
                     ReadInfo ri;
                     if (len <= 0) { memset(&ri, 0, sizeof ri); ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1; ri.flags = RF_BAD_BASE | RF_QSLOW; }
                     else scan_read_serial<MAXC>(rows[m][0].data() + (size_t)r * c.stride, rows[m][1].data() + (size_t)r * c.stride, len, nchunks, m, c.P, ri);
+                    ri.flags |= pre_flags(len_word);
                     info[m][r] = ri;
                     if (ri.flags & RF_QSLOW) tile_slow = true;
                 }
@@ -299,6 +301,14 @@ uint32_t coretest_text_index_pack(const uint8_t* text, uint32_t bytes, uint32_t 
         }
     }
     return flags;
+}
+
+// text path's id parse for the tile / fov removal lists (text_core.cuh id_prefilter)
+uint32_t coretest_id_flags(const snk_params* p, const uint8_t* id, uint32_t n)
+{
+    IdFilter F;
+    make_id_filter(*p, F);
+    return id_prefilter(id, n, F);
 }
 
 // rec_off has n+1 entries; out must hold bytes + 2n + 64. `lanes` mimics the warp width. Returns the clean text size.

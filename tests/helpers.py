@@ -271,3 +271,30 @@ def high_quality_mix(n=6000, L=100, seed=31, every=97):
             pos = rng.integers(0, l, size=max(1, l // 5))
             Q[i, pos] = 33 + rng.integers(42, 61, size=pos.size).astype(np.uint8)
     return d
+
+
+def report_equal(ref_path, mine_path):
+    """Byte equality of one report file, except for what the reference leaves to chance: in
+    Distribution_of_Q20_Q30_bases_by_read_position_*.txt the raw columns of the rows behind the raw
+    `read_length` (= length of the last record a worker saw) are printed from a `new float[]` that was
+    never written (peprocess.cpp / seprocess.cpp:289-353), i.e. whatever the heap held - usually 0.0000,
+    sometimes garbage. Those rows (where this writer prints 0.0000 for both raw columns) are compared
+    on their other columns only."""
+    import filecmp
+    if filecmp.cmp(ref_path, mine_path, shallow=False):
+        return True
+    if "Distribution_of_Q20_Q30" not in os.path.basename(ref_path):
+        return False
+    a = open(ref_path).read().split("\n")
+    b = open(mine_path).read().split("\n")
+    if len(a) != len(b):
+        return False
+    for la, lb in zip(a, b):
+        if la == lb:
+            continue
+        fa, fb = la.split("\t"), lb.split("\t")
+        if len(fa) != len(fb) or len(fb) < 3 or fb[1] != "0.0000" or fb[2] != "0.0000":
+            return False
+        if fa[0] != fb[0] or fa[3:] != fb[3:]:
+            return False
+    return True

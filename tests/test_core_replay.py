@@ -77,6 +77,26 @@ def test_core_replay_matches_oracle_filtersRNA(cfg):
     assert_same((c1, None, cst), (o1, None, ost), name)
 
 
+@pytest.mark.parametrize("pe", [True, False], ids=["pe", "se"])
+def test_tile_fov_flags_in_len(pe):
+    """SNK_PRE_TILE / SNK_PRE_FOV bits of len[] (the ids never cross the SoA boundary): first test of the
+    discard cascade, plain counters, only mate 1's flags count for a pair."""
+    import oracle_py as orc
+    n = 8000
+    d = synth.gen_pairs(n, L=100, seed=61, se=not pe, var_len=True)
+    p = abi.make_params(is_pe=pe, adapter1=A1, adapter2=A2 if pe else None, ada_trim=True, tile="1102,2201", fov="C002R003", threads=2, patch_size=50)
+    ids = [a if i % 3 else b for i, (a, b) in enumerate(zip(synth.tile_ids(n, 1), synth.fov_ids(n, 1)))]
+    d["len1"] = d["len1"] | orc.id_flags(p, ids)
+    if pe:
+        d["len2"] = d["len2"] | np.where(np.arange(n) % 11 == 0, abi.PRE_TILE, 0).astype(np.uint16)     # mate 2's flags are ignored
+    o1, o2, ost, oerr = oracle_run(p, d)
+    c1, c2, cst, cerr = core_replay(p, d, grid=5)
+    assert oerr == cerr == 0
+    cats = np.bincount(o1["category"], minlength=14)
+    assert cats[12] > 200 and cats[13] > 50 and cats[0] > 2000, cats
+    assert_same((c1, c2, cst), (o1, o2, ost), "tile/fov")
+
+
 def test_mixed_checked_and_unchecked_tiles(monkeypatch):
     """A few records with qualities above the shared-memory bins: their tiles take the checked
     histogram path (out-of-bin qualities go straight to the global tables, mirrored into the clean

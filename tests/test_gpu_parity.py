@@ -68,6 +68,26 @@ def test_engine_matches_oracle_filtersRNA(cfg, engine_lib):
     assert_same((r1, None, st), (o1, None, ost), name)
 
 
+@pytest.mark.parametrize("pe", [True, False], ids=["pe", "se"])
+def test_tile_fov_flags_in_len(pe, engine_lib):
+    """SNK_PRE_TILE / SNK_PRE_FOV bits of len[] through the SoA entry points (see the CPU tier's test)."""
+    import oracle_py as orc
+    n = 40000
+    d = synth.gen_pairs(n, L=100, seed=61, se=not pe, var_len=True)
+    p = abi.make_params(is_pe=pe, adapter1=A1, adapter2=A2 if pe else None, ada_trim=True, tile="1102,2201", fov="C002R003", threads=2, patch_size=500)
+    ids = [a if i % 3 else b for i, (a, b) in enumerate(zip(synth.tile_ids(n, 1), synth.fov_ids(n, 1)))]
+    d["len1"] = d["len1"] | orc.id_flags(p, ids)
+    if pe:
+        d["len2"] = d["len2"] | np.where(np.arange(n) % 11 == 0, abi.PRE_TILE, 0).astype(np.uint16)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    with Engine(engine_lib, p) as e:
+        r1, r2 = e.filter_host(d)
+        st = e.stats()
+        flags, _ = e.error_flags()
+    assert flags == oerr == 0
+    assert_same((r1, r2, st), (o1, o2, ost), "tile/fov")
+
+
 def test_mixed_checked_and_unchecked_tiles(engine_lib):
     """Records with qualities above the shared-memory bins scattered through the batch (see the CPU
     tier's test of the same name): checked and unchecked tiles, raw and delta cells must add up."""
