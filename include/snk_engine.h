@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNK_ABI_VERSION 3
+#define SNK_ABI_VERSION 4
 
 /* ---- limits (global_variable.h:9-11 READ_MAX_LEN / MAX_QUAL) ---- */
 #define SNK_MAX_READ_LEN   1000   /* READ_MAX_LEN: per-position tables have this many rows        */
@@ -42,6 +42,7 @@ extern "C" {
 #define SNK_MAX_ADAPTERS   8      /* adapters per mate (-f/-r list files), read_filter.cpp:177     */
 #define SNK_MAX_ADAPTER_LEN 128
 #define SNK_MAX_SLOTS      256    /* logical reference threads whose tables are kept apart         */
+#define SNK_MAX_CONTAMS    8      /* contaminant sequences per mate (contam1 / contam2 lists)       */
 #define SNK_MAX_ID_FILTERS 64     /* entries of the tile / fov removal lists                        */
 #define SNK_ID_FILTER_LEN  8      /* a tile is up to 4 digits, a fov 8 characters (C001R003)        */
 
@@ -101,6 +102,17 @@ typedef struct snk_params {
     int32_t n_tile, n_fov;
     char    tile[SNK_MAX_ID_FILTERS][SNK_ID_FILTER_LEN];
     char    fov[SNK_MAX_ID_FILTERS][SNK_ID_FILTER_LEN];
+    /* contaminant sequences (config keys contam1 / contam2 / ctMatchR; hasContam / hasContams,
+     * read_filter.cpp:483-706): a read that contains one is dropped while contam_discard is set
+     * (gp.contam_discard_or_trim == "discard", the default; `contam_trim` only switches that off).
+     * contam_seg_thr = segMatchThr = (int)ceil(contamLen * ctMatchR), evaluated by the caller with the
+     * reference's types: double product for a single contaminant (:609), float product for a list (:499,:514).
+     * The matcher uses the mate's own adaMis / adaEdge (read 2: adaMis2 / adaEdge2, sequence.cpp:183-188). */
+    int32_t contam_discard;
+    int32_t n_contams[2];
+    int32_t contam_len[2][SNK_MAX_CONTAMS];
+    int32_t contam_seg_thr[2][SNK_MAX_CONTAMS];
+    char    contam[2][SNK_MAX_CONTAMS][SNK_MAX_ADAPTER_LEN];
 } snk_params;
 
 /* ---- one mate of a batch, fixed-stride SoA ---- */
@@ -134,7 +146,8 @@ enum snk_category {
     SNK_DROP_NO3ADAPTER = 10,    /* filtersRNA: no 3' adapter found (sequence.cpp:36-39), counted but never reported */
     SNK_DROP_INSERTNULL = 11,    /* filtersRNA: 3' adapter within the first 3 bases (sequence.cpp:40-44), never reported */
     SNK_DROP_TILE = 12,          /* "Reads with filtered tile" (first test of pe_discard / se_discard) */
-    SNK_DROP_FOV = 13            /* "Reads with filtered fov" */
+    SNK_DROP_FOV = 13,           /* "Reads with filtered fov" */
+    SNK_DROP_CONTAM = 14         /* "Reads with contam sequence" */
 };
 typedef struct snk_read_result {
     uint16_t head_cut;     /* bases removed from the 5' end of this mate */
@@ -159,6 +172,7 @@ enum snk_fs {
     SNK_FS_INSERTNULL,           /* fs.int_insertNull_num (filtersRNA) */
     SNK_FS_TILE,                 /* fs.tile_num */
     SNK_FS_FOV,                  /* fs.fov_num */
+    SNK_FS_CONTAM, SNK_FS_CONTAM1, SNK_FS_CONTAM2, SNK_FS_CONTAM_OV,   /* fs.include_contam_seq_num[1|2|_overlap] */
     SNK_FS_COUNT = 40
 };
 /* C_general_stat (global_variable.h:88-100), index into a file block's gs[] */

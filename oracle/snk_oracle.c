@@ -132,6 +132,55 @@ ORC_EXPORT int orc_srna_has_adapter(const uint8_t* read, int readLen, const uint
     return 0;
 }
 
+/* read_filter.cpp:596-706 hasContam() (the list variant :507-595 only differs in where segMatchThr comes
+ * from: the caller passes it). Three phases like adapter_pos, but: an 'N' of the read is neither a match
+ * nor a mismatch (and does not break a run of matches), phases 1 and 3 accept a run of segMatchTemp =
+ * 7 + r1/segGrad matches, and the mismatch budget grows with r1/misGrad. Float quotients are assigned to
+ * int as on x86 (NaN / inf -> INT_MIN). Read positions outside the read compare as mismatches (the
+ * reference reads out of bounds there). adaMis / adaEdge are the mate's own: read 2 is analysed with a
+ * parameter copy that carries adaMis2 / adaEdge2 (sequence.cpp:183-188). */
+ORC_EXPORT int orc_has_contam(const uint8_t* read, int readLen, const uint8_t* contam, int contamLen, int segMatchThr,
+                              int adaMis, int adaEdge)
+{
+    if (contamLen == 0) return -1;
+    float misGrad = (float)((contamLen - adaEdge) / (adaMis + 1));
+    float segGrad = (segMatchThr - 7 + 1 == 0) ? 0.0f : (float)((contamLen - adaEdge) / (segMatchThr - 7 + 1));
+    int r1, mis, seg, misT, segT;
+    for (r1 = 0; r1 < contamLen - adaEdge; ++r1) {                       /* contaminant's tail at the read's head */
+        mis = 0; seg = 0;
+        misT = float_to_int_x86((float)r1 / misGrad);
+        segT = segGrad != 0 ? float_to_int_x86(7 + (float)r1 / segGrad) : 7;
+        for (int c = 0; c < r1 + adaEdge; ++c) {
+            int rc = c < readLen ? read[c] : -1;
+            if (rc >= 0 && contam[contamLen - r1 - adaEdge + c] == rc) { if (++seg >= segT) return 0; }
+            else if (rc != 'N') { mis++; seg = 0; if (mis > misT) break; }
+        }
+        if (mis <= misT) return 0;
+    }
+    for (r1 = 0; r1 <= readLen - contamLen; ++r1) {                      /* whole contaminant inside the read */
+        seg = 0; mis = 0;
+        for (int c = 0; c < contamLen; ++c) {
+            if (contam[c] == read[r1 + c]) { if (++seg >= segMatchThr) return r1; }
+            else if (read[r1 + c] != 'N') { mis++; seg = 0; if (mis > adaMis) break; }
+        }
+        if (mis <= adaMis) return r1;
+    }
+    for (r1 = 0; r1 < contamLen - adaEdge; ++r1) {                       /* contaminant's head at the read's tail */
+        mis = 0; seg = 0;
+        misT = float_to_int_x86((float)r1 / misGrad);
+        segT = float_to_int_x86(7 + (float)r1 / segGrad);               /* no zero test here (:686) */
+        int base = readLen - r1 - adaEdge;
+        for (int c = 0; c < r1 + adaEdge; ++c) {
+            int idx = base + c;
+            int rc = (idx >= 0 && idx < readLen) ? read[idx] : -1;
+            if (rc >= 0 && contam[c] == rc) { if (++seg >= segT) return base; }
+            else if (rc != 'N') { mis++; seg = 0; if (mis > misT) break; }
+        }
+        if (mis <= misT) return base;
+    }
+    return -1;
+}
+
 /* stat_read's id parse (read_filter.cpp:86-148) + check_tile_or_fov (:14-79): SNK_PRE_TILE / SNK_PRE_FOV
  * bits for one record id (idlen bytes, no terminator needed). The tile is the (up to) 4 digits behind the
  * 2nd ':' (seqType 0) or the 4th ':' (seqType 1); the fov the 8 bytes from the first 'C' that has an 'R'
@@ -181,6 +230,7 @@ typedef struct {
     float n_ratio, a_ratio, lowq_ratio, mean_q;
     int has_adapter;
     int include_3_adapter;      /* filtersRNA: sRNA_findAdapter() of the raw read */
+    int include_contam;         /* some contaminant of the mate's list was found */
     /* C_fastq cut bookkeeping (sequence.h:69), -1 as set by C_fastq_init (peprocess.cpp:1674-1689) */
     int head_hdcut, head_lqcut, tail_hdcut, tail_lqcut, adacut_pos;
     int head_cut, clean_len;    /* result of fastq_trim */
@@ -221,6 +271,10 @@ static void orc_stat_and_trim(const snk_params* p, int mate, const uint8_t* seq,
             if (ada_pos >= 0) break;
         }
         if (ada_pos >= 0) { r->has_adapter = 1; r->adacut_pos = len - ada_pos; }
+        /* :188-206 hasContam / hasContams: any hit sets include_contam (the list's early break cannot change that) */
+        for (int i = 0; i < p->n_contams[mate]; i++)
+            if (orc_has_contam(seq, len, (const uint8_t*)p->contam[mate][i], p->contam_len[mate][i], p->contam_seg_thr[mate][i],
+                               p->ada_mis[mate], p->ada_edge[mate]) >= 0) { r->include_contam = 1; break; }
     }
     /* :255-287 base loop */
     int last_char = 'Q', contig = 0, max_contig = 1;
@@ -377,6 +431,7 @@ static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_rea
         b = (uint64_t)r2->clean_len > (uint64_t)(int64_t)p->max_read_length;
         DIS(SNK_DROP_LONG, SNK_FS_LONG);
     }
+    if (p->contam_discard) { a = r1->include_contam; b = r2->include_contam; DIS(SNK_DROP_CONTAM, SNK_FS_CONTAM); }   /* :274-288 */
     if (p->n_ratio != -1) { a = r1->n_ratio >= p->n_ratio; b = r2->n_ratio >= p->n_ratio; DIS(SNK_DROP_N, SNK_FS_N); }
     if (p->highA_ratio != -1) { a = r1->a_ratio >= p->highA_ratio; b = r2->a_ratio >= p->highA_ratio; DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA); }
     if (p->polyX_num != -1) { a = r1->contig >= p->polyX_num; b = r2->contig >= p->polyX_num; DIS(SNK_DROP_POLYX, SNK_FS_POLYX); }
@@ -399,6 +454,7 @@ static int orc_se_discard(const snk_params* p, const orc_read* r, uint32_t pre, 
     if (pre & SNK_PRE_FOV) { fs[SNK_FS_FOV]++; return SNK_DROP_FOV; }
     if (p->min_read_length != -1 && (uint64_t)r->clean_len < (uint64_t)(int64_t)p->min_read_length) { fs[SNK_FS_SHORT]++; return SNK_DROP_SHORT; }
     if (p->max_read_length != -1 && (uint64_t)r->clean_len > (uint64_t)(int64_t)p->max_read_length) { fs[SNK_FS_LONG]++; return SNK_DROP_LONG; }
+    if (p->contam_discard && r->include_contam) { fs[SNK_FS_CONTAM]++; return SNK_DROP_CONTAM; }                       /* :116-128 */
     if (p->n_ratio != -1 && r->n_ratio >= p->n_ratio) { fs[SNK_FS_N]++; return SNK_DROP_N; }
     if (p->highA_ratio != -1 && r->a_ratio >= p->highA_ratio) { fs[SNK_FS_HIGHA]++; return SNK_DROP_HIGHA; }
     if (p->polyX_num != -1 && r->contig >= p->polyX_num) { fs[SNK_FS_POLYX]++; return SNK_DROP_POLYX; }

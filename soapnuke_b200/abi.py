@@ -11,13 +11,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ENGINE_LIB = os.path.join(HERE, "lib", "libsnk_engine.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_READ_LEN = 1000
 QBINS = 64
 MAX_ADAPTERS = 8
 MAX_ADAPTER_LEN = 128
 MAX_SLOTS = 256
 MAX_ID_FILTERS = 64
+MAX_CONTAMS = 8
 ID_FILTER_LEN = 8
 LEN_MASK, PRE_TILE, PRE_FOV = 0x3FFF, 0x4000, 0x8000
 
@@ -39,7 +40,7 @@ RAW1, RAW2, CLEAN1, CLEAN2 = 0, 1, 2, 3
 GS_READS, GS_BASES, GS_A, GS_C, GS_G, GS_T, GS_N, GS_Q20, GS_Q30, GS_LAST_KEY = range(10)
 
 CATEGORY_NAMES = ["keep", "short", "long", "n", "highA", "polyX", "lowq", "meanq", "adapter", "empty", "no3adapter", "insertnull",
-                  "tile", "fov"]
+                  "tile", "fov", "contam"]
 FS_BASE = {"adapter": 0, "n": 4, "highA": 8, "polyX": 12, "lowq": 16, "meanq": 20, "short": 24, "long": 28}
 
 
@@ -95,6 +96,11 @@ class Params(C.Structure):
         ("n_fov", C.c_int32),
         ("tile", (C.c_char * ID_FILTER_LEN) * MAX_ID_FILTERS),
         ("fov", (C.c_char * ID_FILTER_LEN) * MAX_ID_FILTERS),
+        ("contam_discard", C.c_int32),
+        ("n_contams", C.c_int32 * 2),
+        ("contam_len", (C.c_int32 * MAX_CONTAMS) * 2),
+        ("contam_seg_thr", (C.c_int32 * MAX_CONTAMS) * 2),
+        ("contam", ((C.c_char * MAX_ADAPTER_LEN) * MAX_CONTAMS) * 2),
     ]
 
 
@@ -191,7 +197,8 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
                 ada_mis=(2, 2), ada_mr=(0.5, 0.5), ada_edge=(6, 6), hard_trim=None,
                 trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
                 contam_trim=False, index_remove=False, patch_size=None, srna=False, ada_rctg=6, ada_rar=0.8,
-                ada_rma=5, ada_rer=0.4, ada_rmm=4, tile=None, fov=None, seq_type1=False):
+                ada_rma=5, ada_rer=0.4, ada_rmm=4, tile=None, fov=None, seq_type1=False,
+                contam1=None, contam2=None, ct_match_r="0.2"):
     """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
     Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
     p = Params()
@@ -245,6 +252,25 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
     p.max_base_quality = max_base_quality
     p.srna = 1 if srna else 0       # filtersRNA: adapter1 = 5' adapter, adapter2 = 3' adapter, SE only
     p.ada_rctg, p.ada_rar, p.ada_rma, p.ada_rer, p.ada_rmm = ada_rctg, ada_rar, ada_rma, ada_rer, ada_rmm
+    # contam1 / contam2 / ctMatchR config values as strings, comma separated lists allowed (read_filter.cpp:188-206)
+    p.contam_discard = 0 if contam_trim else 1
+    import math
+    for m, val in enumerate((contam1, contam2)):
+        if not val:
+            continue
+        if "," not in val:
+            seqs, thr = [val], [int(math.ceil(len(val) * float(ct_match_r)))]                        # double product (:609)
+        else:
+            seqs, mrs = val.split(","), ct_match_r.split(",")
+            assert len(seqs) == len(mrs), "the number of ctMatchR value should equal to that of contam sequences"
+            thr = [int(math.ceil(float(_np.float32(len(sq)) * _np.float32(float(mr))))) for sq, mr in zip(seqs, mrs)]   # float product (:514)
+        assert len(seqs) <= MAX_CONTAMS
+        p.n_contams[m] = len(seqs)
+        for i, sq in enumerate(seqs):
+            assert len(sq) < MAX_ADAPTER_LEN
+            p.contam_len[m][i] = len(sq)
+            p.contam_seg_thr[m][i] = thr[i]
+            p.contam[m][i].value = sq.encode()
     p.seq_type1 = 1 if seq_type1 else 0
     for name, val in (("tile", tile), ("fov", fov)):          # config keys tile= / fov= (comma separated)
         ents = [e for e in (val.split(",") if val else []) if 0 < len(e) <= ID_FILTER_LEN]

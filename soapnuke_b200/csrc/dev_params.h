@@ -53,9 +53,43 @@ inline void prepare_adapter(const snk_params& p, int mate, int idx, AdapterDev& 
     a.a1_lo = (uint32_t)b1; a.a1_hi = (uint32_t)(b1 >> 32);
 }
 
+// hasContam's per-offset tables (read_filter.cpp:603-626, 683-686)
+inline void prepare_contam(const snk_params& p, int mate, int idx, ContamDev& k)
+{
+    memset(&k, 0, sizeof(k));
+    const int C = p.contam_len[mate][idx];
+    const int adaMis = p.ada_mis[mate], adaEdge = p.ada_edge[mate];      // read 2 is analysed with adaMis2 / adaEdge2 (sequence.cpp:183-188)
+    k.len = C;
+    memcpy(k.seq, p.contam[mate][idx], (size_t)C);
+    if (C == 0) return;
+    k.seg_thr = p.contam_seg_thr[mate][idx];
+    k.budget2 = adaMis;
+    k.edge = adaEdge;
+    k.n13 = C - adaEdge > 0 ? C - adaEdge : 0;
+    const float misGrad = (float)((C - adaEdge) / (adaMis + 1));
+    const float segGrad = (k.seg_thr - 7 + 1 == 0) ? 0.0f : (float)((C - adaEdge) / (k.seg_thr - 7 + 1));
+    for (int r1 = 0; r1 < k.n13 && r1 < SNK_MAX_ADAPTER_LEN; r1++) {
+        k.mis_t[r1] = float_to_int_x86((float)r1 / misGrad);
+        k.seg1_t[r1] = segGrad != 0 ? float_to_int_x86(7 + (float)r1 / segGrad) : 7;
+        k.seg3_t[r1] = float_to_int_x86(7 + (float)r1 / segGrad);
+    }
+}
+// all contaminant records of a run, [2][SNK_MAX_CONTAMS]; DevParams::contams must point to a copy the kernel can read
+inline void prepare_contams(const snk_params& p, ContamDev* out)
+{
+    for (int m = 0; m < 2; m++)
+        for (int i = 0; i < SNK_MAX_CONTAMS; i++) {
+            if (i < p.n_contams[m]) prepare_contam(p, m, i, out[m * SNK_MAX_CONTAMS + i]);
+            else memset(&out[m * SNK_MAX_CONTAMS + i], 0, sizeof(ContamDev));
+        }
+}
+
 inline void prepare_params(const snk_params& p, DevParams& d)
 {
     memset(&d, 0, sizeof(d));
+    d.contam_discard = p.contam_discard;
+    d.n_contams[0] = p.n_contams[0]; d.n_contams[1] = p.n_contams[1];
+    d.contams = nullptr;
     d.is_pe = p.is_pe;
     d.phred = p.quality_phred;
     d.low_qual = p.low_qual;

@@ -68,6 +68,7 @@ struct snk_engine {
     size_t stats_words = 0;
     unsigned int* d_err = nullptr;           // [0] flags
     unsigned long long* d_err_index = nullptr;
+    ContamDev* d_contams = nullptr;          // [2][SNK_MAX_CONTAMS] when contaminants are configured
     Lane lanes[kLanes];
     uint64_t launches = 0;
     std::mutex mu;
@@ -363,6 +364,17 @@ int snk_engine_create(const snk_params* p, int device, snk_engine** out)
     e->num_sms = prop.multiProcessorCount;
     e->params = *p;
     prepare_params(*p, e->dev);
+    if (p->n_contams[0] > 0 || p->n_contams[1] > 0) {
+        std::vector<ContamDev> host(2 * SNK_MAX_CONTAMS);
+        prepare_contams(*p, host.data());
+        if (cudaMalloc(&e->d_contams, host.size() * sizeof(ContamDev)) != cudaSuccess ||
+            cudaMemcpy(e->d_contams, host.data(), host.size() * sizeof(ContamDev), cudaMemcpyHostToDevice) != cudaSuccess) {
+            snk::set_error("cudaMalloc failed for the contaminant tables");
+            delete e;
+            return 1;
+        }
+        e->dev.contams = e->d_contams;
+    }
     e->stats_words = (size_t)p->n_slots * SNK_SLOT_WORDS;
     if (cudaMalloc(&e->d_stats, e->stats_words * 8) != cudaSuccess ||
         cudaMalloc(&e->d_err, 16) != cudaSuccess || cudaMalloc(&e->d_err_index, 8) != cudaSuccess) {
@@ -386,6 +398,7 @@ int snk_engine_destroy(snk_engine* e)
         if (e->lanes[i].d_meta) cudaFree(e->lanes[i].d_meta);
     }
     cudaFree(e->d_stats); cudaFree(e->d_err); cudaFree(e->d_err_index);
+    if (e->d_contams) cudaFree(e->d_contams);
     delete e;
     return 0;
 }

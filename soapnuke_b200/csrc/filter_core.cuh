@@ -152,6 +152,19 @@ struct AdapterDev {
     uint8_t  seq[SNK_MAX_ADAPTER_LEN];
 };
 
+// One contaminant sequence (config keys contam1 / contam2), preprocessed on the host like an adapter: the
+// per-offset mismatch budgets and run thresholds of hasContam (read_filter.cpp:596-706) are evaluated once
+// with the reference's expression types. The records live in device memory (DevParams::contams).
+struct ContamDev {
+    int32_t len, seg_thr, budget2, edge;
+    int32_t n13;                              // offsets of phases 1 and 3 = max(0, len - edge)
+    int32_t pad_[3];
+    int32_t mis_t[SNK_MAX_ADAPTER_LEN];       // (int)(r1 / misGrad)
+    int32_t seg1_t[SNK_MAX_ADAPTER_LEN];      // phase 1: segGrad != 0 ? 7 + r1/segGrad : 7
+    int32_t seg3_t[SNK_MAX_ADAPTER_LEN];      // phase 3: 7 + r1/segGrad (no zero test, read_filter.cpp:686)
+    uint8_t seq[SNK_MAX_ADAPTER_LEN];
+};
+
 // The fields of a `fast` adapter the bit-plane sweep reads, compact enough to keep one per mate in shared
 // memory. Budgets are clamped to [-1, 64]: any negative budget behaves like -1 and, windows being at most
 // 64 bases, any budget above 64 like 64.
@@ -193,6 +206,8 @@ struct DevParams {
     int32_t ada_rctg, ada_rma, ada_rmm;
     float   ada_rar, ada_rer;
     int32_t qb;            // quality bins kept in shared memory (max_base_quality+1, <= SNK_QBINS)
+    int32_t contam_discard, n_contams[2];
+    const ContamDev* contams;      // [2][SNK_MAX_CONTAMS], device memory (null when no contaminant is configured)
     int64_t slot_block;
     AdapterDev ada[2][SNK_MAX_ADAPTERS];
 };
@@ -209,7 +224,8 @@ enum : uint16_t {
     RF_LOWQ_GT1 = 64, RF_BAD_BASE = 128, RF_BAD_QUAL = 256,
     RF_QSLOW = 512,       // some quality falls outside the shared-memory bins: histogram takes the checked path
     RF_NO3 = 1024, RF_INSNULL = 2048,    // filtersRNA: no 3' adapter / 3' adapter within the first three bases
-    RF_TILE = 4096, RF_FOV = 8192        // the id selected the read for removal (SNK_PRE_TILE / SNK_PRE_FOV of len[])
+    RF_TILE = 4096, RF_FOV = 8192,       // the id selected the read for removal (SNK_PRE_TILE / SNK_PRE_FOV of len[])
+    RF_CONTAM = 16384                    // a contaminant sequence of the mate's list was found
 };
 SNK_HD uint16_t pre_flags(uint32_t len_word) { return (uint16_t)(((len_word & SNK_PRE_TILE) ? RF_TILE : 0) | ((len_word & SNK_PRE_FOV) ? RF_FOV : 0)); }
 enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
@@ -567,6 +583,42 @@ SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
     return -1;
 }
 
+// ---- contaminant search, hasContam (read_filter.cpp:596-706), byte-wise (an uncommon option). Like
+// adapter_pos, with three differences: an uppercase 'N' of the read is neither match nor mismatch (and does
+// not break a run), phases 1 and 3 accept runs of seg1_t / seg3_t matches, and their budgets grow with the
+// overlap. Read positions outside the read are mismatches.
+SNK_HD bool contam_window(const uint8_t* read, int len, int roff, const uint8_t* ct, int coff, int winlen, int budget, int seg_thr)
+{
+    int mis = 0, seg = 0;
+    for (int c = 0; c < winlen; c++) {
+        const int ri = roff + c;
+        const int rc = (ri >= 0 && ri < len) ? (int)read[ri] : -1;
+        if (rc >= 0 && (int)ct[coff + c] == rc) { if (++seg >= seg_thr) return true; }
+        else if (rc != 'N') { mis++; seg = 0; if (mis > budget) return false; }
+    }
+    return mis <= budget;
+}
+SNK_HD int contam_pos_bytes(const uint8_t* seq, int len, const ContamDev& k)
+{
+    const int C = k.len;
+    if (C == 0) return -1;
+    for (int r1 = 0; r1 < k.n13; r1++)
+        if (contam_window(seq, len, 0, k.seq, C - r1 - k.edge, r1 + k.edge, k.mis_t[r1], k.seg1_t[r1])) return 0;
+    for (int r1 = 0; r1 <= len - C; r1++)
+        if (contam_window(seq, len, r1, k.seq, 0, C, k.budget2, k.seg_thr)) return r1;
+    for (int r1 = 0; r1 < k.n13; r1++) {
+        const int base = len - r1 - k.edge;
+        if (contam_window(seq, len, base, k.seq, 0, r1 + k.edge, k.mis_t[r1], k.seg3_t[r1])) return base;
+    }
+    return -1;
+}
+SNK_HD bool has_contam(const uint8_t* seq, int len, int mate, const DevParams& P)
+{
+    for (int i = 0; i < P.n_contams[mate]; i++)
+        if (contam_pos_bytes(seq, len, P.contams[mate * SNK_MAX_CONTAMS + i]) >= 0) return true;
+    return false;
+}
+
 // ---- filtersRNA adapter finders (byte-wise ungapped alignments; reads are short)
 // read_filter.cpp:791-862 sRNA_findAdapter: 3' adapter. Alignments in the reference's order: adapter
 // offsets 2,1,0 at read position 0, then offset 0 at read positions 1..len-adaRMa; an 'N' of the read is
@@ -824,8 +876,8 @@ SNK_HD int srna_cut_len(const DevParams& P, int ada_pos, int len)
 template <int NW>
 // ada_pos: adapter_pos() result (filter) or sRNA_findAdapter() result (filtersRNA); has5: sRNA_hasAdapter();
 // cur = sequence length fastq_trim applies the cuts to (len, or the 3' adapter position in filtersRNA)
-SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, bool has5, int cur, const TrimPart& T, int len,
-                        int mate, const DevParams& P, ReadInfo& R)
+SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, bool has5, bool contam, int cur, const TrimPart& T,
+                        int len, int mate, const DevParams& P, ReadInfo& R)
 {
     uint16_t flags = 0;
     if (S.viol) flags |= RF_BAD_BASE;
@@ -848,6 +900,7 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
     if (P.n_ratio != -1 && n_ratio >= P.n_ratio) flags |= RF_N;
     if (P.highA_ratio != -1 && a_ratio >= P.highA_ratio) flags |= RF_HIGHA;
     if (polyx) flags |= RF_POLYX;
+    if (contam) flags |= RF_CONTAM;
     if (P.low_qual_ratio != -1 && lowq_ratio >= P.low_qual_ratio) flags |= RF_LOWQ;
     if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
     if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
@@ -934,7 +987,8 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
     TrimPart T, T2;
     trim_part(seq, qual, len, cur, P, 0, T);
     for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, cur, P, h, T2); merge_trim(T, T2); }
-    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, cur, T, len, mate, P, R);
+    const bool contam = !P.srna && P.n_contams[mate] > 0 && has_contam(seq, len, mate, P);
+    finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, contam, cur, T, len, mate, P, R);
 }
 
 // ------------------------------------------------------------------ discard cascade
@@ -955,6 +1009,7 @@ SNK_HD int decide_pair(const DevParams& P, const ReadInfo& a, const ReadInfo& b,
         x = (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len; y = (uint64_t)b.clean_len > (uint64_t)(int64_t)P.max_len;
         SNK_DIS(SNK_DROP_LONG, SNK_FS_LONG);
     }
+    if (P.contam_discard) { x = a.flags & RF_CONTAM; y = b.flags & RF_CONTAM; SNK_DIS(SNK_DROP_CONTAM, SNK_FS_CONTAM); }   // sequence.cpp:274-288
     x = a.flags & RF_N; y = b.flags & RF_N; SNK_DIS(SNK_DROP_N, SNK_FS_N);
     x = a.flags & RF_HIGHA; y = b.flags & RF_HIGHA; SNK_DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA);
     x = a.flags & RF_POLYX; y = b.flags & RF_POLYX; SNK_DIS(SNK_DROP_POLYX, SNK_FS_POLYX);
@@ -972,6 +1027,7 @@ SNK_HD int decide_se(const DevParams& P, const ReadInfo& a, int* fs_base)
     if (a.flags & RF_FOV) { *fs_base = SNK_FS_FOV; return SNK_DROP_FOV; }
     if (P.min_len != -1 && (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len) { *fs_base = SNK_FS_SHORT; return SNK_DROP_SHORT; }
     if (P.max_len != -1 && (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len) { *fs_base = SNK_FS_LONG; return SNK_DROP_LONG; }
+    if (P.contam_discard && (a.flags & RF_CONTAM)) { *fs_base = SNK_FS_CONTAM; return SNK_DROP_CONTAM; }      // sequence.cpp:116-122
     if (a.flags & RF_N) { *fs_base = SNK_FS_N; return SNK_DROP_N; }
     if (a.flags & RF_HIGHA) { *fs_base = SNK_FS_HIGHA; return SNK_DROP_HIGHA; }
     if (a.flags & RF_POLYX) { *fs_base = SNK_FS_POLYX; return SNK_DROP_POLYX; }

@@ -2,9 +2,10 @@
 // Flag surface, defaults, derived values and error texts follow process_argv.cpp (getopt table
 // :77-170, option handling :181-520, derived values :533-544, check_parameter :554-917, config
 // file :1158-1638). Options that select parts of the reference this engine does not implement
-// (contaminants, tile/fov, rmdup, output split/subsample, trim-only outputs, stLFR) are rejected
+// (global contaminants, rmdup, output split/subsample, trim-only outputs, stLFR) are rejected
 // with an explicit error instead of being silently ignored.
 #include "cli_params.h"
+#include <cmath>
 #include <getopt.h>
 #include <sys/sysinfo.h>
 #include <cstdio>
@@ -125,6 +126,10 @@ void init_from_config(HostParams& hp, const char* path)
             if (value.find(",") == std::string::npos) { hp.ada_mr = (float)atof(value.c_str()); hp.ada_mr2 = hp.ada_mr; }
             else { auto v = split(value, ','); if (v.size() < 2) die("expected two values in -A parameter"); hp.ada_mr = (float)atof(v[0].c_str()); hp.ada_mr2 = (float)atof(v[1].c_str()); }
         }
+        else if (key == "contam1") hp.contam1 = value;                                     // process_argv.cpp:1286-1300
+        else if (key == "contam2") hp.contam2 = value;
+        else if (key == "ctMatchR") hp.ct_match_r = value;
+        else if (key == "contam_trim") hp.contam_trim = true;
         else if (key == "tile") hp.tile = value;                                           // process_argv.cpp:1314-1320
         else if (key == "fov") hp.fov = value;
         else if (key == "log") hp.log = value;
@@ -162,6 +167,7 @@ void print_usage(const std::string& module)
               << "  -h, --help   -v, --version\n"
               << "config file keys: seqType outFileType index qualSys outQualSys maxBaseQuality pe_info patch maxReadLen\n"
               << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log tile fov\n"
+              << "                  contam1 contam2 ctMatchR contam_trim\n"
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
 }
@@ -299,7 +305,7 @@ void to_engine_params(const HostParams& hp, snk_params& p)
     p.low_qual = hp.low_qual; p.low_qual_ratio = hp.low_qual_ratio; p.mean_quality = hp.mean_quality;
     p.n_ratio = hp.n_ratio; p.highA_ratio = hp.highA_ratio; p.polyG_tail = hp.polyG_tail; p.polyX_num = hp.polyX_num;
     p.min_read_length = hp.min_read_length; p.max_read_length = hp.max_read_length;
-    p.ada_trim = hp.ada_trim; p.contam_trim = 0;
+    p.ada_trim = hp.ada_trim;
     p.ada_mis[0] = hp.ada_mis; p.ada_mis[1] = hp.ada_mis2;
     p.ada_mr[0] = hp.ada_mr; p.ada_mr[1] = hp.ada_mr2;
     p.ada_edge[0] = hp.ada_edge; p.ada_edge[1] = hp.ada_edge2;
@@ -329,6 +335,39 @@ void to_engine_params(const HostParams& hp, snk_params& p)
     }
     p.index_remove = hp.index_remove;
     p.max_base_quality = hp.max_base_quality;
+    p.contam_discard = hp.contam_trim ? 0 : 1;
+    p.contam_trim = hp.contam_trim ? 1 : 0;
+    {
+        const std::string* lists[2] = {&hp.contam1, &hp.contam2};
+        for (int m = 0; m < 2; m++) {
+            const std::string& v = *lists[m];
+            if (v.empty() || (m == 1 && !hp.is_pe)) continue;
+            std::vector<std::string> seqs;
+            std::vector<int> thr;
+            if (v.find(",") == std::string::npos) {               // hasContam(): double product (read_filter.cpp:609)
+                seqs.push_back(v);
+                thr.push_back((int)ceil((double)v.size() * atof(hp.ct_match_r.c_str())));
+            } else {                                              // hasContams(): one ratio per sequence, float product (:499,:514)
+                seqs = split(v, ',');
+                if (hp.ct_match_r.find(",") == std::string::npos) die("the number of ctMatchR value should equal to that of contam sequences");
+                const std::vector<std::string> mrs = split(hp.ct_match_r, ',');
+                if (mrs.size() != seqs.size())
+                    die("the number of ctMatchR value should equal to that of contam sequences," + std::to_string(seqs.size()) + ".vs." + std::to_string(mrs.size()));
+                for (size_t i = 0; i < seqs.size(); i++) {
+                    const float mr = (float)atof(mrs[i].c_str());
+                    thr.push_back((int)ceil((int)seqs[i].size() * mr));
+                }
+            }
+            if (seqs.size() > SNK_MAX_CONTAMS) die("too many contaminant sequences");
+            p.n_contams[m] = (int)seqs.size();
+            for (size_t i = 0; i < seqs.size(); i++) {
+                if (seqs[i].size() >= SNK_MAX_ADAPTER_LEN) die("contaminant sequence longer than the supported maximum");
+                p.contam_len[m][i] = (int)seqs[i].size();
+                p.contam_seg_thr[m][i] = thr[i];
+                memcpy(p.contam[m][i], seqs[i].data(), seqs[i].size());
+            }
+        }
+    }
     p.seq_type1 = hp.seq_type != "0";
     {
         struct { const std::string* src; int32_t* n; char (*dst)[SNK_ID_FILTER_LEN]; } lists[2] = {{&hp.tile, &p.n_tile, p.tile}, {&hp.fov, &p.n_fov, p.fov}};

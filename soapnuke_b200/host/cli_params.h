@@ -30,6 +30,8 @@ struct HostParams {
     int ada_mis = 2, ada_mis2 = 2, ada_edge = 6, ada_edge2 = 6;
     float ada_mr = 0.5f, ada_mr2 = 0.5f;
     bool is_pe = false;
+    std::string contam1, contam2, ct_match_r = "0.2";   // config keys contam1= / contam2= / ctMatchR= (lists: comma separated)
+    bool contam_trim = false;          // config key contam_trim: no discard (the trim itself is commented out in 2.1.9)
     std::string tile, fov;             // config keys tile= / fov= (removal lists, comma separated)
     // filtersRNA module (global_parameter.h:54-58)
     bool srna = false;

@@ -31,6 +31,16 @@ int params_check(const snk_params& p)
         // sRNA_hasAdapter starts at adapter offset adptLen - adaRCtg (read_filter.cpp:872)
         if (p.n_adapters[0] > 0 && p.adapter_len[0][0] < p.ada_rctg) { set_error("adapter1 is shorter than adaRCtg"); return 1; }
     }
+    for (int m = 0; m < 2; m++) {
+        if (p.n_contams[m] < 0 || p.n_contams[m] > SNK_MAX_CONTAMS) { set_error("too many contaminant sequences"); return 1; }
+        if (p.n_contams[m] > 0 && p.ada_mis[m] + 1 == 0) { set_error("adaMis must not be -1"); return 1; }
+        if (p.n_contams[m] > 0 && p.srna) { set_error("contaminant sequences are not part of filtersRNA"); return 1; }
+        for (int i = 0; i < p.n_contams[m]; i++) {
+            const int L = p.contam_len[m][i];
+            if (L < 0 || L >= SNK_MAX_ADAPTER_LEN) { set_error("contaminant sequence too long"); return 1; }
+            if ((int)strnlen(p.contam[m][i], SNK_MAX_ADAPTER_LEN) < L) { set_error("contam_len exceeds the contaminant string"); return 1; }
+        }
+    }
     if (p.n_tile < 0 || p.n_tile > SNK_MAX_ID_FILTERS || p.n_fov < 0 || p.n_fov > SNK_MAX_ID_FILTERS) { set_error("too many tile / fov entries"); return 1; }
     if (p.n_fov > 0 && p.seq_type1) { set_error("Zebra-500 data(--fov), --seqType is 0"); return 1; }     // read_filter.cpp:131-134
     if (p.has_hard_trim) for (int m = 0; m < 2; m++)

@@ -138,6 +138,42 @@ def gen_srna(n, L=50, seed=1004, adapter5=SRNA_ADAPTER5, adapter3=SRNA_ADAPTER3,
     return dict(seq1=S, qual1=Q, len1=length, n=n, L=L, stride=stride)
 
 
+CONTAM1 = b"GATCGGAAGAGCACACGTCTGAACTCCAGTCAC"
+CONTAM2 = b"CTGTCTCTTATACACATCTCCGAGCCCACGAGAC"
+CONTAM3 = b"ACACTCTTTCCCTACACGACGCTCTTCCGATCT"
+
+
+def add_contams(d, contams, seed, frac=0.15):
+    """Plants (sometimes mutated / truncated / overhanging) copies of the contaminant sequences into a
+    fraction of the reads of every mate of a gen_pairs() batch, plus a few N's next to them."""
+    rng = np.random.default_rng(seed)
+    n = d["n"]
+    for m in (1, 2):
+        if f"seq{m}" not in d:
+            continue
+        S, Ln = d[f"seq{m}"], d[f"len{m}"]
+        for i in np.nonzero(rng.random(n) < frac)[0]:
+            c = np.frombuffer(contams[int(rng.integers(0, len(contams)))], dtype=np.uint8).copy()
+            l = int(Ln[i])
+            for _ in range(int(rng.integers(0, 4))):
+                c[rng.integers(0, c.size)] = _ACGT[rng.integers(0, 4)]
+            mode = int(rng.integers(0, 4))
+            if mode == 0:
+                off = int(rng.integers(0, max(1, l - c.size + 1)))                 # inside
+            elif mode == 1:
+                off = -int(rng.integers(1, c.size - 5))                            # tail of the contaminant at the read's head
+            elif mode == 2:
+                off = l - int(rng.integers(5, c.size))                             # head of the contaminant at the read's tail
+            else:
+                c = c[: int(rng.integers(8, c.size))]; off = int(rng.integers(0, max(1, l - c.size + 1)))
+            a0, b0 = max(off, 0), min(l, off + c.size)
+            if b0 > a0:
+                S[i, a0:b0] = c[a0 - off:b0 - off]
+                if rng.random() < 0.3:
+                    S[i, int(rng.integers(a0, b0))] = ord("N")
+    return d
+
+
 def read_ids(n, mate, first=0):
     return [b"@SYN:1:1101:%d:%d/%d" % ((first + i) // 1000, (first + i) % 1000, mate) for i in range(n)]
 

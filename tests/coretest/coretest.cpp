@@ -240,6 +240,9 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
 
     Ctx c;
     prepare_params(*p, c.P);
+    std::vector<ContamDev> contams(2 * SNK_MAX_CONTAMS);
+    prepare_contams(*p, contams.data());
+    c.P.contams = contams.data();
     if (qb_override >= 0) c.P.qb = qb_override;
     c.stats = stats;
     c.mates = p->is_pe ? 2 : 1;

@@ -33,13 +33,15 @@ def read_maybe_gz(path):
 
 
 def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False,
-             module="filter", idfn=None):
+             module="filter", idfn=None, contams=None):
     w = os.path.join(str(tmp), name)
     os.makedirs(w)
     if module == "filtersRNA":
         d = synth.gen_srna(n, L=L, seed=zlib.crc32(name.encode()) % 100000, **(gkw or {}))
     else:
         d = synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 100000, se=not pe, **(gkw or {}))
+    if contams:
+        synth.add_contams(d, contams, seed=n)
     ext_in = ".fq.gz" if gz_in else ".fq"
     ext_out = ".fq.gz" if gz_out else ".fq"
     def write(path, m):
@@ -104,6 +106,25 @@ def test_cli_matches_reference_binary(cli, tmp_path, case):
 ], ids=lambda c: c["name"])
 def test_cli_tile_fov_matches_reference_binary(cli, tmp_path, case):
     """Config keys tile= / fov=: the ids are parsed on the device by the FASTQ text path."""
+    run_both(cli, tmp_path, **case)
+
+
+CT = [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3]
+CT1, CT2, CT3 = (c.decode() for c in CT)
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
+@pytest.mark.parametrize("case", [
+    dict(name="contam_pe_single", pe=True, n=30000, L=100, T=2, flags=["-f", A1, "-r", A2, "-J"], cfg=[f"contam1={CT1}", f"contam2={CT2}"], contams=CT),
+    dict(name="contam_se_list_gz", pe=False, n=20000, L=120, T=1, flags=[], cfg=[f"contam1={CT1},{CT3}", "ctMatchR=0.3,0.5"], contams=CT,
+         gkw=dict(var_len=True), gz_in=True, gz_out=True),
+    dict(name="contam_pe_list_budgets", pe=True, n=20000, L=150, T=3, flags=["-f", A1, "-r", A2], patch=20,
+         cfg=[f"contam1={CT3},{CT2},{CT1}", f"contam2={CT1},{CT2},{CT3[:20]}", "ctMatchR=0.2,0.6,0.9", "adaMis=1,3", "adaEdge=4,8"], contams=CT),
+    dict(name="contam_trim_mode", pe=True, n=20000, L=100, T=1, flags=["-f", A1, "-r", A2, "-J"],
+         cfg=[f"contam1={CT1}", f"contam2={CT2}", "contam_trim", "ctMatchR=0.4"], contams=CT),
+], ids=lambda c: c["name"])
+def test_cli_contam_matches_reference_binary(cli, tmp_path, case):
+    """Config keys contam1= / contam2= / ctMatchR= / contam_trim."""
     run_both(cli, tmp_path, **case)
 
 

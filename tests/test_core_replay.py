@@ -97,6 +97,35 @@ def test_tile_fov_flags_in_len(pe):
     assert_same((c1, c2, cst), (o1, o2, ost), "tile/fov")
 
 
+CONTAM_CONFIGS = [
+    ("contam_pe_single", True, 6000, 100, dict(), dict(adapter1=A1, adapter2=A2, ada_trim=True, contam1=synth.CONTAM1.decode(), contam2=synth.CONTAM2.decode())),
+    ("contam_se_list_varlen", False, 6000, 120, dict(var_len=True),
+     dict(contam1=f"{synth.CONTAM1.decode()},{synth.CONTAM3.decode()}", ct_match_r="0.3,0.5")),
+    ("contam_pe_list_budgets", True, 5000, 150, dict(),
+     dict(adapter1=A1, adapter2=A2, contam1=",".join(c.decode() for c in (synth.CONTAM3, synth.CONTAM2, synth.CONTAM1)),
+          contam2=",".join([synth.CONTAM1.decode(), synth.CONTAM2.decode(), synth.CONTAM3.decode()[:20]]), ct_match_r="0.2,0.6,0.9",
+          ada_mis=(1, 3), ada_edge=(4, 8))),
+    ("contam_short_reads_tiny_thr", True, 4000, 40, dict(), dict(contam1=synth.CONTAM1.decode(), contam2=synth.CONTAM2.decode(), ct_match_r="0.1",
+                                                                  min_read_length=20)),     # reads shorter than the contaminant, segThr-6 <= 0
+    ("contam_trim_mode", True, 3000, 100, dict(), dict(adapter1=A1, adapter2=A2, ada_trim=True, contam1=synth.CONTAM1.decode(),
+                                                       contam2=synth.CONTAM2.decode(), ct_match_r="0.4", contam_trim=True)),
+]
+
+
+@pytest.mark.parametrize("cfg", CONTAM_CONFIGS, ids=[c[0] for c in CONTAM_CONFIGS])
+def test_core_replay_matches_oracle_contam(cfg):
+    """Contaminant sequences (hasContam / hasContams): per-offset budget / run tables, N handling, discard order."""
+    name, pe, n, L, gkw, pkw = cfg
+    d = synth.add_contams(synth.gen_pairs(n, L=L, seed=len(name) * 13, se=not pe, **gkw), [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3], seed=L)
+    p = abi.make_params(is_pe=pe, threads=2, patch_size=60, **pkw)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    c1, c2, cst, cerr = core_replay(p, d, grid=4)
+    assert oerr == cerr == 0
+    if not pkw.get("contam_trim"):
+        assert (o1["category"] == 14).sum() > n // 50
+    assert_same((c1, c2, cst), (o1, o2, ost), name)
+
+
 def test_mixed_checked_and_unchecked_tiles(monkeypatch):
     """A few records with qualities above the shared-memory bins: their tiles take the checked
     histogram path (out-of-bin qualities go straight to the global tables, mirrored into the clean

@@ -88,6 +88,21 @@ def test_tile_fov_flags_in_len(pe, engine_lib):
     assert_same((r1, r2, st), (o1, o2, ost), "tile/fov")
 
 
+def test_engine_matches_oracle_contam(engine_lib):
+    """Contaminant sequences on the engine (the CPU tier's CONTAM_CONFIGS, larger batches)."""
+    from test_core_replay import CONTAM_CONFIGS
+    for name, pe, n, L, gkw, pkw in CONTAM_CONFIGS:
+        d = synth.add_contams(synth.gen_pairs(5 * n, L=L, seed=len(name) * 13, se=not pe, **gkw), [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3], seed=L)
+        p = abi.make_params(is_pe=pe, threads=2, patch_size=600, **pkw)
+        o1, o2, ost, oerr = oracle_run(p, d)
+        with Engine(engine_lib, p) as e:
+            r1, r2 = e.filter_host(d)
+            st = e.stats()
+            flags, _ = e.error_flags()
+        assert flags == oerr == 0
+        assert_same((r1, r2, st), (o1, o2, ost), name)
+
+
 def test_mixed_checked_and_unchecked_tiles(engine_lib):
     """Records with qualities above the shared-memory bins scattered through the batch (see the CPU
     tier's test of the same name): checked and unchecked tiles, raw and delta cells must add up."""

@@ -235,6 +235,55 @@ def test_device_id_parse_matches_oracle():
             assert lib.coretest_id_flags(C.byref(p), i, len(i)) == orc.lib().orc_id_flags(C.byref(p), i, len(i)), (st1, i)
 
 
+# ---- contaminant sequences (config keys contam1 / contam2 / ctMatchR / contam_trim): oracle vs the reference binary
+C1, C2, C3 = synth.CONTAM1.decode(), synth.CONTAM2.decode(), synth.CONTAM3.decode()
+CONTAM_LIVE = [
+    # name, pe, n, L, T, flags, config lines, params kwargs
+    ("contam_pe_single", True, 5000, 100, 2, ["-f", A1, "-r", A2, "-J"], [f"contam1={C1}", f"contam2={C2}", "patch=20"],
+     dict(adapter1=A1, adapter2=A2, ada_trim=True, contam1=C1, contam2=C2)),
+    ("contam_se_list", False, 5000, 120, 1, [], [f"contam1={C1},{C3}", "ctMatchR=0.3,0.5"], dict(contam1=f"{C1},{C3}", ct_match_r="0.3,0.5")),
+    ("contam_pe_list_mr_adamis", True, 4000, 150, 3, ["-f", A1, "-r", A2], [f"contam1={C3},{C2},{C1}", f"contam2={C1},{C2},{C3[:20]}", "ctMatchR=0.2,0.6,0.9", "adaMis=1,3", "adaEdge=4,8"],
+     dict(adapter1=A1, adapter2=A2, contam1=f"{C3},{C2},{C1}", contam2=f"{C1},{C2},{C3[:20]}", ct_match_r="0.2,0.6,0.9", ada_mis=(1, 3), ada_edge=(4, 8))),
+    ("contam_trim_mode", True, 3000, 100, 1, ["-f", A1, "-r", A2, "-J"], [f"contam1={C1}", f"contam2={C2}", "contam_trim", "ctMatchR=0.4"],
+     dict(adapter1=A1, adapter2=A2, ada_trim=True, contam1=C1, contam2=C2, ct_match_r="0.4", contam_trim=True)),
+]
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", CONTAM_LIVE, ids=[c[0] for c in CONTAM_LIVE])
+def test_oracle_matches_reference_binary_contam(case, engine_lib, tmp_path):
+    name, pe, n, L, T, flags, cfg, pkw = case
+    data = synth.add_contams(synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, var_len=(L == 120)),
+                             [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3], seed=len(name))
+    w = str(tmp_path)
+    synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
+    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    if pe:
+        synth.write_fastq(f"{w}/r2.fq", data["seq2"], data["qual2"], data["len2"], 2)
+        args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+    open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg))
+    patch = next((int(l.split("=")[1]) for l in cfg if l.startswith("patch=")), None)
+    r = orc.run_reference(args + ["-c", f"{w}/cfg.txt"] + flags)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
+    if pe:
+        r1, r2, st, err = orc.filter_pe(p, data)
+    else:
+        r1, st, err = orc.filter_se(p, data); r2 = None
+    assert err == 0
+    cats = np.bincount(r1["category"], minlength=15)
+    assert cats[0] > n // 4 and (cats[14] > n // 50) == (not pkw.get("contam_trim", False)), cats
+    for m, rs in ((1, r1), (2, r2)):
+        if rs is None:
+            continue
+        order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
+        mine = synth.clean_fastq_bytes(data[f"seq{m}"], data[f"qual{m}"], data[f"len{m}"], rs, m, order=order)
+        assert mine == open(f"{w}/out/c{m}.fq", "rb").read(), f"clean fq{m} differs from the reference binary"
+    fn = engine_lib.snk_report_write_pe if pe else engine_lib.snk_report_write_se
+    write_reports(fn, p, st, f"{w}/mine")
+    compare_reports(f"{w}/out", f"{w}/mine")
+
+
 # ---- known answers measured on the reference binary (A=32: segThr=16, misGrad=8, misGrad5=9)
 def body(n, rng):
     return bytes(rng.choice(np.frombuffer(b"CT", dtype=np.uint8), size=n))
