@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNK_ABI_VERSION 4
+#define SNK_ABI_VERSION 5
 
 /* ---- limits (global_variable.h:9-11 READ_MAX_LEN / MAX_QUAL) ---- */
 #define SNK_MAX_READ_LEN   1000   /* READ_MAX_LEN: per-position tables have this many rows        */
@@ -113,6 +113,15 @@ typedef struct snk_params {
     int32_t contam_len[2][SNK_MAX_CONTAMS];
     int32_t contam_seg_thr[2][SNK_MAX_CONTAMS];
     char    contam[2][SNK_MAX_CONTAMS][SNK_MAX_ADAPTER_LEN];
+    /* global contaminants (config keys global_contams / glob_cotm_mR / glob_cotm_mM; hasGlobalContams /
+     * global_contam_pos, read_filter.cpp:927-1053): every sequence is searched forward and reverse
+     * complemented in both mates; a hit drops the read while contam_discard is set.
+     * gcontam_min_match = int(len * matchRatio) with a float product (:970). */
+    int32_t n_gcontams;
+    int32_t gcontam_len[SNK_MAX_CONTAMS];
+    int32_t gcontam_min_match[SNK_MAX_CONTAMS];
+    int32_t gcontam_mismatch[SNK_MAX_CONTAMS];
+    char    gcontam[SNK_MAX_CONTAMS][SNK_MAX_ADAPTER_LEN];
 } snk_params;
 
 /* ---- one mate of a batch, fixed-stride SoA ---- */
@@ -147,7 +156,8 @@ enum snk_category {
     SNK_DROP_INSERTNULL = 11,    /* filtersRNA: 3' adapter within the first 3 bases (sequence.cpp:40-44), never reported */
     SNK_DROP_TILE = 12,          /* "Reads with filtered tile" (first test of pe_discard / se_discard) */
     SNK_DROP_FOV = 13,           /* "Reads with filtered fov" */
-    SNK_DROP_CONTAM = 14         /* "Reads with contam sequence" */
+    SNK_DROP_CONTAM = 14,        /* "Reads with contam sequence" */
+    SNK_DROP_GCONTAM = 15        /* "Reads with global contam sequence" */
 };
 typedef struct snk_read_result {
     uint16_t head_cut;     /* bases removed from the 5' end of this mate */
@@ -173,7 +183,8 @@ enum snk_fs {
     SNK_FS_TILE,                 /* fs.tile_num */
     SNK_FS_FOV,                  /* fs.fov_num */
     SNK_FS_CONTAM, SNK_FS_CONTAM1, SNK_FS_CONTAM2, SNK_FS_CONTAM_OV,   /* fs.include_contam_seq_num[1|2|_overlap] */
-    SNK_FS_COUNT = 40
+    SNK_FS_GCONTAM, SNK_FS_GCONTAM1, SNK_FS_GCONTAM2, SNK_FS_GCONTAM_OV,   /* fs.include_global_contam_seq_num[1|2|_overlap] */
+    SNK_FS_COUNT = 48
 };
 /* C_general_stat (global_variable.h:88-100), index into a file block's gs[] */
 enum snk_gs {

@@ -181,6 +181,86 @@ ORC_EXPORT int orc_has_contam(const uint8_t* read, int readLen, const uint8_t* c
     return -1;
 }
 
+/* read_filter.cpp:961-1053 global_contam_pos(): a scoring walk (match +1, mismatch -200) over three
+ * placements of the contaminant; total_score / overlap are NOT reset between the start positions of the
+ * second and third placement, only before each placement. */
+ORC_EXPORT int orc_global_contam_pos(const uint8_t* read, int rl, const uint8_t* ct, int cl, int min_match_len, int mismatch_number)
+{
+    const int mismatch_score = -200, match_score = 1;
+    int total_mismatch_score = mismatch_number * mismatch_score;
+    int lower_score = (min_match_len - mismatch_number) + total_mismatch_score;
+    int total_score = -1000, overlap = 0;
+    for (int i = cl - min_match_len; i >= 0; i--) {                       /* contaminant in front of the read */
+        int j_max = cl - i > rl ? rl : cl - i;
+        for (int j = 0; j != j_max; j++) {
+            if (read[j] == ct[i + j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { if (j_max - j < min_match_len) break; total_score = match_score; overlap = 1; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (j_max - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return 0;
+        }
+    }
+    total_score = -1000; overlap = 0;
+    for (int i = 0; i <= rl - cl; i++) {                                  /* in the middle */
+        for (int j = 0; j != cl; j++) {
+            if (read[i + j] == ct[j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { if (cl - j < min_match_len) break; total_score = match_score; overlap = 1; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (cl - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return i + j - overlap + 1;
+        }
+    }
+    total_score = -1000; overlap = 0;
+    int i_min = cl > rl ? cl - rl : 0;
+    for (int i = i_min; i <= cl - min_match_len; i++) {                   /* at the tail */
+        for (int j = 0; j != cl - i; j++) {
+            if (read[rl - (cl - i) + j] == ct[j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { total_score = match_score; overlap = 1; if (cl - i - j < min_match_len) break; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (cl - i - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return rl - cl + i + j - overlap + 1;
+        }
+    }
+    return -1;
+}
+/* read_filter.cpp:1055-1075 reversecomplementary() of a contaminant; returns 0 on an unrecognized base */
+static int orc_revcomp(const char* a, int n, uint8_t* out)
+{
+    for (int k = 0; k < n; k++) {
+        int ch = a[n - 1 - k];
+        if (ch >= 'a' && ch <= 'z') ch -= 32;
+        switch (ch) {
+            case 'A': out[k] = 'T'; break; case 'T': out[k] = 'A'; break;
+            case 'G': out[k] = 'C'; break; case 'C': out[k] = 'G'; break;
+            case 'N': out[k] = 'N'; break;
+            default: return 0;
+        }
+    }
+    return 1;
+}
+/* :207-249 of stat_read restricted to what the discard uses: include_global_contam = some sequence, forward
+ * or reverse complemented, is found (hasGlobalContams :927-960; its early break cannot change that) */
+static int orc_has_global_contam(const snk_params* p, const uint8_t* seq, int len)
+{
+    for (int i = 0; i < p->n_gcontams; i++) {
+        const int cl = p->gcontam_len[i];
+        uint8_t rev[SNK_MAX_ADAPTER_LEN];
+        if (orc_global_contam_pos(seq, len, (const uint8_t*)p->gcontam[i], cl, p->gcontam_min_match[i], p->gcontam_mismatch[i]) >= 0) return 1;
+        if (orc_revcomp(p->gcontam[i], cl, rev) &&
+            orc_global_contam_pos(seq, len, rev, cl, p->gcontam_min_match[i], p->gcontam_mismatch[i]) >= 0) return 1;
+    }
+    return 0;
+}
+
 /* stat_read's id parse (read_filter.cpp:86-148) + check_tile_or_fov (:14-79): SNK_PRE_TILE / SNK_PRE_FOV
  * bits for one record id (idlen bytes, no terminator needed). The tile is the (up to) 4 digits behind the
  * 2nd ':' (seqType 0) or the 4th ':' (seqType 1); the fov the 8 bytes from the first 'C' that has an 'R'
@@ -231,6 +311,7 @@ typedef struct {
     int has_adapter;
     int include_3_adapter;      /* filtersRNA: sRNA_findAdapter() of the raw read */
     int include_contam;         /* some contaminant of the mate's list was found */
+    int include_global_contam;  /* some global contaminant (either strand) was found */
     /* C_fastq cut bookkeeping (sequence.h:69), -1 as set by C_fastq_init (peprocess.cpp:1674-1689) */
     int head_hdcut, head_lqcut, tail_hdcut, tail_lqcut, adacut_pos;
     int head_cut, clean_len;    /* result of fastq_trim */
@@ -275,6 +356,7 @@ static void orc_stat_and_trim(const snk_params* p, int mate, const uint8_t* seq,
         for (int i = 0; i < p->n_contams[mate]; i++)
             if (orc_has_contam(seq, len, (const uint8_t*)p->contam[mate][i], p->contam_len[mate][i], p->contam_seg_thr[mate][i],
                                p->ada_mis[mate], p->ada_edge[mate]) >= 0) { r->include_contam = 1; break; }
+        r->include_global_contam = orc_has_global_contam(p, seq, len);
     }
     /* :255-287 base loop */
     int last_char = 'Q', contig = 0, max_contig = 1;
@@ -431,6 +513,7 @@ static int orc_pe_discard(const snk_params* p, const orc_read* r1, const orc_rea
         b = (uint64_t)r2->clean_len > (uint64_t)(int64_t)p->max_read_length;
         DIS(SNK_DROP_LONG, SNK_FS_LONG);
     }
+    if (p->contam_discard) { a = r1->include_global_contam; b = r2->include_global_contam; DIS(SNK_DROP_GCONTAM, SNK_FS_GCONTAM); }   /* :262-273 */
     if (p->contam_discard) { a = r1->include_contam; b = r2->include_contam; DIS(SNK_DROP_CONTAM, SNK_FS_CONTAM); }   /* :274-288 */
     if (p->n_ratio != -1) { a = r1->n_ratio >= p->n_ratio; b = r2->n_ratio >= p->n_ratio; DIS(SNK_DROP_N, SNK_FS_N); }
     if (p->highA_ratio != -1) { a = r1->a_ratio >= p->highA_ratio; b = r2->a_ratio >= p->highA_ratio; DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA); }
@@ -455,6 +538,7 @@ static int orc_se_discard(const snk_params* p, const orc_read* r, uint32_t pre, 
     if (p->min_read_length != -1 && (uint64_t)r->clean_len < (uint64_t)(int64_t)p->min_read_length) { fs[SNK_FS_SHORT]++; return SNK_DROP_SHORT; }
     if (p->max_read_length != -1 && (uint64_t)r->clean_len > (uint64_t)(int64_t)p->max_read_length) { fs[SNK_FS_LONG]++; return SNK_DROP_LONG; }
     if (p->contam_discard && r->include_contam) { fs[SNK_FS_CONTAM]++; return SNK_DROP_CONTAM; }                       /* :116-128 */
+    if (p->contam_discard && r->include_global_contam) { fs[SNK_FS_GCONTAM]++; return SNK_DROP_GCONTAM; }
     if (p->n_ratio != -1 && r->n_ratio >= p->n_ratio) { fs[SNK_FS_N]++; return SNK_DROP_N; }
     if (p->highA_ratio != -1 && r->a_ratio >= p->highA_ratio) { fs[SNK_FS_HIGHA]++; return SNK_DROP_HIGHA; }
     if (p->polyX_num != -1 && r->contig >= p->polyX_num) { fs[SNK_FS_POLYX]++; return SNK_DROP_POLYX; }

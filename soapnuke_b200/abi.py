@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 ENGINE_LIB = os.path.join(HERE, "lib", "libsnk_engine.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_READ_LEN = 1000
 QBINS = 64
 MAX_ADAPTERS = 8
@@ -22,7 +22,7 @@ MAX_CONTAMS = 8
 ID_FILTER_LEN = 8
 LEN_MASK, PRE_TILE, PRE_FOV = 0x3FFF, 0x4000, 0x8000
 
-FS_COUNT = 40
+FS_COUNT = 48
 GS_COUNT = 16
 FILE_COUNT = 4
 TS_COUNT = 5
@@ -40,7 +40,7 @@ RAW1, RAW2, CLEAN1, CLEAN2 = 0, 1, 2, 3
 GS_READS, GS_BASES, GS_A, GS_C, GS_G, GS_T, GS_N, GS_Q20, GS_Q30, GS_LAST_KEY = range(10)
 
 CATEGORY_NAMES = ["keep", "short", "long", "n", "highA", "polyX", "lowq", "meanq", "adapter", "empty", "no3adapter", "insertnull",
-                  "tile", "fov", "contam"]
+                  "tile", "fov", "contam", "gcontam"]
 FS_BASE = {"adapter": 0, "n": 4, "highA": 8, "polyX": 12, "lowq": 16, "meanq": 20, "short": 24, "long": 28}
 
 
@@ -101,6 +101,11 @@ class Params(C.Structure):
         ("contam_len", (C.c_int32 * MAX_CONTAMS) * 2),
         ("contam_seg_thr", (C.c_int32 * MAX_CONTAMS) * 2),
         ("contam", ((C.c_char * MAX_ADAPTER_LEN) * MAX_CONTAMS) * 2),
+        ("n_gcontams", C.c_int32),
+        ("gcontam_len", C.c_int32 * MAX_CONTAMS),
+        ("gcontam_min_match", C.c_int32 * MAX_CONTAMS),
+        ("gcontam_mismatch", C.c_int32 * MAX_CONTAMS),
+        ("gcontam", (C.c_char * MAX_ADAPTER_LEN) * MAX_CONTAMS),
     ]
 
 
@@ -198,7 +203,8 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
                 trim_bad_head=None, trim_bad_tail=None, threads=1, nprocs=None, max_base_quality=42,
                 contam_trim=False, index_remove=False, patch_size=None, srna=False, ada_rctg=6, ada_rar=0.8,
                 ada_rma=5, ada_rer=0.4, ada_rmm=4, tile=None, fov=None, seq_type1=False,
-                contam1=None, contam2=None, ct_match_r="0.2"):
+                contam1=None, contam2=None, ct_match_r="0.2",
+                global_contams=None, glob_cotm_mR="", glob_cotm_mM=""):
     """Build snk_params the way process_argv.cpp would from `SOAPnuke filter` flags.
     Float thresholds go through double -> float exactly like `gp.x = atof(optarg)`."""
     p = Params()
@@ -271,6 +277,15 @@ def make_params(is_pe=True, adapter1=None, adapter2=None, ada_trim=False, low_qu
             p.contam_len[m][i] = len(sq)
             p.contam_seg_thr[m][i] = thr[i]
             p.contam[m][i].value = sq.encode()
+    if global_contams:                 # config keys global_contams / glob_cotm_mR / glob_cotm_mM (read_filter.cpp:927-944)
+        seqs, mrs, mms = global_contams.split(","), glob_cotm_mR.split(","), glob_cotm_mM.split(",")
+        assert len(seqs) == len(mrs) == len(mms) <= MAX_CONTAMS, "the number of global contamination sequences should equal to that of related parameters"
+        p.n_gcontams = len(seqs)
+        for i, sq in enumerate(seqs):
+            p.gcontam_len[i] = len(sq)
+            p.gcontam_min_match[i] = int(_np.float32(len(sq)) * _np.float32(float(mrs[i])))      # int(cl*min_matchRatio), float product
+            p.gcontam_mismatch[i] = int(mms[i])
+            p.gcontam[i].value = sq.encode()
     p.seq_type1 = 1 if seq_type1 else 0
     for name, val in (("tile", tile), ("fov", fov)):          # config keys tile= / fov= (comma separated)
         ents = [e for e in (val.split(",") if val else []) if 0 < len(e) <= ID_FILTER_LEN]

@@ -84,12 +84,40 @@ inline void prepare_contams(const snk_params& p, ContamDev* out)
         }
 }
 
+// reversecomplementary() of a contaminant (read_filter.cpp:1055-1075); false on an unrecognized base
+inline bool revcomp_contam(const char* a, int n, uint8_t* out)
+{
+    for (int k = 0; k < n; k++) {
+        int ch = (unsigned char)a[n - 1 - k];
+        if (ch >= 'a' && ch <= 'z') ch -= 32;
+        switch (ch) {
+            case 'A': out[k] = 'T'; break; case 'T': out[k] = 'A'; break;
+            case 'G': out[k] = 'C'; break; case 'C': out[k] = 'G'; break;
+            case 'N': out[k] = 'N'; break;
+            default: return false;
+        }
+    }
+    return true;
+}
+inline void prepare_gcontams(const snk_params& p, GContamDev* out)
+{
+    for (int i = 0; i < SNK_MAX_CONTAMS; i++) {
+        memset(&out[i], 0, sizeof(GContamDev));
+        if (i >= p.n_gcontams) continue;
+        out[i].len = p.gcontam_len[i]; out[i].min_match = p.gcontam_min_match[i]; out[i].mismatch = p.gcontam_mismatch[i];
+        memcpy(out[i].fwd, p.gcontam[i], (size_t)p.gcontam_len[i]);
+        revcomp_contam(p.gcontam[i], p.gcontam_len[i], out[i].rev);       // validity is checked by params_check
+    }
+}
+
 inline void prepare_params(const snk_params& p, DevParams& d)
 {
     memset(&d, 0, sizeof(d));
     d.contam_discard = p.contam_discard;
     d.n_contams[0] = p.n_contams[0]; d.n_contams[1] = p.n_contams[1];
     d.contams = nullptr;
+    d.n_gcontams = p.n_gcontams;
+    d.gcontams = nullptr;
     d.is_pe = p.is_pe;
     d.phred = p.quality_phred;
     d.low_qual = p.low_qual;

@@ -69,6 +69,7 @@ struct snk_engine {
     unsigned int* d_err = nullptr;           // [0] flags
     unsigned long long* d_err_index = nullptr;
     ContamDev* d_contams = nullptr;          // [2][SNK_MAX_CONTAMS] when contaminants are configured
+    GContamDev* d_gcontams = nullptr;        // [SNK_MAX_CONTAMS] when global contaminants are configured
     Lane lanes[kLanes];
     uint64_t launches = 0;
     std::mutex mu;
@@ -375,6 +376,17 @@ int snk_engine_create(const snk_params* p, int device, snk_engine** out)
         }
         e->dev.contams = e->d_contams;
     }
+    if (p->n_gcontams > 0) {
+        std::vector<GContamDev> host(SNK_MAX_CONTAMS);
+        prepare_gcontams(*p, host.data());
+        if (cudaMalloc(&e->d_gcontams, host.size() * sizeof(GContamDev)) != cudaSuccess ||
+            cudaMemcpy(e->d_gcontams, host.data(), host.size() * sizeof(GContamDev), cudaMemcpyHostToDevice) != cudaSuccess) {
+            snk::set_error("cudaMalloc failed for the global contaminant table");
+            delete e;
+            return 1;
+        }
+        e->dev.gcontams = e->d_gcontams;
+    }
     e->stats_words = (size_t)p->n_slots * SNK_SLOT_WORDS;
     if (cudaMalloc(&e->d_stats, e->stats_words * 8) != cudaSuccess ||
         cudaMalloc(&e->d_err, 16) != cudaSuccess || cudaMalloc(&e->d_err_index, 8) != cudaSuccess) {
@@ -399,6 +411,7 @@ int snk_engine_destroy(snk_engine* e)
     }
     cudaFree(e->d_stats); cudaFree(e->d_err); cudaFree(e->d_err_index);
     if (e->d_contams) cudaFree(e->d_contams);
+    if (e->d_gcontams) cudaFree(e->d_gcontams);
     delete e;
     return 0;
 }

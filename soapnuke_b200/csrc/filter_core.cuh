@@ -165,6 +165,12 @@ struct ContamDev {
     uint8_t seq[SNK_MAX_ADAPTER_LEN];
 };
 
+// One global contaminant (config key global_contams): both strands, thresholds of global_contam_pos
+struct GContamDev {
+    int32_t len, min_match, mismatch, pad_;
+    uint8_t fwd[SNK_MAX_ADAPTER_LEN], rev[SNK_MAX_ADAPTER_LEN];
+};
+
 // The fields of a `fast` adapter the bit-plane sweep reads, compact enough to keep one per mate in shared
 // memory. Budgets are clamped to [-1, 64]: any negative budget behaves like -1 and, windows being at most
 // 64 bases, any budget above 64 like 64.
@@ -208,6 +214,8 @@ struct DevParams {
     int32_t qb;            // quality bins kept in shared memory (max_base_quality+1, <= SNK_QBINS)
     int32_t contam_discard, n_contams[2];
     const ContamDev* contams;      // [2][SNK_MAX_CONTAMS], device memory (null when no contaminant is configured)
+    int32_t n_gcontams, pad_gc;
+    const GContamDev* gcontams;    // [SNK_MAX_CONTAMS], device memory
     int64_t slot_block;
     AdapterDev ada[2][SNK_MAX_ADAPTERS];
 };
@@ -225,7 +233,8 @@ enum : uint16_t {
     RF_QSLOW = 512,       // some quality falls outside the shared-memory bins: histogram takes the checked path
     RF_NO3 = 1024, RF_INSNULL = 2048,    // filtersRNA: no 3' adapter / 3' adapter within the first three bases
     RF_TILE = 4096, RF_FOV = 8192,       // the id selected the read for removal (SNK_PRE_TILE / SNK_PRE_FOV of len[])
-    RF_CONTAM = 16384                    // a contaminant sequence of the mate's list was found
+    RF_CONTAM = 16384,                   // a contaminant sequence of the mate's list was found
+    RF_GCONTAM = 32768                   // a global contaminant (either strand) was found
 };
 SNK_HD uint16_t pre_flags(uint32_t len_word) { return (uint16_t)(((len_word & SNK_PRE_TILE) ? RF_TILE : 0) | ((len_word & SNK_PRE_FOV) ? RF_FOV : 0)); }
 enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
@@ -612,11 +621,79 @@ SNK_HD int contam_pos_bytes(const uint8_t* seq, int len, const ContamDev& k)
     }
     return -1;
 }
+// read_filter.cpp:961-1053 global_contam_pos(): scoring walk (match +1, mismatch -200) over three placements of
+// the contaminant; score and overlap are reset before each placement only, not between its start positions.
+SNK_HD int global_contam_pos(const uint8_t* read, int rl, const uint8_t* ct, int cl, int min_match_len, int mismatch_number)
+{
+    const int mismatch_score = -200, match_score = 1;
+    const int total_mismatch_score = mismatch_number * mismatch_score;
+    const int lower_score = (min_match_len - mismatch_number) + total_mismatch_score;
+    int total_score = -1000, overlap = 0;
+    for (int i = cl - min_match_len; i >= 0; i--) {
+        const int j_max = cl - i > rl ? rl : cl - i;
+        for (int j = 0; j != j_max; j++) {
+            if (read[j] == ct[i + j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { if (j_max - j < min_match_len) break; total_score = match_score; overlap = 1; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (j_max - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return 0;
+        }
+    }
+    total_score = -1000; overlap = 0;
+    for (int i = 0; i <= rl - cl; i++) {
+        for (int j = 0; j != cl; j++) {
+            if (read[i + j] == ct[j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { if (cl - j < min_match_len) break; total_score = match_score; overlap = 1; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (cl - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return i + j - overlap + 1;
+        }
+    }
+    total_score = -1000; overlap = 0;
+    for (int i = cl > rl ? cl - rl : 0; i <= cl - min_match_len; i++) {
+        for (int j = 0; j != cl - i; j++) {
+            if (read[rl - (cl - i) + j] == ct[j]) {
+                if (total_score > total_mismatch_score) { total_score += match_score; overlap++; }
+                else { total_score = match_score; overlap = 1; if (cl - i - j < min_match_len) break; }
+            } else {
+                if (total_score > total_mismatch_score) { total_score += mismatch_score; overlap++; }
+                else if (cl - i - j < min_match_len) break;
+            }
+            if (total_score >= lower_score && overlap >= min_match_len) return rl - cl + i + j - overlap + 1;
+        }
+    }
+    return -1;
+}
+// include_global_contam of stat_read (read_filter.cpp:207-249, hasGlobalContams :927-960): either strand of some sequence
+SNK_HD bool has_global_contam(const uint8_t* seq, int len, const DevParams& P)
+{
+    for (int i = 0; i < P.n_gcontams; i++) {
+        const GContamDev& g = P.gcontams[i];
+        if (global_contam_pos(seq, len, g.fwd, g.len, g.min_match, g.mismatch) >= 0) return true;
+        if (global_contam_pos(seq, len, g.rev, g.len, g.min_match, g.mismatch) >= 0) return true;
+    }
+    return false;
+}
 SNK_HD bool has_contam(const uint8_t* seq, int len, int mate, const DevParams& P)
 {
     for (int i = 0; i < P.n_contams[mate]; i++)
         if (contam_pos_bytes(seq, len, P.contams[mate * SNK_MAX_CONTAMS + i]) >= 0) return true;
     return false;
+}
+
+SNK_HD uint16_t contam_flags(const uint8_t* seq, int len, int mate, const DevParams& P)
+{
+    if (P.srna) return 0;
+    uint16_t f = 0;
+    if (P.n_contams[mate] > 0 && has_contam(seq, len, mate, P)) f |= RF_CONTAM;
+    if (P.n_gcontams > 0 && has_global_contam(seq, len, P)) f |= RF_GCONTAM;
+    return f;
 }
 
 // ---- filtersRNA adapter finders (byte-wise ungapped alignments; reads are short)
@@ -876,7 +953,8 @@ SNK_HD int srna_cut_len(const DevParams& P, int ada_pos, int len)
 template <int NW>
 // ada_pos: adapter_pos() result (filter) or sRNA_findAdapter() result (filtersRNA); has5: sRNA_hasAdapter();
 // cur = sequence length fastq_trim applies the cuts to (len, or the 3' adapter position in filtersRNA)
-SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, bool has5, bool contam, int cur, const TrimPart& T,
+// contam: RF_CONTAM / RF_GCONTAM bits found by the contaminant searches
+SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_pos, bool has5, uint16_t contam, int cur, const TrimPart& T,
                         int len, int mate, const DevParams& P, ReadInfo& R)
 {
     uint16_t flags = 0;
@@ -900,7 +978,7 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
     if (P.n_ratio != -1 && n_ratio >= P.n_ratio) flags |= RF_N;
     if (P.highA_ratio != -1 && a_ratio >= P.highA_ratio) flags |= RF_HIGHA;
     if (polyx) flags |= RF_POLYX;
-    if (contam) flags |= RF_CONTAM;
+    flags |= contam;
     if (P.low_qual_ratio != -1 && lowq_ratio >= P.low_qual_ratio) flags |= RF_LOWQ;
     if (lowq_ratio > 1) flags |= RF_LOWQ_GT1;
     if (P.mean_quality != -1 && mean_q < (float)P.mean_quality) flags |= RF_MEANQ;
@@ -987,7 +1065,7 @@ SNK_HD void scan_read_serial(uint8_t* seq, uint8_t* qual, int len, int nchunks, 
     TrimPart T, T2;
     trim_part(seq, qual, len, cur, P, 0, T);
     for (int h = 1; h < kNT; h++) { trim_part(seq, qual, len, cur, P, h, T2); merge_trim(T, T2); }
-    const bool contam = !P.srna && P.n_contams[mate] > 0 && has_contam(seq, len, mate, P);
+    const uint16_t contam = contam_flags(seq, len, mate, P);
     finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, contam, cur, T, len, mate, P, R);
 }
 
@@ -1009,6 +1087,7 @@ SNK_HD int decide_pair(const DevParams& P, const ReadInfo& a, const ReadInfo& b,
         x = (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len; y = (uint64_t)b.clean_len > (uint64_t)(int64_t)P.max_len;
         SNK_DIS(SNK_DROP_LONG, SNK_FS_LONG);
     }
+    if (P.contam_discard) { x = a.flags & RF_GCONTAM; y = b.flags & RF_GCONTAM; SNK_DIS(SNK_DROP_GCONTAM, SNK_FS_GCONTAM); }   // sequence.cpp:262-273
     if (P.contam_discard) { x = a.flags & RF_CONTAM; y = b.flags & RF_CONTAM; SNK_DIS(SNK_DROP_CONTAM, SNK_FS_CONTAM); }   // sequence.cpp:274-288
     x = a.flags & RF_N; y = b.flags & RF_N; SNK_DIS(SNK_DROP_N, SNK_FS_N);
     x = a.flags & RF_HIGHA; y = b.flags & RF_HIGHA; SNK_DIS(SNK_DROP_HIGHA, SNK_FS_HIGHA);
@@ -1028,6 +1107,7 @@ SNK_HD int decide_se(const DevParams& P, const ReadInfo& a, int* fs_base)
     if (P.min_len != -1 && (uint64_t)a.clean_len < (uint64_t)(int64_t)P.min_len) { *fs_base = SNK_FS_SHORT; return SNK_DROP_SHORT; }
     if (P.max_len != -1 && (uint64_t)a.clean_len > (uint64_t)(int64_t)P.max_len) { *fs_base = SNK_FS_LONG; return SNK_DROP_LONG; }
     if (P.contam_discard && (a.flags & RF_CONTAM)) { *fs_base = SNK_FS_CONTAM; return SNK_DROP_CONTAM; }      // sequence.cpp:116-122
+    if (P.contam_discard && (a.flags & RF_GCONTAM)) { *fs_base = SNK_FS_GCONTAM; return SNK_DROP_GCONTAM; }   // :123-127
     if (a.flags & RF_N) { *fs_base = SNK_FS_N; return SNK_DROP_N; }
     if (a.flags & RF_HIGHA) { *fs_base = SNK_FS_HIGHA; return SNK_DROP_HIGHA; }
     if (a.flags & RF_POLYX) { *fs_base = SNK_FS_POLYX; return SNK_DROP_POLYX; }

@@ -201,10 +201,10 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     trim_part(seq, qual, len, cur, P, h, T);
     OT.hix = __shfl_xor_sync(pm, T.hix, 1); OT.tix = __shfl_xor_sync(pm, T.tix, 1); OT.ng = __shfl_xor_sync(pm, T.ng, 1);
     merge_trim(T, OT);
-    bool contam = false;
-    if (!P.srna && P.n_contams[mate] > 0) {        // uncommon option: the group's first lane runs the byte-wise search
-        const int v = (h == 0) ? (int)has_contam(seq, len, mate, P) : 0;
-        contam = (v | __shfl_xor_sync(pm, v, 1)) != 0;
+    uint16_t contam = 0;
+    if (!P.srna && (P.n_contams[mate] > 0 || P.n_gcontams > 0)) {      // uncommon options: the group's first lane runs the byte-wise searches
+        const int v = (h == 0) ? (int)contam_flags(seq, len, mate, P) : 0;
+        contam = (uint16_t)(v | __shfl_xor_sync(pm, v, 1));
     }
     finish_read<NW>(S, S.qbad && qual_violation(qual, len, P.phred), polyx, ada_pos, has5, contam, cur, T, len, mate, P, R);
 }

@@ -130,6 +130,9 @@ void init_from_config(HostParams& hp, const char* path)
         else if (key == "contam2") hp.contam2 = value;
         else if (key == "ctMatchR") hp.ct_match_r = value;
         else if (key == "contam_trim") hp.contam_trim = true;
+        else if (key == "global_contams") hp.global_contams = value;                       // process_argv.cpp:1302-1312
+        else if (key == "glob_cotm_mR") hp.g_mrs = value;
+        else if (key == "glob_cotm_mM") hp.g_mms = value;
         else if (key == "tile") hp.tile = value;                                           // process_argv.cpp:1314-1320
         else if (key == "fov") hp.fov = value;
         else if (key == "log") hp.log = value;
@@ -167,7 +170,7 @@ void print_usage(const std::string& module)
               << "  -h, --help   -v, --version\n"
               << "config file keys: seqType outFileType index qualSys outQualSys maxBaseQuality pe_info patch maxReadLen\n"
               << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log tile fov\n"
-              << "                  contam1 contam2 ctMatchR contam_trim\n"
+              << "                  contam1 contam2 ctMatchR contam_trim global_contams glob_cotm_mR glob_cotm_mM\n"
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
 }
@@ -366,6 +369,21 @@ void to_engine_params(const HostParams& hp, snk_params& p)
                 p.contam_seg_thr[m][i] = thr[i];
                 memcpy(p.contam[m][i], seqs[i].data(), seqs[i].size());
             }
+        }
+    }
+    if (!hp.global_contams.empty()) {            // hasGlobalContams (read_filter.cpp:927-944)
+        const std::vector<std::string> seqs = split(hp.global_contams, ','), mrs = split(hp.g_mrs, ','), mms = split(hp.g_mms, ',');
+        if (seqs.size() != mrs.size() || seqs.size() != mms.size() || hp.g_mrs.empty() || hp.g_mms.empty())
+            die("the number of global contamination sequences should equal to that of related parameters");
+        if (seqs.size() > SNK_MAX_CONTAMS) die("too many global contaminant sequences");
+        p.n_gcontams = (int)seqs.size();
+        for (size_t i = 0; i < seqs.size(); i++) {
+            if (seqs[i].empty() || seqs[i].size() >= SNK_MAX_ADAPTER_LEN) die("global contaminant sequence length out of range");
+            const float mr = (float)atof(mrs[i].c_str());
+            p.gcontam_len[i] = (int)seqs[i].size();
+            p.gcontam_min_match[i] = (int)((int)seqs[i].size() * mr);            // int(cl*min_matchRatio) (:970)
+            p.gcontam_mismatch[i] = atoi(mms[i].c_str());
+            memcpy(p.gcontam[i], seqs[i].data(), seqs[i].size());
         }
     }
     p.seq_type1 = hp.seq_type != "0";

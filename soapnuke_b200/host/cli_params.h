@@ -32,6 +32,7 @@ struct HostParams {
     bool is_pe = false;
     std::string contam1, contam2, ct_match_r = "0.2";   // config keys contam1= / contam2= / ctMatchR= (lists: comma separated)
     bool contam_trim = false;          // config key contam_trim: no discard (the trim itself is commented out in 2.1.9)
+    std::string global_contams, g_mrs, g_mms;          // config keys global_contams= / glob_cotm_mR= / glob_cotm_mM=
     std::string tile, fov;             // config keys tile= / fov= (removal lists, comma separated)
     // filtersRNA module (global_parameter.h:54-58)
     bool srna = false;

@@ -41,6 +41,17 @@ int params_check(const snk_params& p)
             if ((int)strnlen(p.contam[m][i], SNK_MAX_ADAPTER_LEN) < L) { set_error("contam_len exceeds the contaminant string"); return 1; }
         }
     }
+    if (p.n_gcontams < 0 || p.n_gcontams > SNK_MAX_CONTAMS) { set_error("too many global contaminant sequences"); return 1; }
+    if (p.n_gcontams > 0 && p.srna) { set_error("global contaminants are not part of filtersRNA"); return 1; }
+    for (int i = 0; i < p.n_gcontams; i++) {
+        const int L = p.gcontam_len[i];
+        if (L <= 0 || L >= SNK_MAX_ADAPTER_LEN || (int)strnlen(p.gcontam[i], SNK_MAX_ADAPTER_LEN) < L) { set_error("global contaminant sequence length out of range"); return 1; }
+        if (p.gcontam_min_match[i] < 0 || p.gcontam_min_match[i] > L) { set_error("global contaminant match ratio must be in [0,1]"); return 1; }
+        for (int k = 0; k < L; k++) {
+            const char ch = (char)(p.gcontam[i][k] & ~0x20);
+            if (ch != 'A' && ch != 'C' && ch != 'G' && ch != 'T' && ch != 'N') { set_error("unrecognized base in a global contaminant sequence"); return 1; }   // reversecomplementary()
+        }
+    }
     if (p.n_tile < 0 || p.n_tile > SNK_MAX_ID_FILTERS || p.n_fov < 0 || p.n_fov > SNK_MAX_ID_FILTERS) { set_error("too many tile / fov entries"); return 1; }
     if (p.n_fov > 0 && p.seq_type1) { set_error("Zebra-500 data(--fov), --seqType is 0"); return 1; }     // read_filter.cpp:131-134
     if (p.has_hard_trim) for (int m = 0; m < 2; m++)

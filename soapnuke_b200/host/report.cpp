@@ -168,13 +168,20 @@ struct FilterRow { const char* label; int fs_base; };
 // label order of peprocess.cpp:226-241 restricted to the categories the engine produces
 const FilterRow kPeRows[] = {
     {"Reads with filtered tile", SNK_FS_TILE}, {"Reads with filtered fov", SNK_FS_FOV},
-    {"Reads too short", SNK_FS_SHORT}, {"Reads too long", SNK_FS_LONG}, {"Reads with contam sequence", SNK_FS_CONTAM},
+    {"Reads too short", SNK_FS_SHORT}, {"Reads too long", SNK_FS_LONG},
+    {"Reads with global contam sequence", SNK_FS_GCONTAM}, {"Reads with contam sequence", SNK_FS_CONTAM},
     {"Reads with n rate exceed", SNK_FS_N}, {"Reads with highA", SNK_FS_HIGHA},
     {"Reads with polyX", SNK_FS_POLYX}, {"Reads with low quality", SNK_FS_LOWQ},
     {"Reads with low mean quality", SNK_FS_MEANQ}, {"Reads with adapter", SNK_FS_ADAPTER}};
-// seprocess.cpp:136-150 has the same relative order for these categories
-const FilterRow* const kSeRows = kPeRows;
-const int kRows = 11;
+// seprocess.cpp:136-150: the global contaminants come last there
+const FilterRow kSeRows[] = {
+    {"Reads with filtered tile", SNK_FS_TILE}, {"Reads with filtered fov", SNK_FS_FOV},
+    {"Reads too short", SNK_FS_SHORT}, {"Reads too long", SNK_FS_LONG}, {"Reads with contam sequence", SNK_FS_CONTAM},
+    {"Reads with n rate exceed", SNK_FS_N}, {"Reads with highA", SNK_FS_HIGHA},
+    {"Reads with polyX", SNK_FS_POLYX}, {"Reads with low quality", SNK_FS_LOWQ},
+    {"Reads with low mean quality", SNK_FS_MEANQ}, {"Reads with adapter", SNK_FS_ADAPTER},
+    {"Reads with global contam sequence", SNK_FS_GCONTAM}};
+const int kRows = 12;
 
 uint64_t filtered_total(const Global& G)
 {

@@ -143,6 +143,10 @@ CONTAM2 = b"CTGTCTCTTATACACATCTCCGAGCCCACGAGAC"
 CONTAM3 = b"ACACTCTTTCCCTACACGACGCTCTTCCGATCT"
 
 
+def revcomp(b):
+    return bytes(b.translate(bytes.maketrans(b"ACGTN", b"TGCAN"))[::-1])
+
+
 def add_contams(d, contams, seed, frac=0.15):
     """Plants (sometimes mutated / truncated / overhanging) copies of the contaminant sequences into a
     fraction of the reads of every mate of a gen_pairs() batch, plus a few N's next to them."""

@@ -243,6 +243,9 @@ int coretest_filter(const snk_params* p, const snk_batch* r1, const snk_batch* r
     std::vector<ContamDev> contams(2 * SNK_MAX_CONTAMS);
     prepare_contams(*p, contams.data());
     c.P.contams = contams.data();
+    std::vector<GContamDev> gcontams(SNK_MAX_CONTAMS);
+    prepare_gcontams(*p, gcontams.data());
+    c.P.gcontams = gcontams.data();
     if (qb_override >= 0) c.P.qb = qb_override;
     c.stats = stats;
     c.mates = p->is_pe ? 2 : 1;

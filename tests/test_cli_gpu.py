@@ -122,6 +122,10 @@ CT1, CT2, CT3 = (c.decode() for c in CT)
          cfg=[f"contam1={CT3},{CT2},{CT1}", f"contam2={CT1},{CT2},{CT3[:20]}", "ctMatchR=0.2,0.6,0.9", "adaMis=1,3", "adaEdge=4,8"], contams=CT),
     dict(name="contam_trim_mode", pe=True, n=20000, L=100, T=1, flags=["-f", A1, "-r", A2, "-J"],
          cfg=[f"contam1={CT1}", f"contam2={CT2}", "contam_trim", "ctMatchR=0.4"], contams=CT),
+    dict(name="gcontam_pe", pe=True, n=20000, L=100, T=2, flags=["-f", A1, "-r", A2, "-J"], patch=20,
+         cfg=[f"global_contams={CT1},{CT3}", "glob_cotm_mR=0.5,0.6", "glob_cotm_mM=1,2"], contams=CT + [synth.revcomp(c) for c in CT]),
+    dict(name="gcontam_se_with_contam", pe=False, n=20000, L=120, T=1, flags=[], gkw=dict(var_len=True),
+         cfg=[f"global_contams={CT2}", "glob_cotm_mR=0.4", "glob_cotm_mM=0", f"contam1={CT1}"], contams=CT + [synth.revcomp(c) for c in CT]),
 ], ids=lambda c: c["name"])
 def test_cli_contam_matches_reference_binary(cli, tmp_path, case):
     """Config keys contam1= / contam2= / ctMatchR= / contam_trim."""

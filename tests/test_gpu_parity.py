@@ -89,10 +89,10 @@ def test_tile_fov_flags_in_len(pe, engine_lib):
 
 
 def test_engine_matches_oracle_contam(engine_lib):
-    """Contaminant sequences on the engine (the CPU tier's CONTAM_CONFIGS, larger batches)."""
-    from test_core_replay import CONTAM_CONFIGS
+    """Contaminant and global contaminant sequences on the engine (the CPU tier's CONTAM_CONFIGS, larger batches)."""
+    from test_core_replay import CONTAM_CONFIGS, CONTAM_PLANTS
     for name, pe, n, L, gkw, pkw in CONTAM_CONFIGS:
-        d = synth.add_contams(synth.gen_pairs(5 * n, L=L, seed=len(name) * 13, se=not pe, **gkw), [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3], seed=L)
+        d = synth.add_contams(synth.gen_pairs(5 * n, L=L, seed=len(name) * 13, se=not pe, **gkw), CONTAM_PLANTS, seed=L)
         p = abi.make_params(is_pe=pe, threads=2, patch_size=600, **pkw)
         o1, o2, ost, oerr = oracle_run(p, d)
         with Engine(engine_lib, p) as e:

@@ -284,6 +284,52 @@ def test_oracle_matches_reference_binary_contam(case, engine_lib, tmp_path):
     compare_reports(f"{w}/out", f"{w}/mine")
 
 
+# ---- global contaminants (config keys global_contams / glob_cotm_mR / glob_cotm_mM)
+GCONTAM_LIVE = [
+    ("gcontam_pe", True, 5000, 100, 2, ["-f", A1, "-r", A2, "-J"], [f"global_contams={C1},{C3}", "glob_cotm_mR=0.5,0.6", "glob_cotm_mM=1,2", "patch=20"],
+     dict(adapter1=A1, adapter2=A2, ada_trim=True, global_contams=f"{C1},{C3}", glob_cotm_mR="0.5,0.6", glob_cotm_mM="1,2")),
+    ("gcontam_se_with_contam", False, 5000, 120, 1, [], [f"global_contams={C2}", "glob_cotm_mR=0.4", "glob_cotm_mM=0", f"contam1={C1}"],
+     dict(global_contams=C2, glob_cotm_mR="0.4", glob_cotm_mM="0", contam1=C1)),
+    ("gcontam_pe_short_loose", True, 4000, 60, 3, [], [f"global_contams={C3},{C1[:18]},{C2}", "glob_cotm_mR=0.5,1.0,0.9", "glob_cotm_mM=1,0,2", f"contam2={C2}"],
+     dict(global_contams=f"{C3},{C1[:18]},{C2}", glob_cotm_mR="0.5,1.0,0.9", glob_cotm_mM="1,0,2", contam2=C2)),
+]
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", GCONTAM_LIVE, ids=[c[0] for c in GCONTAM_LIVE])
+def test_oracle_matches_reference_binary_global_contam(case, engine_lib, tmp_path):
+    name, pe, n, L, T, flags, cfg, pkw = case
+    plants = [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3, synth.revcomp(synth.CONTAM1), synth.revcomp(synth.CONTAM3)]
+    data = synth.add_contams(synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, var_len=(L == 120)), plants, seed=len(name), frac=0.25)
+    w = str(tmp_path)
+    synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
+    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    if pe:
+        synth.write_fastq(f"{w}/r2.fq", data["seq2"], data["qual2"], data["len2"], 2)
+        args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+    open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg))
+    patch = next((int(l.split("=")[1]) for l in cfg if l.startswith("patch=")), None)
+    r = orc.run_reference(args + ["-c", f"{w}/cfg.txt"] + flags)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
+    if pe:
+        r1, r2, st, err = orc.filter_pe(p, data)
+    else:
+        r1, st, err = orc.filter_se(p, data); r2 = None
+    assert err == 0
+    cats = np.bincount(r1["category"], minlength=16)
+    assert cats[0] > n // 5 and cats[15] > n // 50, cats
+    for m, rs in ((1, r1), (2, r2)):
+        if rs is None:
+            continue
+        order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
+        mine = synth.clean_fastq_bytes(data[f"seq{m}"], data[f"qual{m}"], data[f"len{m}"], rs, m, order=order)
+        assert mine == open(f"{w}/out/c{m}.fq", "rb").read(), f"clean fq{m} differs from the reference binary"
+    fn = engine_lib.snk_report_write_pe if pe else engine_lib.snk_report_write_se
+    write_reports(fn, p, st, f"{w}/mine")
+    compare_reports(f"{w}/out", f"{w}/mine")
+
+
 # ---- known answers measured on the reference binary (A=32: segThr=16, misGrad=8, misGrad5=9)
 def body(n, rng):
     return bytes(rng.choice(np.frombuffer(b"CT", dtype=np.uint8), size=n))
