@@ -265,7 +265,8 @@ int snk_engine_lane_sync(snk_engine* e, int lane);
 typedef struct snk_text_format {
     int32_t strip;        /* characters every input line loses at its end, newline included: 1 for plain
                              input, spaceNum of the first line for .gz input (peprocess.cpp:2066-2076) */
-    int32_t pe_info;      /* gp.whether_add_pe_info */
+    int32_t pe_info;      /* how many "/1" ("/2") suffixes preOutput appends to the id: gp.whether_add_pe_info (0|1); 2 for the
+                             clean records when trim files are written as well (preOutput runs twice on them) */
     int32_t fasta;        /* gp.output_file_type == "fasta" */
     int32_t id_mode;      /* 0: ids unchanged; 1: gp.index_remove with seqType "0"; 2: gp.index_remove otherwise */
     int32_t reserved[4];

@@ -18,7 +18,8 @@ namespace snkcore {
 
 struct TextFormat {
     int32_t strip;      // characters every input line loses at its end, the newline included
-    int32_t pe_info;    // gp.whether_add_pe_info
+    int32_t pe_info;    // number of "/1" ("/2") suffixes preOutput appends: gp.whether_add_pe_info, twice for the clean
+                        // records when the trim files are written too (peprocess.cpp:1460-1475 calls it on the same record again)
     int32_t fasta;      // gp.output_file_type == "fasta"
     int32_t id_mode;    // 0 keep, 1 index removal with seqType "0", 2 index removal otherwise
     int32_t qshift;     // outputQualityPhred - qualityPhred
@@ -164,7 +165,7 @@ SNK_HD uint32_t id_prefilter(const uint8_t* id, uint32_t n, const IdFilter& F)
 // bytes a kept record adds to the clean file
 SNK_HD uint32_t record_out_len(uint32_t id_out, uint32_t clean_len, const TextFormat& F)
 {
-    const uint32_t head = id_out + (F.pe_info ? 2u : 0u) + 1u;
+    const uint32_t head = id_out + 2u * (uint32_t)F.pe_info + 1u;
     return F.fasta ? head + clean_len + 1u : head + 2u * clean_len + 4u;
 }
 
@@ -173,7 +174,7 @@ SNK_HD uint32_t record_out_len(uint32_t id_out, uint32_t clean_len, const TextFo
 SNK_HD void format_tail(uint8_t* dst, const uint8_t* seq, const uint8_t* qual, uint32_t clean_len, int mate, const TextFormat& F,
                         uint32_t lane, uint32_t nl)
 {
-    const uint32_t sfx = F.pe_info ? 2u : 0u;
+    const uint32_t sfx = 2u * (uint32_t)F.pe_info;
     const uint32_t seq0 = sfx + 1u, seq1 = seq0 + clean_len;               // [seq0, seq1) = bases
     const uint32_t q0 = seq1 + 3u, q1 = q0 + clean_len;                    // [q0, q1) = qualities (fastq)
     const uint32_t total = F.fasta ? seq1 + 1u : q1 + 1u;
@@ -181,7 +182,7 @@ SNK_HD void format_tail(uint8_t* dst, const uint8_t* seq, const uint8_t* qual, u
         uint8_t ch;
         if (j >= seq0 && j < seq1) ch = seq[j - seq0];
         else if (j >= q0 && j < q1) ch = (uint8_t)((int)qual[j - q0] + F.qshift);
-        else if (j < sfx) ch = j == 0 ? (uint8_t)'/' : (uint8_t)(mate ? '2' : '1');
+        else if (j < sfx) ch = (j & 1u) == 0 ? (uint8_t)'/' : (uint8_t)(mate ? '2' : '1');
         else if (j == seq1 + 1u) ch = '+';
         else ch = '\n';
         dst[j] = ch;

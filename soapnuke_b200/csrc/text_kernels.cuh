@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) format_kernel(const __grid_constant__ Tex
     format_tail(dst + id_out, A.seq[m] + row, A.qual[m] + row, r.clean_len, m, A.fmt, lane, 32u);
     if (A.fmt.fasta) {
         __syncwarp();
-        if (lane == 0) fasta_fix(dst, id_out + (A.fmt.pe_info ? 2u : 0u));
+        if (lane == 0) fasta_fix(dst, id_out + 2u * (uint32_t)A.fmt.pe_info);
     }
 }
 

@@ -5,7 +5,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SRCS = [os.path.join(HERE, f) for f in ("main.cpp", "cli_params.cpp", "process.cpp")]
-DEPS = SRCS + [os.path.join(HERE, f) for f in ("cli_params.h", "process.h", "host_common.h")]
+DEPS = SRCS + [os.path.join(HERE, f) for f in ("cli_params.h", "process.h", "host_common.h")] + \
+    [os.path.join(PKG, "csrc", f) for f in ("text_core.cuh", "filter_core.cuh")]
 
 
 def build(force=False):
@@ -16,7 +17,7 @@ def build(force=False):
     deps = DEPS + [lib]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
         return out
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-pthread", "-o", out] + SRCS + \
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-o", out] + SRCS + \
           ["-L" + os.path.join(PKG, "lib"), "-lsnk_engine", "-lz", "-Wl,-rpath,$ORIGIN/../lib"]
     subprocess.check_call(cmd)
     return out

@@ -126,6 +126,8 @@ void init_from_config(HostParams& hp, const char* path)
             if (value.find(",") == std::string::npos) { hp.ada_mr = (float)atof(value.c_str()); hp.ada_mr2 = hp.ada_mr; }
             else { auto v = split(value, ','); if (v.size() < 2) die("expected two values in -A parameter"); hp.ada_mr = (float)atof(v[0].c_str()); hp.ada_mr2 = (float)atof(v[1].c_str()); }
         }
+        else if (key == "trimFq1") hp.trim_fq1 = value;                                    // process_argv.cpp:1262-1277
+        else if (key == "trimFq2") hp.trim_fq2 = value;
         else if (key == "contam1") hp.contam1 = value;                                     // process_argv.cpp:1286-1300
         else if (key == "contam2") hp.contam2 = value;
         else if (key == "ctMatchR") hp.ct_match_r = value;
@@ -170,7 +172,7 @@ void print_usage(const std::string& module)
               << "  -h, --help   -v, --version\n"
               << "config file keys: seqType outFileType index qualSys outQualSys maxBaseQuality pe_info patch maxReadLen\n"
               << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log tile fov\n"
-              << "                  contam1 contam2 ctMatchR contam_trim global_contams glob_cotm_mR glob_cotm_mM\n"
+              << "                  contam1 contam2 ctMatchR contam_trim global_contams glob_cotm_mR glob_cotm_mM trimFq1 trimFq2\n"
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
 }
@@ -239,6 +241,13 @@ int parse_command_line(int argc, char** argv, HostParams& hp)
         if (hp.fq1_path == hp.fq2_path) die("input fq1 and fq2 are the same,please check the parameters");
     }
     if (hp.clean_fq1.empty()) die("output clean fastq is required");
+    if (!hp.is_pe && !hp.trim_fq2.empty()) die("input file is not pe data");                      // process_argv.cpp:635
+    if (!hp.trim_fq1.empty() || !hp.trim_fq2.empty()) {
+        if (hp.trim_fq1.empty() || (hp.is_pe && hp.trim_fq2.empty())) die("trimFq1 and trimFq2 are both required to write the trim files");
+        // only the gzip branch works in 2.1.9: the plain-text branch opens its files into the clean-file handles
+        // (peprocess.cpp:1784-1789) and peWrite is always given the gzFile handles (:1940)
+        if (!ends_with_gz(hp.trim_fq1) || (hp.is_pe && !ends_with_gz(hp.trim_fq2))) die("trim fq file names must end with .gz (gz format)");
+    }
     if (hp.is_pe) {
         if (hp.clean_fq2.empty()) die("output clean fastq2 is required");
         if (ends_with_gz(hp.clean_fq1) != ends_with_gz(hp.clean_fq2)) die("the format of clean fastq1 is inconsistent with fastq2");

@@ -12,6 +12,7 @@ namespace snk {
 struct HostParams {
     std::string module_name;
     std::string fq1_path, fq2_path, clean_fq1, clean_fq2, output_dir, log = "log";
+    std::string trim_fq1, trim_fq2;    // config keys trimFq1= / trimFq2=: every record after trimming, gzip only
     std::string seq_type = "0", output_file_type = "fastq";
     bool input_gz = true, clean_gz = true;
     bool ada_trim = false;

@@ -9,6 +9,7 @@
 //   gzip level 2 members                  peprocess.cpp:1803-1810
 #include "process.h"
 #include "host_common.h"
+#include "../csrc/text_core.cuh"      // id_transform (host-compilable header; the record formatting of the trim files)
 #include <zlib.h>
 #include <sys/stat.h>
 #include <fcntl.h>
@@ -223,7 +224,8 @@ struct PinnedBuf {
     void release() { if (p) snk_host_free(p); p = nullptr; cap = 0; }
 };
 // a run of output bytes: kind 0 = in place, 1 = deferred (see FilterRun::writer), 2 = "emit the deferred bytes now"
-struct Piece { int kind; const char* p; size_t len; std::string gz; };
+// Trim pieces (trimFq1/2) carry a record range instead of bytes until a worker has formatted them.
+struct Piece { int kind; const char* p; size_t len; std::string gz; uint32_t r0 = 0, r1 = 0; };
 struct HostBatch {
     uint64_t seq_no = 0, first_index = 0;
     uint32_t n = 0;
@@ -231,11 +233,13 @@ struct HostBatch {
     PinnedBuf in[2], out[2], off[2];      // raw text, clean text, rec_off (uint32 [n+1])
     size_t in_bytes[2] = {0, 0};
     snk_text_meta meta;
-    std::vector<Piece> pieces[2];
+    PinnedBuf res[2];                     // per-read results (only fetched when the trim files are written)
+    std::vector<uint32_t> rec_start[2];   // byte offset of every record in the raw text, n+1 entries (trim files only)
+    std::vector<Piece> pieces[2], tpieces[2];   // clean / trim output runs
     std::atomic<int> tasks{0};            // deflate tasks still running
-    void release() { for (int m = 0; m < 2; m++) { in[m].release(); out[m].release(); off[m].release(); } }
+    void release() { for (int m = 0; m < 2; m++) { in[m].release(); out[m].release(); off[m].release(); res[m].release(); } }
 };
-struct GzTask { HostBatch* b; int mate; size_t piece; };
+struct GzTask { HostBatch* b; int mate; size_t piece; bool trim; };
 
 inline size_t round16(size_t v) { return (v + 15) / 16 * 16; }
 
@@ -259,7 +263,8 @@ private:
     int strip_gz_ = 1;                 // spaceNum of the first line (peprocess.cpp:2066-2076)
     size_t stride_ = 0;                // current row stride (grows when a longer read shows up)
     uint64_t total_reads_ = 0;
-    std::string pending_deferred_[2];  // deferred output (already encoded) waiting for its insertion point
+    std::string pending_deferred_[4];  // deferred output (already encoded) waiting for its insertion point; [2..3] = trim files
+    bool trim_ = false;                // trimFq1/2: every record after trimming, before the discard decision
 
     std::deque<HostBatch> batches_;
     Channel<HostBatch*> free_q_, gpu_q_;
@@ -276,6 +281,9 @@ private:
     void first_batch_checks(const HostBatch& b);
     void gpu_stage();
     void make_pieces(HostBatch& b);
+    template <class F> void walk_runs(const HostBatch& b, F&& emit);
+    void index_records(HostBatch& b, int mate);
+    void format_trim(const HostBatch& b, int mate, uint32_t r0, uint32_t r1, std::string& out) const;
     void finish_batch(HostBatch* b);
     void gz_worker();
     void writer();
@@ -468,8 +476,10 @@ void FilterRun::gpu_stage()
             d->out[m].reserve((size_t)d->meta.out_bytes[m] + 64, 0);
             d->off[m].reserve(((size_t)d->n + 1) * sizeof(uint32_t), 0);
         }
+        if (trim_) for (int m = 0; m < mates_; m++) d->res[m].reserve((size_t)d->n * sizeof(snk_read_result) + 64, 0);
         engine_check(snk_text_fetch_async(engines_[d->gpu], d->lane, d->out[0].p, pe_ ? d->out[1].p : nullptr, (uint32_t*)d->off[0].p,
-                                          pe_ ? (uint32_t*)d->off[1].p : nullptr, nullptr, nullptr));
+                                          pe_ ? (uint32_t*)d->off[1].p : nullptr, trim_ ? (snk_read_result*)d->res[0].p : nullptr,
+                                          (trim_ && pe_) ? (snk_read_result*)d->res[1].p : nullptr));
         engine_check(snk_engine_lane_sync(engines_[d->gpu], d->lane));
         t_gpu_wait_ += now_s() - t0;
         finish_batch(d);
@@ -499,9 +509,31 @@ void FilterRun::encode(const char* p, size_t n, std::string& out)
     deflateEnd(&zs);
 }
 
+// Walks the batch's records in runs of one kind: 0 = in place, 1 = deferred, and markers (kind 2, r0 == r1) where
+// the deferred bytes are emitted (see writer()). Within a cycle of cyc_ reads, [cyc_-defer_len_, cyc_) is
+// deferred, and (from the second cycle on) the deferred bytes are emitted before read insert_off_.
+template <class F>
+void FilterRun::walk_runs(const HostBatch& b, F&& emit)
+{
+    if (!reorder_) { emit(0, 0u, b.n); return; }
+    uint32_t r = 0;
+    while (r < b.n) {
+        const uint64_t gi = b.first_index + r, in_cyc = gi % cyc_;
+        if (gi >= cyc_ && in_cyc == insert_off_) emit(2, r, r);
+        const bool deferred = in_cyc >= cyc_ - defer_len_;
+        uint64_t next = deferred ? cyc_ : cyc_ - defer_len_;          // next boundary inside the cycle
+        if (gi >= cyc_ && in_cyc < insert_off_ && insert_off_ < next) next = insert_off_;
+        else if (gi < cyc_ && !deferred) next = cyc_ - defer_len_;
+        const uint64_t run = std::min<uint64_t>(next - in_cyc, b.n - r);
+        emit(deferred ? 1 : 0, r, r + (uint32_t)run);
+        r += (uint32_t)run;
+    }
+}
+
 // Cuts the batch's clean text (device-formatted, input order) into pieces at the few record
 // boundaries where the reference's emission order departs from input order (see writer()), and
-// into <= 4 MiB runs for the parallel gzip members.
+// into <= 4 MiB runs for the parallel gzip members. The trim files (all records) get the same cuts
+// as record ranges; their text is formatted by the workers.
 void FilterRun::make_pieces(HostBatch& b)
 {
     const size_t max_run = hp_.clean_gz ? (4u << 20) : ~(size_t)0;
@@ -510,7 +542,8 @@ void FilterRun::make_pieces(HostBatch& b)
         out.clear();
         const uint32_t* off = (const uint32_t*)b.off[m].p;
         const char* text = b.out[m].p;
-        auto emit = [&](int kind, uint32_t r0, uint32_t r1) {         // records [r0, r1)
+        walk_runs(b, [&](int kind, uint32_t r0, uint32_t r1) {         // records [r0, r1)
+            if (kind == 2) { out.push_back({2, nullptr, 0, std::string()}); return; }
             size_t a = off[r0];
             const size_t e = off[r1];
             while (a < e) {
@@ -523,21 +556,82 @@ void FilterRun::make_pieces(HostBatch& b)
                 out.push_back({kind, text + a, stop - a, std::string()});
                 a = stop;
             }
-        };
-        if (!reorder_) { emit(0, 0, b.n); continue; }
-        // walk the kind boundaries arithmetically: within a cycle of cyc_ reads, [cyc_-defer_len_, cyc_) is
-        // deferred, and (from the second cycle on) the deferred bytes are emitted before read insert_off_
-        uint32_t r = 0;
-        while (r < b.n) {
-            const uint64_t gi = b.first_index + r, in_cyc = gi % cyc_;
-            if (gi >= cyc_ && in_cyc == insert_off_) out.push_back({2, nullptr, 0, std::string()});
-            const bool deferred = in_cyc >= cyc_ - defer_len_;
-            uint64_t next = deferred ? cyc_ : cyc_ - defer_len_;          // next boundary inside the cycle
-            if (gi >= cyc_ && in_cyc < insert_off_ && insert_off_ < next) next = insert_off_;
-            else if (gi < cyc_ && !deferred) next = cyc_ - defer_len_;
-            const uint64_t run = std::min<uint64_t>(next - in_cyc, b.n - r);
-            emit(deferred ? 1 : 0, r, r + (uint32_t)run);
-            r += (uint32_t)run;
+        });
+        if (!trim_) continue;
+        index_records(b, m);
+        std::vector<Piece>& tout = b.tpieces[m];
+        tout.clear();
+        constexpr uint32_t kTrimRun = 8192;                                // records per gzip member
+        walk_runs(b, [&](int kind, uint32_t r0, uint32_t r1) {
+            if (kind == 2) { tout.push_back({2, nullptr, 0, std::string()}); return; }
+            for (uint32_t a = r0; a < r1; a += kTrimRun) {
+                Piece p{kind, nullptr, 0, std::string()};
+                p.r0 = a; p.r1 = std::min(r1, a + kTrimRun);
+                tout.push_back(std::move(p));
+            }
+        });
+    }
+}
+
+// byte offset of every record of the mate's raw text (every 4th newline)
+void FilterRun::index_records(HostBatch& b, int mate)
+{
+    std::vector<uint32_t>& rs = b.rec_start[mate];
+    rs.resize((size_t)b.n + 1);
+    const char* p = b.in[mate].p;
+    const size_t end = b.in_bytes[mate];
+    size_t pos = 0;
+    for (uint32_t i = 0; i < b.n; i++) {
+        rs[i] = (uint32_t)pos;
+        size_t c = 0;
+        pos += nth_newline(p + pos, end - pos, 4, &c);
+    }
+    rs[b.n] = (uint32_t)end;
+}
+
+// The trim files hold EVERY record as fastq_trim left it (peprocess.cpp:1460-1466, output_fastqs :3383-3433):
+// id (index removal applied, one "/1" "/2" suffix with pe_info), the trimmed bases and qualities - possibly empty.
+void FilterRun::format_trim(const HostBatch& b, int mate, uint32_t r0, uint32_t r1, std::string& out) const
+{
+    const char* text = b.in[mate].p;
+    const snk_read_result* res = (const snk_read_result*)b.res[mate].p;
+    const size_t strip = (size_t)fmt_.strip;
+    const int qshift = hp_.out_quality_phred - hp_.quality_phred;
+    out.clear();
+    out.reserve((size_t)(r1 - r0) * (avg_rec_bytes_[mate] + 8));
+    std::vector<uint8_t> idbuf;
+    for (uint32_t r = r0; r < r1; r++) {
+        const size_t rec_end = b.rec_start[mate][r + 1];
+        size_t pos = b.rec_start[mate][r];
+        const char* line[4]; size_t vis[4];
+        for (int k = 0; k < 4; k++) {
+            const char* nl = pos < rec_end ? (const char*)memchr(text + pos, '\n', rec_end - pos) : nullptr;
+            const size_t raw = nl ? (size_t)(nl - (text + pos)) + 1 : rec_end - pos;
+            line[k] = text + pos; vis[k] = raw > strip ? raw - strip : 0;
+            pos += raw;
+        }
+        const size_t id0 = out.size();
+        if (fmt_.id_mode == 0) out.append(line[0], vis[0]);
+        else {
+            idbuf.resize(vis[0] + 1);
+            const uint32_t n = snkcore::id_transform((const uint8_t*)line[0], (uint32_t)vis[0], fmt_.id_mode, idbuf.data());
+            out.append((const char*)idbuf.data(), n);
+        }
+        if (pe_ && hp_.pe_info) { out.push_back('/'); out.push_back(mate ? '2' : '1'); }
+        if (fmt_.fasta) {
+            const size_t at = out.find('@', id0);
+            if (at != std::string::npos) out[at] = '>';
+        }
+        out.push_back('\n');
+        const size_t h = res[r].head_cut, l = res[r].clean_len;
+        out.append(line[1] + h, l);
+        out.push_back('\n');
+        if (!fmt_.fasta) {
+            out.append("+\n", 2);
+            const size_t q0 = out.size();
+            out.append(line[3] + h, l);
+            if (qshift) for (size_t k = q0; k < out.size(); k++) out[k] = (char)(out[k] + qshift);
+            out.push_back('\n');
         }
     }
 }
@@ -549,15 +643,23 @@ void FilterRun::finish_batch(HostBatch* b)
     if (hp_.clean_gz)
         for (int m = 0; m < mates_; m++)
             for (const Piece& p : b->pieces[m]) tasks += p.kind != 2 && p.len > 0;
+    if (trim_)
+        for (int m = 0; m < mates_; m++)
+            for (const Piece& p : b->tpieces[m]) tasks += p.kind != 2;
     if (tasks == 0) {
         { std::lock_guard<std::mutex> g(done_mu_); done_[b->seq_no] = b; }
         done_cv_.notify_all();
         return;
     }
     b->tasks = tasks;
-    for (int m = 0; m < mates_; m++)
-        for (size_t i = 0; i < b->pieces[m].size(); i++)
-            if (b->pieces[m][i].kind != 2 && b->pieces[m][i].len > 0) gz_q_.push({b, m, i});
+    if (hp_.clean_gz)
+        for (int m = 0; m < mates_; m++)
+            for (size_t i = 0; i < b->pieces[m].size(); i++)
+                if (b->pieces[m][i].kind != 2 && b->pieces[m][i].len > 0) gz_q_.push({b, m, i, false});
+    if (trim_)
+        for (int m = 0; m < mates_; m++)
+            for (size_t i = 0; i < b->tpieces[m].size(); i++)
+                if (b->tpieces[m][i].kind != 2) gz_q_.push({b, m, i, true});
 }
 
 void FilterRun::gz_worker()
@@ -565,8 +667,12 @@ void FilterRun::gz_worker()
     GzTask t;
     while (gz_q_.pop(t)) {
         const double t0 = now_s();
-        Piece& p = t.b->pieces[t.mate][t.piece];
-        encode(p.p, p.len, p.gz);
+        Piece& p = t.trim ? t.b->tpieces[t.mate][t.piece] : t.b->pieces[t.mate][t.piece];
+        if (t.trim) {
+            std::string text;
+            format_trim(*t.b, t.mate, p.r0, p.r1, text);
+            encode(text.data(), text.size(), p.gz);
+        } else encode(p.p, p.len, p.gz);
         p.p = p.gz.data(); p.len = p.gz.size();
         t_gz_us_ += (uint64_t)((now_s() - t0) * 1e6);
         if (--t.b->tasks == 0) {
@@ -586,12 +692,16 @@ void FilterRun::gz_worker()
 // all .gz-input and all SE runs) is input order.
 void FilterRun::writer()
 {
-    int out[2] = {-1, -1};
-    off_t pos[2] = {0, 0};
-    const std::string names[2] = {hp_.output_dir + "/" + hp_.clean_fq1, hp_.output_dir + "/" + hp_.clean_fq2};
-    for (int m = 0; m < mates_; m++) {
-        out[m] = open(names[m].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
-        if (out[m] < 0) die("cannot write to the file," + names[m]);
+    // files 0,1 = clean fq1/fq2; files 2,3 = trim fq1/fq2 (trimFq1/2)
+    int out[4] = {-1, -1, -1, -1};
+    off_t pos[4] = {0, 0, 0, 0};
+    const std::string names[4] = {hp_.output_dir + "/" + hp_.clean_fq1, hp_.output_dir + "/" + hp_.clean_fq2,
+                                  hp_.output_dir + "/" + hp_.trim_fq1, hp_.output_dir + "/" + hp_.trim_fq2};
+    const int nfiles = trim_ ? 4 : 2;
+    for (int f = 0; f < nfiles; f++) {
+        if (f % 2 >= mates_) continue;
+        out[f] = open(names[f].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        if (out[f] < 0) die("cannot write to the file," + names[f]);
     }
     // the order is fixed here (every run of bytes gets its file offset), the copying is done by a small pool
     struct WriteTask { int m; const char* p; size_t len; off_t at; HostBatch* owner; std::shared_ptr<std::string> hold; };
@@ -627,15 +737,16 @@ void FilterRun::writer()
             b = it->second; done_.erase(it);
         }
         mine.clear();
-        for (int m = 0; m < mates_; m++) {
-            for (Piece& p : b->pieces[m]) {
-                if (p.kind == 0) { if (p.len) mine.push_back({m, p.p, p.len, pos[m], b, nullptr}); pos[m] += (off_t)p.len; }
-                else if (p.kind == 1) pending_deferred_[m].append(p.p, p.len);
-                else if (!pending_deferred_[m].empty()) {
-                    auto hold = std::make_shared<std::string>(std::move(pending_deferred_[m]));
-                    pending_deferred_[m].clear();
-                    mine.push_back({m, hold->data(), hold->size(), pos[m], nullptr, hold});
-                    pos[m] += (off_t)hold->size();
+        for (int f = 0; f < nfiles; f++) {
+            if (f % 2 >= mates_) continue;
+            for (Piece& p : (f < 2 ? b->pieces[f] : b->tpieces[f - 2])) {
+                if (p.kind == 0) { if (p.len) mine.push_back({f, p.p, p.len, pos[f], b, nullptr}); pos[f] += (off_t)p.len; }
+                else if (p.kind == 1) pending_deferred_[f].append(p.p, p.len);
+                else if (!pending_deferred_[f].empty()) {
+                    auto hold = std::make_shared<std::string>(std::move(pending_deferred_[f]));
+                    pending_deferred_[f].clear();
+                    mine.push_back({f, hold->data(), hold->size(), pos[f], nullptr, hold});
+                    pos[f] += (off_t)hold->size();
                 }
             }
         }
@@ -645,7 +756,7 @@ void FilterRun::writer()
         for (const WriteTask& t : mine) owned += t.owner != nullptr;
         if (owned == 0) {
             for (const WriteTask& t : mine) tasks.push(t);
-            for (int m = 0; m < mates_; m++) b->pieces[m].clear();
+            for (int m = 0; m < mates_; m++) { b->pieces[m].clear(); b->tpieces[m].clear(); }
             free_q_.push(b);
         } else {
             b->tasks = owned;                 // the batch (its pinned text and gzip strings) is recycled by the last write
@@ -664,9 +775,10 @@ void FilterRun::writer()
         const uint64_t into_last = total_reads_ - (total_reads_ / cyc_) * cyc_;
         drop = into_last <= (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 2);
     }
-    for (int m = 0; m < mates_; m++) {
-        if (!drop && !pending_deferred_[m].empty()) write_at({m, pending_deferred_[m].data(), pending_deferred_[m].size(), pos[m], nullptr, nullptr});
-        if (close(out[m]) != 0) die("cannot write to the file," + names[m]);
+    for (int f = 0; f < nfiles; f++) {
+        if (f % 2 >= mates_) continue;
+        if (!drop && !pending_deferred_[f].empty()) write_at({f, pending_deferred_[f].data(), pending_deferred_[f].size(), pos[f], nullptr, nullptr});
+        if (close(out[f]) != 0) die("cannot write to the file," + names[f]);
     }
 }
 
@@ -681,7 +793,10 @@ void FilterRun::process()
     if (hp_.output_file_type != "fasta" && hp_.output_file_type != "fastq") die("output_file_type value error");
     memset(&fmt_, 0, sizeof fmt_);
     fmt_.strip = 1;
-    fmt_.pe_info = (pe_ && hp_.pe_info) ? 1 : 0;      // seProcess::preOutput has no /1 (seprocess.cpp:919)
+    trim_ = !hp_.trim_fq1.empty();
+    // seProcess::preOutput has no /1 (seprocess.cpp:919). With the trim files on, preOutput runs on the same record once
+    // for the trim copy and once more for the clean copy (peprocess.cpp:1460-1475): the clean ids get the suffix twice.
+    fmt_.pe_info = (pe_ && hp_.pe_info) ? (trim_ ? 2 : 1) : 0;
     fmt_.fasta = hp_.output_file_type == "fasta";
     fmt_.id_mode = hp_.index_remove ? (hp_.seq_type == "0" ? 1 : 2) : 0;
     for (int g = 0; g < hp_.n_gpus; g++) {
@@ -698,7 +813,7 @@ void FilterRun::process()
     for (auto& b : batches_) free_q_.push(&b);
 
     t_setup_ = now_s() - t_begin;
-    const int nworkers = hp_.clean_gz ? std::max(2, hp_.threads) : 0;
+    const int nworkers = (hp_.clean_gz || trim_) ? std::max(2, hp_.threads) : 0;
     std::thread t_ingest([&] { ingest(); });
     std::thread t_gpu([&] { gpu_stage(); });
     std::vector<std::thread> workers;

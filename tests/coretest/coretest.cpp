@@ -345,7 +345,7 @@ uint64_t coretest_text_format(const uint8_t* text, const uint32_t* line_off, con
         const size_t row = (size_t)i * stride + res[i].head_cut;
         for (uint32_t lane = 0; lane < lanes; lane++)
             format_tail(dst + id_out, seq + row, qual + row, res[i].clean_len, mate, F, lane, lanes);
-        if (fasta) fasta_fix(dst, id_out + (pe_info ? 2u : 0u));
+        if (fasta) fasta_fix(dst, id_out + 2u * (uint32_t)pe_info);
     }
     return total;
 }

@@ -220,8 +220,7 @@ def ref_clean_text(ids, seq, qual, res, mate, pe_info=0, fasta=0, id_mode=0, qsh
         if res["category"][i] != 0:
             continue
         rid = ref_id_transform(ids[i], id_mode)
-        if pe_info:
-            rid += b"/2" if mate else b"/1"
+        rid += (b"/2" if mate else b"/1") * int(pe_info)
         h = int(res["head_cut"][i]); l = int(res["clean_len"][i])
         if fasta:
             rec = rid.replace(b"@", b">", 1) + b"\n" + seq[i, h:h + l].tobytes() + b"\n"

@@ -33,7 +33,7 @@ def read_maybe_gz(path):
 
 
 def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False,
-             module="filter", idfn=None, contams=None):
+             module="filter", idfn=None, contams=None, trim=False):
     w = os.path.join(str(tmp), name)
     os.makedirs(w)
     if module == "filtersRNA":
@@ -55,6 +55,8 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
     if pe:
         write(f"{w}/r2{ext_in}", 2)
         base += ["-2", f"{w}/r2{ext_in}", "-D", "c2" + ext_out]
+    if trim:                              # config keys trimFq1/2: every record after trimming (gzip only)
+        cfg = list(cfg or []) + ["trimFq1=t1.fq.gz"] + (["trimFq2=t2.fq.gz"] if pe else [])
     if patch or cfg:
         open(f"{w}/cfg.txt", "w").write((f"patch={patch}\n" if patch else "") + "".join(l + "\n" for l in (cfg or [])))
         base += ["-c", f"{w}/cfg.txt"]
@@ -68,6 +70,11 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
         a = read_maybe_gz(f"{w}/ref/c{mate}{ext_out}")
         b = read_maybe_gz(f"{w}/mine/c{mate}{ext_out}")
         assert a == b, f"{name}: clean fq{mate} differs ({len(a)} vs {len(b)} bytes)"
+    if trim:
+        for mate in (1, 2) if pe else (1,):
+            a = read_maybe_gz(f"{w}/ref/t{mate}.fq.gz")
+            b = read_maybe_gz(f"{w}/mine/t{mate}.fq.gz")
+            assert len(a) > 0 and a == b, f"{name}: trim fq{mate} differs ({len(a)} vs {len(b)} bytes)"
     reports = sorted(glob.glob(f"{w}/ref/*.txt"))
     assert len(reports) == (10 if pe else 6)
     for f in reports:
@@ -106,6 +113,23 @@ def test_cli_matches_reference_binary(cli, tmp_path, case):
 ], ids=lambda c: c["name"])
 def test_cli_tile_fov_matches_reference_binary(cli, tmp_path, case):
     """Config keys tile= / fov=: the ids are parsed on the device by the FASTQ text path."""
+    run_both(cli, tmp_path, **case)
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
+@pytest.mark.parametrize("case", [
+    dict(name="trim_pe_T1", pe=True, n=20000, L=100, T=1, flags=CFG2_FLAGS, trim=True),
+    dict(name="trim_pe_peinfo_index_multicycle", pe=True, n=12000, L=100, T=3, flags=["-f", A1, "-r", A2, "-J", "-x", "20,10", "-y", "20,30"], patch=17,
+         cfg=["index", "pe_info"], index_ids=True, trim=True),
+    dict(name="trim_pe_gz_T4_emptied_reads", pe=True, n=20000, L=100, T=4, flags=["-f", A1, "-r", A2, "-J", "-t", "30,30,40,45", "-4", "10"], patch=25,
+         gz_in=True, gz_out=True, trim=True, cfg=["outQualSys=1"]),
+    dict(name="trim_se_fasta", pe=False, n=15000, L=120, T=2, flags=["-f", A1, "-J", "-g", "8"], gkw=dict(var_len=True),
+         cfg=["outFileType=fasta"], trim=True),
+    dict(name="trim_pe_small_batches", pe=True, n=30000, L=150, T=2, flags=CFG2_FLAGS, patch=40, trim=True, env={"SNK_BATCH_READS": "3000"}),
+], ids=lambda c: c["name"])
+def test_cli_trim_files_match_reference_binary(cli, tmp_path, case):
+    """Config keys trimFq1= / trimFq2=: the trim files hold every record as fastq_trim left it, before the discard
+    decision; with pe_info the clean ids then carry the mate suffix twice (preOutput runs again on the same record)."""
     run_both(cli, tmp_path, **case)
 
 

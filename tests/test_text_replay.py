@@ -71,7 +71,7 @@ def test_pack_flags():
 
 
 @pytest.mark.parametrize("opts", [dict(), dict(pe_info=1), dict(fasta=1), dict(fasta=1, pe_info=1, id_mode=1), dict(id_mode=1),
-                                  dict(id_mode=2, pe_info=1), dict(qshift=31), dict(id_mode=2, fasta=1)],
+                                  dict(id_mode=2, pe_info=1), dict(qshift=31), dict(id_mode=2, fasta=1), dict(pe_info=2), dict(pe_info=2, fasta=1, id_mode=1)],
                          ids=lambda o: "-".join(f"{k}{v}" for k, v in o.items()) or "plain")
 @pytest.mark.parametrize("lanes", [1, 32])
 def test_format_matches_reference_model(opts, lanes):
