@@ -75,19 +75,29 @@ def main():
         def fmap(path):
             fm, cur = {}, "?"
             for i, l in enumerate(open(path).read().splitlines(), 1):
-                m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:SNK_HD|__device__|__global__|inline|__host__ __device__ inline)\s+[\w:<>\s\*&]*?\b(\w+)\s*\(", l)
+                m = re.match(r"\s*(?:template\s*<[^>]*>\s*)?(?:SNK_HD_NOINLINE|SNK_HD_MEMBER|SNK_HD|__device__ __forceinline__|__device__|__global__|inline|__host__ __device__ inline)\s+[\w:<>\s\*&]*?\b(\w+)\s*\(", l)
                 if m and not l.strip().startswith("//"):
                     cur = m.group(1)
+                if l.startswith("filter_kernel("):          # the kernel's declarator sits on its own line behind __launch_bounds__
+                    cur = "filter_kernel"
                 fm[i] = cur
             return fm
         fmc = fmap(os.path.join(ROOT, "soapnuke_b200/csrc/filter_core.cuh"))
         ksrc = open(os.path.join(ROOT, "soapnuke_b200/csrc/filter_kernel.cuh")).read().splitlines()
 
+        fmk = fmap(os.path.join(ROOT, "soapnuke_b200/csrc/filter_kernel.cuh"))
+
         def kphase(l):
+            # inside filter_kernel: the nearest "// ---- phase" marker above the line; elsewhere: the enclosing function
+            fn = fmk.get(l, "?")
+            if fn != "filter_kernel":
+                return fn
             for i in range(l - 1, 0, -1):
                 if "// ---- " in ksrc[i - 1]:
                     return ksrc[i - 1].strip()[8:30]
-            return "prologue/flush"
+                if "filter_kernel(" in ksrc[i - 1]:
+                    break
+            return "filter_kernel prologue / tile loop"
         g_inst, g_samp, g_thr = collections.Counter(), collections.Counter(), collections.Counter()
         if len(seq) == len(data):
             for fl, r in zip(seq, data):
