@@ -8,7 +8,11 @@ import gzip
 import json
 import os
 import shutil
+import atexit
+import concurrent.futures
 import subprocess
+import tempfile
+import threading
 import zlib
 
 import pytest
@@ -32,9 +36,25 @@ def read_maybe_gz(path):
     return gzip.open(path).read() if path.endswith(".gz") else open(path, "rb").read()
 
 
-def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False,
+# Every reference run sleeps in 5 s polling quanta (peprocess.cpp:3039), so the reference sides of ALL cases are
+# started together in the background the first time one of them is needed; a test then only waits for its own.
+_ALL_CASES = []
+_FUTURES = {}
+_LOCK = threading.Lock()
+_ROOT = None
+
+
+def reg(cases, **common):
+    for c in cases:
+        c.update(common)
+    _ALL_CASES.extend(cases)
+    return cases
+
+
+def _prepare(root, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=False, gz_out=False, env=None, cfg=None, index_ids=False,
              module="filter", idfn=None, contams=None, trim=False):
-    w = os.path.join(str(tmp), name)
+    """Writes the case's input files and runs the reference binary on them."""
+    w = os.path.join(root, name)
     os.makedirs(w)
     if module == "filtersRNA":
         d = synth.gen_srna(n, L=L, seed=zlib.crc32(name.encode()) % 100000, **(gkw or {}))
@@ -61,6 +81,24 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
         open(f"{w}/cfg.txt", "w").write((f"patch={patch}\n" if patch else "") + "".join(l + "\n" for l in (cfg or [])))
         base += ["-c", f"{w}/cfg.txt"]
     r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags, module=module)
+    return dict(w=w, base=base, ext_out=ext_out, ref=r)
+
+
+def _reference_side(name):
+    global _ROOT
+    with _LOCK:
+        if _ROOT is None:
+            _ROOT = tempfile.mkdtemp(prefix="snk_cli_")
+            atexit.register(shutil.rmtree, _ROOT, ignore_errors=True)
+            pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) // 2)))
+            for c in _ALL_CASES:
+                _FUTURES[c["name"]] = pool.submit(_prepare, _ROOT, **c)
+    return _FUTURES[name].result()
+
+
+def run_both(cli, tmp, name, pe, flags, env=None, module="filter", trim=False, **_unused):
+    st = _reference_side(name)
+    w, base, ext_out, r = st["w"], st["base"], st["ext_out"], st["ref"]
     assert r.returncode == 0, r.stderr.decode()
     e = dict(os.environ)
     e.update(env or {})
@@ -82,7 +120,7 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
-@pytest.mark.parametrize("case", [
+@pytest.mark.parametrize("case", reg([
     dict(name="pe_cfg2_plain_T1", pe=True, n=30000, L=150, T=1, flags=CFG2_FLAGS),
     dict(name="pe_cfg2_plain_T4_multicycle", pe=True, n=30000, L=150, T=4, flags=CFG2_FLAGS, patch=25),
     dict(name="pe_cfg2_gz_T3", pe=True, n=20000, L=150, T=3, flags=CFG2_FLAGS, patch=40, gz_in=True, gz_out=True),
@@ -98,26 +136,26 @@ def run_both(cli, tmp, name, pe, n, L, T, flags, gkw=None, patch=None, gz_in=Fal
     dict(name="pe_cfg2_gz_big_members", pe=True, n=120000, L=150, T=4, flags=CFG2_FLAGS, gz_in=True, gz_out=True),
     dict(name="se_default", pe=False, n=30000, L=150, T=1, flags=[]),
     dict(name="se_adapter_T4", pe=False, n=30000, L=100, T=4, flags=["-f", A1, "-J", "-g", "10"], patch=11, gz_in=True),
-], ids=lambda c: c["name"])
+]), ids=lambda c: c["name"])
 def test_cli_matches_reference_binary(cli, tmp_path, case):
     run_both(cli, tmp_path, **case)
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
-@pytest.mark.parametrize("case", [
+@pytest.mark.parametrize("case", reg([
     dict(name="tile_pe", pe=True, n=30000, L=100, T=2, flags=["-f", A1, "-r", A2, "-J"], cfg=["tile=1102,2201,9999"], idfn=synth.tile_ids),
     dict(name="tile_se_gz", pe=False, n=20000, L=100, T=1, flags=["-f", A1], cfg=["tile=1103"], idfn=synth.tile_ids, gz_in=True, gz_out=True),
     dict(name="fov_pe_multicycle", pe=True, n=20000, L=100, T=3, flags=["-f", A1, "-r", A2, "-J"], patch=20,
          cfg=["fov=C002R003,C004R001,C001R005"], idfn=synth.fov_ids),
     dict(name="fov_and_tile_se", pe=False, n=20000, L=100, T=1, flags=[], cfg=["fov=C003R002", "tile=0123"], idfn=synth.fov_ids),
-], ids=lambda c: c["name"])
+]), ids=lambda c: c["name"])
 def test_cli_tile_fov_matches_reference_binary(cli, tmp_path, case):
     """Config keys tile= / fov=: the ids are parsed on the device by the FASTQ text path."""
     run_both(cli, tmp_path, **case)
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
-@pytest.mark.parametrize("case", [
+@pytest.mark.parametrize("case", reg([
     dict(name="trim_pe_T1", pe=True, n=20000, L=100, T=1, flags=CFG2_FLAGS, trim=True),
     dict(name="trim_pe_peinfo_index_multicycle", pe=True, n=12000, L=100, T=3, flags=["-f", A1, "-r", A2, "-J", "-x", "20,10", "-y", "20,30"], patch=17,
          cfg=["index", "pe_info"], index_ids=True, trim=True),
@@ -126,7 +164,7 @@ def test_cli_tile_fov_matches_reference_binary(cli, tmp_path, case):
     dict(name="trim_se_fasta", pe=False, n=15000, L=120, T=2, flags=["-f", A1, "-J", "-g", "8"], gkw=dict(var_len=True),
          cfg=["outFileType=fasta"], trim=True),
     dict(name="trim_pe_small_batches", pe=True, n=30000, L=150, T=2, flags=CFG2_FLAGS, patch=40, trim=True, env={"SNK_BATCH_READS": "3000"}),
-], ids=lambda c: c["name"])
+]), ids=lambda c: c["name"])
 def test_cli_trim_files_match_reference_binary(cli, tmp_path, case):
     """Config keys trimFq1= / trimFq2=: the trim files hold every record as fastq_trim left it, before the discard
     decision; with pe_info the clean ids then carry the mate suffix twice (preOutput runs again on the same record)."""
@@ -138,7 +176,7 @@ CT1, CT2, CT3 = (c.decode() for c in CT)
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
-@pytest.mark.parametrize("case", [
+@pytest.mark.parametrize("case", reg([
     dict(name="contam_pe_single", pe=True, n=30000, L=100, T=2, flags=["-f", A1, "-r", A2, "-J"], cfg=[f"contam1={CT1}", f"contam2={CT2}"], contams=CT),
     dict(name="contam_se_list_gz", pe=False, n=20000, L=120, T=1, flags=[], cfg=[f"contam1={CT1},{CT3}", "ctMatchR=0.3,0.5"], contams=CT,
          gkw=dict(var_len=True), gz_in=True, gz_out=True),
@@ -150,7 +188,7 @@ CT1, CT2, CT3 = (c.decode() for c in CT)
          cfg=[f"global_contams={CT1},{CT3}", "glob_cotm_mR=0.5,0.6", "glob_cotm_mM=1,2"], contams=CT + [synth.revcomp(c) for c in CT]),
     dict(name="gcontam_se_with_contam", pe=False, n=20000, L=120, T=1, flags=[], gkw=dict(var_len=True),
          cfg=[f"global_contams={CT2}", "glob_cotm_mR=0.4", "glob_cotm_mM=0", f"contam1={CT1}"], contams=CT + [synth.revcomp(c) for c in CT]),
-], ids=lambda c: c["name"])
+]), ids=lambda c: c["name"])
 def test_cli_contam_matches_reference_binary(cli, tmp_path, case):
     """Config keys contam1= / contam2= / ctMatchR= / contam_trim."""
     run_both(cli, tmp_path, **case)
@@ -160,17 +198,17 @@ SA5, SA3 = synth.SRNA_ADAPTER5.decode(), synth.SRNA_ADAPTER3.decode()
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")
-@pytest.mark.parametrize("case", [
+@pytest.mark.parametrize("case", reg([
     dict(name="srna_trim_T1", n=40000, L=50, T=1, flags=["-f", SA5, "-r", SA3, "-J"]),
     dict(name="srna_trim_polyg_T3_gz", n=30000, L=50, T=3, flags=["-f", SA5, "-r", SA3, "-J", "-g", "6", "-p", "0.6", "-X", "12"],
          gkw=dict(var_len=True), patch=15, gz_in=True, gz_out=True),
     dict(name="srna_discard_L44", n=20000, L=44, T=2, flags=["-f", SA5, "-r", SA3]),
     dict(name="srna_hard_cfg", n=20000, L=75, T=2, flags=["-f", SA5, "-r", SA3, "-J", "-t", "2,1", "-4", "15"],
          cfg=["maxReadLen=60", "adaRCtg=7", "adaRAr=0.7", "adaRMa=6", "adaREr=0.3", "adaRMm=3"], env={"SNK_BATCH_READS": "3000"}),
-], ids=lambda c: c["name"])
+], pe=False, module="filtersRNA"), ids=lambda c: c["name"])
 def test_cli_filtersRNA_matches_reference_binary(cli, tmp_path, case):
     """`SOAPnuke filtersRNA` (seProcess + sRNA_findAdapter / sRNA_hasAdapter / sRNA_discard)."""
-    run_both(cli, tmp_path, pe=False, module="filtersRNA", **case)
+    run_both(cli, tmp_path, **case)
 
 
 def test_cli_reproduces_golden_outputs(cli, tmp_path):
