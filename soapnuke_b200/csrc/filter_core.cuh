@@ -1353,8 +1353,14 @@ SNK_HD void unit_q_raw(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, int
     const uint8_t* pq = rows_q + J * w;
     const uint32_t sh = 8u * (uint32_t)j0;
     const int c_raw = cell0_raw + j0 * jstep;
-    for (uint32_t r = 0; r < cnt; r++)
-        qual_update_all<CounterT, JN>(load4(pq + (size_t)r * stride) >> sh, qcells, c_raw, jstep, bstep);
+    // the row word of the next record is loaded before the current one's cells are updated: the compiler cannot move
+    // a shared-memory load above the counter stores by itself (it cannot prove that rows and cells do not alias)
+    uint32_t w0 = cnt ? load4(pq) : 0u;
+    for (uint32_t r = 0; r < cnt; r++) {
+        const uint32_t w1 = (r + 1 < cnt) ? load4(pq + (size_t)(r + 1) * stride) : 0u;
+        qual_update_all<CounterT, JN>(w0 >> sh, qcells, c_raw, jstep, bstep);
+        w0 = w1;
+    }
 }
 template <typename CounterT, int J, int JN>
 SNK_HD void unit_q_delta(const uint8_t* rows_q, const DeltaEnt* dl, uint32_t nd, int w, int j0, uint8_t* qcells, int cell0_del, int jstep, int bstep)
