@@ -562,11 +562,14 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
             int s0 = first3 > 32 * kw ? first3 - 32 * kw : 0;
             s0 += ((s0 % kNT) != h) ? 1 : 0;                       // first offset of my parity (kNT == 2)
             const int send = (last3 - 32 * kw) >= 31 ? 32 : (last3 - 32 * kw + 1);
-            for (int sft = s0; sft < send; sft += kNT) {
-                const int winlen = len - (32 * kw + sft);
+            // window length and its low-bit mask are carried along (the window shrinks by kNT per step; it is
+            // shorter than the adapter, so at most 63 bases)
+            int winlen = len - (32 * kw + s0);
+            uint64_t wmask = winlen > 0 ? ((1ull << winlen) - 1ull) : 0ull;
+            for (int sft = s0; sft < send; sft += kNT, winlen -= kNT, wmask >>= kNT) {
                 const int budget = a.budget3[winlen - edge];
                 const int nb = budget < 0 ? 0 : budget;
-                const uint32_t pm = winlen < 32 ? (pm2 & ((1u << winlen) - 1u)) : pm2;
+                const uint32_t pm = pm2 & (uint32_t)wmask;
                 const uint32_t x0 = funnel_r(l0, m0, sft) ^ a0lo;
                 if ((int)popc32(x0 & pm) > nb) continue;
                 if (SNK_VERIFY(kw, sft, x0, pm, nb, winlen, budget)) out.pos3 = 32 * kw + sft;
