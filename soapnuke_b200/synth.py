@@ -55,7 +55,7 @@ def gen_pairs(n, L=150, seed=1002, polyg_frac=0.04, adapter1=ADAPTER1, adapter2=
         if ada.size:
             idx = np.nonzero(cls_ada)[0]
             for i in idx:                      # 10 % of reads; small python loop is fine for tests
-                s = int(k[i]); e = min(L, s + ada.size)
+                s = min(int(k[i]), L); e = min(L, s + ada.size)
                 seq[i, s:e] = ada[: e - s]
         nmask = cls_n[:, None] & (rng.random((n, L)) < 0.08)
         seq[nmask] = ord("N")
@@ -64,11 +64,11 @@ def gen_pairs(n, L=150, seed=1002, polyg_frac=0.04, adapter1=ADAPTER1, adapter2=
         if m == 2 or se:
             pg = np.nonzero(cls_pg)[0]
             for i in pg:
-                t = 5 + int(k[i]) // 3
+                t = min(L, 5 + int(k[i]) // 3)
                 seq[i, L - t:] = ord("G")
         length = np.full(n, L, dtype=np.uint16)
         if var_len:
-            length = rng.integers(max(35, L // 2), L + 1, size=n).astype(np.uint16)
+            length = rng.integers(min(L, max(35, L // 2)), L + 1, size=n).astype(np.uint16)
         S = np.zeros((n, stride), dtype=np.uint8)
         Q = np.zeros((n, stride), dtype=np.uint8)
         S[:, :L] = seq

@@ -279,3 +279,68 @@ def test_adapter_matcher_adversarial(adapter, L, kw):
         c1, _, cst, cerr = core_replay(p, d)
         assert (o1["adacut_pos"] >= 0).sum() > 500, "generator should produce many adapter hits"
         assert_same((c1, None, cst), (o1, None, ost), f"adapter len {len(adapter)} trim={trim}")
+
+
+def random_case(seed):
+    """Random option set + random batch (the offline twin of this generator, run against the reference binary
+    over several hundred seeds, found no discrepancy outside the reference's undefined behaviour)."""
+    import random
+    rnd = random.Random(seed)
+    pe = rnd.random() < 0.6
+    L = rnd.choice([17, 36, 50, 75, 100, 150, 151, 250])
+    n = rnd.choice([300, 700, 1100])
+    kw = dict(threads=rnd.choice([1, 2, 3, 5]), patch_size=rnd.choice([7, 20, 33]))
+    if rnd.random() < 0.8:
+        kw["adapter1"] = rnd.choice([A1, [A2.lower(), A1], A1[:10], A1 + A2[:31]])
+        if pe:
+            kw["adapter2"] = A2
+        kw["ada_trim"] = rnd.random() < 0.6
+    kw["low_qual"] = rnd.choice([2, 5, 10, 20])
+    kw["low_qual_ratio"] = rnd.choice([0.1, 0.3, 0.5, 0.9, -1.0])
+    kw["mean_quality"] = rnd.choice([-1, 10, 20, 30])
+    kw["n_ratio"] = rnd.choice([0.01, 0.05, 0.2, -1.0])
+    kw["highA_ratio"] = rnd.choice([-1.0, 0.3, 0.5, 0.8])
+    kw["polyG_tail"] = rnd.choice([-1.0, 3, 8, 15])
+    kw["polyX_num"] = rnd.choice([-1, 1, 6, 12, 40])
+    kw["min_read_length"] = rnd.choice([-1, 0, 10, 30, 60])
+    kw["max_read_length"] = rnd.choice([-1, -1, 40, 100, 140])
+    if rnd.random() < 0.5:
+        kw["trim_bad_head"] = (rnd.choice([10, 20, 30]), rnd.choice([0, 5, 10, 400]))
+    if rnd.random() < 0.5:
+        kw["trim_bad_tail"] = (rnd.choice([10, 20, 30]), rnd.choice([0, 5, 20, 400]))
+    if rnd.random() < 0.4:
+        kw["hard_trim"] = tuple(rnd.choice([0, 2, 7, 60]) for _ in range(4))
+    if rnd.random() < 0.3:
+        kw["ada_mis"] = (rnd.choice([0, 1, 3, 7]), rnd.choice([0, 2, 4]))
+    if rnd.random() < 0.3:
+        kw["ada_edge"] = (rnd.choice([0, 3, 6, 10]), rnd.choice([4, 6, 12, 40]))
+    if rnd.random() < 0.3:
+        kw["ada_mr"] = (rnd.choice([0.1, 0.3, 0.5, 0.8, 1.0]), rnd.choice([0.4, 0.5, 0.9]))
+    if rnd.random() < 0.25:
+        kw["contam1"] = rnd.choice([_C1, f"{_C1},{_C3}"])
+        kw["ct_match_r"] = "0.3" if "," not in kw["contam1"] else "0.3,0.6"
+        if pe:
+            kw["contam2"] = _C2 if "," not in kw["contam1"] else f"{_C2},{_C1}"
+        kw["contam_trim"] = rnd.random() < 0.2
+    if rnd.random() < 0.2:
+        kw["global_contams"] = _C3; kw["glob_cotm_mR"] = rnd.choice(["0.4", "0.7"]); kw["glob_cotm_mM"] = rnd.choice(["0", "2"])
+    kw["quality_phred"] = 33
+    kw["max_base_quality"] = rnd.choice([42, 42, 30, 63])
+    d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=rnd.random() < 0.5, polyg_frac=rnd.choice([0.04, 0.3]))
+    if "contam1" in kw or "global_contams" in kw:
+        synth.add_contams(d, CONTAM_PLANTS, seed=seed)
+    if rnd.random() < 0.3:                    # tile / fov flags as a caller of the SoA entry points would set them
+        fl = np.random.default_rng(seed).choice(np.array([0, 0, 0, abi.PRE_TILE, abi.PRE_FOV, abi.PRE_TILE | abi.PRE_FOV], dtype=np.uint16), size=n)
+        d["len1"] = d["len1"] | fl
+    return pe, kw, d, dict(first=rnd.choice([0, 12345, 10**9]), tile_r=rnd.choice([0, 8, 24]), grid=rnd.choice([1, 3, 7]))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_options_replay_matches_oracle(seed):
+    pe, kw, d, rkw = random_case(seed)
+    p = abi.make_params(is_pe=pe, **kw)
+    o1, o2, ost, oerr = oracle_run(p, d, first=rkw["first"])
+    c1, c2, cst, cerr = core_replay(p, d, **rkw)
+    assert oerr == cerr
+    if oerr == 0:
+        assert_same((c1, c2, cst), (o1, o2, ost), f"seed {seed}: {kw}")

@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""TEST INFRASTRUCTURE: random option sets against the unmodified reference binary (oracle/_ref/SOAPnuke).
+
+    python tools/ref_fuzz.py FIRST_SEED LAST_SEED
+
+For every seed: random PE/SE shape, read length, worker count, patch size and a random subset of the filter / trim /
+adapter options; runs the reference binary and the oracle (oracle/snk_oracle.c + host report writer) on the same
+FASTQ and prints the seeds whose clean FASTQ or reports differ. Known non-issues it filters or that show up as
+reference crashes: uninitialised buffers printed when no read survives, low-quality end trims longer than the read.
+The committed twin of this generator (tests/test_core_replay.py: random_case) checks the device code against the
+oracle in the CPU tier.
+"""
+import sys, os, zlib, tempfile, glob, shutil, ctypes as C, concurrent.futures, random
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for _p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
+    sys.path.insert(0, _p)
+import numpy as np
+import oracle_py as orc
+from soapnuke_b200 import abi, synth
+from helpers import A1, A2, report_equal
+lib = abi.load_engine()
+def one(seed):
+    rnd = random.Random(seed)
+    pe = rnd.random() < 0.6
+    L = rnd.choice([36, 50, 75, 100, 150, 151, 250])
+    n = rnd.choice([800, 1500, 3000])
+    T = rnd.choice([1, 2, 3, 5])
+    patch = rnd.choice([None, 7, 20, 33])
+    var = rnd.random() < 0.4
+    flags = []; kw = {}
+    if rnd.random() < 0.8:
+        flags += ["-f", A1]; kw["adapter1"] = A1
+        if pe: flags += ["-r", A2]; kw["adapter2"] = A2
+        if rnd.random() < 0.6: flags += ["-J"]; kw["ada_trim"] = True
+    v = rnd.choice([2, 5, 10, 20]); flags += ["-l", str(v)]; kw["low_qual"] = v
+    v = rnd.choice([0.1, 0.3, 0.5, 0.9]); flags += ["-q", str(v)]; kw["low_qual_ratio"] = v
+    if rnd.random() < 0.5: v = rnd.choice([10, 20, 30]); flags += ["-m", str(v)]; kw["mean_quality"] = v
+    v = rnd.choice([0.01, 0.05, 0.2]); flags += ["-n", str(v)]; kw["n_ratio"] = v
+    if rnd.random() < 0.5: v = rnd.choice([0.3, 0.5, 0.8]); flags += ["-p", str(v)]; kw["highA_ratio"] = v
+    if rnd.random() < 0.5: v = rnd.choice([3, 8, 15]); flags += ["-g", str(v)]; kw["polyG_tail"] = v
+    if rnd.random() < 0.5: v = rnd.choice([6, 12, 40]); flags += ["-X", str(v)]; kw["polyX_num"] = v
+    v = rnd.choice([10, 30, 60]); flags += ["-4", str(v)]; kw["min_read_length"] = v
+    if pe and rnd.random() < 0.5:
+        a, b = rnd.choice([10, 20, 30]), rnd.choice([5, 10, 17]); flags += ["-x", f"{a},{b}"]; kw["trim_bad_head"] = (a, b)
+    if pe and rnd.random() < 0.5:
+        a, b = rnd.choice([10, 20, 30]), rnd.choice([5, 12, 17]); flags += ["-y", f"{a},{b}"]; kw["trim_bad_tail"] = (a, b)
+    if rnd.random() < 0.4:
+        ht = [rnd.choice([0, 2, 7]) for _ in range(4 if pe else 2)]
+        flags += ["-t", ",".join(map(str, ht))]; kw["hard_trim"] = tuple(ht)
+    cfg = []
+    if patch: cfg.append(f"patch={patch}")
+    if rnd.random() < 0.3:
+        m1, m2 = rnd.choice([0, 1, 3]), rnd.choice([0, 2, 4]); cfg.append(f"adaMis={m1},{m2}"); kw["ada_mis"] = (m1, m2)
+    if rnd.random() < 0.3:
+        e1, e2 = rnd.choice([3, 6, 10]), rnd.choice([4, 6, 12]); cfg.append(f"adaEdge={e1},{e2}"); kw["ada_edge"] = (e1, e2)
+    if rnd.random() < 0.3:
+        r1, r2 = rnd.choice([0.3, 0.5, 0.8]), rnd.choice([0.4, 0.5, 0.9]); cfg.append(f"adaMR={r1},{r2}"); kw["ada_mr"] = (r1, r2)
+    if rnd.random() < 0.3: v = rnd.choice([40, 100, 140]); cfg.append(f"maxReadLen={v}"); kw["max_read_length"] = v
+    d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=var, polyg_frac=rnd.choice([0.04, 0.3]))
+    w = tempfile.mkdtemp(prefix="fz")
+    synth.write_fastq(f"{w}/r1.fq", d["seq1"], d["qual1"], d["len1"], 1)
+    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    if pe:
+        synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2); args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+    if cfg:
+        open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
+    r = orc.run_reference(args + flags)
+    if r.returncode != 0:
+        return seed, "ref rc %d %s" % (r.returncode, r.stderr.decode()[-120:]), flags, cfg
+    p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **kw)
+    if pe: r1, r2, st, err = orc.filter_pe(p, d)
+    else: r1, st, err = orc.filter_se(p, d); r2 = None
+    bad = []
+    for m, rs in ((1, r1), (2, r2)):
+        if rs is None: continue
+        order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
+        mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"], rs, m, order=order)
+        if mine != open(f"{w}/out/c{m}.fq", "rb").read(): bad.append(f"clean{m}")
+    os.makedirs(f"{w}/mine")
+    fn = lib.snk_report_write_pe if pe else lib.snk_report_write_se
+    fn(C.byref(p), st.ctypes.data, f"{w}/mine".encode())
+    for f in glob.glob(f"{w}/out/*.txt"):
+        if not report_equal(f, f"{w}/mine/" + os.path.basename(f)):
+            if "Basic_Statistics" in f and (r1["category"] == 0).sum() == 0: continue      # reference prints uninitialised buffers
+            bad.append(os.path.basename(f))
+    if not bad: shutil.rmtree(w)
+    return seed, bad, flags + cfg, (w if bad else "")
+with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
+    for seed, bad, fl, w in ex.map(one, range(int(sys.argv[1]), int(sys.argv[2]))):
+        if bad: print(seed, bad, " ".join(fl), w)
+print("done")
