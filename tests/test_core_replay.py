@@ -281,15 +281,15 @@ def test_adapter_matcher_adversarial(adapter, L, kw):
         assert_same((c1, None, cst), (o1, None, ost), f"adapter len {len(adapter)} trim={trim}")
 
 
-def random_case(seed):
+def random_case(seed, scale=1):
     """Random option set + random batch (the offline twin of this generator, run against the reference binary
     over several hundred seeds, found no discrepancy outside the reference's undefined behaviour)."""
     import random
     rnd = random.Random(seed)
     pe = rnd.random() < 0.6
     L = rnd.choice([17, 36, 50, 75, 100, 150, 151, 250])
-    n = rnd.choice([300, 700, 1100])
-    kw = dict(threads=rnd.choice([1, 2, 3, 5]), patch_size=rnd.choice([7, 20, 33]))
+    n = rnd.choice([300, 700, 1100]) * scale
+    kw = dict(threads=rnd.choice([1, 2, 3, 5]), patch_size=rnd.choice([7, 20, 33]) * scale)
     if rnd.random() < 0.8:
         kw["adapter1"] = rnd.choice([A1, [A2.lower(), A1], A1[:10], A1 + A2[:31]])
         if pe:

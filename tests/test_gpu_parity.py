@@ -103,6 +103,22 @@ def test_engine_matches_oracle_contam(engine_lib):
         assert_same((r1, r2, st), (o1, o2, ost), name)
 
 
+@pytest.mark.parametrize("seed,scale", [(s, 1) for s in range(24)] + [(s, 40) for s in range(100, 112)])
+def test_random_options_engine_matches_oracle(seed, scale, engine_lib):
+    """Random option sets (the CPU tier's generator) through the engine: small ragged batches and larger ones."""
+    from test_core_replay import random_case
+    pe, kw, d, rkw = random_case(seed, scale)
+    p = abi.make_params(is_pe=pe, **kw)
+    o1, o2, ost, oerr = oracle_run(p, d, first=rkw["first"])
+    with Engine(engine_lib, p) as e:
+        r1, r2 = e.filter_host(d, first=rkw["first"])
+        st = e.stats()
+        flags, _ = e.error_flags()
+    assert flags == oerr
+    if oerr == 0:
+        assert_same((r1, r2, st), (o1, o2, ost), f"seed {seed} x{scale}: {kw}")
+
+
 def test_mixed_checked_and_unchecked_tiles(engine_lib):
     """Records with qualities above the shared-memory bins scattered through the batch (see the CPU
     tier's test of the same name): checked and unchecked tiles, raw and delta cells must add up."""
