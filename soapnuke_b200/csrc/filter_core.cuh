@@ -1164,7 +1164,9 @@ SNK_HD void trim_stat_indices(int which, int slen, int raw_length, int head_hd, 
 // ------------------------------------------------------------------ per-position histograms
 // One histogram item = J consecutive positions of one table; the thread that owns an item is the
 // only writer of its counters, so no atomics are needed.
-//   quality x position counts: shared memory, CounterT cells, index (q*J + j) * qstride + item
+//   quality x position counts: shared memory, 16-bit CounterT cells; cell (q, j) of item x lives in 32-bit word
+//                              (q*(J/2) + j/2) * X + x, half j&1 (qcell_index): the lanes of a warp own consecutive items,
+//                              so whatever their q rows are they hit 32 different banks (X is a multiple of 32)
 //   base x position counts:    packed J x 8 bit per symbol while walking a tile (BaseAcc), then
 //                              added to the owner's 5*J register counters (BaseCnt) for the whole launch.
 // RAW items count every record of the tile: rows are padded by scan_chunks (bases 0, qualities in the
@@ -1274,18 +1276,24 @@ SNK_HD void base_update_range(uint32_t s, int lo, int hi, BaseAcc& acc)
     base_acc_add(acc, s & lane_mask(lo, hi) & jmask);
 }
 
+// element index of quality cell (q, j) of item x in a table of row pitch X items
+template <int J>
+SNK_HD uint32_t qcell_index(uint32_t q, uint32_t j, uint32_t x, uint32_t X) { return ((q * (uint32_t)(J / 2) + (j >> 1)) * X + x) * 2u + (j & 1u); }
+// byte offset of sub-position j (relative to sub-position 0 of the same item and q); rowstep = X * 4 bytes
+SNK_HD int qj_off(int j, int rowstep) { return (j >> 1) * rowstep + (j & 1) * 2; }
 // Quality cells: qcells = the quality table as bytes; the cell of (byte value b, sub-position j) is
-// at qcells + cell0 + j*jstep + b*bstep, where cell0 already folds in the item and the Phred base.
+// at qcells + cell0 + qj_off(j, rowstep) + b*bstep, where cell0 already folds in the item and the Phred base
+// and bstep = (J/2) * rowstep. Units start at an even sub-position, so qj_off(j0 + j) = qj_off(j0) + qj_off(j).
 // The J cells belong to different sub-positions, so they never alias: load them all, then store them
 // all - one shared-memory round trip per record.
 template <typename CounterT, int J>
-SNK_HD void qual_update_all(uint32_t q, uint8_t* qcells, int cell0, int jstep, int bstep)
+SNK_HD void qual_update_all(uint32_t q, uint8_t* qcells, int cell0, int rowstep, int bstep)
 {
     CounterT* cell[J];
     CounterT val[J];
 #pragma unroll
     for (int j = 0; j < J; j++) {
-        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + qj_off(j, rowstep)) + (int)byte_of(q, j) * bstep);
         val[j] = *cell[j];
     }
 #pragma unroll
@@ -1293,13 +1301,13 @@ SNK_HD void qual_update_all(uint32_t q, uint8_t* qcells, int cell0, int jstep, i
 }
 // sub-positions lo <= j < hi only, inc = +1 / -1 (cells wrap: delta cells are read as signed)
 template <typename CounterT, int J>
-SNK_HD void qual_update_range(uint32_t q, int lo, int hi, int inc, uint8_t* qcells, int cell0, int jstep, int bstep)
+SNK_HD void qual_update_range(uint32_t q, int lo, int hi, int inc, uint8_t* qcells, int cell0, int rowstep, int bstep)
 {
     CounterT* cell[J];
     CounterT val[J];
 #pragma unroll
     for (int j = 0; j < J; j++) {
-        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + j * jstep) + (int)byte_of(q, j) * bstep);
+        cell[j] = reinterpret_cast<CounterT*>(qcells + (cell0 + qj_off(j, rowstep)) + (int)byte_of(q, j) * bstep);
         val[j] = (j >= lo && j < hi) ? *cell[j] : (CounterT)0;
     }
 #pragma unroll
@@ -1314,7 +1322,7 @@ SNK_HD void qual_update_range(uint32_t q, int lo, int hi, int inc, uint8_t* qcel
 // [0,SNK_QBINS) raises the error flag. Returns error bits.
 template <typename CounterT, int J>
 SNK_HD uint32_t qual_update_checked(const uint8_t* qual, int off, int w, int lo, int hi, int phred, int qb, int cell_inc,
-                                    CounterT* qhist /* item's first cell */, int qstride, long long g_inc,
+                                    CounterT* qhist /* cell (q 0, j 0) of the item */, int qstride /* row pitch X */, long long g_inc,
                                     unsigned long long* file_base, unsigned long long* mirror_base)
 {
     const uint32_t q = hist_load_word<J>(qual, off, w);
@@ -1323,7 +1331,10 @@ SNK_HD uint32_t qual_update_checked(const uint8_t* qual, int off, int w, int lo,
     for (int j = 0; j < J; j++) {
         if (j >= lo && j < hi) {
             const int qq = (int)((q >> (8 * j)) & 0xFFu) - phred;
-            if ((unsigned)qq < (unsigned)qb) qhist[(qq * J + j) * qstride] = (CounterT)(qhist[(qq * J + j) * qstride] + cell_inc);
+            if ((unsigned)qq < (unsigned)qb) {
+                CounterT& cell = qhist[qcell_index<J>((uint32_t)qq, (uint32_t)j, 0u, (uint32_t)qstride)];
+                cell = (CounterT)(cell + cell_inc);
+            }
             else if ((unsigned)qq < (unsigned)SNK_QBINS) {
                 const size_t cell = SNK_FILE_QS_OFF + (size_t)(J * w + j) * SNK_QBINS + qq;
                 unsigned long long* bases[2] = {file_base, mirror_base};
@@ -1351,32 +1362,32 @@ SNK_HD uint32_t qual_update_checked(const uint8_t* qual, int off, int w, int lo,
 // (and the delta entries k = r0, r0+rstep, ...). With two units per item every thread of a CTA
 // sized for phase A (two threads per read) has phase-B work.
 template <typename CounterT, int J, int JN>
-SNK_HD void unit_q_raw(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, int w, int j0, uint8_t* qcells, int cell0_raw, int jstep, int bstep)
+SNK_HD void unit_q_raw(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, int w, int j0, uint8_t* qcells, int cell0_raw, int rowstep, int bstep)
 {
     const uint8_t* pq = rows_q + J * w;
     const uint32_t sh = 8u * (uint32_t)j0;
-    const int c_raw = cell0_raw + j0 * jstep;
+    const int c_raw = cell0_raw + qj_off(j0, rowstep);
     // the row word of the next record is loaded before the current one's cells are updated: the compiler cannot move
     // a shared-memory load above the counter stores by itself (it cannot prove that rows and cells do not alias)
     uint32_t w0 = cnt ? load4(pq) : 0u;
     for (uint32_t r = 0; r < cnt; r++) {
         const uint32_t w1 = (r + 1 < cnt) ? load4(pq + (size_t)(r + 1) * stride) : 0u;
-        qual_update_all<CounterT, JN>(w0 >> sh, qcells, c_raw, jstep, bstep);
+        qual_update_all<CounterT, JN>(w0 >> sh, qcells, c_raw, rowstep, bstep);
         w0 = w1;
     }
 }
 template <typename CounterT, int J, int JN>
-SNK_HD void unit_q_delta(const uint8_t* rows_q, const DeltaEnt* dl, uint32_t nd, int w, int j0, uint8_t* qcells, int cell0_del, int jstep, int bstep)
+SNK_HD void unit_q_delta(const uint8_t* rows_q, const DeltaEnt* dl, uint32_t nd, int w, int j0, uint8_t* qcells, int cell0_del, int rowstep, int bstep)
 {
     const uint32_t sh = 8u * (uint32_t)j0;
-    const int c_del = cell0_del + j0 * jstep;
+    const int c_del = cell0_del + qj_off(j0, rowstep);
     const int first = J * w + j0;
     for (uint32_t k = 0; k < nd; k++) {
         const DeltaEnt d = dl[k];
         const int hi = (int)(d.d0 & 0x3FFu) - first, lo = (int)(d.d1 & 0x3FFu) - first;
         if (hi <= 0 || lo >= JN) continue;
         qual_update_range<CounterT, JN>(hist_load_word<J>(rows_q, (int)((d.d0 >> 10) & 0x1FFFFFu), w) >> sh, lo, hi,
-                                        (d.d1 & kDeltaAdd) ? -1 : 1, qcells, c_del, jstep, bstep);
+                                        (d.d1 & kDeltaAdd) ? -1 : 1, qcells, c_del, rowstep, bstep);
     }
 }
 // delta entries of a b-unit (shared by the fast and the checked path)
@@ -1423,7 +1434,7 @@ SNK_HD void unit_b_raw(const uint8_t* rows_s, uint32_t stride, uint32_t cnt, int
 // the slot's global tables. Returns error bits.
 template <typename CounterT, int J>
 SNK_HD uint32_t unit_q_checked(const uint8_t* rows_q, const uint32_t* desc, uint32_t cnt, const DeltaEnt* dl, uint32_t nd, int w,
-                               int j0, int jn, int phred, int qb, CounterT* cell_raw /* raw item's first cell */, uint32_t nraw,
+                               int j0, int jn, int phred, int qb, CounterT* cell_raw /* cell (q 0, j 0) of the raw item */, uint32_t nraw,
                                int qstride, unsigned long long* f_raw, unsigned long long* f_clean)
 {
     uint32_t err = 0;
@@ -1442,7 +1453,7 @@ SNK_HD uint32_t unit_q_checked(const uint8_t* rows_q, const uint32_t* desc, uint
         if (lo < j0) lo = j0;
         if (hi <= lo) continue;
         const bool add = (d.d1 & kDeltaAdd) != 0;
-        err |= qual_update_checked<CounterT, J>(rows_q, (int)((d.d0 >> 10) & 0x1FFFFFu), w, lo, hi, phred, qb, add ? -1 : 1, cell_raw + nraw,
+        err |= qual_update_checked<CounterT, J>(rows_q, (int)((d.d0 >> 10) & 0x1FFFFFu), w, lo, hi, phred, qb, add ? -1 : 1, cell_raw + 2u * nraw,
                                                 qstride, add ? 1ll : -1ll, f_clean, nullptr);
     }
     return err;

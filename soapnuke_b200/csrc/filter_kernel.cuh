@@ -219,7 +219,7 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
     unsigned long long* S = A.stats + (size_t)slot * SNK_SLOT_WORDS;
     const uint32_t X = A.X, W = A.items_w;
     const uint32_t nraw = (uint32_t)mates * W;         // raw items; the delta item of raw item x is x + nraw
-    // quality cells: entry e = (q*J + j)*X + x. A thread keeps one raw item x (hence one table) and strides
+    // quality cells (qcell_index). A thread keeps one raw item x (hence one table) and strides
     // over the (q, j) rows, so the q20/q30 totals stay in registers until one 32-bit shared atomic each
     // (all per-interval sums fit 32 bits: at most kQCounterMax records x 1008 positions).
     const uint32_t qrows = (uint32_t)P.qb * (uint32_t)J;
@@ -230,12 +230,12 @@ __device__ void flush_hist(const KernelArgs& A, const DevParams& P, int mates, Q
         unsigned long long* FC = S + SNK_SLOT_FILE_OFF(file_of_tab(mates, (int)tab + mates)) + SNK_FILE_QS_OFF + (size_t)(J * w) * SNK_QBINS;
         uint32_t r20 = 0, r30 = 0, c20 = 0, c30 = 0;
         for (uint32_t qj = threadIdx.x / nraw; qj < qrows; qj += rows_par) {
-            const uint32_t e = qj * X + x;
-            const uint32_t vr = qhist[e];
-            const int vd = (int)(int16_t)qhist[e + nraw];
-            if (!vr && !vd) continue;
-            qhist[e] = 0; qhist[e + nraw] = 0;
             const uint32_t j = qj % (uint32_t)J, q = qj / (uint32_t)J;
+            const uint32_t e = qcell_index<J>(q, j, x, X), ed = qcell_index<J>(q, j, x + nraw, X);
+            const uint32_t vr = qhist[e];
+            const int vd = (int)(int16_t)qhist[ed];
+            if (!vr && !vd) continue;
+            qhist[e] = 0; qhist[ed] = 0;
             const uint32_t vc = (uint32_t)((int)vr - vd);      // records of the clean set in this cell: never negative
             if (vr) atomicAdd(&FR[(size_t)j * SNK_QBINS + q], (unsigned long long)vr);
             if (vc) atomicAdd(&FC[(size_t)j * SNK_QBINS + q], (unsigned long long)vc);
@@ -359,10 +359,10 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
     const uint32_t my_w = item % W;
     const int my_m = (int)(item / W) % MATES;
     const bool my_item = q_role || b_role;
-    // byte offsets into the quality table: cell(b, j) = cell0 + j*jstep + b*bstep
-    const int q_jstep = (int)A.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
-    const int q_cell0 = (int)item * (int)sizeof(QCounter) - P.phred * q_bstep;
-    const int q_cell0_del = q_cell0 + (int)nraw * (int)sizeof(QCounter);
+    // byte offsets into the quality table: cell(b, j) = cell0 + qj_off(j, rowstep) + b*bstep (filter_core.cuh)
+    const int q_jstep = (int)A.X * 2 * (int)sizeof(QCounter), q_bstep = (J / 2) * q_jstep;      // q_jstep = rowstep
+    const int q_cell0 = (int)item * 2 * (int)sizeof(QCounter) - P.phred * q_bstep;
+    const int q_cell0_del = q_cell0 + (int)nraw * 2 * (int)sizeof(QCounter);
     const uint32_t* my_desc = desc + (size_t)my_m * A.R;
     const DeltaEnt* my_dlist = dlist + (size_t)my_m * 2u * A.R;
     const uint32_t flush_item = b_role ? item : 0xFFFFFFFFu;
@@ -555,7 +555,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 uint32_t err = 0;
                 if (q_role)
                     err = unit_q_checked<QCounter, J>(rows_q, my_desc, cnt, my_dlist, nd, (int)my_w, wide ? (int)half * (J / 2) : 0, wide ? J / 2 : J,
-                                                      P.phred, P.qb, qhist + item, nraw, (int)A.X, f_raw, f_clean);
+                                                      P.phred, P.qb, qhist + 2u * item, nraw, (int)A.X, f_raw, f_clean);
                 if (b_role) unit_b_checked<J>(rows_s, my_desc, cnt, my_dlist, nd, (int)my_w, wide ? half : 0u, wide ? 2u : 1u, bc);
                 if (err) report_error(A, err, g0);
             }

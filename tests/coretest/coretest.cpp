@@ -41,11 +41,11 @@ void flush(Ctx& c, int slot)
     // raw cells count all records, delta cells "removed - added": raw += raw, clean += raw - delta
     for (uint32_t qj = 0; qj < (uint32_t)c.P.qb * J; qj++)
         for (uint32_t x = 0; x < nraw; x++) {
-            const uint32_t e = qj * c.X + x;
-            const uint32_t vr = c.qhist[e];
-            const int vd = (int)(int16_t)c.qhist[e + nraw];
-            c.qhist[e] = 0; c.qhist[e + nraw] = 0;
             const uint32_t j = qj % J, q = qj / J;
+            const uint32_t e = qcell_index<4>(q, j, x, c.X), ed = qcell_index<4>(q, j, x + nraw, c.X);
+            const uint32_t vr = c.qhist[e];
+            const int vd = (int)(int16_t)c.qhist[ed];
+            c.qhist[e] = 0; c.qhist[ed] = 0;
             const uint32_t tab = x / c.W, w = x % c.W;
             const uint64_t vc = (uint64_t)((int64_t)vr - (int64_t)vd);
             uint64_t* FR = S + SNK_SLOT_FILE_OFF(file_of(c.mates, tab));
@@ -191,15 +191,15 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                 for (uint32_t r = 0; r < cnt; r++) rawdesc[m][r] = hist_desc(info[m][r].len, r * c.stride, info[m][r].flags & RF_QSLOW);
             }
             const uint32_t n_units = wide ? 2u * nraw : nraw;
-            const int q_jstep = (int)c.X * (int)sizeof(QCounter), q_bstep = J * q_jstep;
+            const int q_jstep = (int)c.X * 2 * (int)sizeof(QCounter), q_bstep = (J / 2) * q_jstep;      // rowstep, bstep (filter_core.cuh)
             for (uint32_t u = 0; u < n_units; u++) {
                 const uint32_t x = wide ? u % nraw : u, half = wide ? u / nraw : 0u;
                 const uint32_t w = x % c.W;
                 const int m = (int)(x / c.W) % M;
                 unsigned long long* f_raw = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, m)));
                 unsigned long long* f_clean = (unsigned long long*)(S + SNK_SLOT_FILE_OFF(file_of(M, m + M)));
-                const int q_cell0 = (int)x * (int)sizeof(QCounter) - c.P.phred * q_bstep;
-                const int q_cell0_del = q_cell0 + (int)nraw * (int)sizeof(QCounter);
+                const int q_cell0 = (int)x * 2 * (int)sizeof(QCounter) - c.P.phred * q_bstep;
+                const int q_cell0_del = q_cell0 + (int)nraw * 2 * (int)sizeof(QCounter);
                 const uint8_t* rs = rows[m][0].data();
                 const uint8_t* rq = rows[m][1].data();
                 const DeltaEnt* dl = dlist[m].data();
@@ -216,7 +216,7 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
                     unit_b_delta<J>(rs, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
                 } else {
                     c.err |= unit_q_checked<QCounter, J>(rq, rawdesc[m].data(), cnt, dl, nd, (int)w, wide ? (int)half * (J / 2) : 0, wide ? J / 2 : J,
-                                                         c.P.phred, c.P.qb, c.qhist.data() + x, nraw, (int)c.X, f_raw, f_clean);
+                                                         c.P.phred, c.P.qb, c.qhist.data() + 2u * x, nraw, (int)c.X, f_raw, f_clean);
                     unit_b_checked<J>(rs, rawdesc[m].data(), cnt, dl, nd, (int)w, wide ? half : 0u, wide ? 2u : 1u, c.bc[u]);
                 }
             }
