@@ -540,10 +540,16 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
                 const int cmin2 = cc < cd ? cc : cd;
                 cmin = cmin < cmin2 ? cmin : cmin2;
                 if (cmin > nb2) continue;
-                if (ca <= nb2 && SNK_VERIFY(kw, sft, xa, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft; break; }
-                if (cb <= nb2 && SNK_VERIFY(kw, sft + kNT, xb, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + kNT; break; }
-                if (cc <= nb2 && SNK_VERIFY(kw, sft + 2 * kNT, xc, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + 2 * kNT; break; }
-                if (cd <= nb2 && SNK_VERIFY(kw, sft + 3 * kNT, xd, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + sft + 3 * kNT; break; }
+                // rare: some of the four offsets passed level 1. One verification site for all of them (in offset
+                // order) keeps the sweep's code small
+                uint32_t cand = (ca <= nb2 ? 1u : 0u) | (cb <= nb2 ? 2u : 0u) | (cc <= nb2 ? 4u : 0u) | (cd <= nb2 ? 8u : 0u);
+                while (cand) {
+                    const int off = sft + ctz32(cand) * kNT;
+                    cand &= cand - 1u;
+                    const uint32_t x0 = funnel_r(l0, m0, off) ^ a0lo;
+                    if (SNK_VERIFY(kw, off, x0, pm2, nb2, A, budget2)) { out.pos2 = 32 * kw + off; break; }
+                }
+                if (out.pos2 >= 0) break;
             }
             if (out.pos2 < 0)
                 for (; sft < send; sft += kNT) {
