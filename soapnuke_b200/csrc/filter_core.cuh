@@ -587,7 +587,7 @@ SNK_HD void adapter_part(int len, const uint32_t* p0, const uint32_t* p1, const 
 
 // byte-wise adapter_pos: adapters with N / lowercase / length > 64, and reads shorter than the
 // adapter (windows that start before the read). Same phase order as the reference. One thread does it.
-SNK_HD int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
+SNK_HD_NOINLINE int adapter_pos_bytes(const uint8_t* seq, int len, const AdapterDev& a)
 {
     const int A = a.len;
     for (int r1 = 1; r1 <= 5; r1++)
@@ -696,7 +696,8 @@ SNK_HD bool has_contam(const uint8_t* seq, int len, int mate, const DevParams& P
     return false;
 }
 
-SNK_HD uint16_t contam_flags(const uint8_t* seq, int len, int mate, const DevParams& P)
+// (out of line like the other cold paths: they must not sit between the hot blocks of phase A)
+SNK_HD_NOINLINE uint16_t contam_flags(const uint8_t* seq, int len, int mate, const DevParams& P)
 {
     if (P.srna) return 0;
     uint16_t f = 0;

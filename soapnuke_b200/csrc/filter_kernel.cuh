@@ -150,9 +150,9 @@ __device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s
 }
 
 // phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
-template <int MAXC>
 // ada0 = shared-memory AdaHot array of the mate's adapters (the compiler re-derives the parameter-space
 // address of a dynamically indexed adapter at every use; a shared copy costs one pointer register)
+template <int MAXC, int MATES>
 __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P,
                                                const AdaHot* ada0, int h, unsigned pm, ReadInfo& R)
 {
@@ -165,8 +165,9 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
     bool has5 = false;
-    if (P.srna) {
-        // filtersRNA: the group's first lane aligns the 3' adapter, the second the 5' adapter
+    if (MATES == 1 && P.srna) {
+        // filtersRNA (single-end only: the paired kernels carry none of its code): the group's first lane aligns the
+        // 3' adapter, the second the 5' adapter
         uint32_t q0[NW + 2], q1[NW + 2], qn[NW + 2], ql[NW + 2];
 #pragma unroll
         for (int k = 0; k < NW + 2; k++) { q0[k] = k < NW ? S.p0[k] : 0u; q1[k] = k < NW ? S.p1[k] : 0u; qn[k] = k < NW ? S.pn[k] : 0u; ql[k] = k < NW ? S.pl[k] : 0u; }
@@ -418,7 +419,7 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
                 ri.len = 0; ri.head_cut = 0; ri.clean_len = 0; ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1;
                 ri.flags = RF_BAD_BASE | RF_QSLOW;      // row left as staged: not safe for the unchecked histogram walk
             } else {
-                scan_read_coop<MAXC>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
+                scan_read_coop<MAXC, MATES>(smem + sp.off_rows[m][0] + (size_t)r * A.stride, smem + sp.off_rows[m][1] + (size_t)r * A.stride,
                                      len, nchunks, m, P, reinterpret_cast<const AdaHot*>(smem + sp.off_ada) + ada_first_slot(P.n_adapters, m), h, pm, ri);
             }
             if (h == 0) {
