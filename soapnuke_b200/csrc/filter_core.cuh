@@ -342,33 +342,28 @@ SNK_HD ScanConst scan_const(const DevParams& P)
     return c;
 }
 
-// One 16-byte chunk (4 words of bases sw, 4 of qualities qw) of which the first nv bytes (1..16) lie
-// inside the read; FULL = (nv == 16) drops all masking. Per word:
+// One 16-byte chunk (4 words of bases sw, 4 of qualities qw), every byte inside the read (a chunk the read ends in
+// is padded by the caller with 'A' / phred bytes and corrected afterwards, see scan_chunks). Per word:
 //   bases      fold case, look the expected byte up by bits 3..1 (A 000, C 001, T 010, G 011, N 111;
 //              100/101/110 -> 0) with one PRMT and compare: exact membership in {A,C,G,T,N,a,c,g,t,n}
 //   qualities  three packed subtractions on (q | 0x80) give "q >= phred", "q >= phred+qb", "q >= low_k"
 //              per byte lane in bit 7 (no borrow between lanes); DP4A sums the flags and the bytes
 // and per pair of words one DP4A per plane gathers bit b of 8 consecutive bytes into 8 adjacent bits.
-template <bool FULL>
-SNK_HD void scan_chunk16(const uint32_t* sw, const uint32_t* qw, int nv, const ScanConst& K, uint32_t& c0, uint32_t& c1, uint32_t& cn,
+SNK_HD void scan_chunk16(const uint32_t* sw, const uint32_t* qw, const ScanConst& K, uint32_t& c0, uint32_t& c1, uint32_t& cn,
                          uint32_t& cl, uint32_t& low128, uint32_t& qsum, uint32_t& viol, uint32_t& qbad)
 {
-    uint32_t w[4], f[4];
+    uint32_t f[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const uint32_t mk = FULL ? 0xFFFFFFFFu : low_lanes(nv - 4 * k);
-        w[k] = FULL ? sw[k] : (sw[k] & mk);
-        f[k] = w[k] & 0xDFDFDFDFu;                                   // fold case
+        f[k] = sw[k] & 0xDFDFDFDFu;                                  // fold case
         const uint32_t t = (f[k] >> 1) & 0x07070707u;
         const uint32_t u = t | (t >> 4);
         const uint32_t e = perm8(0x47544341u, 0x4E000000u, perm8(u, 0u, 0x4420u));
-        viol |= FULL ? (e ^ f[k]) : ((e ^ f[k]) & mk);
-        const uint32_t q = FULL ? qw[k] : (qw[k] & mk);
-        const uint32_t qin = FULL ? q : (q | (K.phred4 & ~mk));     // padding lanes read as phred: in range
-        const uint32_t g = qin | 0x80808080u;
-        qbad |= (~(g - K.phred4) | (g - K.over4) | qin) & 0x80808080u;
-        const uint32_t lowf = ~(g - K.low4) & 0x80808080u;
-        low128 = dot4(FULL ? lowf : (lowf & mk), 0x01010101u, low128);
+        viol |= e ^ f[k];
+        const uint32_t q = qw[k];
+        const uint32_t g = q | 0x80808080u;
+        qbad |= (~(g - K.phred4) | (g - K.over4) | q) & 0x80808080u;
+        low128 = dot4(~(g - K.low4) & 0x80808080u, 0x01010101u, low128);
         qsum = dot4(q, 0x01010101u, qsum);
     }
 #pragma unroll
@@ -376,7 +371,7 @@ SNK_HD void scan_chunk16(const uint32_t* sw, const uint32_t* qw, int nv, const S
         // bits 3..1 of word 2pr in the low nibbles, of word 2pr+1 in the high nibbles; weights 1,2,4,8 turn
         // bit b of the 8 bytes into 8 adjacent bits starting at bit b
         const uint32_t x = (f[2 * pr] & 0x0E0E0E0Eu) | ((f[2 * pr + 1] & 0x0E0E0E0Eu) << 4);
-        const uint32_t y = ((w[2 * pr] >> 4) & 0x02020202u) | (w[2 * pr + 1] & 0x20202020u);     // bit 5: lowercase
+        const uint32_t y = ((sw[2 * pr] >> 4) & 0x02020202u) | (sw[2 * pr + 1] & 0x20202020u);     // bit 5: lowercase
         c0 |= (dot4(x & 0x22222222u, 0x08040201u, 0u) >> 1) << (8 * pr);
         c1 |= (dot4(x & 0x44444444u, 0x08040201u, 0u) >> 2) << (8 * pr);
         cn |= (dot4(x & 0x88888888u, 0x08040201u, 0u) >> 3) << (8 * pr);
@@ -416,17 +411,24 @@ SNK_HD void scan_chunks(uint8_t* seq, uint8_t* qual, int len, int nchunks, const
         const uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
         const int nv = len - 16 * c;
-        if (nv >= 16) scan_chunk16<true>(sw, qw, 16, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
+        if (nv >= 16) scan_chunk16(sw, qw, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
         else {                                                 // the read ends inside this chunk
-            uint32_t ss[4], qq[4];
+            // the tile copy gets its final padding (bases 0, qualities in the dump bin); the scan itself sees 'A'
+            // bases (code 00: no plane bit, valid) and phred qualities (in range) behind the read, and the two
+            // sums those bytes disturb are corrected afterwards
+            uint32_t ss[4], qq[4], sa[4], qa[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const uint32_t mk = low_lanes(nv - 4 * k);
                 ss[k] = sw[k] & mk; qq[k] = (qw[k] & mk) | (K.qpad & ~mk);
+                sa[k] = ss[k] | (0x41414141u & ~mk); qa[k] = (qw[k] & mk) | (K.phred4 & ~mk);
             }
             const U4 s4 = {ss[0], ss[1], ss[2], ss[3]}, q4 = {qq[0], qq[1], qq[2], qq[3]};
             store16(seq + 16 * c, s4); store16(qual + 16 * c, q4);
-            scan_chunk16<false>(sw, qw, nv, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
+            scan_chunk16(sa, qa, K, c0, c1, cn, cl, S.low128, S.qsum, S.viol, S.qbad);
+            const uint32_t pad = (uint32_t)(16 - nv), phred = K.phred4 & 0xFFu;
+            S.qsum -= pad * phred;
+            if (phred < (K.low4 & 0xFFu)) S.low128 -= 128u * pad;      // a phred byte counts as low quality when low_k > phred
         }
         const int sh = 16 * h;
         S.p0[cc] = c0 << sh; S.p1[cc] = c1 << sh; S.pn[cc] = cn << sh; S.pl[cc] = cl << sh;
