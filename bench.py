@@ -49,11 +49,28 @@ UNIQUE_PAIRS = 1 << 18          # generated once, tiled to the batch size
 
 
 def measured_peak():
+    """HBM copy bandwidth the roofline is reported against: the driver-written MEASURED_PEAKS.json when present (the
+    kernel is timed alone, so a burst figure is preferred over a sustained one), else the profiling recipe's fallback."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+            peaks = json.load(f)
+        flat = {}
+
+        def walk(prefix, obj):
+            if isinstance(obj, dict):
+                for k, v in obj.items():
+                    walk(f"{prefix}.{k}" if prefix else str(k), v)
+            elif isinstance(obj, (int, float)) and not isinstance(obj, bool):
+                flat[prefix] = float(obj)
+        walk("", peaks)
+        hbm = {k: v for k, v in flat.items() if "hbm" in k.lower() and v > 100}      # GB/s figures, not fractions
+        for test in (lambda k: k == "hbm_gbs", lambda k: "burst" in k.lower(), lambda k: True):
+            for k in sorted(hbm):
+                if test(k):
+                    return hbm[k], f"measured (MEASURED_PEAKS.json {k})"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
 
 
 def recorded_traffic():
