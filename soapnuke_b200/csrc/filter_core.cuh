@@ -974,12 +974,12 @@ SNK_HD void finish_read(const ScanPart<NW>& S, bool qviol, bool polyx, int ada_p
     if (qviol) flags |= RF_BAD_QUAL;
     if (S.qbad) flags |= RF_QSLOW;
     // A and N counts from the planes (only A and N feed predicates: highA, n_ratio)
-    int nN = 0, nA = 0;
+    // (the planes carry no bit behind the read; a base with no plane bit at all is an A)
+    int nN = 0, nA = len;
 #pragma unroll(NW <= 8 ? NW : 1)
     for (int k = 0; k < NW; k++) {
-        const uint32_t vm = plane_valid(len, k);
-        nN += (int)popc32(S.pn[k] & vm);
-        nA += (int)popc32(~(S.p0[k] | S.p1[k] | S.pn[k]) & vm);
+        nN += (int)popc32(S.pn[k]);
+        nA -= (int)popc32(S.p0[k] | S.p1[k] | S.pn[k]);
     }
     const int nLow = (int)(S.low128 >> 7);
     const int total_q = (int)S.qsum - len * P.phred;
@@ -1378,9 +1378,11 @@ SNK_HD void unit_q_raw(const uint8_t* rows_q, uint32_t stride, uint32_t cnt, int
     const int c_raw = cell0_raw + qj_off(j0, rowstep);
     // the row word of the next record is loaded before the current one's cells are updated: the compiler cannot move
     // a shared-memory load above the counter stores by itself (it cannot prove that rows and cells do not alias)
-    uint32_t w0 = cnt ? load4(pq) : 0u;
+    // (the load behind the last record reads the row after the tile's rows: always inside the CTA's shared memory / the
+    // replay's buffers, value unused)
+    uint32_t w0 = load4(pq);
     for (uint32_t r = 0; r < cnt; r++) {
-        const uint32_t w1 = (r + 1 < cnt) ? load4(pq + (size_t)(r + 1) * stride) : 0u;
+        const uint32_t w1 = load4(pq + (size_t)(r + 1) * stride);
         qual_update_all<CounterT, JN>(w0 >> sh, qcells, c_raw, rowstep, bstep);
         w0 = w1;
     }

@@ -90,7 +90,7 @@ void run(Ctx& c, const snk_batch* b[2], snk_read_result* out[2], uint64_t first,
     std::vector<uint8_t> keep(c.R);
     std::vector<DeltaEnt> dlist[2];
     const int nchunks = (int)(c.stride / 16);
-    for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)c.R * c.stride + 16, 0xAB); rows[m][1].assign((size_t)c.R * c.stride + 16, 0xAB); info[m].resize(c.R); }
+    for (int m = 0; m < M; m++) { rows[m][0].assign((size_t)(c.R + 1) * c.stride + 16, 0xAB); rows[m][1].assign((size_t)(c.R + 1) * c.stride + 16, 0xAB); info[m].resize(c.R); }   // (+ one row: unit_q_raw loads one record ahead)
     c.qhist.assign((size_t)(c.P.qb + 1) * (size_t)J * c.X, 0);
     const uint32_t nraw = (uint32_t)M * c.W;
     const bool wide = c.threads >= 4u * nraw;               // same rule as the kernel
