@@ -142,7 +142,10 @@ void init_from_config(HostParams& hp, const char* path)
         else if (key == "trimBadHead") hp.trim_bad_head = value;
         else if (key == "trimBadTail") hp.trim_bad_tail = value;
         else if (key == "adaRCtg" || key == "adaRAr" || key == "adaRMa" || key == "adaREr" || key == "adaRMm") {
-            if (!hp.srna) die("these parameters should not appear in the module,--" + key);      // filtersRNA-only (process_argv.cpp:763-770)
+            if (!hp.srna) {                                       // filtersRNA-only (process_argv.cpp:1447-1470 + :763-770)
+                const char* flag = key == "adaRCtg" ? "-S|--" : key == "adaRAr" ? "-s|--" : key == "adaRMa" ? "-U|--" : key == "adaREr" ? "-u|--" : "-b|--";
+                die(std::string("these parameters should not appear in the module,") + flag + key);
+            }
             if (key == "adaRCtg") hp.ada_rctg = atoi(value.c_str());                               // process_argv.cpp:1447-1470
             else if (key == "adaRAr") hp.ada_rar = (float)atof(value.c_str());
             else if (key == "adaRMa") hp.ada_rma = atoi(value.c_str());

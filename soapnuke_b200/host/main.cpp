@@ -21,7 +21,7 @@ int main(int argc, char** argv)
         if (module == "filterStLFR" || module == "filterHts")
             std::cerr << "Error:module " << module << " is not served by the GPU filter engine (only filter / filterMeta / filtersRNA)" << std::endl;
         else
-            std::cerr << "Error:no such module," << module << std::endl;
+            std::cerr << "Error:no such module,type -h/--help for help" << std::endl;      // process_argv.cpp:16-36
         return 1;
     }
     snk::HostParams hp;
