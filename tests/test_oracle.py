@@ -9,7 +9,11 @@ import glob
 import gzip
 import json
 import os
+import atexit
+import concurrent.futures
 import shutil
+import tempfile
+import threading
 import zlib
 
 import numpy as np
@@ -17,6 +21,32 @@ import pytest
 
 import oracle_py as orc
 from helpers import A1, A2, CFG2_FLAGS, CFG2_KW, ROOT, abi, report_equal, synth
+
+# Every run of the reference binary sleeps in 5 s polling quanta (peprocess.cpp:3039): the reference sides of all
+# live cases (input files + reference run) are prepared concurrently the first time one of them is needed.
+_FAMILIES = []          # (prepare function, cases)
+_PREPARED = {}
+_PREP_LOCK = threading.Lock()
+
+
+def live_family(prepare, cases):
+    _FAMILIES.append((prepare, cases))
+    return cases
+
+
+def prepared(name):
+    with _PREP_LOCK:
+        if not _PREPARED:
+            root = tempfile.mkdtemp(prefix="snk_oracle_")
+            atexit.register(shutil.rmtree, root, ignore_errors=True)
+            pool = concurrent.futures.ThreadPoolExecutor(max_workers=max(2, min(6, (os.cpu_count() or 2) // 2)))
+            for prepare, cases in _FAMILIES:
+                for case in cases:
+                    w = os.path.join(root, case[0])
+                    os.makedirs(w)
+                    _PREPARED[case[0]] = pool.submit(prepare, case, w)
+    return _PREPARED[name].result()
+
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 CASES = sorted(d for d in os.listdir(GOLDEN) if os.path.isdir(os.path.join(GOLDEN, d)))
@@ -92,12 +122,9 @@ LIVE = [
 ]
 
 
-@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
-@pytest.mark.parametrize("case", LIVE, ids=[c[0] for c in LIVE])
-def test_oracle_matches_reference_binary(case, engine_lib, tmp_path):
+def _prepare_live(case, w):
     name, pe, n, L, T, flags, pkw, patch, gkw = case
     data = synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, **gkw)
-    w = str(tmp_path)
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
@@ -108,6 +135,15 @@ def test_oracle_matches_reference_binary(case, engine_lib, tmp_path):
         args += ["-c", f"{w}/cfg.txt"]
     r = orc.run_reference(args + flags)
     assert r.returncode == 0, r.stderr.decode()
+    return dict(locals())
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", live_family(_prepare_live, LIVE), ids=[c[0] for c in LIVE])
+def test_oracle_matches_reference_binary(case, engine_lib):
+    ctx = prepared(case[0])
+    name, pe, n, L, T, flags, pkw, patch, gkw = case
+    data, w, r = ctx["data"], ctx["w"], ctx["r"]
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
     if pe:
         r1, r2, st, err = orc.filter_pe(p, data)
@@ -140,12 +176,9 @@ SRNA_LIVE = [
 ]
 
 
-@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
-@pytest.mark.parametrize("case", SRNA_LIVE, ids=[c[0] for c in SRNA_LIVE])
-def test_oracle_matches_reference_binary_filtersRNA(case, engine_lib, tmp_path):
+def _prepare_srna(case, w):
     name, n, L, T, flags, pkw, gkw, cfg = case
     data = synth.gen_srna(n, L=L, seed=sum(map(ord, name)), **gkw)
-    w = str(tmp_path)
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     patch = None
@@ -157,6 +190,16 @@ def test_oracle_matches_reference_binary_filtersRNA(case, engine_lib, tmp_path):
                 patch = int(l.split("=")[1])
     r = orc.run_reference(args + flags, module="filtersRNA")
     assert r.returncode == 0, r.stderr.decode()
+    return dict(locals())
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", live_family(_prepare_srna, SRNA_LIVE), ids=[c[0] for c in SRNA_LIVE])
+def test_oracle_matches_reference_binary_filtersRNA(case, engine_lib):
+    ctx = prepared(case[0])
+    name, n, L, T, flags, pkw, gkw, cfg = case
+    data, w, r = ctx["data"], ctx["w"], ctx["r"]
+    patch = ctx["patch"]
     kw = dict(min_read_length=18, max_read_length=49)       # filtersRNA defaults (process_argv.cpp:174-178)
     kw.update(pkw)
     p = abi.make_params(is_pe=False, srna=True, adapter1=A5, adapter2=A3, threads=T, patch_size=patch, **kw)
@@ -180,12 +223,9 @@ TILE_LIVE = [
 ]
 
 
-@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
-@pytest.mark.parametrize("case", TILE_LIVE, ids=[c[0] for c in TILE_LIVE])
-def test_oracle_matches_reference_binary_tile_fov(case, engine_lib, tmp_path):
+def _prepare_tile(case, w):
     name, pe, n, L, T, cfg, pkw, idfn = case
     data = synth.gen_pairs(n, L=L, seed=sum(map(ord, name)), se=not pe)
-    w = str(tmp_path)
     ids1 = idfn(n, 1)
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1, ids=ids1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T), "-f", A1, "-J"]
@@ -196,6 +236,16 @@ def test_oracle_matches_reference_binary_tile_fov(case, engine_lib, tmp_path):
     patch = next((int(l.split("=")[1]) for l in cfg if l.startswith("patch=")), None)
     r = orc.run_reference(args + ["-c", f"{w}/cfg.txt"])
     assert r.returncode == 0, r.stderr.decode()[-400:]
+    return dict(locals())
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", live_family(_prepare_tile, TILE_LIVE), ids=[c[0] for c in TILE_LIVE])
+def test_oracle_matches_reference_binary_tile_fov(case, engine_lib):
+    ctx = prepared(case[0])
+    name, pe, n, L, T, cfg, pkw, idfn = case
+    data, w, r = ctx["data"], ctx["w"], ctx["r"]
+    patch, ids1 = ctx["patch"], ctx["ids1"]
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, adapter1=A1, adapter2=A2 if pe else None, ada_trim=True, **pkw)
     d = dict(data)
     d["len1"] = data["len1"] | orc.id_flags(p, ids1)          # ids never cross the SoA boundary: flag bits in len[]
@@ -249,13 +299,10 @@ CONTAM_LIVE = [
 ]
 
 
-@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
-@pytest.mark.parametrize("case", CONTAM_LIVE, ids=[c[0] for c in CONTAM_LIVE])
-def test_oracle_matches_reference_binary_contam(case, engine_lib, tmp_path):
+def _prepare_contam(case, w):
     name, pe, n, L, T, flags, cfg, pkw = case
     data = synth.add_contams(synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, var_len=(L == 120)),
                              [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3], seed=len(name))
-    w = str(tmp_path)
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
@@ -265,6 +312,16 @@ def test_oracle_matches_reference_binary_contam(case, engine_lib, tmp_path):
     patch = next((int(l.split("=")[1]) for l in cfg if l.startswith("patch=")), None)
     r = orc.run_reference(args + ["-c", f"{w}/cfg.txt"] + flags)
     assert r.returncode == 0, r.stderr.decode()[-400:]
+    return dict(locals())
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", live_family(_prepare_contam, CONTAM_LIVE), ids=[c[0] for c in CONTAM_LIVE])
+def test_oracle_matches_reference_binary_contam(case, engine_lib):
+    ctx = prepared(case[0])
+    name, pe, n, L, T, flags, cfg, pkw = case
+    data, w, r = ctx["data"], ctx["w"], ctx["r"]
+    patch = ctx["patch"]
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
     if pe:
         r1, r2, st, err = orc.filter_pe(p, data)
@@ -295,13 +352,10 @@ GCONTAM_LIVE = [
 ]
 
 
-@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
-@pytest.mark.parametrize("case", GCONTAM_LIVE, ids=[c[0] for c in GCONTAM_LIVE])
-def test_oracle_matches_reference_binary_global_contam(case, engine_lib, tmp_path):
+def _prepare_gcontam(case, w):
     name, pe, n, L, T, flags, cfg, pkw = case
     plants = [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3, synth.revcomp(synth.CONTAM1), synth.revcomp(synth.CONTAM3)]
     data = synth.add_contams(synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, var_len=(L == 120)), plants, seed=len(name), frac=0.25)
-    w = str(tmp_path)
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
@@ -311,6 +365,16 @@ def test_oracle_matches_reference_binary_global_contam(case, engine_lib, tmp_pat
     patch = next((int(l.split("=")[1]) for l in cfg if l.startswith("patch=")), None)
     r = orc.run_reference(args + ["-c", f"{w}/cfg.txt"] + flags)
     assert r.returncode == 0, r.stderr.decode()[-400:]
+    return dict(locals())
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", live_family(_prepare_gcontam, GCONTAM_LIVE), ids=[c[0] for c in GCONTAM_LIVE])
+def test_oracle_matches_reference_binary_global_contam(case, engine_lib):
+    ctx = prepared(case[0])
+    name, pe, n, L, T, flags, cfg, pkw = case
+    data, w, r = ctx["data"], ctx["w"], ctx["r"]
+    patch = ctx["patch"]
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **pkw)
     if pe:
         r1, r2, st, err = orc.filter_pe(p, data)
