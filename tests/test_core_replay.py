@@ -326,7 +326,17 @@ def random_case(seed, scale=1):
         kw["global_contams"] = _C3; kw["glob_cotm_mR"] = rnd.choice(["0.4", "0.7"]); kw["glob_cotm_mM"] = rnd.choice(["0", "2"])
     kw["quality_phred"] = 33
     kw["max_base_quality"] = rnd.choice([42, 42, 30, 63])
-    d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=rnd.random() < 0.5, polyg_frac=rnd.choice([0.04, 0.3]))
+    if not pe and rnd.random() < 0.25:        # the filtersRNA module
+        for k in ("contam1", "contam2", "ct_match_r", "contam_trim", "global_contams", "glob_cotm_mR", "glob_cotm_mM", "mean_quality", "n_ratio"):
+            kw.pop(k, None)
+        kw.update(srna=True, adapter1=rnd.choice([synth.SRNA_ADAPTER5, synth.SRNA_ADAPTER5[:12], synth.SRNA_ADAPTER5 + synth.SRNA_ADAPTER5[:20]]),
+                  adapter2=rnd.choice([synth.SRNA_ADAPTER3, synth.SRNA_ADAPTER3 + synth.SRNA_ADAPTER3, synth.SRNA_ADAPTER3[:9]]),
+                  ada_rctg=rnd.choice([4, 6, 7]), ada_rar=rnd.choice([0.5, 0.8, 0.95]), ada_rma=rnd.choice([3, 5, 8]),
+                  ada_rer=rnd.choice([0.2, 0.4, 0.7]), ada_rmm=rnd.choice([0, 2, 4, 6]))
+        kw.pop("ada_mis", None); kw.pop("ada_edge", None); kw.pop("ada_mr", None)
+        d = synth.gen_srna(n, L=max(L, 36), seed=seed, var_len=rnd.random() < 0.5)
+    else:
+        d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=rnd.random() < 0.5, polyg_frac=rnd.choice([0.04, 0.3]))
     if "contam1" in kw or "global_contams" in kw:
         synth.add_contams(d, CONTAM_PLANTS, seed=seed)
     if rnd.random() < 0.3:                    # tile / fov flags as a caller of the SoA entry points would set them

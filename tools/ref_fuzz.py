@@ -56,25 +56,74 @@ def one(seed):
     if rnd.random() < 0.3:
         r1, r2 = rnd.choice([0.3, 0.5, 0.8]), rnd.choice([0.4, 0.5, 0.9]); cfg.append(f"adaMR={r1},{r2}"); kw["ada_mr"] = (r1, r2)
     if rnd.random() < 0.3: v = rnd.choice([40, 100, 140]); cfg.append(f"maxReadLen={v}"); kw["max_read_length"] = v
-    d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=var, polyg_frac=rnd.choice([0.04, 0.3]))
+    # less common options: contaminants, global contaminants, tile / fov lists (ids to match), the filtersRNA module
+    C1, C2, C3 = synth.CONTAM1.decode(), synth.CONTAM2.decode(), synth.CONTAM3.decode()
+    module, idfn, plants = "filter", None, None
+    mode = rnd.random()
+    if mode < 0.25:
+        lst = rnd.random() < 0.5
+        kw["contam1"] = f"{C1},{C3}" if lst else C1
+        kw["ct_match_r"] = rnd.choice(["0.3,0.6", "0.2,0.9"]) if lst else rnd.choice(["0.2", "0.4", "0.15"])
+        cfg += [f"contam1={kw['contam1']}", f"ctMatchR={kw['ct_match_r']}"]
+        if pe:
+            kw["contam2"] = f"{C2},{C1}" if lst else C2; cfg.append(f"contam2={kw['contam2']}")
+        if rnd.random() < 0.2: kw["contam_trim"] = True; cfg.append("contam_trim")
+        plants = [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3]
+    elif mode < 0.45:
+        two = rnd.random() < 0.5
+        kw["global_contams"] = f"{C3},{C1}" if two else C2
+        kw["glob_cotm_mR"] = rnd.choice(["0.5,0.7", "0.6,0.4"]) if two else rnd.choice(["0.4", "0.6", "0.8"])
+        kw["glob_cotm_mM"] = rnd.choice(["1,0", "2,2"]) if two else rnd.choice(["0", "1", "2"])
+        cfg += [f"global_contams={kw['global_contams']}", f"glob_cotm_mR={kw['glob_cotm_mR']}", f"glob_cotm_mM={kw['glob_cotm_mM']}"]
+        plants = [synth.CONTAM1, synth.CONTAM2, synth.CONTAM3, synth.revcomp(synth.CONTAM1), synth.revcomp(synth.CONTAM2), synth.revcomp(synth.CONTAM3)]
+    elif mode < 0.6:
+        if rnd.random() < 0.5:
+            kw["tile"] = rnd.choice(["1102", "1102,2201", "1103,1104,9999"]); cfg.append(f"tile={kw['tile']}"); idfn = synth.tile_ids
+        else:
+            kw["fov"] = rnd.choice(["C002R003", "C001R001,C004R005"]); cfg.append(f"fov={kw['fov']}"); idfn = synth.fov_ids
+    elif mode < 0.75 and not pe:
+        module = "filtersRNA"
+    if module == "filtersRNA":
+        A5, A3 = synth.SRNA_ADAPTER5.decode(), synth.SRNA_ADAPTER3.decode()
+        L = rnd.choice([36, 44, 50, 75]); n = rnd.choice([800, 2000])
+        flags = ["-f", A5, "-r", A3]; kw = dict(srna=True, adapter1=A5, adapter2=A3, min_read_length=18, max_read_length=49)
+        cfg = [c for c in cfg if c.startswith("patch=")]
+        if rnd.random() < 0.7: flags.append("-J"); kw["ada_trim"] = True
+        if rnd.random() < 0.5: v = rnd.choice([4, 6, 10]); flags += ["-g", str(v)]; kw["polyG_tail"] = v
+        if rnd.random() < 0.5: v = rnd.choice([0.4, 0.6]); flags += ["-p", str(v)]; kw["highA_ratio"] = v
+        if rnd.random() < 0.5: v = rnd.choice([8, 12]); flags += ["-X", str(v)]; kw["polyX_num"] = v
+        if rnd.random() < 0.5: v = rnd.choice([10, 15, 25]); flags += ["-4", str(v)]; kw["min_read_length"] = v
+        if rnd.random() < 0.4: v = rnd.choice([40, 60]); cfg.append(f"maxReadLen={v}"); kw["max_read_length"] = v
+        if rnd.random() < 0.4:
+            vals = dict(adaRCtg=rnd.choice([5, 7]), adaRAr=rnd.choice([0.7, 0.9]), adaRMa=rnd.choice([4, 6]), adaREr=rnd.choice([0.3, 0.5]), adaRMm=rnd.choice([2, 3, 5]))
+            cfg += [f"{k}={v}" for k, v in vals.items()]
+            kw.update(ada_rctg=vals["adaRCtg"], ada_rar=vals["adaRAr"], ada_rma=vals["adaRMa"], ada_rer=vals["adaREr"], ada_rmm=vals["adaRMm"])
+        d = synth.gen_srna(n, L=L, seed=seed, var_len=var)
+    else:
+        d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=var, polyg_frac=rnd.choice([0.04, 0.3]))
+    if plants:
+        synth.add_contams(d, plants, seed=seed, frac=0.25)
     w = tempfile.mkdtemp(prefix="fz")
-    synth.write_fastq(f"{w}/r1.fq", d["seq1"], d["qual1"], d["len1"], 1)
+    ids1 = idfn(n, 1) if idfn else None
+    synth.write_fastq(f"{w}/r1.fq", d["seq1"], d["qual1"], d["len1"], 1, ids=ids1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
-        synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2); args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+        synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2, ids=idfn(n, 2) if idfn else None); args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
-    r = orc.run_reference(args + flags)
+    r = orc.run_reference(args + flags, module=module)
     if r.returncode != 0:
         return seed, "ref rc %d %s" % (r.returncode, r.stderr.decode()[-120:]), flags, cfg
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **kw)
+    if ids1 is not None:
+        d = dict(d); d["len1"] = d["len1"] | orc.id_flags(p, ids1)
     if pe: r1, r2, st, err = orc.filter_pe(p, d)
     else: r1, st, err = orc.filter_se(p, d); r2 = None
     bad = []
     for m, rs in ((1, r1), (2, r2)):
         if rs is None: continue
         order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
-        mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"], rs, m, order=order)
+        mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"] & abi.LEN_MASK, rs, m, order=order, ids=idfn(n, m) if idfn else None)
         if mine != open(f"{w}/out/c{m}.fq", "rb").read(): bad.append(f"clean{m}")
     os.makedirs(f"{w}/mine")
     fn = lib.snk_report_write_pe if pe else lib.snk_report_write_se
