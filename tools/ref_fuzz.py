@@ -19,7 +19,7 @@ import oracle_py as orc
 from soapnuke_b200 import abi, synth
 from helpers import A1, A2, report_equal
 lib = abi.load_engine()
-def one(seed):
+def gen(seed):
     rnd = random.Random(seed)
     pe = rnd.random() < 0.6
     L = rnd.choice([36, 50, 75, 100, 150, 151, 250])
@@ -103,12 +103,19 @@ def one(seed):
         d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=var, polyg_frac=rnd.choice([0.04, 0.3]))
     if plants:
         synth.add_contams(d, plants, seed=seed, frac=0.25)
+    return dict(module=module, pe=pe, n=n, L=L, T=T, patch=patch, flags=flags, cfg=cfg, kw=kw, d=d, idfn=idfn)
+
+
+def one(seed):
+    g = gen(seed)
+    module, pe, n, L, T, patch, flags, cfg, kw, d, idfn = (g[k] for k in ("module", "pe", "n", "L", "T", "patch", "flags", "cfg", "kw", "d", "idfn"))
     w = tempfile.mkdtemp(prefix="fz")
     ids1 = idfn(n, 1) if idfn else None
     synth.write_fastq(f"{w}/r1.fq", d["seq1"], d["qual1"], d["len1"], 1, ids=ids1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
         synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2, ids=idfn(n, 2) if idfn else None); args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+    cfg = list(cfg)
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
     r = orc.run_reference(args + flags, module=module)
@@ -134,7 +141,8 @@ def one(seed):
             bad.append(os.path.basename(f))
     if not bad: shutil.rmtree(w)
     return seed, bad, flags + cfg, (w if bad else "")
-with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
-    for seed, bad, fl, w in ex.map(one, range(int(sys.argv[1]), int(sys.argv[2]))):
-        if bad: print(seed, bad, " ".join(fl), w)
-print("done")
+if __name__ == "__main__":
+    with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
+        for seed, bad, fl, w in ex.map(one, range(int(sys.argv[1]), int(sys.argv[2]))):
+            if bad: print(seed, bad, " ".join(fl), w)
+    print("done")
