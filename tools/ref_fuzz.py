@@ -6,7 +6,8 @@
 For every seed: random PE/SE shape, read length, worker count, patch size and a random subset of the filter / trim /
 adapter options; runs the reference binary and the oracle (oracle/snk_oracle.c + host report writer) on the same
 FASTQ and prints the seeds whose clean FASTQ or reports differ. Known non-issues it filters or that show up as
-reference crashes: uninitialised buffers printed when no read survives, low-quality end trims longer than the read.
+reference crashes: uninitialised buffers printed when no read survives, low-quality end trims longer than the read,
+the single-end abort behind the Q20/Q30 report (outputs written before it are still compared).
 The committed twin of this generator (tests/test_core_replay.py: random_case) checks the device code against the
 oracle in the CPU tier.
 """
@@ -19,6 +20,7 @@ import oracle_py as orc
 from soapnuke_b200 import abi, synth
 from helpers import A1, A2, report_equal
 lib = abi.load_engine()
+ABORTED = []          # seeds on which the reference aborted after writing outputs that all matched
 def gen(seed):
     rnd = random.Random(seed)
     pe = rnd.random() < 0.6
@@ -119,7 +121,10 @@ def one(seed):
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
     r = orc.run_reference(args + flags, module=module)
-    if r.returncode != 0:
+    # single-end input with variable read lengths can abort the reference at the end of its Q20/Q30 report (DESIGN.md
+    # section 3): everything written before that is still compared, the trimming-position table that follows is not
+    aborted = r.returncode != 0
+    if aborted and not (os.path.exists(f"{w}/out/c1.fq") and glob.glob(f"{w}/out/Distribution_of_Q20_Q30*")):
         return seed, "ref rc %d %s" % (r.returncode, r.stderr.decode()[-120:]), flags, cfg
     p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, **kw)
     if ids1 is not None:
@@ -136,13 +141,15 @@ def one(seed):
     fn = lib.snk_report_write_pe if pe else lib.snk_report_write_se
     fn(C.byref(p), st.ctypes.data, f"{w}/mine".encode())
     for f in glob.glob(f"{w}/out/*.txt"):
+        if aborted and "Statistics_of_Trimming_Position" in f: continue
         if not report_equal(f, f"{w}/mine/" + os.path.basename(f)):
             if "Basic_Statistics" in f and (r1["category"] == 0).sum() == 0: continue      # reference prints uninitialised buffers
             bad.append(os.path.basename(f))
     if not bad: shutil.rmtree(w)
+    if aborted and not bad: ABORTED.append(seed)
     return seed, bad, flags + cfg, (w if bad else "")
 if __name__ == "__main__":
     with concurrent.futures.ThreadPoolExecutor(max_workers=6) as ex:
         for seed, bad, fl, w in ex.map(one, range(int(sys.argv[1]), int(sys.argv[2]))):
             if bad: print(seed, bad, " ".join(fl), w)
-    print("done")
+    print("done; reference aborted after matching outputs on seeds", sorted(ABORTED))
