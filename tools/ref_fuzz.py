@@ -11,7 +11,7 @@ the single-end abort behind the Q20/Q30 report (outputs written before it are st
 The committed twin of this generator (tests/test_core_replay.py: random_case) checks the device code against the
 oracle in the CPU tier.
 """
-import sys, os, zlib, tempfile, glob, shutil, ctypes as C, concurrent.futures, random
+import sys, os, zlib, gzip, tempfile, glob, shutil, ctypes as C, concurrent.futures, random
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for _p in (ROOT, os.path.join(ROOT, 'oracle'), os.path.join(ROOT, 'tests')):
     sys.path.insert(0, _p)
@@ -20,6 +20,7 @@ import oracle_py as orc
 from soapnuke_b200 import abi, synth
 from helpers import A1, A2, report_equal
 lib = abi.load_engine()
+GZ = {}
 ABORTED = []          # seeds on which the reference aborted after writing outputs that all matched
 def gen(seed):
     rnd = random.Random(seed)
@@ -105,6 +106,7 @@ def gen(seed):
         d = synth.gen_pairs(n, L=L, seed=seed, se=not pe, var_len=var, polyg_frac=rnd.choice([0.04, 0.3]))
     if plants:
         synth.add_contams(d, plants, seed=seed, frac=0.25)
+    GZ[seed] = rnd.random() < 0.3          # .gz input: the reference labels its batches differently (abi.ref_output_order)
     return dict(module=module, pe=pe, n=n, L=L, T=T, patch=patch, flags=flags, cfg=cfg, kw=kw, d=d, idfn=idfn)
 
 
@@ -114,9 +116,14 @@ def one(seed):
     w = tempfile.mkdtemp(prefix="fz")
     ids1 = idfn(n, 1) if idfn else None
     synth.write_fastq(f"{w}/r1.fq", d["seq1"], d["qual1"], d["len1"], 1, ids=ids1)
-    args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
+    gz = GZ[seed]
+    sfx = ".gz" if gz else ""
+    args = ["-1", f"{w}/r1.fq{sfx}", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
-        synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2, ids=idfn(n, 2) if idfn else None); args += ["-2", f"{w}/r2.fq", "-D", "c2.fq"]
+        synth.write_fastq(f"{w}/r2.fq", d["seq2"], d["qual2"], d["len2"], 2, ids=idfn(n, 2) if idfn else None); args += ["-2", f"{w}/r2.fq{sfx}", "-D", "c2.fq"]
+    if gz:
+        for f in glob.glob(f"{w}/r?.fq"):
+            open(f + ".gz", "wb").write(gzip.compress(open(f, "rb").read(), 1)); os.remove(f)
     cfg = list(cfg)
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
@@ -134,7 +141,7 @@ def one(seed):
     bad = []
     for m, rs in ((1, r1), (2, r2)):
         if rs is None: continue
-        order = abi.ref_output_order(n, T, None, patch, gz_input=False, pe=pe)
+        order = abi.ref_output_order(n, T, None, patch, gz_input=gz, pe=pe)
         mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"] & abi.LEN_MASK, rs, m, order=order, ids=idfn(n, m) if idfn else None)
         if mine != open(f"{w}/out/c{m}.fq", "rb").read(): bad.append(f"clean{m}")
     os.makedirs(f"{w}/mine")
