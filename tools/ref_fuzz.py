@@ -107,6 +107,13 @@ def gen(seed):
     if plants:
         synth.add_contams(d, plants, seed=seed, frac=0.25)
     GZ[seed] = rnd.random() < 0.3          # .gz input: the reference labels its batches differently (abi.ref_output_order)
+    if rnd.random() < 0.2:                  # Phred+64 input (qualSys=1), output in either system
+        outsys = rnd.choice([1, 2])
+        cfg += ["qualSys=1", f"outQualSys={outsys}"]
+        kw["quality_phred"] = 64; kw["out_quality_phred"] = 64 if outsys == 1 else 33
+        for m in ("1", "2"):
+            if "qual" + m in d:
+                q = d["qual" + m]; q[q != 0] += 31
     return dict(module=module, pe=pe, n=n, L=L, T=T, patch=patch, flags=flags, cfg=cfg, kw=kw, d=d, idfn=idfn)
 
 
@@ -142,7 +149,8 @@ def one(seed):
     for m, rs in ((1, r1), (2, r2)):
         if rs is None: continue
         order = abi.ref_output_order(n, T, None, patch, gz_input=gz, pe=pe)
-        mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"] & abi.LEN_MASK, rs, m, order=order, ids=idfn(n, m) if idfn else None)
+        mine = synth.clean_fastq_bytes(d[f"seq{m}"], d[f"qual{m}"], d[f"len{m}"] & abi.LEN_MASK, rs, m, order=order, ids=idfn(n, m) if idfn else None,
+                                       phred_shift=kw.get("out_quality_phred", 33) - kw.get("quality_phred", 33))
         if mine != open(f"{w}/out/c{m}.fq", "rb").read(): bad.append(f"clean{m}")
     os.makedirs(f"{w}/mine")
     fn = lib.snk_report_write_pe if pe else lib.snk_report_write_se
