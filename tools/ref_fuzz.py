@@ -21,6 +21,7 @@ from soapnuke_b200 import abi, synth
 from helpers import A1, A2, report_equal
 lib = abi.load_engine()
 GZ = {}
+ADALIST = {}
 ABORTED = []          # seeds on which the reference aborted after writing outputs that all matched
 def gen(seed):
     rnd = random.Random(seed)
@@ -114,6 +115,17 @@ def gen(seed):
         for m in ("1", "2"):
             if "qual" + m in d:
                 q = d["qual" + m]; q[q != 0] += 31
+    if module == "filter" and "adapter1" in kw and rnd.random() < 0.25:      # adapter LIST files (one adapter per line)
+        extra = [C1, C2, A1.lower(), C3[:20]]
+        l1 = [A1, rnd.choice(extra)] + ([rnd.choice(extra)] if rnd.random() < 0.3 else [])
+        rnd.shuffle(l1)
+        l2 = None
+        if pe:
+            l2 = [A2, rnd.choice(extra)]; rnd.shuffle(l2)
+        ADALIST[seed] = (l1, l2)
+        kw["adapter1"] = l1
+        if l2: kw["adapter2"] = l2
+        synth.add_contams(d, [x.upper().encode() for x in l1 + (l2 or [])], seed=seed + 1, frac=0.15)
     return dict(module=module, pe=pe, n=n, L=L, T=T, patch=patch, flags=flags, cfg=cfg, kw=kw, d=d, idfn=idfn)
 
 
@@ -134,6 +146,12 @@ def one(seed):
     cfg = list(cfg)
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg)); args += ["-c", f"{w}/cfg.txt"]
+    if seed in ADALIST:
+        flags = list(flags)
+        for opt, lst, fn in (("-f", ADALIST[seed][0], "ada1.list"), ("-r", ADALIST[seed][1], "ada2.list")):
+            if lst:
+                open(f"{w}/{fn}", "w").write("".join(a + "\n" for a in lst))
+                flags[flags.index(opt) + 1] = f"{w}/{fn}"
     r = orc.run_reference(args + flags, module=module)
     # single-end input with variable read lengths can abort the reference at the end of its Q20/Q30 report (DESIGN.md
     # section 3): everything written before that is still compared, the trimming-position table that follows is not
