@@ -119,12 +119,26 @@ LIVE = [
     ("pe_hard_var", True, 3000, 120, 2, ["-f", A1, "-r", A2, "-J", "-t", "3,2,4,1"], dict(adapter1=A1, adapter2=A2, ada_trim=True, hard_trim=(3, 2, 4, 1)), 9, dict(var_len=True)),
     ("se_default", False, 6000, 150, 1, [], {}, None, {}),
     ("se_ada_T4_ms", False, 6000, 100, 4, ["-f", A1, "-J", "-g", "10"], dict(adapter1=A1, ada_trim=True, polyG_tail=10), 11, {}),
+    # adapter LIST files (process_argv.cpp:242-272: -f / -r name a readable file -> one adapter per line); a tuple in the
+    # flags stands for such a file. Lower-case and short entries included; the extra adapters are planted below
+    ("pe_ada_lists", True, 4000, 150, 2, ["-f", ("list", [synth.CONTAM1.decode(), A1, A2.lower()]), "-r", ("list", [A2, synth.CONTAM3.decode()[:20]]), "-J"],
+     dict(adapter1=[synth.CONTAM1.decode(), A1, A2.lower()], adapter2=[A2, synth.CONTAM3.decode()[:20]], ada_trim=True), 13, dict(var_len=True)),
+    ("se_ada_list_discard", False, 4000, 100, 3, ["-f", ("list", [A1, synth.CONTAM2.decode()])],
+     dict(adapter1=[A1, synth.CONTAM2.decode()]), 9, {}),
 ]
 
 
 def _prepare_live(case, w):
     name, pe, n, L, T, flags, pkw, patch, gkw = case
     data = synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, **gkw)
+    lists = [f[1] for f in flags if isinstance(f, tuple)]
+    if lists:
+        synth.add_contams(data, [a.upper().encode() for l in lists for a in l], seed=len(name), frac=0.2)
+        flags = list(flags)
+        for k, f in enumerate(flags):
+            if isinstance(f, tuple):
+                open(f"{w}/ada{k}.list", "w").write("".join(a + "\n" for a in f[1]))
+                flags[k] = f"{w}/ada{k}.list"
     synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
     args = ["-1", f"{w}/r1.fq", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T)]
     if pe:
