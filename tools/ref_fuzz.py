@@ -115,6 +115,10 @@ def gen(seed):
         for m in ("1", "2"):
             if "qual" + m in d:
                 q = d["qual" + m]; q[q != 0] += 31
+    if rnd.random() < 0.15:
+        # even values only: the reference reads position_qual[pos][maxBaseQuality], one past its allocation; an odd size leaves no
+        # allocator slack behind the array and the next chunk's header is printed as a count
+        v = rnd.choice([44, 50, 60]); cfg.append(f"maxBaseQuality={v}"); kw["max_base_quality"] = v
     if module == "filter" and "adapter1" in kw and rnd.random() < 0.25:      # adapter LIST files (one adapter per line)
         extra = [C1, C2, A1.lower(), C3[:20]]
         l1 = [A1, rnd.choice(extra)] + ([rnd.choice(extra)] if rnd.random() < 0.3 else [])
