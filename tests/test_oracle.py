@@ -494,3 +494,59 @@ def test_reference_se_varlen_abort_outputs_still_match(engine_lib, tmp_path):
             continue
         assert report_equal(f, f"{w}/mine/{b}"), f"report {b} differs from the reference"
     assert os.path.getsize(f"{w}/mine/Statistics_of_Trimming_Position_of_Reads_1.txt") > 0
+
+
+# ---- quality system / maxBaseQuality config keys and .gz input: oracle + report writer vs the reference binary
+QSYS_LIVE = [
+    # name, pe, n, L, T, patch, outQualSys, maxBaseQuality, gz input
+    ("pe_phred64_out33_gz", True, 3000, 100, 3, 20, 2, None, True),
+    ("se_phred64_out64_maxq50", False, 3000, 150, 2, 33, 1, 50, False),
+    ("pe_phred33_maxq60_gz", True, 2000, 75, 2, 7, None, 60, True),
+]
+
+
+@pytest.mark.skipif(not orc.have_reference(), reason="reference binary oracle/_ref/SOAPnuke not built")
+@pytest.mark.parametrize("case", QSYS_LIVE, ids=[c[0] for c in QSYS_LIVE])
+def test_oracle_matches_reference_binary_qualsys(case, engine_lib, tmp_path):
+    """qualSys=1 input (process_argv.cpp:1326-1336) with either output system, maxBaseQuality (even values: DESIGN.md
+    section 3) and gzip input, whose batches the reference labels differently (abi.ref_output_order)."""
+    name, pe, n, L, T, patch, outsys, maxq, gz = case
+    w = str(tmp_path)
+    data = synth.gen_pairs(n, L=L, seed=zlib.crc32(name.encode()) % 10000, se=not pe, var_len=pe)
+    cfg, kw = [f"patch={patch}"], {}
+    if outsys is not None:
+        cfg += ["qualSys=1", f"outQualSys={outsys}"]
+        kw.update(quality_phred=64, out_quality_phred=64 if outsys == 1 else 33)
+        for m in ("1", "2"):
+            if "qual" + m in data:
+                q = data["qual" + m]; q[q != 0] += 31
+    if maxq is not None:
+        cfg.append(f"maxBaseQuality={maxq}"); kw["max_base_quality"] = maxq
+    open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg))
+    sfx = ".gz" if gz else ""
+    args = ["-1", f"{w}/r1.fq{sfx}", "-C", "c1.fq", "-o", f"{w}/out", "-T", str(T), "-c", f"{w}/cfg.txt", "-f", A1, "-J"]
+    synth.write_fastq(f"{w}/r1.fq", data["seq1"], data["qual1"], data["len1"], 1)
+    if pe:
+        synth.write_fastq(f"{w}/r2.fq", data["seq2"], data["qual2"], data["len2"], 2)
+        args += ["-2", f"{w}/r2.fq{sfx}", "-D", "c2.fq", "-r", A2]
+    if gz:
+        for f in glob.glob(f"{w}/r?.fq"):
+            open(f + ".gz", "wb").write(gzip.compress(open(f, "rb").read(), 1)); os.remove(f)
+    r = orc.run_reference(args)
+    assert r.returncode == 0, r.stderr.decode()[-400:]
+    p = abi.make_params(is_pe=pe, threads=T, patch_size=patch, adapter1=A1, adapter2=A2 if pe else None, ada_trim=True, **kw)
+    if pe:
+        r1, r2, st, err = orc.filter_pe(p, data)
+    else:
+        r1, st, err = orc.filter_se(p, data); r2 = None
+    assert err == 0
+    shift = kw.get("out_quality_phred", 33) - kw.get("quality_phred", 33)
+    for m, rs in ((1, r1), (2, r2)):
+        if rs is None:
+            continue
+        order = abi.ref_output_order(n, T, None, patch, gz_input=gz, pe=pe)
+        mine = synth.clean_fastq_bytes(data[f"seq{m}"], data[f"qual{m}"], data[f"len{m}"], rs, m, order=order, phred_shift=shift)
+        assert mine == open(f"{w}/out/c{m}.fq", "rb").read(), f"clean fq{m} differs from the reference binary"
+    fn = engine_lib.snk_report_write_pe if pe else engine_lib.snk_report_write_se
+    write_reports(fn, p, st, f"{w}/mine")
+    compare_reports(f"{w}/out", f"{w}/mine")
