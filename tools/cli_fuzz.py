@@ -43,8 +43,10 @@ def prepare(seed):
     if g["module"] == "filter" and rnd.random() < 0.3 and pe: cfg.append("pe_info")
     # (never both: with fasta output the reference skips the quality conversion but still subtracts the OUTPUT Phred
     # base in the clean statistics - negative table indices, undefined behaviour)
-    if rnd.random() < 0.2: cfg.append("outQualSys=1")
-    elif rnd.random() < 0.25: cfg.append("outFileType=fasta")
+    r_out, r_fa = rnd.random(), rnd.random()
+    if not any(c.startswith("qualSys") for c in cfg):          # (the generator may already have chosen Phred+64 in / either out)
+        if r_out < 0.2: cfg.append("outQualSys=1")
+        elif r_fa < 0.25: cfg.append("outFileType=fasta")
     trim = rnd.random() < 0.3
     if trim: cfg += ["trimFq1=t1.fq.gz"] + (["trimFq2=t2.fq.gz"] if pe else [])
     env = dict(os.environ)
@@ -59,8 +61,14 @@ def prepare(seed):
     if cfg:
         open(f"{w}/cfg.txt", "w").write("".join(l + "\n" for l in cfg))
         base += ["-c", f"{w}/cfg.txt"]
-    r = orc.run_reference(base + ["-o", f"{w}/ref"] + g["flags"], module=g["module"])
-    return dict(seed=seed, w=w, base=base, flags=g["flags"], module=g["module"], pe=pe, eo=eo, trim=trim, env=env, ref=r, cfg=cfg)
+    flags = list(g["flags"])
+    if seed in ref_fuzz.ADALIST:             # adapter list files instead of the literal adapters
+        for opt, lst, fn in (("-f", ref_fuzz.ADALIST[seed][0], "ada1.list"), ("-r", ref_fuzz.ADALIST[seed][1], "ada2.list")):
+            if lst:
+                open(f"{w}/{fn}", "w").write("".join(a + "\n" for a in lst))
+                flags[flags.index(opt) + 1] = f"{w}/{fn}"
+    r = orc.run_reference(base + ["-o", f"{w}/ref"] + flags, module=g["module"])
+    return dict(seed=seed, w=w, base=base, flags=flags, module=g["module"], pe=pe, eo=eo, trim=trim, env=env, ref=r, cfg=cfg)
 
 
 def main():
