@@ -316,7 +316,8 @@ int snk_engine_stats_device(snk_engine* e, uint64_t** d_ptr, size_t* words);
 int snk_engine_stats_to_device(snk_engine* e, void* d_dst, void* stream);
 int snk_engine_stats_from_device(snk_engine* e, const void* d_src, void* stream);
 /* sticky error flags raised by kernels: bit0 = unrecognized base (read_filter.cpp:282),
- * bit1 = quality outside [0,SNK_QBINS), bit2 = low quality ratio > 1 (sequence.cpp:335) */
+ * bit1 = quality outside [0,SNK_QBINS), bit2 = low quality ratio > 1 (sequence.cpp:335),
+ * bit3 = a len[] entry exceeds the batch stride or SNK_MAX_READ_LEN (SoA entry points; the row is not processed) */
 int snk_engine_error_flags(snk_engine* e, uint32_t* flags, uint64_t* first_bad_index);
 /* number of kernel launches issued by this engine so far */
 uint64_t snk_engine_launch_count(snk_engine* e);

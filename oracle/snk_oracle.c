@@ -6,7 +6,7 @@
  *
  * Parity pinning: the reference ships no tests or golden vectors, so this
  * restatement is pinned against the UNMODIFIED reference binary compiled into oracle/_ref/SOAPnuke
- * (oracle/Makefile): tests/test_oracle_vs_reference.py runs both on the same FASTQ and compares the
+ * (oracle/Makefile): tests/test_oracle.py runs both on the same FASTQ and compares the
  * clean FASTQ and all report files byte for byte, and tests/golden/ holds outputs of that binary.
  *
  * Each function cites the reference file:line (relative to the reference tree) it follows.

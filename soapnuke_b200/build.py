@@ -18,10 +18,14 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 ENGINE_SRCS = [os.path.join(HERE, "csrc", "engine.cu"),
                os.path.join(HERE, "host", "report.cpp"),
                os.path.join(HERE, "host", "host_common.cpp")]
-ENGINE_DEPS = ENGINE_SRCS + [os.path.join(HERE, "csrc", "filter_kernel.cuh"),
-                             os.path.join(HERE, "csrc", "filter_core.cuh"),
-                             os.path.join(HERE, "host", "host_common.h"),
-                             os.path.join(ROOT, "include", "snk_engine.h")]
+def _engine_deps():
+    """Every file the engine library is compiled from: its sources plus all headers under csrc/, host/ and include/
+    (globbed, so that a new header can never be forgotten and ship a stale .so to the GPU box)."""
+    import glob
+    deps = list(ENGINE_SRCS)
+    for pat in (os.path.join(HERE, "csrc", "*"), os.path.join(HERE, "host", "*.h"), os.path.join(ROOT, "include", "*.h")):
+        deps += glob.glob(pat)
+    return deps + [os.path.abspath(__file__)]
 
 
 def _stale(target, deps):
@@ -34,7 +38,7 @@ def _stale(target, deps):
 def build_engine(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libsnk_engine.so")
-    if not force and not _stale(out, ENGINE_DEPS):
+    if not force and not _stale(out, _engine_deps()):
         return out
     cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas",
                            "-shared", "-cudart", "shared", "-o", out] + ENGINE_SRCS

@@ -73,6 +73,10 @@ struct snk_engine {
     Lane lanes[kLanes];
     uint64_t launches = 0;
     std::mutex mu;
+    // per engine (= per device) launch cache, keyed by kernel instantiation: cudaFuncSetAttribute and the
+    // occupancy query are per device, so they must not be remembered in function-local statics
+    struct KernelCache { const void* fn; int threads; size_t smem; int blocks; bool smem_opt_in; };
+    std::vector<KernelCache> kcache;
 };
 
 namespace {
@@ -81,19 +85,20 @@ template <int MAXC, int MATES, int J>
 int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
 {
     auto kern = filter_kernel<MAXC, MATES, J>;
-    static size_t smem_set = 0;               // per instantiation: raise the opt-in limit only when needed
-    if (lp.smem > smem_set) {
+    snk_engine::KernelCache* kc = nullptr;
+    for (auto& c : e->kcache) if (c.fn == (const void*)kern) kc = &c;
+    if (!kc) { e->kcache.push_back({(const void*)kern, 0, 0, 1, false}); kc = &e->kcache.back(); }
+    if (!kc->smem_opt_in) {                   // once per device and instantiation: raise the opt-in shared-memory limit
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
-        smem_set = kSmemLimit;
+        kc->smem_opt_in = true;
     }
     // persistent grid: resident CTAs per SM (shared memory / registers / threads) x SMs
-    static int occ_threads = 0, occ_blocks = 0; static size_t occ_smem = 0;
-    if (occ_threads != (int)lp.threads || occ_smem != lp.smem) {
+    if (kc->threads != (int)lp.threads || kc->smem != lp.smem) {
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, (int)lp.threads, lp.smem));
-        occ_threads = (int)lp.threads; occ_smem = lp.smem; occ_blocks = nb < 1 ? 1 : nb;
+        kc->threads = (int)lp.threads; kc->smem = lp.smem; kc->blocks = nb < 1 ? 1 : nb;
     }
-    const uint32_t max_grid = (uint32_t)e->num_sms * (uint32_t)occ_blocks;
+    const uint32_t max_grid = (uint32_t)e->num_sms * (uint32_t)kc->blocks;
     const int grid = (int)(lp.ntiles < max_grid ? (lp.ntiles ? lp.ntiles : 1) : max_grid);
     kern<<<grid, lp.threads, lp.smem, stream>>>(dp, ka);
     CUDA_TRY(cudaGetLastError());
@@ -256,7 +261,7 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
     if ((mates == 2) != (e->params.is_pe != 0)) { snk::set_error("engine was created for the other read layout (PE/SE)"); return 1; }
     if (stride == 0 || stride % 16 != 0 || stride > 1008) { snk::set_error("batch stride must be a multiple of 16 in [16,1008]"); return 1; }
     if (n == 0) { snk::set_error("empty text batch"); return 1; }
-    if (fmt->strip < 0 || fmt->id_mode < 0 || fmt->id_mode > 2) { snk::set_error("bad text format"); return 1; }
+    if (fmt->strip < 0 || fmt->id_mode < 0 || fmt->id_mode > 2 || fmt->pe_info < 0 || fmt->pe_info > 2) { snk::set_error("bad text format"); return 1; }
     for (int m = 0; m < mates; m++)
         if (bytes[m] == 0 || bytes[m] > 0xF0000000ull) { snk::set_error("a text batch must hold 1 byte .. 3.75 GiB per mate"); return 1; }
     CUDA_TRY(cudaSetDevice(e->device));
@@ -284,7 +289,8 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
         o_res[m] = need; need += al256((size_t)n * sizeof(snk_read_result));
         o_rec[m] = need; need += al256(((size_t)n + 1) * 4);
         o_blk[m] = need; need += al256((size_t)nblk * 4);
-        o_out[m] = need; need += al256(bytes[m] + 2 * (size_t)n + 64);
+        // clean text <= raw text + the "/1" "/2" id suffixes (pe_info 2 = the reference's double suffix: 4 bytes per record)
+        o_out[m] = need; need += al256(bytes[m] + 4 * (size_t)n + 64);
     }
     if (lane_reserve(L, need)) return 1;
     TextArgs ta;

@@ -237,7 +237,7 @@ enum : uint16_t {
     RF_GCONTAM = 32768                   // a global contaminant (either strand) was found
 };
 SNK_HD uint16_t pre_flags(uint32_t len_word) { return (uint16_t)(((len_word & SNK_PRE_TILE) ? RF_TILE : 0) | ((len_word & SNK_PRE_FOV) ? RF_FOV : 0)); }
-enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4 };
+enum : uint32_t { ERR_BAD_BASE = 1, ERR_BAD_QUAL = 2, ERR_LOWQ_RATIO = 4, ERR_BAD_LEN = 8 };
 
 // ------------------------------------------------------------------ adapter matching
 // Exact restatement of one window of adapter_pos: compare adapter[aoff+c] with read[roff+c] for

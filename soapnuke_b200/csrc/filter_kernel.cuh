@@ -385,6 +385,9 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
         // hands 2*MATES bulk copies to the TMA engine and everybody waits on the mbarrier they complete on
         const uint32_t row_bytes = cnt * A.stride;
         if (tid == 0) {
+            // the previous tile's rows were written (padding normalised) and read through the generic proxy: order those
+            // accesses before the async-proxy writes of the bulk copies into the same bytes
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(stage_bar, 2u * MATES * row_bytes);
 #pragma unroll
             for (int m = 0; m < MATES; m++) {
@@ -413,7 +416,10 @@ filter_kernel(const __grid_constant__ DevParams P, const __grid_constant__ Kerne
             ReadInfo* info = reinterpret_cast<ReadInfo*>(smem + sp.off_info[m]);
             const uint32_t len_word = sl[r];
             int len = (int)(len_word & SNK_LEN_MASK);
-            if (len > (int)A.stride) len = (int)A.stride;
+            if (len > (int)A.stride || len > SNK_MAX_READ_LEN) {      // not a row of this batch / no table row behind READ_MAX_LEN
+                if (h == 0) report_error(A, ERR_BAD_LEN, g0 + r);
+                len = 0;                                               // handled like an empty row (checked path, nothing counted)
+            }
             ReadInfo ri;
             if (len <= 0) {             // "Error:empty sequence" (read_filter.cpp:250)
                 ri.len = 0; ri.head_cut = 0; ri.clean_len = 0; ri.head_hdcut = ri.head_lqcut = ri.tail_hdcut = ri.tail_lqcut = ri.adacut_pos = -1;

@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(kSegThreads) line_offset_kernel(const __grid_c
 __global__ void __launch_bounds__(256) pack_rows_kernel(const __grid_constant__ TextArgs A)
 {
     const int m = blockIdx.y;
+    // wrong number of lines: line_off[] is only partly written, nothing below may follow it (the batch is rejected)
+    if (A.meta->flags & TEXT_LINE_COUNT) return;
     const uint32_t cpr = A.stride / 16u;                 // chunks per row
     const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t rec64 = g / (2u * cpr);

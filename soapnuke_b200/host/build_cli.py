@@ -5,8 +5,9 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SRCS = [os.path.join(HERE, f) for f in ("main.cpp", "cli_params.cpp", "process.cpp")]
-DEPS = SRCS + [os.path.join(HERE, f) for f in ("cli_params.h", "process.h", "host_common.h")] + \
-    [os.path.join(PKG, "csrc", f) for f in ("text_core.cuh", "filter_core.cuh")]
+import glob
+DEPS = SRCS + glob.glob(os.path.join(HERE, "*.h")) + glob.glob(os.path.join(PKG, "csrc", "*.cuh")) + \
+    glob.glob(os.path.join(os.path.dirname(PKG), "include", "*.h")) + [os.path.abspath(__file__)]
 
 
 def build(force=False):

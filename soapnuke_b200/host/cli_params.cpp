@@ -2,8 +2,8 @@
 // Flag surface, defaults, derived values and error texts follow process_argv.cpp (getopt table
 // :77-170, option handling :181-520, derived values :533-544, check_parameter :554-917, config
 // file :1158-1638). Options that select parts of the reference this engine does not implement
-// (global contaminants, rmdup, output split/subsample, trim-only outputs, stLFR) are rejected
-// with an explicit error instead of being silently ignored.
+// (rmdup, output split/subsample, streaming, stLFR, base conversion) are rejected with an explicit
+// error instead of being silently ignored.
 #include "cli_params.h"
 #include <cmath>
 #include <getopt.h>
@@ -177,7 +177,9 @@ void print_usage(const std::string& module)
               << "                  adaMis adaMR adaEdge trim trimBadHead trimBadTail log tile fov\n"
               << "                  contam1 contam2 ctMatchR contam_trim global_contams glob_cotm_mR glob_cotm_mM trimFq1 trimFq2\n"
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
-              << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>\n";
+              << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>,\n"
+              << "             SNK_KEEP_DEFERRED=1 (write the last deferred batch of a plain-text PE run that the reference\n"
+              << "             loses in its final concat; default: drop it like the reference, with a warning on stderr)\n";
 }
 
 int parse_command_line(int argc, char** argv, HostParams& hp)

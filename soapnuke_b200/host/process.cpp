@@ -225,7 +225,7 @@ struct PinnedBuf {
 };
 // a run of output bytes: kind 0 = in place, 1 = deferred (see FilterRun::writer), 2 = "emit the deferred bytes now"
 // Trim pieces (trimFq1/2) carry a record range instead of bytes until a worker has formatted them.
-struct Piece { int kind; const char* p; size_t len; std::string gz; uint32_t r0 = 0, r1 = 0; };
+struct Piece { int kind; const char* p; size_t len; std::string gz; uint32_t r0 = 0, r1 = 0; uint32_t kept = 0; /* records in a deferred clean piece */ };
 struct HostBatch {
     uint64_t seq_no = 0, first_index = 0;
     uint32_t n = 0;
@@ -265,6 +265,7 @@ private:
     uint64_t total_reads_ = 0;
     std::string pending_deferred_[4];  // deferred output (already encoded) waiting for its insertion point; [2..3] = trim files
     bool trim_ = false;                // trimFq1/2: every record after trimming, before the discard decision
+    uint64_t deferred_records_ = 0;    // kept records (pairs) waiting in pending_deferred_[0]
 
     std::deque<HostBatch> batches_;
     Channel<HostBatch*> free_q_, gpu_q_;
@@ -554,6 +555,13 @@ void FilterRun::make_pieces(HostBatch& b)
                     if (stop <= a) stop = (it == off + r1 + 1) ? e : (size_t)*it;
                 }
                 out.push_back({kind, text + a, stop - a, std::string()});
+                if (kind == 1) {                                           // kept records of this run (warning text of writer())
+                    const uint32_t* lo = std::lower_bound(off + r0, off + r1 + 1, (uint32_t)a);
+                    const uint32_t* hi = std::lower_bound(off + r0, off + r1 + 1, (uint32_t)stop);
+                    uint32_t k = 0;
+                    for (const uint32_t* q = lo; q < hi; q++) k += q[1] != q[0];
+                    out.back().kept = k;
+                }
                 a = stop;
             }
         });
@@ -741,8 +749,9 @@ void FilterRun::writer()
             if (f % 2 >= mates_) continue;
             for (Piece& p : (f < 2 ? b->pieces[f] : b->tpieces[f - 2])) {
                 if (p.kind == 0) { if (p.len) mine.push_back({f, p.p, p.len, pos[f], b, nullptr}); pos[f] += (off_t)p.len; }
-                else if (p.kind == 1) pending_deferred_[f].append(p.p, p.len);
+                else if (p.kind == 1) { pending_deferred_[f].append(p.p, p.len); if (f == 0) deferred_records_ += p.kept; }
                 else if (!pending_deferred_[f].empty()) {
+                    if (f == 0) deferred_records_ = 0;
                     auto hold = std::make_shared<std::string>(std::move(pending_deferred_[f]));
                     pending_deferred_[f].clear();
                     mine.push_back({f, hold->data(), hold->size(), pos[f], nullptr, hold});
@@ -775,6 +784,10 @@ void FilterRun::writer()
         const uint64_t into_last = total_reads_ - (total_reads_ / cyc_) * cyc_;
         drop = into_last <= (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 2);
     }
+    if (drop && deferred_records_ > 0)
+        std::cerr << "Warning:" << deferred_records_ << " clean read" << (pe_ ? " pairs" : "s") << " (the last deferred batch before the end of the input) are counted in the"
+                  << " statistics but not written, exactly like SOAPnuke 2.1.9 loses them in its final concat pass (peprocess.cpp:2957-2966);"
+                  << " set SNK_KEEP_DEFERRED=1 to write them" << std::endl;
     for (int f = 0; f < nfiles; f++) {
         if (f % 2 >= mates_) continue;
         if (!drop && !pending_deferred_[f].empty()) write_at({f, pending_deferred_[f].data(), pending_deferred_[f].size(), pos[f], nullptr, nullptr});
@@ -838,6 +851,7 @@ void FilterRun::process()
         if (flags & 1) die("unrecognized sequence, read number " + std::to_string(bad + 1));
         if (flags & 2) die("base quality is out of range,please check the quality system parameter or fastq file, read number " + std::to_string(bad + 1));
         if (flags & 4) die("low quality base ratio stat error, read number " + std::to_string(bad + 1));
+        if (flags & 8) die("read longer than its batch row, read number " + std::to_string(bad + 1));
         engine_check(snk_engine_stats(e, part.data()));
         std::vector<uint64_t> keys;
         for (size_t k : key_words) { keys.push_back(std::max(total[k], part[k])); part[k] = 0; total[k] = 0; }

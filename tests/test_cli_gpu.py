@@ -96,27 +96,27 @@ def _reference_side(name):
     return _FUTURES[name].result()
 
 
-def run_both(cli, tmp, name, pe, flags, env=None, module="filter", trim=False, **_unused):
+def run_both(cli, tmp, name, pe, flags, env=None, module="filter", trim=False, out_name="mine", **_unused):
     st = _reference_side(name)
     w, base, ext_out, r = st["w"], st["base"], st["ext_out"], st["ref"]
     assert r.returncode == 0, r.stderr.decode()
     e = dict(os.environ)
     e.update(env or {})
-    m = subprocess.run([cli, module] + base + ["-o", f"{w}/mine"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=600)
+    m = subprocess.run([cli, module] + base + ["-o", f"{w}/{out_name}"] + flags, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e, timeout=600)
     assert m.returncode == 0, m.stderr.decode()
     for mate in (1, 2) if pe else (1,):
         a = read_maybe_gz(f"{w}/ref/c{mate}{ext_out}")
-        b = read_maybe_gz(f"{w}/mine/c{mate}{ext_out}")
+        b = read_maybe_gz(f"{w}/{out_name}/c{mate}{ext_out}")
         assert a == b, f"{name}: clean fq{mate} differs ({len(a)} vs {len(b)} bytes)"
     if trim:
         for mate in (1, 2) if pe else (1,):
             a = read_maybe_gz(f"{w}/ref/t{mate}.fq.gz")
-            b = read_maybe_gz(f"{w}/mine/t{mate}.fq.gz")
+            b = read_maybe_gz(f"{w}/{out_name}/t{mate}.fq.gz")
             assert len(a) > 0 and a == b, f"{name}: trim fq{mate} differs ({len(a)} vs {len(b)} bytes)"
     reports = sorted(glob.glob(f"{w}/ref/*.txt"))
     assert len(reports) == (10 if pe else 6)
     for f in reports:
-        assert report_equal(f, f"{w}/mine/{os.path.basename(f)}"), f"{name}: {os.path.basename(f)} differs"
+        assert report_equal(f, f"{w}/{out_name}/{os.path.basename(f)}"), f"{name}: {os.path.basename(f)} differs"
 
 
 @pytest.mark.skipif(not orc.have_reference(), reason="reference binary not available")

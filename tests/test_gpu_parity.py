@@ -264,3 +264,21 @@ def test_adapter_matcher_adversarial_on_gpu(engine_lib):
             r1, _ = e.filter_host(d)
             st = e.stats()
         assert_same((r1, None, st), (o1, None, ost), f"adapter len {len(adapter)}")
+
+
+def test_len_beyond_the_row_raises_the_length_flag(engine_lib):
+    """A len[] entry larger than the batch stride (or than SNK_MAX_READ_LEN) is an error of the caller: the row is not
+    processed and error bit 3 names the read, instead of silently clamping and counting into a neighbouring table."""
+    d = synth.gen_pairs(4000, L=150, seed=46, se=True)
+    d["len1"] = d["len1"].copy()
+    d["len1"][321] = 161                      # stride is 160
+    p = abi.make_params(is_pe=False)
+    with Engine(engine_lib, p) as e:
+        r1, _ = e.filter_host(d)
+        flags, idx = e.error_flags()
+        st = e.stats()
+    assert flags & 8 and idx == 321
+    ok = synth.gen_pairs(4000, L=150, seed=46, se=True)
+    keep = np.ones(4000, dtype=bool); keep[321] = False
+    o1, _, _, _ = oracle_run(p, ok)
+    assert np.array_equal(r1[keep], o1[keep]), "the other reads of the batch are unaffected"

@@ -3,6 +3,8 @@ clean FASTQ text out. The device must index and pack the text into the rows the 
 would have been given (same per-read records, same statistics as the oracle) and emit exactly the
 bytes the reference's output_fastqs writes (model: helpers.ref_clean_text, pinned end to end
 against the reference binary by tests/test_cli_gpu.py)."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -115,3 +117,31 @@ def test_text_path_many_segments_equals_soa_path(engine_lib):
     assert_same((ress[0], ress[1], st), (r1, r2, st_soa), "text vs SoA")
     for m, res in ((0, r1), (1, r2)):
         assert outs[m] == synth.clean_fastq_bytes(d[f"seq{m + 1}"], d[f"qual{m + 1}"], d[f"len{m + 1}"], res, m + 1)
+
+
+def test_text_path_double_pe_suffix_with_nothing_dropped(engine_lib):
+    """pe_info = 2 (the reference's double "/1/1" suffix when the trim files are on, peprocess.cpp:1460-1475) adds 4 bytes
+    per kept record: with lenient filters and no drops the clean text is LONGER than the raw text, and both mates' outputs
+    must still come back intact (the device output buffer is sized for it)."""
+    n = 60000
+    d = synth.gen_pairs(n, L=150, seed=31)
+    p = abi.make_params(is_pe=True, low_qual_ratio=-1, n_ratio=-1, min_read_length=1, threads=2, patch_size=1000)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    assert int((o1["category"] == 0).sum()) == n, "case must keep every pair"
+    ids = [synth.read_ids(n, 1), synth.read_ids(n, 2)]
+    texts = texts_of(d, ids, 2)
+    with Engine(engine_lib, p) as e:
+        meta, outs, offs, ress = e.filter_text(texts, n, 160, pe_info=2)
+        st = e.stats()
+    assert meta.flags == 0 and meta.kept == n
+    assert meta.out_bytes[0] == len(texts[0]) + 4 * n and meta.out_bytes[1] == len(texts[1]) + 4 * n
+    assert_same((ress[0], ress[1], st), (o1, o2, ost), "pe_info 2")
+    for m, res in ((0, o1), (1, o2)):
+        want, want_off = ref_clean_text(ids[m], d[f"seq{m + 1}"], d[f"qual{m + 1}"], res, m, pe_info=2)
+        assert np.array_equal(offs[m], want_off)
+        assert outs[m] == want, f"clean text of mate {m + 1} differs"
+    with Engine(engine_lib, p) as e:                       # the ABI rejects values the formatter has no room for
+        fmt = abi.TextFormat(strip=1, pe_info=3)
+        buf = np.frombuffer(texts[0], dtype=np.uint8).copy()
+        rc = e.lib.snk_filter_pe_text_async(e.h, 0, buf.ctypes.data, len(texts[0]), buf.ctypes.data, len(texts[0]), n, 160, C.byref(fmt), 0)
+        assert rc != 0 and b"bad text format" in e.lib.snk_last_error()
