@@ -7,22 +7,31 @@ One "step" = one pass of the hot path (adapter match, trim, predicates, discard 
 per-position histograms) over one batch of P read pairs per GPU with BASELINE config-2 flags
 (`-f A1 -r A2 -J -l 5 -q 0.5 -n 0.05 -m 15 -p 0.7 -X 50 -g 10 -y 20,30 -x 20,10`).
 
- value   whole-job M reads/s with the batch already resident in HBM (one kernel launch per step,
-         timed with CUDA events on the launching stream, max over ranks).
- e2e     same metric through the host-buffer C-ABI entry points (snk_filter_pe_async on pinned host
-         memory): host->device copies of every step's batch and device->host copies of the per-read
-         result records are inside the timed region.
- roofline  algorithmic bytes (2L+8 per read) / average kernel duration vs the
-         measured HBM copy bandwidth of MEASURED_PEAKS.json.
- cpu_baseline  the unmodified reference binary (oracle/_ref/SOAPnuke, `filter -T <ncores>`) timed on
-         this box's cores on a bounded sample of the same workload (rank 0, N=1 only).
+ value     whole-job M reads/s with the batches already resident in HBM: K kernel launches per GPU and, for
+           N > 1, the path's single collective (NCCL all-reduce of the statistics table) INSIDE the region timed
+           with CUDA events on the launching stream, max over ranks.
+ e2e       FILE TO FILE, what a user of the reference runs: `soapnuke_b200/bin/SOAPnuke filter` (one process per
+           GPU) on the same plain FASTQ files in /dev/shm the reference arm reads, wall clock per run including
+           process start, CUDA context, FASTQ parse on the device, clean FASTQ + report files written; at N = 1
+           the outputs are compared byte for byte with the reference binary's.
+ e2e_soa   pinned SoA host buffers -> 8-byte result records through snk_filter_pe_async (host<->device copies in the
+           timed region), with the measured pinned host->device copy bandwidth of the box beside it (`h2d_probe`).
+ e2e_text  raw FASTQ text in pinned memory -> clean FASTQ text in pinned memory (snk_filter_pe_text_async).
+ roofline  algorithmic bytes (2L+8 per read) / average kernel duration vs the measured HBM copy
+           bandwidth of MEASURED_PEAKS.json.
+ stats_parity  outside the timed region: every rank filters a bounded slice of its own data, the tables are
+           all-reduced, and rank 0 compares the result bit for bit with the oracle run over all ranks' slices.
+ cpu_baseline  the unmodified reference binary (oracle/_ref/SOAPnuke, `filter -T <ncores>`) on this box's cores on the
+           SAME files as `e2e` (rank 0, N=1 only): wall, user+sys and the number of 5 s poll quanta in the wall.
 
-`--impl reference` times only that CPU reference and prints the same JSON shape.
+`--impl reference` times only that CPU reference (K+W runs) and prints the same JSON shape with the same `config`.
 """
 import argparse
 import ctypes as C
+import filecmp
 import json
 import os
+import resource
 import shutil
 import subprocess
 import sys
@@ -46,6 +55,15 @@ L = 150
 METRIC = "Mreads/sec PE150 filter (adapter trim + all quality filters + raw/clean statistics)"
 UNIT = "Mreads/s"
 UNIQUE_PAIRS = 1 << 18          # generated once, tiled to the batch size
+CLI = os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke")
+PARITY_PAIRS = 32768            # per rank, stats_parity leg
+
+
+def workload_config(pairs):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": "BASELINE configs[1]: PE 2x150bp, adapter trim + all quality filters (config-2 flags), one batch per GPU per step",
+            "pairs_per_step_per_gpu": pairs, "read_len": L, "flags": " ".join(CFG2_FLAGS[4:]),
+            "l2": "inputs larger than L2 (%.2f GB of rows per step per GPU)" % (4 * pairs * synth.stride_for(L) / 1e9)}
 
 
 def measured_peak():
@@ -149,71 +167,112 @@ def make_host_batch(pairs, seed):
     return out
 
 
+# --------------------------------------------------------------------------- the FASTQ files both arms run on
+def work_dir(need_bytes):
+    """A scratch directory with room for `need_bytes`: /dev/shm when it is large enough, else the default tmp."""
+    for base in ("/dev/shm", None):
+        try:
+            if base is None or (os.path.isdir(base) and shutil.disk_usage(base).free > need_bytes + (1 << 30)):
+                return tempfile.mkdtemp(prefix="snkbench_", dir=base)
+        except Exception:
+            continue
+    return tempfile.mkdtemp(prefix="snkbench_")
+
+
+def write_workload_files(work, pairs, seed=1002):
+    """r1.fq / r2.fq: `pairs` synthetic PE150 pairs (config-2 mix): min(pairs, 2^20) generated pairs tiled with running ids."""
+    unique = min(pairs, 1 << 20)
+    d = synth.gen_pairs(unique, L=L, seed=seed)
+    for m in (1, 2):
+        with open(f"{work}/r{m}.fq", "wb") as f:
+            for k in range(0, pairs, unique):
+                n = min(unique, pairs - k)
+                synth.write_fastq_fixed(f"{work}/part.fq", d[f"seq{m}"][:n], d[f"qual{m}"][:n], L, m, first=k)
+                with open(f"{work}/part.fq", "rb") as g:
+                    shutil.copyfileobj(g, f, 1 << 24)
+                os.unlink(f"{work}/part.fq")
+    return os.path.getsize(f"{work}/r1.fq") + os.path.getsize(f"{work}/r2.fq")
+
+
+def run_timed(cmd, env=None, timeout=3600):
+    r0 = resource.getrusage(resource.RUSAGE_CHILDREN)
+    t0 = time.perf_counter()
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=timeout)
+    wall = time.perf_counter() - t0
+    r1 = resource.getrusage(resource.RUSAGE_CHILDREN)
+    if p.returncode != 0:
+        raise RuntimeError(f"{os.path.basename(cmd[0])} failed: " + p.stderr.decode()[-400:])
+    return {"wall": wall, "cpu": (r1.ru_utime - r0.ru_utime) + (r1.ru_stime - r0.ru_stime)}
+
+
+def file_args(work, out):
+    return ["-1", f"{work}/r1.fq", "-2", f"{work}/r2.fq", "-C", "c1.fq", "-D", "c2.fq", "-o", out]
+
+
 # --------------------------------------------------------------------------- reference arm
-def time_reference(sample_pairs, steps, warmup, seed=1002):
-    """`SOAPnuke filter` (unmodified reference, all host cores) on a bounded sample; returns
-    (Mreads/s, cores, seconds per step list, description)."""
+def reference_runs(work, out, runs, cores):
+    """`SOAPnuke filter -T cores` (unmodified reference, or the oracle port when it did not build) on the files in `work`."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as orc
-    cores = os.cpu_count() or 1
-    work = tempfile.mkdtemp(prefix="snkref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    try:
-        unique = min(sample_pairs, 1 << 20)
-        d = synth.gen_pairs(unique, L=L, seed=seed)
-        for m in (1, 2):                      # the sample = `unique` generated pairs tiled to sample_pairs, ids running on
-            with open(f"{work}/r{m}.fq", "wb") as f:
-                for k in range(0, sample_pairs, unique):
-                    n = min(unique, sample_pairs - k)
-                    synth.write_fastq_fixed(f"{work}/part.fq", d[f"seq{m}"][:n], d[f"qual{m}"][:n], L, m, first=k)
-                    with open(f"{work}/part.fq", "rb") as g:
-                        shutil.copyfileobj(g, f, 1 << 24)
-                    os.unlink(f"{work}/part.fq")
-        if orc.have_reference():
-            kind = "reference"
-            times = []
-            for s in range(warmup + steps):
-                shutil.rmtree(f"{work}/out", ignore_errors=True)
-                t0 = time.perf_counter()
-                r = orc.run_reference(["-1", f"{work}/r1.fq", "-2", f"{work}/r2.fq", "-C", "c1.fq", "-D", "c2.fq",
-                                       "-o", f"{work}/out", "-T", str(cores)] + CFG2_FLAGS, timeout=3600)
-                dt = time.perf_counter() - t0
-                if r.returncode != 0:
-                    raise RuntimeError("reference run failed: " + r.stderr.decode()[-300:])
-                if s >= warmup:
-                    times.append(dt)
-            sample = (f"SOAPnuke 2.1.9 filter -T {cores} on {sample_pairs} synthetic PE150 pairs, plain FASTQ in/out on /dev/shm, "
-                      "whole-program wall time (includes FASTQ parse/format and its 5 s concat poll quantum)")
-        else:
-            kind = "port"
-            cores = 1
-            p = abi.make_params(is_pe=True, **CFG2_KW)
-            d = synth.gen_pairs(sample_pairs, L=L, seed=seed) if unique < sample_pairs else d
-            times = []
-            for s in range(warmup + steps):
-                t0 = time.perf_counter()
-                orc.filter_pe(p, d)
-                dt = time.perf_counter() - t0
-                if s >= warmup:
-                    times.append(dt)
-            sample = f"oracle C restatement, 1 thread, {sample_pairs} synthetic PE150 pairs already parsed in memory"
-        total = sum(times)
-        return 2.0 * sample_pairs * len(times) / total / 1e6, cores, times, kind, sample
-    finally:
-        shutil.rmtree(work, ignore_errors=True)
+    res = []
+    for _ in range(runs):
+        shutil.rmtree(out, ignore_errors=True)
+        res.append(run_timed([orc.REF_BIN, "filter"] + file_args(work, out) + ["-T", str(cores)] + CFG2_FLAGS))
+    return res
+
+
+def have_reference():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "SOAPnuke"))
+
+
+def describe_reference(pairs, cores, runs):
+    wall = float(np.mean([r["wall"] for r in runs])); cpu = float(np.mean([r["cpu"] for r in runs]))
+    return (f"SOAPnuke 2.1.9 filter -T {cores} on {pairs} synthetic PE150 pairs, plain FASTQ in/out on /dev/shm, whole-program wall time "
+            f"{wall:.2f} s per run = {wall / 5.0:.1f} of its 5 s concat-poll quanta (peprocess.cpp:2769,3039), user+sys {cpu:.1f} CPU-s per run")
+
+
+def time_oracle_port(pairs, steps, warmup, seed=1002):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as orc
+    p = abi.make_params(is_pe=True, **CFG2_KW)
+    d = synth.gen_pairs(min(pairs, 1 << 19), L=L, seed=seed)
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.filter_pe(p, d)
+        if s >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 2.0 * d["n"] / (sum(times) / len(times)) / 1e6, d["n"]
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    value, cores, times, kind, sample = time_reference(args.ref_pairs, args.steps, args.warmup)
+    pairs = args.pairs
+    cores = os.cpu_count() or 1
+    if have_reference():
+        work = work_dir(2 * pairs * 2 * (L + 20) * 2)
+        try:
+            write_workload_files(work, pairs)
+            runs = reference_runs(work, f"{work}/out_ref", args.warmup + args.steps, cores)[args.warmup:]
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        wall = float(np.mean([r["wall"] for r in runs]))
+        value = 2.0 * pairs / wall / 1e6
+        base = {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": describe_reference(pairs, cores, runs),
+                "wall_s_per_run": wall, "cpu_s_per_run": float(np.mean([r["cpu"] for r in runs])), "poll_quanta_per_run": wall / 5.0}
+        ms = 1e3 * wall
+    else:
+        value, n = time_oracle_port(pairs, args.steps, args.warmup)
+        base = {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                "sample": f"oracle C restatement, 1 thread, {n} synthetic PE150 pairs already parsed in memory"}
+        ms = 1e3 * 2.0 * n / (value * 1e6)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "BASELINE configs[1]: PE 2x150bp, adapter trim + all quality filters (config-2 flags)",
-                   "pairs_per_step": args.ref_pairs},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(pairs),
+        "cpu_baseline": base,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -224,6 +283,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from soapnuke_b200 import build
+    from soapnuke_b200 import dist as snkdist
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -234,7 +294,10 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    build.build_engine()
+    if rank == 0:
+        build.build_all()
+    if world > 1:
+        dist.barrier()
     lib = abi.load_engine()
 
     pairs = args.pairs
@@ -249,7 +312,7 @@ def run_ours(args):
 
     host = make_host_batch(pairs, seed=1002 + rank)
     stride = host["stride"]
-    # pinned host copies (e2e leg) and device-resident copies (value leg)
+    # pinned host copies (e2e_soa leg) and device-resident copies (value leg)
     pin = {}
     devt = {}
     for k in ("seq1", "qual1", "seq2", "qual2", "len1", "len2"):
@@ -265,10 +328,17 @@ def run_ours(args):
     db2 = abi.Batch(devt["seq2"].data_ptr(), devt["qual2"].data_ptr(), devt["len2"].data_ptr(), pairs, stride)
     stream = torch.cuda.current_stream()
     sptr = C.c_void_p(stream.cuda_stream)
+    table = torch.empty(params.n_slots * abi.SLOT_WORDS, dtype=torch.int64, device=dev)
 
     def step_resident(i):
         check(lib.snk_filter_pe_device(h, C.byref(db1), C.byref(db2), out_dev[0].data_ptr(), out_dev[1].data_ptr(),
                                        C.c_uint64(i * pairs), sptr))
+
+    def reduce_table():
+        """The single collective of the path: the final statistics table (SUM; LAST_KEY words MAX)."""
+        check(lib.snk_engine_stats_to_device(h, table.data_ptr(), sptr))
+        if world > 1:
+            snkdist.allreduce_stats(table, params.n_slots)
 
     def barrier():
         if world > 1:
@@ -282,9 +352,10 @@ def run_ours(args):
             return float(t.item())
         return x
 
-    # ---- value leg: device-resident batches, CUDA events on the launching stream
+    # ---- value leg: device-resident batches + the final collective, CUDA events on the launching stream
     for i in range(args.warmup):
         step_resident(i)
+    reduce_table()                      # warm-up of the collective (NCCL channel setup is not part of a step)
     barrier()
     launches0 = lib.snk_engine_launch_count(h)
     sampler = ClockSampler(local_rank)
@@ -292,25 +363,70 @@ def run_ours(args):
         sampler.start()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
+    evk = torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for i in range(args.steps):
         step_resident(args.warmup + i)
+    evk.record(stream)
+    reduce_table()
     ev1.record(stream)
-    # the single collective of the path: the final statistics table (sum; LAST_KEY words are max-reduced on host)
-    if world > 1:
-        from soapnuke_b200 import dist as snkdist
-        st = torch.empty(params.n_slots * abi.SLOT_WORDS, dtype=torch.int64, device=dev)
-        check(lib.snk_engine_stats_to_device(h, st.data_ptr(), sptr))
-        snkdist.allreduce_stats(st, params.n_slots)
     barrier()
-    kernel_ms = ev0.elapsed_time(ev1)
+    total_ms = ev0.elapsed_time(ev1)
+    kernel_ms = ev0.elapsed_time(evk)
+    collective_us = 1e3 * evk.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     launches = lib.snk_engine_launch_count(h) - launches0
+    total_ms = max_over_ranks(total_ms)
     kernel_ms = max_over_ranks(kernel_ms)
+    collective_us = max_over_ranks(collective_us)
     reads_per_step = 2 * pairs * world
-    value = reads_per_step * args.steps / (kernel_ms * 1e-3) / 1e6
+    value = reads_per_step * args.steps / (total_ms * 1e-3) / 1e6
 
-    # ---- e2e leg: pinned host buffers through the async host API, 3 lanes, sub-batches
+    # ---- stats_parity leg (untimed): bounded slice per rank through the engine, all-reduced, vs the oracle on rank 0
+    npar = min(PARITY_PAIRS, pairs)
+    check(lib.snk_engine_stats_reset(h))
+    pb1 = abi.Batch(devt["seq1"].data_ptr(), devt["qual1"].data_ptr(), devt["len1"].data_ptr(), npar, stride)
+    pb2 = abi.Batch(devt["seq2"].data_ptr(), devt["qual2"].data_ptr(), devt["len2"].data_ptr(), npar, stride)
+    check(lib.snk_filter_pe_device(h, C.byref(pb1), C.byref(pb2), out_dev[0].data_ptr(), out_dev[1].data_ptr(), C.c_uint64(rank * npar), sptr))
+    reduce_table()
+    torch.cuda.synchronize()
+    gathered = {}
+    for k in ("seq1", "qual1", "seq2", "qual2", "len1", "len2"):
+        mine = devt[k][:npar].contiguous()
+        if world > 1:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            gathered[k] = torch.cat(parts).cpu().numpy()
+        else:
+            gathered[k] = mine.cpu().numpy()
+    res_par = [out_dev[m][:npar].cpu().numpy().view(abi.RESULT_DTYPE).copy() for m in range(2)]
+    stats_parity = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as orc
+        dd = {k: (v.view(np.uint16) if k.startswith("len") else v) for k, v in gathered.items()}
+        dd["n"] = npar * world; dd["stride"] = stride
+        o1, o2, ost, oerr = orc.filter_pe(params, dd)
+        got = table.cpu().numpy().view(np.uint64)
+        stats_parity = bool(oerr == 0 and np.array_equal(got, ost) and np.array_equal(res_par[0], o1[:npar]) and np.array_equal(res_par[1], o2[:npar]))
+        if not stats_parity:
+            raise SystemExit("stats_parity FAILED: the all-reduced statistics table differs from the oracle's")
+    check(lib.snk_engine_stats_reset(h))
+
+    # ---- pinned host->device copy bandwidth of this box with all ranks copying at once (ceiling of e2e_soa)
+    probe = torch.empty(1 << 29, dtype=torch.uint8).pin_memory()
+    probe_dev = torch.empty(1 << 29, dtype=torch.uint8, device=dev)
+    probe_dev.copy_(probe, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        probe_dev.copy_(probe, non_blocking=True)
+    torch.cuda.synchronize()
+    h2d_s = max_over_ranks(time.perf_counter() - t0)
+    h2d_gbs = world * 4 * probe.numel() / h2d_s / 1e9
+    del probe, probe_dev
+
+    # ---- e2e_soa leg: pinned host buffers through the async host API, 3 lanes, sub-batches
     nl = lib.snk_engine_lanes(h)
     sub = args.sub_pairs
     chunks = [(a, min(pairs, a + sub)) for a in range(0, pairs, sub)]
@@ -336,9 +452,13 @@ def run_ours(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     if world > 1:
         dist.barrier()
-    e2e_value = reads_per_step * args.steps / e2e_s / 1e6
+    soa_value = reads_per_step * args.steps / e2e_s / 1e6
     h2d = sum(pin[k].numel() * pin[k].element_size() for k in pin)
     d2h = sum(t.numel() * t.element_size() for t in out_pin)
+    step_resident(args.warmup + args.steps)       # same data, resident: the two entry points must agree
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out_dev[0].cpu(), out_pin[0]) and torch.equal(out_dev[1].cpu(), out_pin[1]))
+    kept = int((out_pin[0].numpy().view(abi.RESULT_DTYPE)["category"] == 0).sum())
 
     # ---- e2e_text leg: raw FASTQ text in pinned host memory -> clean FASTQ text in pinned host memory
     # (line index, row packing, filter, record formatting all on the device)
@@ -381,28 +501,113 @@ def run_ours(args):
             while fifo:
                 finish(fifo.pop(0))
 
+        tsteps = max(1, min(args.steps, 5))
         for i in range(e2e_warm):
             text_step(i)
         barrier()
         t0 = time.perf_counter()
-        for i in range(args.steps):
+        for i in range(tsteps):
             text_step(i)
         torch.cuda.synchronize()
         text_s = max_over_ranks(time.perf_counter() - t0)
         if world > 1:
             dist.barrier()
-        text_info = {"value": 2 * tsub * nchunks * world * args.steps / text_s / 1e6, "unit": UNIT,
+        text_info = {"value": 2 * tsub * nchunks * world * tsteps / text_s / 1e6, "unit": UNIT,
                      "h2d_bytes_per_step": int(nchunks * (tin[0].numel() + tin[1].numel())), "d2h_bytes_per_step": int(nchunks * moved[1]),
-                     "sub_batch_pairs": tsub, "lanes": nl,
+                     "sub_batch_pairs": tsub, "lanes": nl, "steps": tsteps,
                      "what": "raw FASTQ text (pinned host) -> clean FASTQ text (pinned host) through snk_filter_pe_text_async"}
 
     flags = C.c_uint32(0); bad = C.c_uint64(0)
     check(lib.snk_engine_error_flags(h, C.byref(flags), C.byref(bad)))
     if flags.value:
         raise SystemExit(f"engine raised error flags {flags.value} at read {bad.value}")
-    # sanity: the resident results of the last step equal the e2e results of the same data
-    same = bool(torch.equal(out_dev[0].cpu(), out_pin[0]) and torch.equal(out_dev[1].cpu(), out_pin[1]))
-    kept = int((out_pin[0].numpy().view(abi.RESULT_DTYPE)["category"] == 0).sum())
+    lib.snk_engine_destroy(h)
+    del devt, out_dev, pin, out_pin, table
+    torch.cuda.empty_cache()
+
+    soa_info = {"value": soa_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "sub_batch_pairs": sub, "lanes": nl, "results_match_resident": same,
+                "h2d_probe": {"aggregate_gbs": h2d_gbs, "what": "pinned cudaMemcpyAsync host->device, all ranks at once, 2 GiB per rank",
+                              "ceiling_mreads_s": h2d_gbs * 1e9 / (h2d / (2.0 * pairs)) / 1e6,
+                              "frac_of_ceiling": soa_value / (h2d_gbs * 1e9 / (h2d / (2.0 * pairs)) / 1e6)}}
+    # ---- e2e leg, file to file: the drop-in CLI, one process per GPU, on the files the reference arm reads
+    fpairs = args.file_pairs or pairs
+    file_bytes = 2 * fpairs * (2 * L + 25)
+    work = None
+    if rank == 0 and not args.no_file:
+        work = work_dir(file_bytes * (1 + world) + (2 << 30))
+        in_bytes = write_workload_files(work, fpairs)
+    if world > 1:
+        box = [work]
+        dist.broadcast_object_list(box, src=0)
+        work = box[0]
+    env = dict(os.environ)
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = visible.split(",")[local_rank] if visible else str(local_rank)
+    env["SNK_GPUS"] = "1"
+    out_mine = f"{work}/out_r{rank}"
+    cores = os.cpu_count() or 1
+    threads = max(2, cores // world)
+    cli_cmd = [CLI, "filter"] + file_args(work, out_mine) + ["-T", str(min(threads, 16))] + CFG2_FLAGS
+    file_info = None
+    cpu_baseline = None
+    try:
+        if args.no_file:
+            raise StopIteration
+        fwarm = max(1, min(args.warmup, 2))
+        for _ in range(fwarm):
+            run_timed(cli_cmd, env)
+        barrier()
+        t0 = time.perf_counter()
+        runs = [run_timed(cli_cmd, env) for _ in range(args.steps)]
+        file_s = max_over_ranks(time.perf_counter() - t0)
+        if world > 1:
+            dist.barrier()
+        file_value = 2.0 * fpairs * world * args.steps / file_s / 1e6
+        out_bytes = os.path.getsize(f"{out_mine}/c1.fq") + os.path.getsize(f"{out_mine}/c2.fq")
+        stage_line = ""
+        try:
+            for ln in open(f"{out_mine}/log") if os.path.exists(f"{out_mine}/log") else []:
+                if "stage seconds" in ln:
+                    stage_line = ln.strip()
+        except Exception:
+            pass
+        if rank == 0:
+            file_info = {"value": file_value, "unit": UNIT, "h2d_bytes_per_step": int(in_bytes), "d2h_bytes_per_step": int(out_bytes),
+                         "what": "soapnuke_b200/bin/SOAPnuke filter, plain FASTQ files on /dev/shm -> clean FASTQ + reports, one process per GPU, "
+                                 "wall clock per run (process start and CUDA context included)",
+                         "pairs_per_run": fpairs, "wall_s_per_run": float(np.mean([r["wall"] for r in runs])),
+                         "cpu_s_per_run": float(np.mean([r["cpu"] for r in runs])), "host_threads": min(threads, 16),
+                         "outputs_match_reference": None, "cli_stage_log": stage_line}
+            if world == 1 and not args.no_cpu_baseline:
+                try:
+                    if have_reference():
+                        rr = reference_runs(work, f"{work}/out_ref", 1, cores)
+                        v = 2.0 * fpairs / rr[0]["wall"] / 1e6
+                        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": describe_reference(fpairs, cores, rr),
+                                        "wall_s_per_run": rr[0]["wall"], "cpu_s_per_run": rr[0]["cpu"], "poll_quanta_per_run": rr[0]["wall"] / 5.0}
+                        same_files = all(filecmp.cmp(f"{work}/out_ref/c{m}.fq", f"{out_mine}/c{m}.fq", shallow=False) for m in (1, 2))
+                        import glob
+                        reports = sorted(glob.glob(f"{work}/out_ref/*.txt"))
+                        same_reports = len(reports) == 10 and all(filecmp.cmp(f, f"{out_mine}/{os.path.basename(f)}", shallow=False) for f in reports)
+                        file_info["outputs_match_reference"] = bool(same_files and same_reports)
+                        if not (same_files and same_reports):
+                            raise SystemExit("e2e FAILED: CLI outputs differ from the reference binary's on the bench files")
+                    else:
+                        v, n = time_oracle_port(fpairs, 1, 0)
+                        cpu_baseline = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"oracle C restatement, 1 thread, {n} synthetic PE150 pairs already parsed in memory"}
+                except SystemExit:
+                    raise
+                except Exception as ex:           # keep the GPU line even if the CPU leg fails
+                    cpu_baseline = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"failed: {ex}"}
+    except StopIteration:
+        file_info = dict(soa_info, what="pinned SoA leg (--no-file)")
+    finally:
+        if world > 1:
+            dist.barrier()
+        if rank == 0 and work:
+            shutil.rmtree(work, ignore_errors=True)
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -415,30 +620,26 @@ def run_ours(args):
             traffic = tr["bytes_per_read"] * 2 * pairs
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "BASELINE configs[1]: PE 2x150bp, adapter trim + all quality filters (config-2 flags), 1xB200 shape per GPU",
-                       "pairs_per_step_per_gpu": pairs, "read_len": L, "stride": stride,
-                       "l2": "inputs larger than L2 (%.2f GB per step per GPU)" % (4 * pairs * stride / 1e9),
-                       "slots": params.n_slots, "slot_block": params.slot_block},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "sub_batch_pairs": sub, "lanes": nl, "results_match_resident": same},
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic", "config": workload_config(pairs),
+            "e2e": file_info,
+            "e2e_soa": soa_info,
             "e2e_text": text_info,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_read": 2 * L + 8,
-                         "kernel": "snkcore::filter_kernel<10,2>", "launch_ms": launch_ms},
+                         "kernel": "snkcore::filter_kernel (PE150 instantiation)", "launch_ms": launch_ms},
+            "collective": {"what": "NCCL all-reduce of the statistics table (SUM + tiny MAX), once per run, inside the timed region",
+                           "us": collective_us, "bytes": int(params.n_slots * abi.SLOT_WORDS * 8), "ranks": world},
+            "stats_parity": stats_parity,
+            "stats_parity_what": f"{npar} pairs per rank through the engine, all-reduced table + rank 0's records == oracle over all ranks' slices",
+            "engine": {"slots": params.n_slots, "slot_block": params.slot_block, "stride": stride},
             "kept_pairs_last_step": kept,
         }
-        if world == 1 and not args.no_cpu_baseline:
-            try:
-                v, cores, times, kind, sample = time_reference(args.ref_pairs, 1, 0)
-                line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
-            except Exception as ex:           # keep the GPU line even if the CPU leg fails
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
-    lib.snk_engine_destroy(h)
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,11 +651,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1 << 22, help="read pairs per step per GPU")
-    ap.add_argument("--sub-pairs", type=int, default=1 << 19, help="pairs per host sub-batch in the e2e leg")
-    ap.add_argument("--ref-pairs", type=int, default=4000000,
-                    help="pairs in the CPU reference sample (8 M reads: the reference's 5 s concat poll quantum stays a small part)")
+    ap.add_argument("--sub-pairs", type=int, default=1 << 19, help="pairs per host sub-batch in the e2e_soa / e2e_text legs")
+    ap.add_argument("--file-pairs", type=int, default=0, help="pairs in the FASTQ files of the e2e leg (default: --pairs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-text", action="store_true", help="skip the FASTQ-text end-to-end leg")
+    ap.add_argument("--no-file", action="store_true", help="skip the file-to-file CLI leg (profiling runs): `e2e` is then the pinned-SoA leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
