@@ -393,10 +393,11 @@ def run_ours(args):
     gathered = {}
     for k in ("seq1", "qual1", "seq2", "qual2", "len1", "len2"):
         mine = devt[k][:npar].contiguous()
-        if world > 1:
-            parts = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(parts, mine)
-            gathered[k] = torch.cat(parts).cpu().numpy()
+        if world > 1:                                   # NCCL has no int16: gather the bytes
+            mb = mine.view(torch.uint8)
+            parts = [torch.empty_like(mb) for _ in range(world)]
+            dist.all_gather(parts, mb)
+            gathered[k] = torch.cat([q.view(mine.dtype) for q in parts]).cpu().numpy()
         else:
             gathered[k] = mine.cpu().numpy()
     res_par = [out_dev[m][:npar].cpu().numpy().view(abi.RESULT_DTYPE).copy() for m in range(2)]
