@@ -13,6 +13,7 @@
 #include <vector>
 #include <mutex>
 #include "filter_kernel.cuh"
+#include "ws_kernel.cuh"
 #include "text_kernels.cuh"
 #include "dev_params.h"
 #include "../host/host_common.h"
@@ -72,6 +73,8 @@ struct snk_engine {
     GContamDev* d_gcontams = nullptr;        // [SNK_MAX_CONTAMS] when global contaminants are configured
     Lane lanes[kLanes];
     uint64_t launches = 0;
+    int kernel_choice = 0;                   // 0 = warp-specialised kernel where its shape fits, 1 = filter_kernel always (SNK_KERNEL=v1)
+    uint32_t ws_wpg = 0;                     // SNK_WS_WPG: force the scan group size (tuning)
     std::mutex mu;
     // per engine (= per device) launch cache, keyed by kernel instantiation: cudaFuncSetAttribute and the
     // occupancy query are per device, so they must not be remembered in function-local statics
@@ -104,6 +107,35 @@ int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const L
     CUDA_TRY(cudaGetLastError());
     e->launches++;
     return 0;
+}
+
+// ---- warp-specialised kernel (ws_kernel.cuh): one CTA per SM, rows up to kWsMaxStride bytes
+template <int MAXC, int MATES>
+int launch_ws_one(snk_engine* e, const DevParams& dp, const WsArgs& wa, cudaStream_t stream)
+{
+    auto kern = filter_ws_kernel<MAXC, MATES>;
+    snk_engine::KernelCache* kc = nullptr;
+    for (auto& c : e->kcache) if (c.fn == (const void*)kern) kc = &c;
+    if (!kc) { e->kcache.push_back({(const void*)kern, 0, 0, 1, false}); kc = &e->kcache.back(); }
+    if (!kc->smem_opt_in) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit));
+        kc->smem_opt_in = true;
+    }
+    const uint32_t nt = wa.k.tm.ntiles;
+    const int grid = (int)(nt < (uint32_t)e->num_sms ? (nt ? nt : 1) : (uint32_t)e->num_sms);
+    kern<<<grid, kWsThreads, wa.s.total, stream>>>(dp, wa);
+    CUDA_TRY(cudaGetLastError());
+    e->launches++;
+    return 0;
+}
+template <int MATES>
+int launch_ws(snk_engine* e, const DevParams& dp, const WsArgs& wa, cudaStream_t stream)
+{
+    const uint32_t chunks = wa.k.stride / 16;
+    if (chunks <= 4) return launch_ws_one<4, MATES>(e, dp, wa, stream);
+    if (chunks <= 7) return launch_ws_one<7, MATES>(e, dp, wa, stream);
+    if (chunks <= 10) return launch_ws_one<10, MATES>(e, dp, wa, stream);
+    return launch_ws_one<16, MATES>(e, dp, wa, stream);
 }
 
 template <int MATES>
@@ -163,7 +195,14 @@ int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch
     if (d1->n == 0) return 0;
     if ((mates == 2) != (e->params.is_pe != 0)) { snk::set_error("engine was created for the other read layout (PE/SE)"); return 1; }
     LaunchPlan lp; TileMap tm;
-    if (make_plan(e, mates, d1->stride, d1->n, first, lp, tm)) return 1;
+    WsArgs wa;
+    memset(&wa, 0, sizeof(wa));
+    const bool use_ws = e->kernel_choice == 0 &&
+        ws_make_shape(mates, d1->stride, e->dev.qb, ada_slots(e->dev.n_adapters), (uint32_t)kSmemLimit, e->ws_wpg, wa.s);
+    if (use_ws) {
+        lp.R = wa.s.R; lp.W = wa.s.W; lp.X = wa.s.X; lp.qb = wa.s.qb;
+        tm = make_tile_map(first, d1->n, wa.s.R, (uint64_t)e->params.slot_block);
+    } else if (make_plan(e, mates, d1->stride, d1->n, first, lp, tm)) return 1;
     KernelArgs ka;
     memset(&ka, 0, sizeof(ka));
     ka.seq[0] = d1->seq; ka.qual[0] = d1->qual; ka.len[0] = d1->len; ka.out[0] = o1;
@@ -178,6 +217,11 @@ int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch
     ka.stride = d1->stride; ka.R = lp.R; ka.items_w = lp.W; ka.X = lp.X; ka.tm = tm;
     DevParams dp = e->dev;
     dp.qb = lp.qb;               // may have been lowered so that this stride's histograms fit
+    if (use_ws) {
+        wa.k = ka;
+        wa.magic = stride_magic(d1->stride);
+        return (mates == 2) ? launch_ws<2>(e, dp, wa, stream) : launch_ws<1>(e, dp, wa, stream);
+    }
     return (mates == 2) ? launch_mates<2>(e, dp, ka, lp, stream) : launch_mates<1>(e, dp, ka, lp, stream);
 }
 
@@ -369,6 +413,8 @@ int snk_engine_create(const snk_params* p, int device, snk_engine** out)
     snk_engine* e = new snk_engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
+    if (const char* k = getenv("SNK_KERNEL")) e->kernel_choice = strcmp(k, "v1") == 0 ? 1 : 0;
+    if (const char* w = getenv("SNK_WS_WPG")) e->ws_wpg = (uint32_t)atoi(w);
     e->params = *p;
     prepare_params(*p, e->dev);
     if (p->n_contams[0] > 0 || p->n_contams[1] > 0) {

@@ -11,6 +11,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "filter_core.cuh"
+#include "ws_core.cuh"
 
 namespace snkcore {
 
@@ -152,9 +153,12 @@ __device__ __forceinline__ void shfl_scan(ScanPart<NW>& d, const ScanPart<NW>& s
 // phase A for one read, executed by the kNT adjacent lanes of its group (h = lane's index in the group)
 // ada0 = shared-memory AdaHot array of the mate's adapters (the compiler re-derives the parameter-space
 // address of a dynamically indexed adapter at every use; a shared copy costs one pointer register)
+// ind != nullptr (warp-specialised kernel): the read's indicator planes are stored for the base-count items
+// (record r of the tile; ws_core.cuh)
 template <int MAXC, int MATES>
 __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int len, int nchunks, int mate, const DevParams& P,
-                                               const AdaHot* ada0, int h, unsigned pm, ReadInfo& R)
+                                               const AdaHot* ada0, int h, unsigned pm, ReadInfo& R, uint32_t* ind = nullptr,
+                                               uint32_t r = 0, int nwd = 0, uint32_t rp = 0)
 {
     static_assert(kNT == 2, "lane exchange below is written for pairs");
     constexpr int NW = (MAXC + 1) / 2;
@@ -162,6 +166,7 @@ __device__ __forceinline__ void scan_read_coop(uint8_t* seq, uint8_t* qual, int 
     scan_chunks<MAXC>(seq, qual, len, nchunks, P, h, S);
     shfl_scan<NW>(O, S, pm);
     merge_scan(S, O);
+    if (ind) store_indicators<NW>(S, len, h, ind, r, nwd, rp);
     const bool polyx = P.polyX_num != -1 && polyx_hit(S, len, P.polyX_num);
     int ada_pos = -1;
     bool has5 = false;

@@ -30,7 +30,8 @@ def load_coretest():
         d = os.path.join(ROOT, "tests", "coretest")
         so = os.path.join(d, "libcoretest.so")
         deps = [os.path.join(d, "coretest.cpp")] + [os.path.join(ROOT, "soapnuke_b200", "csrc", f)
-                                                    for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h", "text_core.cuh")]
+                                                    for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h", "text_core.cuh", "ws_core.cuh",
+                                                              "ws_kernel.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared",
                                    "-I/usr/local/cuda/include", "-o", so, deps[0]])
@@ -38,6 +39,8 @@ def load_coretest():
         lib.coretest_filter.restype = C.c_int
         lib.coretest_filter.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Batch), C.POINTER(abi.Batch), C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.c_int, C.c_int, C.c_int]
+        lib.coretest_filter_ws.restype = C.c_int
+        lib.coretest_filter_ws.argtypes = lib.coretest_filter.argtypes
         lib.coretest_text_index_pack.restype = C.c_uint32
         lib.coretest_text_index_pack.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
@@ -64,6 +67,28 @@ def core_replay(p, d, first=0, tile_r=0, grid=3, qb=-1):
         lib.coretest_filter(C.byref(p), C.byref(b1), None, r1.ctypes.data, None, st.ctypes.data, first,
                             C.byref(err), tile_r, grid, qb)
         r2 = None
+    return r1, r2, st, err.value
+
+
+def core_replay_ws(p, d, first=0, wpg=0, grid=3, qb=-1):
+    """CPU replay of the warp-specialised kernel's work units (coretest_filter_ws); None when the shape is not served."""
+    lib = load_coretest()
+    n = d["seq1"].shape[0]
+    st = np.zeros(p.n_slots * abi.SLOT_WORDS, dtype=np.uint64)
+    err = C.c_uint32(0)
+    b1 = abi.make_batch(d["seq1"], d["qual1"], d["len1"])
+    r1 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+    if p.is_pe:
+        r2 = np.zeros(n, dtype=abi.RESULT_DTYPE)
+        b2 = abi.make_batch(d["seq2"], d["qual2"], d["len2"])
+        rc = lib.coretest_filter_ws(C.byref(p), C.byref(b1), C.byref(b2), r1.ctypes.data, r2.ctypes.data, st.ctypes.data,
+                                    first, C.byref(err), wpg, grid, qb)
+    else:
+        rc = lib.coretest_filter_ws(C.byref(p), C.byref(b1), None, r1.ctypes.data, None, st.ctypes.data, first,
+                                    C.byref(err), wpg, grid, qb)
+        r2 = None
+    if rc:
+        return None
     return r1, r2, st, err.value
 
 
