@@ -224,11 +224,17 @@ SNK_HD void ws_flush_q_item(CounterT* qhist, uint32_t x, uint32_t nraw, uint32_t
 
 // ------------------------------------------------------------------ shapes shared by the kernel, its launcher and the replay
 constexpr int kWsScanWarps = 16;            // scan warps per CTA: groups of wpg warps, one tile per group at a time
-constexpr int kWsHistWarps = 5;             // histogram warps per CTA
+constexpr int kWsHistWarps = 7;             // histogram warps per CTA
 constexpr int kWsHistThreads = 32 * kWsHistWarps;
-constexpr int kWsThreads = 32 * (1 + kWsScanWarps + kWsHistWarps);
+constexpr int kWsThreads = 32 * (kWsScanWarps + kWsHistWarps + 1);   // 24 warps = 6 warpgroups; the last warp is the producer
 constexpr int kWsJ = 4;                     // positions per quality item
-constexpr int kWsMaxRegs = 88;              // 22 warps x 32 lanes x 88 registers = 61 952 of the 65 536 per SM
+// Registers: a scheduler (SM sub-partition) owns 16 384 registers and gets every fourth warp, i.e. 4 scan warps and 2
+// histogram / producer warps. The kernel is launched with 80 registers per thread (6 warps x 32 x 80 = 15 360); the scan
+// warpgroups then raise their share to kWsScanRegs and the other two lower theirs to kWsHistRegs with setmaxnreg
+// (4 x 96 + 2 x 64 = 512 registers per lane slot = all 16 384).
+constexpr int kWsMaxRegs = 80;
+constexpr int kWsScanRegs = 96;
+constexpr int kWsHistRegs = 64;
 constexpr uint32_t kWsMaxStride = 256;      // longer rows stay on filter_kernel
 
 struct WsShape {

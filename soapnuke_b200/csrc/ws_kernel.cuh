@@ -2,7 +2,7 @@
 //
 // One persistent CTA per SM, kWsThreads threads, three roles that never meet at a CTA-wide barrier:
 //
-//   producer   1 thread        walks the CTA's tiles in order; per tile 2*MATES bulk copies (TMA, cp.async.bulk) of
+//   producer   1 thread        (last warp) walks the CTA's tiles in order; per tile 2*MATES bulk copies (TMA, cp.async.bulk) of
 //                              the tile's contiguous seq / qual rows into the next free stage; completion on full[s]
 //   scan       16 warps        groups of `wpg` warps take tiles round robin (tile lt -> group lt % ngroups). A warp
 //                              owns 8 pairs (16 reads) of its group's tile: two adjacent lanes per read run phase A
@@ -10,7 +10,7 @@
 //                              the same warp, so the discard cascade, the 8-byte result records, the filter
 //                              counters, the trim tables and the tile's delta list (phase P) need nothing but warp
 //                              shuffles. The warp also stores each read's five indicator planes. -> scanned[s]
-//   histogram  5 warps         every thread owns whole work items for the launch: a q-item (mate, 4 positions) counts
+//   histogram  7 warps         every thread owns whole work items for the launch: a q-item (mate, 4 positions) counts
 //                              the quality x position cells in shared memory (owner computes, no atomics), a b-item
 //                              (mate, plane word, symbol) adds indicator words into vertical counters (ws_core.cuh);
 //                              raw walk over the tile's rows, then the delta list; items are flushed by their owner
@@ -344,7 +344,13 @@ __global__ void __maxnreg__(kWsMaxRegs) filter_ws_kernel(const __grid_constant__
     const uint32_t t_end = (uint32_t)((uint64_t)nt * (blockIdx.x + 1) / gridDim.x);
     const uint32_t nloc = t_end - t_begin;
 
-    if (warp == 0) {
+    if (warp < kWsScanWarps) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsScanRegs));
+        ws_scan_role<MAXC, MATES>(P, W, smem, bar_full, bar_scanned, t_begin, nloc, warp, lane);
+        return;
+    }
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsHistRegs));
+    if (warp == kWsScanWarps + kWsHistWarps) {
         // ---- producer: one thread keeps the TMA engine fed, one stage per tile
         if (lane != 0) return;
         for (uint32_t lt = 0; lt < nloc; lt++) {
@@ -365,10 +371,8 @@ __global__ void __maxnreg__(kWsMaxRegs) filter_ws_kernel(const __grid_constant__
                 bulk_g2s(st.rows[m][1], A.qual[m] + (size_t)start * A.stride, row_bytes, &bar_full[s]);
             }
         }
-    } else if (warp <= kWsScanWarps) {
-        ws_scan_role<MAXC, MATES>(P, W, smem, bar_full, bar_scanned, t_begin, nloc, warp - 1, lane);
     } else {
-        ws_hist_role<MATES>(P, W, smem, bar_scanned, bar_empty, t_begin, nloc, tid - 32 * (1 + kWsScanWarps), lane);
+        ws_hist_role<MATES>(P, W, smem, bar_scanned, bar_empty, t_begin, nloc, tid - 32 * kWsScanWarps, lane);
     }
 }
 

@@ -4,7 +4,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SRCS = [os.path.join(HERE, f) for f in ("main.cpp", "cli_params.cpp", "process.cpp")]
+SRCS = [os.path.join(HERE, f) for f in ("main.cpp", "cli_params.cpp", "process.cpp", "gz_members.cpp")]
 import glob
 DEPS = SRCS + glob.glob(os.path.join(HERE, "*.h")) + glob.glob(os.path.join(PKG, "csrc", "*.cuh")) + \
     glob.glob(os.path.join(os.path.dirname(PKG), "include", "*.h")) + [os.path.abspath(__file__)]

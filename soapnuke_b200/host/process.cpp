@@ -9,6 +9,7 @@
 //   gzip level 2 members                  peprocess.cpp:1803-1810
 #include "process.h"
 #include "host_common.h"
+#include "gz_members.h"
 #include "../csrc/text_core.cuh"      // id_transform (host-compilable header; the record formatting of the trim files)
 #include <zlib.h>
 #include <sys/stat.h>
@@ -94,8 +95,11 @@ private:
 // ------------------------------------------------------------------ raw byte source (plain via read(2), .gz via zlib)
 class ByteSource {
 public:
-    ByteSource(const std::string& path, bool gz) : path_(path), gz_(gz)
+    // gz_threads > 0: multi-member .gz files are inflated member by member on that many host threads (gz_members.h)
+    ByteSource(const std::string& path, bool gz, int gz_threads = 0) : path_(path), gz_(gz)
     {
+        if (gz_ && gz_threads > 0 && !getenv("SNK_GZ_SERIAL")) members_.reset(GzMemberReader::open(path, gz_threads));
+        if (members_) return;
         if (gz_) {
             f_ = gzopen(path.c_str(), "rb");
             if (!f_) die("cannot open the file," + path);
@@ -111,6 +115,11 @@ public:
     // copy out of the page cache is what limits a single reader)
     size_t read(char* dst, size_t n)
     {
+        if (members_) {
+            const size_t got = members_->read(dst, n);
+            if (got == GzMemberReader::kError) die("cannot read the file," + path_);
+            return got;
+        }
         if (gz_) {
             int got = gzread(f_, dst, (unsigned)std::min<size_t>(n, 1u << 30));
             if (got < 0) die("cannot read the file," + path_);
@@ -155,7 +164,10 @@ public:
     // bytes carried over from the previous batch (text after its last complete record)
     std::vector<char> carry;
     bool eof = false;
+    bool parallel_gz() const { return (bool)members_; }
+    GzMemberReader::Counters gz_counters() const { return members_ ? members_->counters() : GzMemberReader::Counters(); }
 private:
+    std::unique_ptr<GzMemberReader> members_;
     std::string path_;
     bool gz_;
     gzFile f_ = nullptr;
@@ -417,8 +429,10 @@ void FilterRun::ingest()
     }
     if (!stride_) stride_ = 160;
     fmt_.strip = hp_.input_gz ? strip_gz_ : 1;                     // plain: erase(size()-1) (peprocess.cpp:2206)
-    ByteSource r1(hp_.fq1_path, hp_.input_gz);
-    ByteSource* r2 = pe_ ? new ByteSource(hp_.fq2_path, hp_.input_gz) : nullptr;
+    // .gz input: the host threads (-T) are shared by the mates' member decoders
+    const int gz_threads = hp_.input_gz ? std::max(1, hp_.threads / mates_) : 0;
+    ByteSource r1(hp_.fq1_path, hp_.input_gz, gz_threads);
+    ByteSource* r2 = pe_ ? new ByteSource(hp_.fq2_path, hp_.input_gz, gz_threads) : nullptr;
     uint64_t seq_no = 0, first = 0;
     const size_t lanes = (size_t)snk_engine_lanes(engines_[0]);
     for (;;) {
@@ -445,6 +459,11 @@ void FilterRun::ingest()
     }
     total_reads_ = first;
     n_batches_total_ = seq_no;
+    if (r1.parallel_gz()) {
+        const GzMemberReader::Counters c1 = r1.gz_counters(), c2 = r2 ? r2->gz_counters() : GzMemberReader::Counters();
+        log_line("gzip input: " + std::to_string(c1.members + c2.members) + " members inflated on " + std::to_string(gz_threads * mates_) +
+                 " host threads, " + std::to_string(c1.cancelled + c2.cancelled) + " false member candidates dropped");
+    }
     delete r2;
     gpu_q_.close();
 }
