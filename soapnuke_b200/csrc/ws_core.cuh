@@ -229,12 +229,14 @@ constexpr int kWsHistThreads = 32 * kWsHistWarps;
 constexpr int kWsThreads = 32 * (kWsScanWarps + kWsHistWarps + 1);   // 24 warps = 6 warpgroups; the last warp is the producer
 constexpr int kWsJ = 4;                     // positions per quality item
 // Registers: a scheduler (SM sub-partition) owns 16 384 registers and gets every fourth warp, i.e. 4 scan warps and 2
-// histogram / producer warps. The kernel is launched with 80 registers per thread (6 warps x 32 x 80 = 15 360); the scan
-// warpgroups then raise their share to kWsScanRegs and the other two lower theirs to kWsHistRegs with setmaxnreg
-// (4 x 96 + 2 x 64 = 512 registers per lane slot = all 16 384).
+// histogram / producer warps. The kernel is launched with 80 registers per thread (6 warps x 32 x 80 = 15 360); the two
+// histogram / producer warpgroups then lower their share to kWsHistRegs and the four scan warpgroups raise theirs to
+// kWsScanRegs with setmaxnreg. Only registers the CTA was launched with can be handed around (the scheduler's 1 024
+// unallocated ones are not in the CTA's pool: asking for more blocks forever), so 4 x 88 + 2 x 64 = 6 x 80.
 constexpr int kWsMaxRegs = 80;
-constexpr int kWsScanRegs = 96;
+constexpr int kWsScanRegs = 88;
 constexpr int kWsHistRegs = 64;
+static_assert(4 * kWsScanRegs + 2 * kWsHistRegs <= 6 * kWsMaxRegs, "setmaxnreg can only redistribute the launch allocation");
 constexpr uint32_t kWsMaxStride = 256;      // longer rows stay on filter_kernel
 
 struct WsShape {

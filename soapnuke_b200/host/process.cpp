@@ -92,6 +92,8 @@ private:
     bool closed_ = false;
 };
 
+size_t count_newlines(const char* p, size_t n);
+
 // ------------------------------------------------------------------ raw byte source (plain via read(2), .gz via zlib)
 class ByteSource {
 public:
@@ -111,10 +113,13 @@ public:
         }
     }
     ~ByteSource() { if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
-    // up to n bytes into dst; 0 at EOF. Plain files: large requests are split over a few threads (the
-    // copy out of the page cache is what limits a single reader)
-    size_t read(char* dst, size_t n)
+    // up to n bytes into dst; 0 at EOF. Plain files: large requests are split over a few threads (the copy out of the
+    // page cache is what limits a single reader); with `parts` every thread also counts the newlines of its share, so
+    // that the caller's search for a record boundary only has to look into one share.
+    struct Part { size_t off, len, newlines; };
+    size_t read(char* dst, size_t n, std::vector<Part>* parts = nullptr)
     {
+        if (parts) parts->clear();
         if (members_) {
             const size_t got = members_->read(dst, n);
             if (got == GzMemberReader::kError) die("cannot read the file," + path_);
@@ -140,27 +145,32 @@ public:
             }
             return done;
         };
-        constexpr int kParts = 4;
         size_t total = 0;
         if (n < (4u << 20)) total = pread_all(dst, n, off_);
         else {
-            const size_t part = (n / kParts + 4095) & ~(size_t)4095;
-            size_t got[kParts] = {0};
-            std::thread th[kParts];
-            for (int i = 1; i < kParts; i++) {
+            const int np = (int)std::min<size_t>((size_t)read_threads_, n >> 20);
+            const size_t part = (n / np + 4095) & ~(size_t)4095;
+            std::vector<size_t> got(np, 0), nl(np, 0);
+            std::vector<std::thread> th(np);
+            auto work = [&](int i) {
                 const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
-                th[i] = std::thread([&, i, lo, hi] { got[i] = pread_all(dst + lo, hi - lo, off_ + (off_t)lo); });
-            }
-            got[0] = pread_all(dst, std::min(n, part), off_);
-            for (int i = 1; i < kParts; i++) th[i].join();
-            for (int i = 0; i < kParts; i++) {
+                got[i] = pread_all(dst + lo, hi - lo, off_ + (off_t)lo);
+                if (parts) nl[i] = count_newlines(dst + lo, got[i]);
+            };
+            for (int i = 1; i < np; i++) th[i] = std::thread(work, i);
+            work(0);
+            for (int i = 1; i < np; i++) th[i].join();
+            for (int i = 0; i < np; i++) {
+                const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
+                if (parts && got[i]) parts->push_back({lo, got[i], nl[i]});
                 total += got[i];
-                if (got[i] < std::min(n, part * (i + 1)) - std::min(n, part * i)) break;      // end of file inside this part
+                if (got[i] < hi - lo) break;      // end of file inside this part
             }
         }
         off_ += (off_t)total;
         return total;
     }
+    void set_read_threads(int n) { read_threads_ = std::max(1, n); }
     // bytes carried over from the previous batch (text after its last complete record)
     std::vector<char> carry;
     bool eof = false;
@@ -174,6 +184,7 @@ private:
     int fd_ = -1;
     off_t off_ = 0;
     bool seekable_ = true;
+    int read_threads_ = 4;
 };
 
 // ------------------------------------------------------------------ newline search
@@ -202,6 +213,27 @@ __attribute__((target("avx2"))) size_t nth_newline_avx2(const char* p, size_t n,
     return n;
 }
 #endif
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) size_t count_newlines_avx2(const char* p, size_t n)
+{
+    size_t i = 0, c = 0;
+    const __m256i nl = _mm256_set1_epi8('\n');
+    for (; i + 32 <= n; i += 32)
+        c += (size_t)__builtin_popcount((uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_loadu_si256((const __m256i*)(p + i)), nl)));
+    for (; i < n; i++) c += p[i] == '\n';
+    return c;
+}
+#endif
+size_t count_newlines(const char* p, size_t n)
+{
+#if defined(__x86_64__)
+    static const bool has_avx2 = __builtin_cpu_supports("avx2");
+    if (has_avx2) return count_newlines_avx2(p, n);
+#endif
+    size_t c = 0;
+    for (size_t i = 0; i < n; i++) c += p[i] == '\n';
+    return c;
+}
 size_t nth_newline(const char* p, size_t n, size_t need, size_t* count)
 {
     if (need == 0) { *count = 0; return 0; }
@@ -325,6 +357,7 @@ size_t FilterRun::fill_mate(ByteSource& src, HostBatch& b, int mate, size_t max_
     src.carry.clear();
     size_t scanned = 0, lines = 0, end = 0;
     bool complete = false;
+    std::vector<ByteSource::Part> parts;
     for (;;) {
         if (scanned < have) {
             size_t c = 0;
@@ -338,8 +371,13 @@ size_t FilterRun::fill_mate(ByteSource& src, HostBatch& b, int mate, size_t max_
         size_t missing = (want_lines - lines) / 4 * guess + (256u << 10);
         if (missing < (1u << 20)) missing = 1u << 20;
         buf.reserve(have + missing + 64, have);
-        const size_t got = src.read(buf.p + have, missing);
+        const size_t got = src.read(buf.p + have, missing, &parts);
         if (got == 0) src.eof = true;
+        // shares whose newlines were counted by the reading threads: skip the ones that cannot hold the boundary
+        for (const ByteSource::Part& pt : parts) {
+            if (pt.off != scanned - have || lines + pt.newlines >= want_lines) break;
+            lines += pt.newlines; scanned += pt.len;
+        }
         have += got;
         if (have > 0xE0000000ull) die("batch text exceeds 3.5 GiB: lower SNK_BATCH_READS");
     }
@@ -433,6 +471,12 @@ void FilterRun::ingest()
     const int gz_threads = hp_.input_gz ? std::max(1, hp_.threads / mates_) : 0;
     ByteSource r1(hp_.fq1_path, hp_.input_gz, gz_threads);
     ByteSource* r2 = pe_ ? new ByteSource(hp_.fq2_path, hp_.input_gz, gz_threads) : nullptr;
+    {   // plain files: threads per mate that copy out of the page cache (and count newlines) in parallel
+        int rt = std::max(2, std::min(8, hp_.threads / mates_));
+        if (const char* e = getenv("SNK_READ_THREADS")) rt = std::max(1, atoi(e));
+        r1.set_read_threads(rt);
+        if (r2) r2->set_read_threads(rt);
+    }
     uint64_t seq_no = 0, first = 0;
     const size_t lanes = (size_t)snk_engine_lanes(engines_[0]);
     for (;;) {
@@ -742,7 +786,9 @@ void FilterRun::writer()
         }
     };
     std::vector<std::thread> pool;
-    for (int i = 0; i < 4; i++)
+    int nwriters = std::max(2, std::min(8, hp_.threads / 2));
+    if (const char* e = getenv("SNK_WRITE_THREADS")) nwriters = std::max(1, atoi(e));
+    for (int i = 0; i < nwriters; i++)
         pool.emplace_back([&] {
             WriteTask t;
             while (tasks.pop(t)) {
@@ -752,6 +798,7 @@ void FilterRun::writer()
                 if (t.owner && --t.owner->tasks == 0) free_q_.push(t.owner);
             }
         });
+    constexpr size_t kWriteRun = 8u << 20;
     uint64_t next = 0;
     std::vector<WriteTask> mine;
     for (;;) {
@@ -767,7 +814,11 @@ void FilterRun::writer()
         for (int f = 0; f < nfiles; f++) {
             if (f % 2 >= mates_) continue;
             for (Piece& p : (f < 2 ? b->pieces[f] : b->tpieces[f - 2])) {
-                if (p.kind == 0) { if (p.len) mine.push_back({f, p.p, p.len, pos[f], b, nullptr}); pos[f] += (off_t)p.len; }
+                if (p.kind == 0) {
+                    // large runs are written by several threads of the pool (page-cache copies again)
+                    for (size_t a = 0; a < p.len; a += kWriteRun) mine.push_back({f, p.p + a, std::min(kWriteRun, p.len - a), pos[f] + (off_t)a, b, nullptr});
+                    pos[f] += (off_t)p.len;
+                }
                 else if (p.kind == 1) { pending_deferred_[f].append(p.p, p.len); if (f == 0) deferred_records_ += p.kept; }
                 else if (!pending_deferred_[f].empty()) {
                     if (f == 0) deferred_records_ = 0;
@@ -887,7 +938,7 @@ void FilterRun::process()
     }
     {
         char buf[512];
-        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write(sum over 4 threads) %.2f, total %.2f; reads %llu",
+        snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write(sum over the writer pool) %.2f, total %.2f; reads %llu",
                  t_setup_, t_read_, t_gpu_wait_, nworkers, t_gz_us_.load() * 1e-6, t_write_us_.load() * 1e-6, now_s() - t_begin,
                  (unsigned long long)total_reads_);
         log_line(buf);
