@@ -321,6 +321,12 @@ int snk_engine_stats_from_device(snk_engine* e, const void* d_src, void* stream)
 int snk_engine_error_flags(snk_engine* e, uint32_t* flags, uint64_t* first_bad_index);
 /* number of kernel launches issued by this engine so far */
 uint64_t snk_engine_launch_count(snk_engine* e);
+/* Device time per stage of the FASTQ text path, in milliseconds, summed over every batch of every lane whose work has
+ * been synchronised (CUDA events on the lane streams). The reference only logs wall-clock lines per 5 s poll
+ * (peprocess.cpp:3039); this is the per-stage view SURVEY.md section 5 asks for. The same stages are NVTX ranges
+ * ("snk:text_submit", "snk:text_fetch", "snk:lane_sync") for timeline tools. ms has SNK_STAGE_COUNT entries. */
+enum snk_stage { SNK_STAGE_H2D = 0, SNK_STAGE_INDEX_PACK, SNK_STAGE_FILTER, SNK_STAGE_FORMAT, SNK_STAGE_D2H, SNK_STAGE_COUNT };
+int snk_engine_stage_times(snk_engine* e, double* ms);
 /* pinned host memory helpers for callers without a CUDA runtime binding */
 int snk_host_alloc(void** p, size_t bytes);
 int snk_host_free(void* p);

@@ -354,6 +354,7 @@ _PROTOS = {
     "snk_engine_stats_from_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "snk_engine_error_flags": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
     "snk_engine_launch_count": (C.c_uint64, [C.c_void_p]),
+    "snk_engine_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "snk_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "snk_host_free": (C.c_int, [C.c_void_p]),
     "snk_report_write_pe": (C.c_int, [C.POINTER(Params), C.c_void_p, C.c_char_p]),
@@ -372,7 +373,7 @@ def load_engine():
             raise RuntimeError(
                 f"{ENGINE_LIB} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(the engine has no CPU fallback)")
-        lib = C.CDLL(ENGINE_LIB)
+        lib = C.CDLL(os.environ.get("SNK_ENGINE_LIB", ENGINE_LIB))       # SNK_ENGINE_LIB: a tuning build of the same engine
         for name, (res, args) in _PROTOS.items():
             fn = getattr(lib, name)
             fn.restype = res

@@ -37,11 +37,12 @@ def _stale(target, deps):
 
 def build_engine(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    out = os.path.join(LIBDIR, "libsnk_engine.so")
+    out = os.path.join(LIBDIR, os.environ.get("SNK_ENGINE_LIB_NAME", "libsnk_engine.so"))
     if not force and not _stale(out, _engine_deps()):
         return out
     cmd = [NVCC] + ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-Wall,-Wno-unknown-pragmas",
-                           "-shared", "-cudart", "shared", "-o", out] + ENGINE_SRCS
+                           "-shared", "-cudart", "shared", "-o", out] + ENGINE_SRCS + ["-ldl"]
+    cmd += os.environ.get("SNK_CXXFLAGS", "").split()       # tuning builds, e.g. -DSNK_WS_J=2
     if verbose:
         cmd += ["-Xptxas", "-v"]
     subprocess.check_call(cmd)

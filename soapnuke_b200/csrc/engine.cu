@@ -14,6 +14,7 @@
 #include <mutex>
 #include "filter_kernel.cuh"
 #include "ws_kernel.cuh"
+#include <nvtx3/nvToolsExt.h>
 #include "text_kernels.cuh"
 #include "dev_params.h"
 #include "../host/host_common.h"
@@ -48,6 +49,11 @@ struct Lane {
     const uint8_t* d_out[2] = {nullptr, nullptr};
     const uint32_t* d_rec_off[2] = {nullptr, nullptr};
     const snk_read_result* d_res[2] = {nullptr, nullptr};
+    // per-stage device timing of the text path: events on the lane's stream around each stage of the last submission
+    // (0 start, 1 text copied in, 2 line index + row packing done, 3 filter kernel done, 4 clean text formatted) and of
+    // the last fetch (5 start, 6 copied out); folded into snk_engine::stage_ms when the lane is next synchronised
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool ev_submit = false, ev_fetch = false;
 };
 
 struct LaunchPlan {
@@ -73,8 +79,11 @@ struct snk_engine {
     GContamDev* d_gcontams = nullptr;        // [SNK_MAX_CONTAMS] when global contaminants are configured
     Lane lanes[kLanes];
     uint64_t launches = 0;
-    int kernel_choice = 0;                   // 0 = warp-specialised kernel where its shape fits, 1 = filter_kernel always (SNK_KERNEL=v1)
+    double stage_ms[SNK_STAGE_COUNT] = {0};  // device time per stage of the text path, summed over batches and lanes
+    int kernel_choice = 1;                   // 1 = filter_kernel (phase-synchronous CTAs, the production kernel), 0 = the warp-specialised
+                                             // kernel where its shape fits (SNK_KERNEL=ws; measured slower)
     uint32_t ws_wpg = 0;                     // SNK_WS_WPG: force the scan group size (tuning)
+    uint32_t ws_interleave = 1;              // SNK_WS_MAP=block: consecutive warps form a group (tuning)
     std::mutex mu;
     // per engine (= per device) launch cache, keyed by kernel instantiation: cudaFuncSetAttribute and the
     // occupancy query are per device, so they must not be remembered in function-local statics
@@ -83,6 +92,24 @@ struct snk_engine {
 };
 
 namespace {
+
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
+// the lane's stream is idle: add the event intervals of its last submission / fetch to the engine's stage clocks
+void fold_stage_times(snk_engine* e, Lane& L)
+{
+    auto ms = [&](int a, int b) { float t = 0; return cudaEventElapsedTime(&t, L.ev[a], L.ev[b]) == cudaSuccess ? (double)t : 0.0; };
+    std::lock_guard<std::mutex> g(e->mu);
+    if (L.ev_submit) {
+        e->stage_ms[SNK_STAGE_H2D] += ms(0, 1); e->stage_ms[SNK_STAGE_INDEX_PACK] += ms(1, 2);
+        e->stage_ms[SNK_STAGE_FILTER] += ms(2, 3); e->stage_ms[SNK_STAGE_FORMAT] += ms(3, 4);
+        L.ev_submit = false;
+    }
+    if (L.ev_fetch) { e->stage_ms[SNK_STAGE_D2H] += ms(5, 6); L.ev_fetch = false; }
+}
 
 template <int MAXC, int MATES, int J>
 int launch_one(snk_engine* e, const DevParams& dp, const KernelArgs& ka, const LaunchPlan& lp, cudaStream_t stream)
@@ -200,6 +227,7 @@ int launch_filter(snk_engine* e, int mates, const snk_batch* d1, const snk_batch
     const bool use_ws = e->kernel_choice == 0 &&
         ws_make_shape(mates, d1->stride, e->dev.qb, ada_slots(e->dev.n_adapters), (uint32_t)kSmemLimit, e->ws_wpg, wa.s);
     if (use_ws) {
+        wa.s.interleave = e->ws_interleave;
         lp.R = wa.s.R; lp.W = wa.s.W; lp.X = wa.s.X; lp.qb = wa.s.qb;
         tm = make_tile_map(first, d1->n, wa.s.R, (uint64_t)e->params.slot_block);
     } else if (make_plan(e, mates, d1->stride, d1->n, first, lp, tm)) return 1;
@@ -341,6 +369,9 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
     memset(&ta, 0, sizeof ta);
     snk_batch d[2];
     snk_read_result* dres[2] = {nullptr, nullptr};
+    NvtxRange nvtx_submit("snk:text_submit");
+    if (L.ev_submit || L.ev_fetch) { CUDA_TRY(cudaStreamSynchronize(L.stream)); fold_stage_times(e, L); }
+    CUDA_TRY(cudaEventRecord(L.ev[0], L.stream));
     for (int m = 0; m < mates; m++) {
         uint8_t* b = L.d_buf;
         CUDA_TRY(cudaMemcpyAsync(b + o_text[m], text[m], bytes[m], cudaMemcpyHostToDevice, L.stream));
@@ -364,6 +395,7 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
     ta.fmt.qshift = e->params.out_quality_phred - e->params.quality_phred;
     const uint32_t seg_grid = nseg[0] > nseg[1] ? nseg[0] : nseg[1];
     const dim3 gseg(seg_grid, mates), grec(nblk, mates);
+    CUDA_TRY(cudaEventRecord(L.ev[1], L.stream));
     text_meta_init_kernel<<<1, 1, 0, L.stream>>>(L.d_meta);
     newline_count_kernel<<<gseg, kSegThreads, 0, L.stream>>>(ta);
     segment_scan_kernel<<<mates, kScanThreads, 0, L.stream>>>(ta);
@@ -374,6 +406,7 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
         pack_rows_kernel<<<gpack, 256, 0, L.stream>>>(ta);
     }
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(L.ev[2], L.stream));
     {
         std::lock_guard<std::mutex> g(e->mu);
         if (launch_filter(e, mates, &d[0], mates == 2 ? &d[1] : nullptr, dres[0], dres[1], first, L.stream, &L.d_meta->flags,
@@ -381,11 +414,14 @@ int filter_text_async(snk_engine* e, int lane, int mates, const char* const text
             return 1;
         e->launches += 9;      // the text kernels around it
     }
+    CUDA_TRY(cudaEventRecord(L.ev[3], L.stream));
     out_len_kernel<<<grec, kRecThreads, 0, L.stream>>>(ta);
     block_scan_kernel<<<mates, kScanThreads, 0, L.stream>>>(ta);
     out_offset_kernel<<<grec, kRecThreads, 0, L.stream>>>(ta);
     format_kernel<<<dim3((n + 7) / 8, mates), 256, 0, L.stream>>>(ta);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(L.ev[4], L.stream));
+    L.ev_submit = true;
     CUDA_TRY(cudaMemcpyAsync(L.h_meta, L.d_meta, sizeof(TextMeta), cudaMemcpyDeviceToHost, L.stream));
     L.text_mates = mates; L.text_n = n;
     L.pending = true;
@@ -413,8 +449,9 @@ int snk_engine_create(const snk_params* p, int device, snk_engine** out)
     snk_engine* e = new snk_engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
-    if (const char* k = getenv("SNK_KERNEL")) e->kernel_choice = strcmp(k, "v1") == 0 ? 1 : 0;
+    if (const char* k = getenv("SNK_KERNEL")) e->kernel_choice = strcmp(k, "ws") == 0 ? 0 : 1;
     if (const char* w = getenv("SNK_WS_WPG")) e->ws_wpg = (uint32_t)atoi(w);
+    if (const char* w = getenv("SNK_WS_MAP")) e->ws_interleave = strcmp(w, "block") == 0 ? 0u : 1u;
     e->params = *p;
     prepare_params(*p, e->dev);
     if (p->n_contams[0] > 0 || p->n_contams[1] > 0) {
@@ -446,7 +483,10 @@ int snk_engine_create(const snk_params* p, int device, snk_engine** out)
         delete e;
         return 1;
     }
-    for (int i = 0; i < kLanes; i++) CUDA_TRY(cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking));
+    for (int i = 0; i < kLanes; i++) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&e->lanes[i].stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& ev : e->lanes[i].ev) CUDA_TRY(cudaEventCreate(&ev));
+    }
     *out = e;
     return snk_engine_stats_reset(e);
 }
@@ -457,6 +497,7 @@ int snk_engine_destroy(snk_engine* e)
     cudaSetDevice(e->device);
     for (int i = 0; i < kLanes; i++) {
         if (e->lanes[i].stream) { cudaStreamSynchronize(e->lanes[i].stream); cudaStreamDestroy(e->lanes[i].stream); }
+        for (cudaEvent_t ev : e->lanes[i].ev) if (ev) cudaEventDestroy(ev);
         if (e->lanes[i].d_buf) cudaFree(e->lanes[i].d_buf);
         if (e->lanes[i].h_meta) cudaFreeHost(e->lanes[i].h_meta);
         if (e->lanes[i].d_meta) cudaFree(e->lanes[i].d_meta);
@@ -483,8 +524,12 @@ int snk_engine_lane_sync(snk_engine* e, int lane)
 {
     if (!e || lane < 0 || lane >= kLanes) { snk::set_error("bad lane"); return 1; }
     CUDA_TRY(cudaSetDevice(e->device));
-    CUDA_TRY(cudaStreamSynchronize(e->lanes[lane].stream));
+    {
+        NvtxRange r("snk:lane_sync");
+        CUDA_TRY(cudaStreamSynchronize(e->lanes[lane].stream));
+    }
     e->lanes[lane].pending = false;
+    fold_stage_times(e, e->lanes[lane]);
     return 0;
 }
 int snk_filter_pe_host(snk_engine* e, const snk_batch* r1, const snk_batch* r2, snk_read_result* out1,
@@ -531,7 +576,9 @@ int snk_text_fetch_async(snk_engine* e, int lane, char* out1, char* out2, uint32
     Lane& L = e->lanes[lane];
     if (!L.h_meta || !L.text_n) { snk::set_error("no text batch was submitted on this lane"); return 1; }
     CUDA_TRY(cudaSetDevice(e->device));
+    NvtxRange nvtx_fetch("snk:text_fetch");
     CUDA_TRY(cudaStreamSynchronize(L.stream));        // meta is final
+    CUDA_TRY(cudaEventRecord(L.ev[5], L.stream));
     char* outs[2] = {out1, out2}; uint32_t* offs[2] = {rec_off1, rec_off2}; snk_read_result* ress[2] = {res1, res2};
     for (int m = 0; m < L.text_mates; m++) {
         if (outs[m] && L.h_meta->out_bytes[m])
@@ -539,6 +586,8 @@ int snk_text_fetch_async(snk_engine* e, int lane, char* out1, char* out2, uint32
         if (offs[m]) CUDA_TRY(cudaMemcpyAsync(offs[m], L.d_rec_off[m], ((size_t)L.text_n + 1) * 4, cudaMemcpyDeviceToHost, L.stream));
         if (ress[m]) CUDA_TRY(cudaMemcpyAsync(ress[m], L.d_res[m], (size_t)L.text_n * sizeof(snk_read_result), cudaMemcpyDeviceToHost, L.stream));
     }
+    CUDA_TRY(cudaEventRecord(L.ev[6], L.stream));
+    L.ev_fetch = true;
     return 0;
 }
 
@@ -610,6 +659,13 @@ int snk_engine_error_flags(snk_engine* e, uint32_t* flags, uint64_t* first_bad_i
     return 0;
 }
 uint64_t snk_engine_launch_count(snk_engine* e) { return e ? e->launches : 0; }
+int snk_engine_stage_times(snk_engine* e, double* ms)
+{
+    if (!e || !ms) { snk::set_error("null argument"); return 1; }
+    std::lock_guard<std::mutex> g(e->mu);
+    for (int i = 0; i < SNK_STAGE_COUNT; i++) ms[i] = e->stage_ms[i];
+    return 0;
+}
 
 int snk_host_alloc(void** p, size_t bytes)
 {

@@ -227,7 +227,11 @@ constexpr int kWsScanWarps = 16;            // scan warps per CTA: groups of wpg
 constexpr int kWsHistWarps = 7;             // histogram warps per CTA
 constexpr int kWsHistThreads = 32 * kWsHistWarps;
 constexpr int kWsThreads = 32 * (kWsScanWarps + kWsHistWarps + 1);   // 24 warps = 6 warpgroups; the last warp is the producer
-constexpr int kWsJ = 4;                     // positions per quality item
+#ifndef SNK_WS_J
+#define SNK_WS_J 4
+#endif
+constexpr int kWsJ = SNK_WS_J;              // positions per quality item
+constexpr uint32_t kWsMaxStages = 12;
 // Registers: a scheduler (SM sub-partition) owns 16 384 registers and gets every fourth warp, i.e. 4 scan warps and 2
 // histogram / producer warps. The kernel is launched with 80 registers per thread (6 warps x 32 x 80 = 15 360); the two
 // histogram / producer warpgroups then lower their share to kWsHistRegs and the four scan warpgroups raise theirs to
@@ -242,6 +246,7 @@ constexpr uint32_t kWsMaxStride = 256;      // longer rows stay on filter_kernel
 struct WsShape {
     uint32_t wpg;          // scan warps per group
     uint32_t ngroups;      // kWsScanWarps / wpg
+    uint32_t interleave;   // 1: group g = warps {g, g + ngroups, ...} (a scheduler's scan warps work on the same tile), 0: consecutive warps
     uint32_t R;            // tile capacity in reads (SE) or pairs (PE) = wpg * 32 / (2 * mates)
     uint32_t nstages;
     uint32_t nwd;          // plane words per read
@@ -277,7 +282,7 @@ inline bool ws_make_shape(int mates, uint32_t stride, int qb, uint32_t nada, uin
     s.off_qhist = o; o += ((uint32_t)(qb + 1) * kWsJ * s.X * 2u + 15) / 16 * 16;
     s.off_bstate = o; o += bstate_words(s.nb_pitch) * 4u;
     s.off_ada = o; o += (nada * (uint32_t)sizeof(AdaHot) + 15) / 16 * 16;
-    s.off_bars = o; o += 3u * 8u * 8u;                            // full / scanned / empty, up to 8 stages
+    s.off_bars = o; o += 3u * kWsMaxStages * 8u;                  // full / scanned / empty, up to kWsMaxStages stages
     s.off_stage0 = (o + 127) / 128 * 128;
     if (s.off_stage0 >= smem_limit) return false;
     // candidates: group sizes 8, 4, 2, 1; a pipeline needs one stage per scanning group plus one for the histogram
@@ -300,7 +305,7 @@ inline bool ws_make_shape(int mates, uint32_t stride, int qb, uint32_t nada, uin
         c.stage_bytes = (q + 127) / 128 * 128;
         uint32_t ns = (smem_limit - c.off_stage0) / c.stage_bytes;
         const uint32_t full_groups = kWsScanWarps / wpg;
-        if (ns > 8) ns = 8;
+        if (ns > kWsMaxStages) ns = kWsMaxStages;
         if (ns > full_groups + 2) ns = full_groups + 2;
         if (ns >= 2) {
             c.ngroups = ns - 1 < full_groups ? ns - 1 : full_groups;

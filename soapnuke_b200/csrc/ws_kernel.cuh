@@ -68,7 +68,9 @@ __device__ __forceinline__ void ws_scan_role(const DevParams& P, const WsArgs& W
     const KernelArgs& A = W.k;
     const WsShape& S = W.s;
     constexpr uint32_t RPW = 32u / (2u * MATES);          // pairs (reads) per warp
-    const uint32_t g = (uint32_t)sw / S.wpg, wg = (uint32_t)sw % S.wpg;
+    const uint32_t full_groups = (uint32_t)kWsScanWarps / S.wpg;
+    const uint32_t g = S.interleave ? (uint32_t)sw % full_groups : (uint32_t)sw / S.wpg;
+    const uint32_t wg = S.interleave ? (uint32_t)sw / full_groups : (uint32_t)sw % S.wpg;
     if (g >= S.ngroups) return;                            // the pipeline has fewer stages than groups (long rows)
     const int h = lane & 1;
     const int m = (MATES == 2) ? ((lane >> 1) & 1) : 0;
@@ -321,8 +323,8 @@ __global__ void __maxnreg__(kWsMaxRegs) filter_ws_kernel(const __grid_constant__
     if (A.skip_word && (*A.skip_word & A.skip_mask)) return;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     unsigned long long* bar_full = reinterpret_cast<unsigned long long*>(smem + S.off_bars);
-    unsigned long long* bar_scanned = bar_full + 8;
-    unsigned long long* bar_empty = bar_full + 16;
+    unsigned long long* bar_scanned = bar_full + kWsMaxStages;
+    unsigned long long* bar_empty = bar_full + 2 * kWsMaxStages;
 
     for (uint32_t e = tid; e < (S.off_ada - S.off_qhist) / 4; e += blockDim.x) reinterpret_cast<uint32_t*>(smem + S.off_qhist)[e] = 0;   // cells + vertical counters
     for (uint32_t e = tid; e < ada_slots(P.n_adapters); e += blockDim.x) {

@@ -18,7 +18,7 @@ def build(force=False):
     deps = DEPS + [lib]
     if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps if os.path.exists(d)):
         return out
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-o", out] + SRCS + \
-          ["-L" + os.path.join(PKG, "lib"), "-lsnk_engine", "-lz", "-Wl,-rpath,$ORIGIN/../lib"]
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wno-unknown-pragmas", "-pthread", "-I/usr/local/cuda/include", "-o", out] + SRCS + \
+          ["-L" + os.path.join(PKG, "lib"), "-lsnk_engine", "-lz", "-ldl", "-Wl,-rpath,$ORIGIN/../lib"]
     subprocess.check_call(cmd)
     return out

@@ -12,7 +12,10 @@
 #include "gz_members.h"
 #include "../csrc/text_core.cuh"      // id_transform (host-compilable header; the record formatting of the trim files)
 #include <zlib.h>
+#include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a timeline tool is attached
 #include <sys/stat.h>
+#include <sys/mman.h>
+#include <sys/vfs.h>
 #include <fcntl.h>
 #include <unistd.h>
 #if defined(__x86_64__)
@@ -44,6 +47,11 @@ namespace {
     exit(1);
 }
 void engine_check(int rc) { if (rc) die(snk_last_error()); }
+
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 double now_s()
 {
@@ -484,6 +492,7 @@ void FilterRun::ingest()
         if (!free_q_.pop(b)) break;
         size_t n2 = 0;
         std::thread t2;
+        NvtxRange nvtx("snk:ingest_batch");
         const double tp0 = now_s();
         if (pe_) t2 = std::thread([&] { n2 = fill_mate(*r2, *b, 1, hp_.batch_reads); });
         const size_t n1 = fill_mate(r1, *b, 0, hp_.batch_reads);
@@ -518,6 +527,7 @@ void FilterRun::gpu_stage()
     std::deque<HostBatch*> inflight;
     const size_t depth = inflight_depth();
     auto submit = [&](HostBatch* b) {
+        NvtxRange nvtx("snk:gpu_submit");
         if (pe_) engine_check(snk_filter_pe_text_async(engines_[b->gpu], b->lane, b->in[0].p, b->in_bytes[0], b->in[1].p, b->in_bytes[1],
                                                        b->n, (uint32_t)stride_, &fmt_, b->first_index));
         else engine_check(snk_filter_se_text_async(engines_[b->gpu], b->lane, b->in[0].p, b->in_bytes[0], b->n, (uint32_t)stride_, &fmt_,
@@ -525,6 +535,7 @@ void FilterRun::gpu_stage()
     };
     auto retire = [&] {
         HostBatch* d = inflight.front(); inflight.pop_front();
+        NvtxRange nvtx("snk:gpu_retire");
         const double t0 = now_s();
         for (;;) {
             engine_check(snk_text_meta_sync(engines_[d->gpu], d->lane, &d->meta));
@@ -737,6 +748,7 @@ void FilterRun::gz_worker()
 {
     GzTask t;
     while (gz_q_.pop(t)) {
+        NvtxRange nvtx("snk:gzip_member");
         const double t0 = now_s();
         Piece& p = t.trim ? t.b->tpieces[t.mate][t.piece] : t.b->pieces[t.mate][t.piece];
         if (t.trim) {
@@ -769,16 +781,39 @@ void FilterRun::writer()
     const std::string names[4] = {hp_.output_dir + "/" + hp_.clean_fq1, hp_.output_dir + "/" + hp_.clean_fq2,
                                   hp_.output_dir + "/" + hp_.trim_fq1, hp_.output_dir + "/" + hp_.trim_fq2};
     const int nfiles = trim_ ? 4 : 2;
+    bool via_mmap[4] = {false, false, false, false};
+    off_t extended[4] = {0, 0, 0, 0};
+    const long page = sysconf(_SC_PAGESIZE);
     for (int f = 0; f < nfiles; f++) {
         if (f % 2 >= mates_) continue;
-        out[f] = open(names[f].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
+        out[f] = open(names[f].c_str(), O_RDWR | O_CREAT | O_TRUNC, 0644);
+        if (out[f] < 0) out[f] = open(names[f].c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (out[f] < 0) die("cannot write to the file," + names[f]);
+        // Several threads pwrite()-ing ONE file take turns on its inode lock, which caps a tmpfs output at a single
+        // thread's page-cache copy rate. On tmpfs the pool therefore copies through shared mappings of the file (page
+        // faults of different threads do not serialise); everywhere else it keeps pwrite (SNK_WRITE_MMAP=0/1 overrides).
+        struct statfs sfs;
+        struct stat st;
+        const char* force = getenv("SNK_WRITE_MMAP");
+        const bool regular = fstat(out[f], &st) == 0 && S_ISREG(st.st_mode) && (fcntl(out[f], F_GETFL) & O_ACCMODE) == O_RDWR;
+        const bool tmpfs = fstatfs(out[f], &sfs) == 0 && (unsigned long)sfs.f_type == 0x01021994ul;
+        via_mmap[f] = regular && (force ? atoi(force) != 0 : tmpfs);
     }
     // the order is fixed here (every run of bytes gets its file offset), the copying is done by a small pool
     struct WriteTask { int m; const char* p; size_t len; off_t at; HostBatch* owner; std::shared_ptr<std::string> hold; };
     Channel<WriteTask> tasks;
     auto write_at = [&](const WriteTask& t) {
         const char* p = t.p; size_t n = t.len; off_t at = t.at;
+        if (via_mmap[t.m] && n >= (64u << 10)) {            // the file already extends to at + n (ftruncate by the ordering thread)
+            const off_t a0 = at & ~(off_t)(page - 1);
+            const size_t delta = (size_t)(at - a0);
+            void* m = mmap(nullptr, n + delta, PROT_READ | PROT_WRITE, MAP_SHARED, out[t.m], a0);
+            if (m != MAP_FAILED) {
+                memcpy((char*)m + delta, p, n);
+                munmap(m, n + delta);
+                return;
+            }
+        }
         while (n > 0) {
             const ssize_t w = ::pwrite(out[t.m], p, std::min<size_t>(n, 1u << 30), at);
             if (w < 0) die("cannot write to the file," + names[t.m]);
@@ -792,6 +827,7 @@ void FilterRun::writer()
         pool.emplace_back([&] {
             WriteTask t;
             while (tasks.pop(t)) {
+                NvtxRange nvtx("snk:write");
                 const double t0 = now_s();
                 write_at(t);
                 t_write_us_ += (uint64_t)((now_s() - t0) * 1e6);
@@ -831,6 +867,11 @@ void FilterRun::writer()
         }
         if (b->seq_no % 16 == 0) log_line(local_time() + " processed_reads:\t" + std::to_string(b->first_index + b->n));
         next++;
+        for (int f = 0; f < nfiles; f++)
+            if (via_mmap[f] && pos[f] > extended[f]) {
+                if (ftruncate(out[f], pos[f]) != 0) via_mmap[f] = false;
+                else extended[f] = pos[f];
+            }
         int owned = 0;
         for (const WriteTask& t : mine) owned += t.owner != nullptr;
         if (owned == 0) {
@@ -860,7 +901,10 @@ void FilterRun::writer()
                   << " set SNK_KEEP_DEFERRED=1 to write them" << std::endl;
     for (int f = 0; f < nfiles; f++) {
         if (f % 2 >= mates_) continue;
-        if (!drop && !pending_deferred_[f].empty()) write_at({f, pending_deferred_[f].data(), pending_deferred_[f].size(), pos[f], nullptr, nullptr});
+        if (!drop && !pending_deferred_[f].empty()) {
+            if (via_mmap[f] && ftruncate(out[f], pos[f] + (off_t)pending_deferred_[f].size()) != 0) via_mmap[f] = false;
+            write_at({f, pending_deferred_[f].data(), pending_deferred_[f].size(), pos[f], nullptr, nullptr});
+        }
         if (close(out[f]) != 0) die("cannot write to the file," + names[f]);
     }
 }
@@ -928,6 +972,11 @@ void FilterRun::process()
         for (size_t i = 0; i < words; i++) total[i] += part[i];
         for (size_t j = 0; j < key_words.size(); j++) total[key_words[j]] = keys[j];
     }
+    double stage_ms[SNK_STAGE_COUNT] = {0};
+    for (snk_engine* e : engines_) {
+        double ms[SNK_STAGE_COUNT];
+        if (snk_engine_stage_times(e, ms) == 0) for (int i = 0; i < SNK_STAGE_COUNT; i++) stage_ms[i] += ms[i];
+    }
     if (pe_) { if (snk_report_write_pe(&ep_, total.data(), hp_.output_dir.c_str())) die(snk_last_error()); }
     else { if (snk_report_write_se(&ep_, total.data(), hp_.output_dir.c_str())) die(snk_last_error()); }
     if (!hp_.fast_exit) {                        // the CLI leaves device and pinned memory to process exit
@@ -941,6 +990,10 @@ void FilterRun::process()
         snprintf(buf, sizeof buf, "stage seconds: setup %.2f, read(busy) %.2f, gpu-wait %.2f, gzip(sum over %d workers) %.2f, write(sum over the writer pool) %.2f, total %.2f; reads %llu",
                  t_setup_, t_read_, t_gpu_wait_, nworkers, t_gz_us_.load() * 1e-6, t_write_us_.load() * 1e-6, now_s() - t_begin,
                  (unsigned long long)total_reads_);
+        log_line(buf);
+        snprintf(buf, sizeof buf, "device seconds (CUDA events, summed over %zu GPU(s) x lanes): h2d %.3f, line index + row packing %.3f, filter kernel %.3f, clean text formatting %.3f, d2h %.3f",
+                 (size_t)hp_.n_gpus, stage_ms[SNK_STAGE_H2D] * 1e-3, stage_ms[SNK_STAGE_INDEX_PACK] * 1e-3, stage_ms[SNK_STAGE_FILTER] * 1e-3,
+                 stage_ms[SNK_STAGE_FORMAT] * 1e-3, stage_ms[SNK_STAGE_D2H] * 1e-3);
         log_line(buf);
     }
     log_line(local_time() + "\tAnalysis accomplished!");

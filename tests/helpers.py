@@ -33,8 +33,9 @@ def load_coretest():
                                                     for f in ("filter_core.cuh", "filter_kernel.cuh", "dev_params.h", "text_core.cuh", "ws_core.cuh",
                                                               "ws_kernel.cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
+            extra = os.environ.get("SNK_CXXFLAGS", "").split()          # e.g. -DSNK_WS_J=2 (must match the engine build)
             subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wno-unknown-pragmas", "-fPIC", "-shared",
-                                   "-I/usr/local/cuda/include", "-o", so, deps[0]])
+                                   "-I/usr/local/cuda/include", "-o", so, deps[0]] + extra)
         lib = C.CDLL(so)
         lib.coretest_filter.restype = C.c_int
         lib.coretest_filter.argtypes = [C.POINTER(abi.Params), C.POINTER(abi.Batch), C.POINTER(abi.Batch), C.c_void_p,

@@ -46,6 +46,23 @@ def test_engine_matches_oracle(cfg, engine_lib):
     assert_same((r1, r2, st), (o1, o2, ost), name)
 
 
+@pytest.mark.parametrize("cfg", [c for c in CONFIGS if c[3] <= 250], ids=[c[0] for c in CONFIGS if c[3] <= 250])
+def test_warp_specialised_kernel_matches_oracle(cfg, engine_lib, monkeypatch):
+    """The experimental warp-specialised kernel (SNK_KERNEL=ws: TMA producer / scan warps / histogram warps handing
+    tiles over by mbarriers, rows up to 256 bytes) must be bit-exact too; the production kernel is filter_kernel."""
+    monkeypatch.setenv("SNK_KERNEL", "ws")
+    name, pe, n, L, gkw, pkw = cfg
+    d = synth.gen_pairs(n, L=L, se=not pe, **gkw)
+    p = abi.make_params(is_pe=pe, **pkw)
+    o1, o2, ost, oerr = oracle_run(p, d)
+    with Engine(engine_lib, p) as e:
+        r1, r2 = e.filter_host(d)
+        st = e.stats()
+        flags, _ = e.error_flags()
+    assert flags == oerr == 0
+    assert_same((r1, r2, st), (o1, o2, ost), name + " (ws kernel)")
+
+
 @pytest.mark.parametrize("cfg", [
     ("srna_discard_L44", 60000, 44, dict(), dict()),
     ("srna_trim_polyg_varlen", 60000, 50, dict(var_len=True), dict(ada_trim=True, polyG_tail=6, highA_ratio=0.6, polyX_num=12)),

@@ -56,6 +56,8 @@ def main():
     ap.add_argument("--threads", type=int, default=os.cpu_count())
     ap.add_argument("--skip-reference", action="store_true")
     ap.add_argument("--batch-sweep", default="", help="comma list of SNK_BATCH_READS values to time the B200 CLI with")
+    ap.add_argument("--env-sweep", default="", help="';'-separated settings, each a ','-separated list of VAR=value, to time the B200 CLI with")
+    ap.add_argument("--gz-members", type=int, default=0, help="with --gz: compress the input in members of this many MiB of text (0 = one member per file)")
     a = ap.parse_args()
     work = "/dev/shm/snk_cli_compare"
     shutil.rmtree(work, ignore_errors=True)
@@ -73,7 +75,12 @@ def main():
                 with open(tmp, "rb") as g:
                     shutil.copyfileobj(g, f, 1 << 24)
                 os.unlink(tmp)
-        if a.gz:
+        if a.gz and a.gz_members:
+            subprocess.check_call(["split", "-b", f"{a.gz_members}M", "-d", "-a", "5", path, path + ".part."])
+            os.unlink(path)
+            subprocess.check_call(f"ls {path}.part.* | xargs -P {os.cpu_count()} -n 4 gzip -2", shell=True)
+            subprocess.check_call(f"cat {path}.part.*.gz > {path}.gz && rm {path}.part.*.gz", shell=True)
+        elif a.gz:
             subprocess.check_call(["gzip", "-2", path])
     base = ["-1", f"{work}/r1{ext}", "-2", f"{work}/r2{ext}", "-C", "c1" + ext, "-D", "c2" + ext, "-T", str(a.threads)]
     out = {"pairs": a.pairs, "gz": a.gz, "threads": a.threads, "cores": os.cpu_count()}
@@ -96,6 +103,17 @@ def main():
             t = timed([os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke"), "filter"] + base + ["-o", f"{work}/sweep"] + FLAGS, env=env)
             t["log"] = [l.strip() for l in open(f"{work}/sweep/log") if "stage seconds" in l]
             out["batch_sweep"][br] = t
+        shutil.rmtree(f"{work}/sweep", ignore_errors=True)
+    if a.env_sweep:
+        out["env_sweep"] = {}
+        for setting in a.env_sweep.split(";"):
+            env = dict(os.environ)
+            env.update(kv.split("=", 1) for kv in setting.split(",") if kv)
+            shutil.rmtree(f"{work}/sweep", ignore_errors=True)
+            t = timed([os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke"), "filter"] + base + ["-o", f"{work}/sweep"] + FLAGS, env=env)
+            t["mreads_per_s"] = 2 * a.pairs / t["wall"] / 1e6
+            t["log"] = [l.strip() for l in open(f"{work}/sweep/log") if "stage seconds" in l or "gzip input" in l]
+            out["env_sweep"][setting] = t
         shutil.rmtree(f"{work}/sweep", ignore_errors=True)
     try:
         out["b200_log"] = [l.strip() for l in open(f"{work}/mine/log") if "stage seconds" in l]
