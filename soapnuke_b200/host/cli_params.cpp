@@ -179,7 +179,10 @@ void print_usage(const std::string& module)
               << "filtersRNA: -f 5' adapter, -r 3' adapter, defaults minReadLen 18 / maxReadLen 49; config keys adaRCtg adaRAr adaRMa adaREr adaRMm\n"
               << "environment: SNK_GPUS=<n> (GPUs to shard batches over), SNK_BATCH_READS=<n>,\n"
               << "             SNK_KEEP_DEFERRED=1 (write the last deferred batch of a plain-text PE run that the reference\n"
-              << "             loses in its final concat; default: drop it like the reference, with a warning on stderr)\n";
+              << "             loses in its final concat; default: drop it like the reference, with a warning on stderr),\n"
+              << "             SNK_GZ_CODEC=zlib (.gz outputs through zlib level 2 instead of the in-tree fast deflate encoder),\n"
+              << "             SNK_GZ_SERIAL=1 (.gz inputs through one gzread stream instead of the parallel member reader),\n"
+              << "             SNK_READ_THREADS / SNK_WRITE_THREADS (page-cache copy threads per input / for the outputs)\n";
 }
 
 int parse_command_line(int argc, char** argv, HostParams& hp)

@@ -10,6 +10,7 @@
 #include "process.h"
 #include "host_common.h"
 #include "gz_members.h"
+#include "fast_deflate.h"
 #include "../csrc/text_core.cuh"      // id_transform (host-compilable header; the record formatting of the trim files)
 #include <zlib.h>
 #include <nvtx3/nvToolsExt.h>     // header-only; ranges cost nothing unless a timeline tool is attached
@@ -573,6 +574,10 @@ void FilterRun::gpu_stage()
 
 void FilterRun::encode(const char* p, size_t n, std::string& out)
 {
+    // one gzip member per run. Default: the in-tree fast encoder (fast_deflate.h); SNK_GZ_CODEC=zlib: zlib level 2 as the
+    // reference configures it (peprocess.cpp:1803-1810). Either way only the decompressed bytes are comparable.
+    static const bool use_zlib = [] { const char* c = getenv("SNK_GZ_CODEC"); return c && strcmp(c, "zlib") == 0; }();
+    if (!use_zlib) { out.clear(); fast_gzip_member((const uint8_t*)p, n, out); return; }
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (deflateInit2(&zs, 2, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("zlib deflateInit2 failed");

@@ -100,3 +100,44 @@ def test_plain_text_is_left_to_gzread(gzcat, tmp_path):
     path = str(tmp_path / "plain.gz")
     open(path, "wb").write(TEXT[:4096])
     assert run(gzcat, path, 2, 4096)[0] == 3
+
+
+# ---------------------------------------------------------------- the output side: soapnuke_b200/host/fast_deflate.cpp
+@pytest.fixture(scope="module")
+def fastgz(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("fastgz") / "fastgz")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", out, os.path.join(ROOT, "tests", "gztest", "fastgz.cpp"),
+                           os.path.join(ROOT, "soapnuke_b200", "host", "fast_deflate.cpp"), "-lz"])
+    return out
+
+
+def fast_deflate_cases():
+    rnd = random.Random(11)
+    return {
+        "fastq": TEXT,
+        "empty": b"", "one": b"A", "seven": b"ACGTACG", "eight": b"ACGTACGT", "nine": b"ACGTACGTA",
+        "zeros": b"\0" * 300001,
+        "random": bytes(rnd.randrange(256) for _ in range(300001)),
+        "repeat_text": b"@SYN:1:1101:0000000:000/1\nACGT\n+\nIIII\n" * 20000,
+        "period_251": bytes((i * 7) % 251 for i in range(200001)),
+        "long_matches": bytes(rnd.randrange(256) for _ in range(1000)) * 300,
+        "skewed": bytes((65 if rnd.random() < 0.999 else rnd.randrange(256)) for _ in range(200000)),
+    }
+
+
+FD_CASES = fast_deflate_cases()
+
+
+@pytest.mark.parametrize("name", list(FD_CASES))
+@pytest.mark.parametrize("piece", [4 << 20, 65537, 1001])
+def test_fast_deflate_members_are_valid_gzip(fastgz, tmp_path, name, piece):
+    """Every member the output encoder writes inflates (zlib, via Python's gzip: header, CRC-32 and ISIZE checked) to its
+    input; the concatenation of members is what the clean .gz files consist of."""
+    data = FD_CASES[name]
+    path = str(tmp_path / "in.bin")
+    open(path, "wb").write(data)
+    p = subprocess.run([fastgz, path, str(piece)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=120)
+    assert p.returncode == 0
+    assert gzip.decompress(p.stdout) == data
+    if name == "fastq":
+        assert len(p.stdout) < 0.6 * len(data)
