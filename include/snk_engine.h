@@ -232,7 +232,9 @@ int snk_engine_destroy(snk_engine* e);
  * batch. Copies the batch host->device, runs the kernels, copies the per-read results back into
  * out1/out2 (host) and accumulates the statistics on the device. Synchronous on return.
  * first_index = number of pairs (reads for SE) that precede this batch in the input; it selects
- * the slot per read. */
+ * the slot per read. These two calls may be issued from several threads at once (the reference calls
+ * filter_pe_fqs from its T workers, peprocess.cpp:1915): they take turns on the engine's first lane. The
+ * asynchronous entry points below are single-producer per lane. */
 int snk_filter_pe_host(snk_engine* e, const snk_batch* r1, const snk_batch* r2,
                        snk_read_result* out1, snk_read_result* out2, uint64_t first_index);
 int snk_filter_se_host(snk_engine* e, const snk_batch* r1, snk_read_result* out1, uint64_t first_index);

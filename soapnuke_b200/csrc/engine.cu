@@ -85,6 +85,7 @@ struct snk_engine {
     uint32_t ws_wpg = 0;                     // SNK_WS_WPG: force the scan group size (tuning)
     uint32_t ws_interleave = 1;              // SNK_WS_MAP=block: consecutive warps form a group (tuning)
     std::mutex mu;
+    std::mutex host_mu;                      // the synchronous *_host entry points share lane 0: one caller at a time
     // per engine (= per device) launch cache, keyed by kernel instantiation: cudaFuncSetAttribute and the
     // occupancy query are per device, so they must not be remembered in function-local statics
     struct KernelCache { const void* fn; int threads; size_t smem; int blocks; bool smem_opt_in; };
@@ -535,11 +536,15 @@ int snk_engine_lane_sync(snk_engine* e, int lane)
 int snk_filter_pe_host(snk_engine* e, const snk_batch* r1, const snk_batch* r2, snk_read_result* out1,
                        snk_read_result* out2, uint64_t first_index)
 {
+    if (!e) { snk::set_error("null engine"); return 1; }
+    std::lock_guard<std::mutex> g(e->host_mu);        // callable from the reference's T worker threads at once
     if (filter_host_async(e, 0, 2, r1, r2, out1, out2, first_index)) return 1;
     return snk_engine_lane_sync(e, 0);
 }
 int snk_filter_se_host(snk_engine* e, const snk_batch* r1, snk_read_result* out1, uint64_t first_index)
 {
+    if (!e) { snk::set_error("null engine"); return 1; }
+    std::lock_guard<std::mutex> g(e->host_mu);
     if (filter_host_async(e, 0, 1, r1, nullptr, out1, nullptr, first_index)) return 1;
     return snk_engine_lane_sync(e, 0);
 }

@@ -4,11 +4,24 @@
 #include <iostream>
 #include <string>
 #include <unistd.h>
+#include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include "cli_params.h"
 #include "process.h"
 
+// SNK_TIMESTAMPS=1: wall-clock marks on stderr, to separate process start / driver teardown from the run itself
+static void timestamp(const char* what)
+{
+    if (!getenv("SNK_TIMESTAMPS")) return;
+    struct timespec ts;
+    clock_gettime(CLOCK_REALTIME, &ts);
+    fprintf(stderr, "snk-ts %s %.6f\n", what, ts.tv_sec + 1e-9 * ts.tv_nsec);
+}
+
 int main(int argc, char** argv)
 {
+    timestamp("main");
     if (argc < 2) {
         std::cout << "\nProgram: SOAPnuke (b200 filter engine)\nCommand:\n         filter        preprocessing normal Fastq files\n"
                      "         filterMeta    preprocessing Meta Fastq files\n         filtersRNA    preprocessing sRNA Fastq files\n\n";
@@ -32,5 +45,6 @@ int main(int argc, char** argv)
     // every output file is written and closed: skip the CUDA context / pinned memory teardown
     std::cout.flush();
     std::cerr.flush();
+    timestamp("exit");
     _exit(0);
 }

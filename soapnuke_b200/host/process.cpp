@@ -119,6 +119,9 @@ public:
             fd_ = open(path.c_str(), O_RDONLY);
             if (fd_ < 0) die("cannot open the file," + path);
             seekable_ = lseek(fd_, 0, SEEK_CUR) != (off_t)-1;
+#ifdef F_SETPIPE_SZ
+            if (!seekable_) fcntl(fd_, F_SETPIPE_SZ, 1 << 20);     // a FIFO / pipe: 1 MiB of buffering instead of 64 KiB
+#endif
         }
     }
     ~ByteSource() { if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
@@ -460,10 +463,23 @@ void FilterRun::ingest()
 {
     // spaceNum: trailing whitespace of the very first line of fq1 (peprocess.cpp:2066-2076); the
     // reference probes it with gzopen/gzgets, which also reads plain files
+    // .gz input: the host threads (-T) are shared by the mates' member decoders
+    const int gz_threads = hp_.input_gz ? std::max(1, hp_.threads / mates_) : 0;
+    struct stat st1;
+    const bool fifo1 = stat(hp_.fq1_path.c_str(), &st1) == 0 && !S_ISREG(st1.st_mode);
+    std::unique_ptr<ByteSource> r1_early;
     {
-        ByteSource probe(hp_.fq1_path, true);
+        // a pipe / FIFO cannot be opened twice: probe through the real reader and hand the bytes back to it as carry
         std::vector<char> head(1 << 16);
-        const size_t got = probe.read(head.data(), head.size());
+        size_t got = 0;
+        if (fifo1) {
+            r1_early.reset(new ByteSource(hp_.fq1_path, hp_.input_gz, gz_threads));
+            while (got < head.size()) { const size_t g = r1_early->read(head.data() + got, head.size() - got); if (!g) break; got += g; }
+            r1_early->carry.assign(head.data(), head.data() + got);
+        } else {
+            ByteSource probe(hp_.fq1_path, true);
+            got = probe.read(head.data(), head.size());
+        }
         const char* nl = (const char*)memchr(head.data(), '\n', got);
         size_t n = nl ? (size_t)(nl - head.data()) + 1 : got;
         int sp = 0;
@@ -476,9 +492,8 @@ void FilterRun::ingest()
     }
     if (!stride_) stride_ = 160;
     fmt_.strip = hp_.input_gz ? strip_gz_ : 1;                     // plain: erase(size()-1) (peprocess.cpp:2206)
-    // .gz input: the host threads (-T) are shared by the mates' member decoders
-    const int gz_threads = hp_.input_gz ? std::max(1, hp_.threads / mates_) : 0;
-    ByteSource r1(hp_.fq1_path, hp_.input_gz, gz_threads);
+    std::unique_ptr<ByteSource> r1_own(r1_early ? r1_early.release() : new ByteSource(hp_.fq1_path, hp_.input_gz, gz_threads));
+    ByteSource& r1 = *r1_own;
     ByteSource* r2 = pe_ ? new ByteSource(hp_.fq2_path, hp_.input_gz, gz_threads) : nullptr;
     {   // plain files: threads per mate that copy out of the page cache (and count newlines) in parallel
         int rt = std::max(2, std::min(8, hp_.threads / mates_));
