@@ -33,7 +33,7 @@ from soapnuke_b200 import abi, synth  # noqa: E402
 
 A1, A2 = synth.ADAPTER1.decode(), synth.ADAPTER2.decode()
 SA3 = synth.SRNA_ADAPTER3.decode()
-CLI = os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke")
+CLI = os.environ.get("SNK_CLI", os.path.join(ROOT, "soapnuke_b200", "bin", "SOAPnuke"))
 REF = os.path.join(ROOT, "oracle", "_ref", "SOAPnuke")
 WORK = "/dev/shm/snk_configs"
 
@@ -217,7 +217,10 @@ def run_config(num, a):
         for k in mates:
             os.mkfifo(f"{w}/in{k}.fq")
             os.symlink("/dev/null", f"{od}/c{k}.fq")
-            feeders.append(subprocess.Popen(["cat"] + [f"{w}/blk{k}.fq"] * nblk, stdout=open(f"{w}/in{k}.fq", "wb")))
+            # the FIFO is opened by the feeder's own shell: opening it here would block until the CLI opens the other end
+            listing = f"{w}/feed{k}.txt"
+            open(listing, "w").write((f"{w}/blk{k}.fq\n") * nblk)
+            feeders.append(subprocess.Popen(f"xargs cat < {listing} > {w}/in{k}.fq", shell=True))
         how = f"block of {block} {out['units']} replayed {nblk}x through FIFOs -> clean FASTQ to /dev/null, reports to disk"
     m, wall = sh([CLI, "filter"] + args(f"{w}/in", od, T), env=env, timeout=a.timeout)
     for f in feeders:
