@@ -5,6 +5,7 @@
 // (rmdup, output split/subsample, streaming, stLFR, base conversion) are rejected with an explicit
 // error instead of being silently ignored.
 #include "cli_params.h"
+#include <sys/stat.h>
 #include <cmath>
 #include <getopt.h>
 #include <sys/sysinfo.h>
@@ -45,6 +46,10 @@ std::string strip(const std::string& s)
 }
 bool file_exists_and_not_empty(const std::string& path)
 {
+    // a FIFO / device can be opened only once without losing data (and opening it blocks until the other end is there):
+    // its existence is all that is checked here
+    struct stat st;
+    if (stat(path.c_str(), &st) == 0 && !S_ISREG(st.st_mode) && !S_ISDIR(st.st_mode)) return true;
     std::ifstream f(path.c_str());
     return f && f.peek() != EOF;
 }

@@ -220,10 +220,18 @@ def run_config(num, a):
             # the FIFO is opened by the feeder's own shell: opening it here would block until the CLI opens the other end
             listing = f"{w}/feed{k}.txt"
             open(listing, "w").write((f"{w}/blk{k}.fq\n") * nblk)
-            feeders.append(subprocess.Popen(f"xargs cat < {listing} > {w}/in{k}.fq", shell=True))
+            feeders.append(subprocess.Popen(f"xargs cat < {listing} > {w}/in{k}.fq", shell=True, start_new_session=True))
         how = f"block of {block} {out['units']} replayed {nblk}x through FIFOs -> clean FASTQ to /dev/null, reports to disk"
-    m, wall = sh([CLI, "filter"] + args(f"{w}/in", od, T), env=env, timeout=a.timeout)
-    for f in feeders:
+    try:
+        m, wall = sh([CLI, "filter"] + args(f"{w}/in", od, T), env=env, timeout=a.timeout)
+    except subprocess.TimeoutExpired:
+        m, wall = subprocess.CompletedProcess([], 124, b"", b"timed out"), float(a.timeout)
+    for f in feeders:                                             # a feeder that never found its reader is still blocked in open()
+        if f.poll() is None:
+            try:
+                os.killpg(f.pid, 15)
+            except OSError:
+                pass
         f.wait()
     reads = total_units * len(mates)
     out["e2e_file"] = dict(value=reads / wall / 1e6, unit="Mreads/s", wall_s=wall, reads=reads, ok=m.returncode == 0, how=how, threads=T,
