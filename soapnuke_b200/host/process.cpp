@@ -353,6 +353,7 @@ private:
     bool reorder_ = false;
     // busy seconds per stage (log only)
     double t_read_ = 0, t_gpu_wait_ = 0, t_setup_ = 0;
+    double t0_ = 0, tl_first_batch_ = 0, tl_ingest_done_ = 0, tl_gpu_done_ = 0, tl_writer_done_ = 0, tl_stats_done_ = 0;   // timeline marks (log only)
     std::atomic<uint64_t> t_gz_us_{0}, t_write_us_{0};
     size_t avg_rec_bytes_[2] = {0, 0};
 };
@@ -521,13 +522,14 @@ void FilterRun::ingest()
         b->n = (uint32_t)n1; b->seq_no = seq_no; b->first_index = first;
         b->gpu = (int)(seq_no % engines_.size());
         b->lane = (int)((seq_no / engines_.size()) % lanes);
-        if (seq_no == 0) first_batch_checks(*b);
+        if (seq_no == 0) { first_batch_checks(*b); tl_first_batch_ = now_s() - t0_; }
         first += n1; seq_no++;
         gpu_q_.push(b);
         if (n1 < hp_.batch_reads) break;
     }
     total_reads_ = first;
     n_batches_total_ = seq_no;
+    tl_ingest_done_ = now_s() - t0_;
     if (r1.parallel_gz()) {
         const GzMemberReader::Counters c1 = r1.gz_counters(), c2 = r2 ? r2->gz_counters() : GzMemberReader::Counters();
         log_line("gzip input: " + std::to_string(c1.members + c2.members) + " members inflated on " + std::to_string(gz_threads * mates_) +
@@ -582,6 +584,7 @@ void FilterRun::gpu_stage()
         inflight.push_back(b);
     }
     while (!inflight.empty()) retire();
+    tl_gpu_done_ = now_s() - t0_;
     { std::lock_guard<std::mutex> g(done_mu_); all_submitted_ = true; }
     done_cv_.notify_all();
     gz_q_.close();
@@ -932,6 +935,7 @@ void FilterRun::writer()
 void FilterRun::process()
 {
     const double t_begin = now_s();
+    t0_ = t_begin;
     mkdir_p(hp_.output_dir);
     log_.open(hp_.log.c_str());
     if (!log_) die("cannot open such file," + hp_.log);
@@ -970,6 +974,7 @@ void FilterRun::process()
     t_gpu.join();
     for (auto& w : workers) w.join();
     t_writer.join();
+    tl_writer_done_ = now_s() - t0_;
     free_q_.close();
 
     // ---- statistics: per-GPU tables -> one table (counters add, LAST_KEY words take the max)
@@ -992,6 +997,7 @@ void FilterRun::process()
         for (size_t i = 0; i < words; i++) total[i] += part[i];
         for (size_t j = 0; j < key_words.size(); j++) total[key_words[j]] = keys[j];
     }
+    tl_stats_done_ = now_s() - t0_;
     double stage_ms[SNK_STAGE_COUNT] = {0};
     for (snk_engine* e : engines_) {
         double ms[SNK_STAGE_COUNT];
@@ -1014,6 +1020,9 @@ void FilterRun::process()
         snprintf(buf, sizeof buf, "device seconds (CUDA events, summed over %zu GPU(s) x lanes): h2d %.3f, line index + row packing %.3f, filter kernel %.3f, clean text formatting %.3f, d2h %.3f",
                  (size_t)hp_.n_gpus, stage_ms[SNK_STAGE_H2D] * 1e-3, stage_ms[SNK_STAGE_INDEX_PACK] * 1e-3, stage_ms[SNK_STAGE_FILTER] * 1e-3,
                  stage_ms[SNK_STAGE_FORMAT] * 1e-3, stage_ms[SNK_STAGE_D2H] * 1e-3);
+        log_line(buf);
+        snprintf(buf, sizeof buf, "timeline seconds since start: engines ready %.2f, first batch read %.2f, input exhausted %.2f, last batch off the GPU %.2f, outputs written %.2f, statistics gathered %.2f, reports written %.2f",
+                 t_setup_, tl_first_batch_, tl_ingest_done_, tl_gpu_done_, tl_writer_done_, tl_stats_done_, now_s() - t_begin);
         log_line(buf);
     }
     log_line(local_time() + "\tAnalysis accomplished!");
