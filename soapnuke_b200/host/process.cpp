@@ -950,10 +950,16 @@ void FilterRun::process()
     fmt_.pe_info = (pe_ && hp_.pe_info) ? (trim_ ? 2 : 1) : 0;
     fmt_.fasta = hp_.output_file_type == "fasta";
     fmt_.id_mode = hp_.index_remove ? (hp_.seq_type == "0" ? 1 : 2) : 0;
-    for (int g = 0; g < hp_.n_gpus; g++) {
-        snk_engine* e = nullptr;
-        engine_check(snk_engine_create(&ep_, g, &e));
-        engines_.push_back(e);
+    {
+        // one engine per GPU; the CUDA contexts of different devices come up in parallel (0.3 - 1 s each)
+        engines_.assign((size_t)hp_.n_gpus, nullptr);
+        std::vector<std::string> errs((size_t)hp_.n_gpus);
+        std::vector<std::thread> th;
+        auto create = [&](int g) { if (snk_engine_create(&ep_, g, &engines_[g])) errs[g] = snk_last_error(); };   // the error text is per thread
+        for (int g = 1; g < hp_.n_gpus; g++) th.emplace_back(create, g);
+        create(0);
+        for (auto& t : th) t.join();
+        for (const std::string& e : errs) if (!e.empty()) die(e);
     }
     // emission-order quirk applies to plain-text PE input with more than one worker
     cyc_ = (uint64_t)ep_.slot_block * (uint64_t)ep_.n_slots;
