@@ -187,7 +187,8 @@ void print_usage(const std::string& module)
               << "             loses in its final concat; default: drop it like the reference, with a warning on stderr),\n"
               << "             SNK_GZ_CODEC=zlib (.gz outputs through zlib level 2 instead of the in-tree fast deflate encoder),\n"
               << "             SNK_GZ_SERIAL=1 (.gz inputs through one gzread stream instead of the parallel member reader),\n"
-              << "             SNK_READ_THREADS / SNK_WRITE_THREADS (page-cache copy threads per input / for the outputs)\n";
+              << "             SNK_READ_THREADS / SNK_WRITE_THREADS (page-cache copy threads per input / for the outputs),\n"
+              << "             SNK_PREFETCH_MB=<n> (plain inputs: MiB per file read ahead while the CUDA contexts are created; default 2048, 0 = off)\n";
 }
 
 int parse_command_line(int argc, char** argv, HostParams& hp)

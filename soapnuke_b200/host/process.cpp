@@ -124,7 +124,53 @@ public:
 #endif
         }
     }
-    ~ByteSource() { if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
+    ~ByteSource() { stop_prefetch(); if (pf_buf_) free(pf_buf_); if (f_) gzclose(f_); if (fd_ >= 0) close(fd_); }
+    // Read-ahead for the seconds in which nothing else can happen: creating the CUDA contexts takes 0.3 - 2 s and the
+    // pinned batch buffers cannot be allocated before it is done. A plain, seekable input is meanwhile copied out of the
+    // page cache into ordinary memory (up to max_bytes); read() then serves those offsets with memcpy. stop_prefetch()
+    // is called when the first batch buffer becomes available - from there on reading ahead would only copy twice.
+    void start_prefetch(size_t max_bytes, int threads)
+    {
+        if (gz_ || members_ || !seekable_ || fd_ < 0 || max_bytes == 0) return;
+        struct stat st;
+        if (fstat(fd_, &st) != 0 || st.st_size <= 0) return;
+        pf_cap_ = std::min<size_t>(max_bytes, (size_t)st.st_size);
+        pf_buf_ = (char*)malloc(pf_cap_);
+        if (!pf_buf_) { pf_cap_ = 0; return; }
+        pf_thread_ = std::thread([this, threads] {
+            constexpr size_t kStep = 32u << 20;
+            const int np = std::max(1, threads);
+            size_t done = 0;
+            while (done < pf_cap_ && !pf_stop_.load(std::memory_order_acquire)) {
+                const size_t n = std::min(kStep, pf_cap_ - done);
+                const size_t part = (n / np + 4095) & ~(size_t)4095;
+                std::vector<std::thread> th;
+                std::atomic<bool> short_read{false};
+                for (int i = 0; i < np; i++) {
+                    const size_t lo = std::min(n, part * i), hi = std::min(n, part * (i + 1));
+                    if (lo == hi) continue;
+                    th.emplace_back([&, lo, hi] {
+                        size_t got = 0;
+                        while (got < hi - lo) {
+                            const ssize_t g = ::pread(fd_, pf_buf_ + done + lo + got, hi - lo - got, (off_t)(done + lo + got));
+                            if (g <= 0) { short_read = true; break; }
+                            got += (size_t)g;
+                        }
+                    });
+                }
+                for (auto& t : th) t.join();
+                if (short_read) break;                      // the file changed under us: the rest is read the normal way
+                done += n;
+                pf_done_.store(done, std::memory_order_release);
+            }
+        });
+    }
+    void stop_prefetch()
+    {
+        pf_stop_.store(true, std::memory_order_release);
+        if (pf_thread_.joinable()) pf_thread_.join();
+    }
+    size_t prefetched() const { return pf_done_.load(std::memory_order_acquire); }
     // up to n bytes into dst; 0 at EOF. Plain files: large requests are split over a few threads (the copy out of the
     // page cache is what limits a single reader); with `parts` every thread also counts the newlines of its share, so
     // that the caller's search for a record boundary only has to look into one share.
@@ -148,6 +194,7 @@ public:
             return (size_t)got;
         }
         auto pread_all = [&](char* d, size_t want, off_t at) -> size_t {
+            if ((size_t)at + want <= pf_done_.load(std::memory_order_acquire)) { memcpy(d, pf_buf_ + at, want); return want; }   // read ahead earlier
             size_t done = 0;
             while (done < want) {
                 const ssize_t got = ::pread(fd_, d + done, want - done, at + (off_t)done);
@@ -197,6 +244,11 @@ private:
     off_t off_ = 0;
     bool seekable_ = true;
     int read_threads_ = 4;
+    char* pf_buf_ = nullptr;
+    size_t pf_cap_ = 0;
+    std::atomic<size_t> pf_done_{0};
+    std::atomic<bool> pf_stop_{false};
+    std::thread pf_thread_;
 };
 
 // ------------------------------------------------------------------ newline search
@@ -353,6 +405,7 @@ private:
     bool reorder_ = false;
     // busy seconds per stage (log only)
     double t_read_ = 0, t_gpu_wait_ = 0, t_setup_ = 0;
+    double tl_prefetched_ = 0;           // GB read ahead while the engines came up
     double t0_ = 0, tl_first_batch_ = 0, tl_ingest_done_ = 0, tl_gpu_done_ = 0, tl_writer_done_ = 0, tl_stats_done_ = 0;   // timeline marks (log only)
     std::atomic<uint64_t> t_gz_us_{0}, t_write_us_{0};
     size_t avg_rec_bytes_[2] = {0, 0};
@@ -502,11 +555,26 @@ void FilterRun::ingest()
         r1.set_read_threads(rt);
         if (r2) r2->set_read_threads(rt);
     }
+    // the engines (CUDA contexts) are still being created by process(): read ahead until the first batch buffer arrives
+    {
+        size_t pf_mb = 2048;
+        if (const char* e = getenv("SNK_PREFETCH_MB")) pf_mb = (size_t)std::max(0, atoi(e));
+        const int rt = std::max(2, std::min(8, hp_.threads / mates_));
+        r1.start_prefetch(pf_mb << 20, rt);
+        if (r2) r2->start_prefetch(pf_mb << 20, rt);
+    }
     uint64_t seq_no = 0, first = 0;
-    const size_t lanes = (size_t)snk_engine_lanes(engines_[0]);
+    const size_t lanes = (size_t)snk_engine_lanes(nullptr);
+    bool prefetching = true;
     for (;;) {
         HostBatch* b;
         if (!free_q_.pop(b)) break;
+        if (prefetching) {
+            r1.stop_prefetch();
+            if (r2) r2->stop_prefetch();
+            prefetching = false;
+            tl_prefetched_ = (double)(r1.prefetched() + (r2 ? r2->prefetched() : 0)) / 1e9;
+        }
         size_t n2 = 0;
         std::thread t2;
         NvtxRange nvtx("snk:ingest_batch");
@@ -950,6 +1018,14 @@ void FilterRun::process()
     fmt_.pe_info = (pe_ && hp_.pe_info) ? (trim_ ? 2 : 1) : 0;
     fmt_.fasta = hp_.output_file_type == "fasta";
     fmt_.id_mode = hp_.index_remove ? (hp_.seq_type == "0" ? 1 : 2) : 0;
+    // emission-order quirk applies to plain-text PE input with more than one worker
+    cyc_ = (uint64_t)ep_.slot_block * (uint64_t)ep_.n_slots;
+    defer_len_ = (uint64_t)hp_.patch_size;
+    insert_off_ = (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 1);
+    reorder_ = pe_ && !hp_.input_gz && ep_.n_slots > 1;
+    // The reader starts first: it opens the inputs and reads ahead while the CUDA contexts come up; it gets its first batch
+    // buffer (pinned memory needs a context) only after that.
+    std::thread t_ingest([&] { ingest(); });
     {
         // one engine per GPU; the CUDA contexts of different devices come up in parallel (0.3 - 1 s each)
         engines_.assign((size_t)hp_.n_gpus, nullptr);
@@ -961,17 +1037,11 @@ void FilterRun::process()
         for (auto& t : th) t.join();
         for (const std::string& e : errs) if (!e.empty()) die(e);
     }
-    // emission-order quirk applies to plain-text PE input with more than one worker
-    cyc_ = (uint64_t)ep_.slot_block * (uint64_t)ep_.n_slots;
-    defer_len_ = (uint64_t)hp_.patch_size;
-    insert_off_ = (uint64_t)ep_.slot_block * (uint64_t)(ep_.n_slots - 1);
-    reorder_ = pe_ && !hp_.input_gz && ep_.n_slots > 1;
     batches_.resize(inflight_depth() + 3);       // in flight on the GPUs + being read + being compressed/written
     for (auto& b : batches_) free_q_.push(&b);
 
     t_setup_ = now_s() - t_begin;
     const int nworkers = (hp_.clean_gz || trim_) ? std::max(2, hp_.threads) : 0;
-    std::thread t_ingest([&] { ingest(); });
     std::thread t_gpu([&] { gpu_stage(); });
     std::vector<std::thread> workers;
     for (int i = 0; i < nworkers; i++) workers.emplace_back([&] { gz_worker(); });
@@ -1027,8 +1097,8 @@ void FilterRun::process()
                  (size_t)hp_.n_gpus, stage_ms[SNK_STAGE_H2D] * 1e-3, stage_ms[SNK_STAGE_INDEX_PACK] * 1e-3, stage_ms[SNK_STAGE_FILTER] * 1e-3,
                  stage_ms[SNK_STAGE_FORMAT] * 1e-3, stage_ms[SNK_STAGE_D2H] * 1e-3);
         log_line(buf);
-        snprintf(buf, sizeof buf, "timeline seconds since start: engines ready %.2f, first batch read %.2f, input exhausted %.2f, last batch off the GPU %.2f, outputs written %.2f, statistics gathered %.2f, reports written %.2f",
-                 t_setup_, tl_first_batch_, tl_ingest_done_, tl_gpu_done_, tl_writer_done_, tl_stats_done_, now_s() - t_begin);
+        snprintf(buf, sizeof buf, "timeline seconds since start: engines ready %.2f (%.2f GB of input read ahead meanwhile), first batch read %.2f, input exhausted %.2f, last batch off the GPU %.2f, outputs written %.2f, statistics gathered %.2f, reports written %.2f",
+                 t_setup_, tl_prefetched_, tl_first_batch_, tl_ingest_done_, tl_gpu_done_, tl_writer_done_, tl_stats_done_, now_s() - t_begin);
         log_line(buf);
     }
     log_line(local_time() + "\tAnalysis accomplished!");
