@@ -1,5 +1,6 @@
 #!/bin/bash
 # Experiment session 1 (round 2): ws kernel variants (group mapping, group size, J) + CLI host pipeline sweeps.
+# (record of the experiment: the J=2 tuning build libsnk_engine_j2.so - SNK_CXXFLAGS=-DSNK_WS_J=2 SNK_ENGINE_LIB_NAME=... - aborted on the GPU and was dropped)
 OUT=gpurun_out; TAG=exp1; mkdir -p $OUT
 timeout 120 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; rc=$?; tail -1 $OUT/${TAG}_smoke.log
 if [ $rc -ne 0 ]; then echo "smoke failed rc=$rc: stopping"; exit 1; fi

@@ -1,5 +1,6 @@
 #!/bin/bash
 # Session 8 (round 2), one GPU: writer variants on a 4 Mi-pair run (parent holds a CUDA context, like bench.py).
+# (record of the experiment: SNK_WRITE_POPULATE and SNK_POOL_EXTRA existed only for this session and were removed afterwards - neither helped)
 OUT=gpurun_out; mkdir -p $OUT
 timeout 60 python __graft_entry__.py smoke > $OUT/exp8_smoke.log 2>&1; rc=$?; tail -1 $OUT/exp8_smoke.log
 if [ $rc -ne 0 ]; then echo "smoke failed rc=$rc: stopping"; exit 1; fi
