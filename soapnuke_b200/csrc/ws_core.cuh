@@ -231,6 +231,9 @@ constexpr int kWsThreads = 32 * (kWsScanWarps + kWsHistWarps + 1);   // 24 warps
 #define SNK_WS_J 4
 #endif
 constexpr int kWsJ = SNK_WS_J;              // positions per quality item
+// J = 2 (twice as many, half as long quality items) passes the CPU replay but its tuning build aborted on the GPU in round 2
+// and was not pursued: only 4 is supported.
+static_assert(kWsJ == 4, "the warp-specialised kernel is validated for 4 positions per quality item only");
 constexpr uint32_t kWsMaxStages = 12;
 // Registers: a scheduler (SM sub-partition) owns 16 384 registers and gets every fourth warp, i.e. 4 scan warps and 2
 // histogram / producer warps. The kernel is launched with 80 registers per thread (6 warps x 32 x 80 = 15 360); the two
