@@ -7,7 +7,9 @@ For every seed: random PE/SE shape, read length, worker count, patch size and a 
 adapter options; runs the reference binary and the oracle (oracle/snk_oracle.c + host report writer) on the same
 FASTQ and prints the seeds whose clean FASTQ or reports differ. Known non-issues it filters or that show up as
 reference crashes: uninitialised buffers printed when no read survives, low-quality end trims longer than the read,
-the single-end abort behind the Q20/Q30 report (outputs written before it are still compared).
+the single-end abort behind the Q20/Q30 report (outputs written before it are still compared), and - rarely, with reads
+shorter than an adapter - a trimming-position count that depends on the heap bytes behind a read string (phase 1 of adapter_pos
+reads past the end of short reads; re-running the reference with trimFq1/2 set changes the answer: seed 7556).
 The committed twin of this generator (tests/test_core_replay.py: random_case) checks the device code against the
 oracle in the CPU tier.
 """
