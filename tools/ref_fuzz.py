@@ -9,7 +9,7 @@ FASTQ and prints the seeds whose clean FASTQ or reports differ. Known non-issues
 reference crashes: uninitialised buffers printed when no read survives, low-quality end trims longer than the read,
 the single-end abort behind the Q20/Q30 report (outputs written before it are still compared), and - rarely, with reads
 shorter than an adapter - a trimming-position count that depends on the heap bytes behind a read string (phase 1 of adapter_pos
-reads past the end of short reads; re-running the reference with trimFq1/2 set changes the answer: seed 7556).
+reads past the end of short reads; re-running the reference with trimFq1/2 set changes the answer: seeds 7556, 11312).
 The committed twin of this generator (tests/test_core_replay.py: random_case) checks the device code against the
 oracle in the CPU tier.
 """
