@@ -1,7 +1,7 @@
 // gpu_process.h — the reference-side binding: subclasses of the REFERENCE's own peProcess / seProcess
 // (/root/reference/src/peprocess.h:56, seprocess.h:32) whose per-batch work goes through the C ABI of
 // include/snk_engine.h. Compiled against the reference sources by tests/integration/build.sh (which states the
-// three-line patch the reference headers need) into oracle/_ref/SOAPnuke_gpu; tests/test_integration_gpu.py runs that
+// patch the reference needs: five `virtual` keywords and the two constructor calls in main.cpp) into oracle/_ref/SOAPnuke_gpu; tests/test_integration_gpu.py runs that
 // binary against the unmodified reference binary. Test / integration material, not part of the product.
 //
 // What stays the reference's: argv parsing, the reader threads and their block partition, temp files, `cat`, the
